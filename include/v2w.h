@@ -1,0 +1,253 @@
+/*
+ * v2w.h -- C-ABI of the B200-native Vec2Wav generator forward pass.
+ *
+ * The reference (p1an-lin-jung/WavThruVec_pytorch) has no FFI layer: its boundary for this
+ * path is the Python class `Generator` (vec2wav/models.py:77-156) constructed as
+ * `Generator(h)` (vec2wav/train.py:65) and called as `generator(wv_feat, spk_emb, noise)`
+ * (vec2wav/train.py:167,262).  This header is the boundary a binding would sit on: the
+ * Python drop-in (`wavthruvec_pytorch_b200.models.Generator`) binds it with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; opaque handles; every function returns V2W_OK (0) or a negative
+ *     error code and records a message retrievable with v2w_last_error() (thread-local).
+ *   - no exceptions cross the boundary; no torch types appear in any signature.
+ *   - "host" pointers are ordinary process memory, "dev" pointers are CUDA device memory
+ *     owned by the caller (PyTorch's allocator on the Python side).
+ *   - every function that touches the GPU takes the cudaStream_t to work on (as void*).
+ *   - a model/plan is used by one host thread and one stream at a time; distinct plans are
+ *     independent.  There is NO CPU execution path: calling a device function without a
+ *     usable sm_100 GPU fails with V2W_ERR_CUDA.
+ *
+ * Object model
+ *   v2w_model : hyper-parameters (vec2wav/hparams.py:24-57 subset read by
+ *               vec2wav/models.py:81-110) -> static table of tap-GEMM layers + the packed
+ *               weight format.  Pure host object.
+ *   v2w_plan  : model x (batch, frames, precision) -> ordered op list, workspace layout,
+ *               TMA descriptors.  Bound to device buffers with v2w_plan_bind().
+ */
+#ifndef V2W_H_
+#define V2W_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2W_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define V2W_OK 0
+#define V2W_ERR_INVALID (-1)   /* bad argument / unsupported hyper-parameter combination */
+#define V2W_ERR_CUDA (-2)      /* CUDA runtime / driver error, or no usable GPU */
+#define V2W_ERR_STATE (-3)     /* call order violated (e.g. forward before bind) */
+#define V2W_ERR_NOMEM (-4)
+
+/* ---- limits ------------------------------------------------------------------------ */
+#define V2W_MAX_STAGES 8
+#define V2W_MAX_KERNELS 4     /* resblock kernel sizes per stage (reference: 3) */
+#define V2W_MAX_DILATIONS 4
+#define V2W_MAX_TAPS 16
+#define V2W_MAX_TILES 8
+
+/* ---- precision of a plan ----------------------------------------------------------- */
+#define V2W_PREC_FP32 0  /* FFMA kernels, fp32 everywhere: parity bar max-abs <= 1e-4 */
+#define V2W_PREC_BF16 1  /* tcgen05 bf16 x bf16 -> fp32 (TMEM), fp32 residual stream: SNR >= 45 dB */
+
+/* Hyper-parameters.  Replaces the attribute bag `h` of Generator.__init__
+ * (vec2wav/models.py:78-114; values in vec2wav/hparams.py:26-27,30,40-44,51). */
+typedef struct v2w_config {
+  int32_t num_wv_feat;                 /* 768 | 1024 ; any multiple of 16 accepted */
+  int32_t upsample_initial_channel;    /* must be 512: CBN widths are hard-coded 256>>i (models.py:113) */
+  int32_t num_upsamples;
+  int32_t upsample_rates[V2W_MAX_STAGES];
+  int32_t upsample_kernel_sizes[V2W_MAX_STAGES];
+  int32_t resblock_type;               /* 1 = ResBlock1 (h.resblock == '1'), 2 = ResBlock2 (anything else; models.py:84) */
+  int32_t num_kernels;
+  int32_t resblock_kernel_sizes[V2W_MAX_KERNELS];
+  int32_t num_dilations;               /* entries per row below (reference: 3; ResBlock2 reads the first 2) */
+  int32_t resblock_dilation_sizes[V2W_MAX_KERNELS][V2W_MAX_DILATIONS];
+  int32_t spk_dim;                     /* 192 */
+  int32_t noise_dim;                   /* 192 */
+} v2w_config;
+
+/* One weight-normalised convolution of the state_dict (models.py:83,89-92,18-33,58-61,100).
+ * All pointers are HOST fp32, contiguous, in PyTorch's native layout:
+ *   Conv1d          v:[Cout,Cin,K]  g:[Cout] (weight_g[Cout,1,1])   bias:[Cout]
+ *   ConvTranspose1d v:[Cin,Cout,K]  g:[Cin]  (weight_g[Cin,1,1])    bias:[Cout]
+ * g == NULL means weight norm was removed (Generator.remove_weight_norm, models.py:149-156):
+ * v is then the plain `weight`. */
+typedef struct v2w_conv_params {
+  const float* v;
+  const float* g;
+  const float* bias;
+} v2w_conv_params;
+
+/* Conditioning parameters of one upsample stage (models.py:109-113,131-134; modules.py:14-18). */
+typedef struct v2w_cond_params {
+  const float* fc_weight;     /* fcs.i.weight [128, spk_dim+noise_dim] */
+  const float* fc_bias;       /* fcs.i.bias   [128] */
+  const float* sn_weight_orig;/* cbns.i.layer.weight_orig [2C,128] */
+  const float* sn_u;          /* cbns.i.layer.weight_u [2C] */
+  const float* sn_v;          /* cbns.i.layer.weight_v [128] */
+  const float* sn_bias;       /* cbns.i.layer.bias [2C] */
+  const float* bn_mean;       /* cbns.i.batch_nrom.running_mean [C] */
+  const float* bn_var;        /* cbns.i.batch_nrom.running_var  [C] */
+} v2w_cond_params;
+
+/* The whole state_dict, by reference.  `convs` is ordered: conv_pre, ups[0..U), then the
+ * resblock convolutions in EXECUTION order (for n in resblocks: ResBlock2 convs[0],convs[1];
+ * ResBlock1 convs1[0],convs2[0],convs1[1],convs2[1],convs1[2],convs2[2]), then conv_post. */
+typedef struct v2w_params {
+  int32_t num_convs;
+  const v2w_conv_params* convs;
+  int32_t num_stages;
+  const v2w_cond_params* cond;
+} v2w_params;
+
+/* Role of a layer in the generator. */
+#define V2W_ROLE_CONV_PRE 0
+#define V2W_ROLE_UPSAMPLE 1
+#define V2W_ROLE_RESBLOCK 2
+#define V2W_ROLE_CONV_POST 3
+
+/* Static description of one convolution as a "tap-GEMM":
+ *   out[b, q, n] = sum_j sum_c in[b, q + tap_off[j], c] * W[j][n][c]      (rows outside [0,L) read 0)
+ * Conv1d: n = co, tap_off[j] = (j - (K-1)/2) * dilation.
+ * ConvTranspose1d (polyphase): n = p*Cout + co for output phase p in [0,stride); the output
+ * row q of width stride*Cout IS rows q*stride .. q*stride+stride-1 of the channels-last
+ * upsampled signal.  Taps are the union over phases; (phase,tap) pairs without a kernel
+ * element hold zero weights. */
+typedef struct v2w_layer_desc {
+  int32_t role, stage;
+  int32_t conv_index;          /* index into v2w_params.convs */
+  int32_t cin, cout;
+  int32_t up;                  /* 1 for Conv1d, stride for ConvTranspose1d */
+  int32_t n_total;             /* up * cout */
+  int32_t kernel_size, dilation, padding;
+  int32_t num_taps;            /* size of the union tap set */
+  int32_t tap_off[V2W_MAX_TAPS];
+  /* tap_mask[j] bit p set  <=>  (tap j, phase p) carries a kernel element */
+  uint32_t tap_mask[V2W_MAX_TAPS];
+  int64_t w16_off;             /* byte offset in the packed buffer: bf16 [num_taps][n_total][cin]  */
+  int64_t w32_off;             /* byte offset: fp32 [num_taps][cin][n_total] */
+  int64_t bias_off;            /* byte offset: fp32 [cout] */
+  int64_t macs_per_row;        /* real multiply-accumulates per input row (zero blocks excluded) */
+} v2w_layer_desc;
+
+/* Kinds of op in a plan's execution list. */
+#define V2W_OP_TRANSPOSE_IN 0  /* x[B,Cin,T] fp32 -> [B,T,Cin] (fp32 or bf16) */
+#define V2W_OP_COND_AFFINE 1   /* fcs + spectral-norm Linear + BN fold -> scale/shift per (b, stage, c) */
+#define V2W_OP_TAPGEMM 2
+#define V2W_OP_CONV_POST 3     /* lrelu(0.01) -> Conv1d(16->1,k7) -> tanh */
+
+#define V2W_ENGINE_SIMT 0      /* FFMA tap-GEMM */
+#define V2W_ENGINE_TC 1        /* tcgen05 / TMEM / TMA tap-GEMM */
+
+/* One executed op (introspection for tests, DESIGN.md tables and bench accounting).
+ * Buffer fields are byte offsets into the bound workspace, or -1 when unused. */
+typedef struct v2w_op_desc {
+  int32_t kind, engine;
+  int32_t layer;               /* index into the model's layer table, -1 if none */
+  int32_t batch, rows;         /* GEMM rows per utterance (input time steps of this op) */
+  int32_t n_tile, n_tiles;
+  int32_t num_taps[V2W_MAX_TILES];
+  int32_t tap_index[V2W_MAX_TILES][V2W_MAX_TAPS]; /* indices into the layer's tap set */
+  int64_t in_act;              /* input activation: bf16 (TC) / fp32 or bf16 (SIMT) [B,rows,cin] */
+  int32_t in_is_bf16;
+  float in_slope;              /* leaky-relu slope applied when LOADING the input (1 = none) */
+  int32_t cond_stage;          /* >=0: apply scale/shift of that stage after bias (CBN fold) */
+  int64_t residual;            /* fp32 [B,rows,n_total] added after the affine */
+  int64_t accum_in;            /* fp32 running MRF sum added next */
+  float out_scale;             /* multiplies the total (1/num_kernels on the last MRF branch) */
+  int64_t out_f32;             /* fp32 result [B,rows,n_total] */
+  int64_t out_bf16;            /* bf16 leaky_relu(result, out_slope): the next conv's operand */
+  float out_slope;
+  int64_t flops;               /* 2 * real MACs of this op (0 for non-GEMM ops) */
+} v2w_op_desc;
+
+/* ---- library ------------------------------------------------------------------------ */
+int32_t v2w_abi_version(void);
+const char* v2w_last_error(void);
+/* Number of CUDA devices usable by this build (compute capability 10.x); 0 on a CPU box. */
+int32_t v2w_device_count(void);
+
+/* ---- model (host only) -------------------------------------------------------------- */
+int32_t v2w_model_create(const v2w_config* cfg, struct v2w_model** out);
+void v2w_model_destroy(struct v2w_model* m);
+int32_t v2w_model_num_layers(const struct v2w_model* m);
+int32_t v2w_model_get_layer(const struct v2w_model* m, int32_t index, v2w_layer_desc* out);
+int32_t v2w_model_num_convs(const struct v2w_model* m);   /* expected v2w_params.num_convs */
+int64_t v2w_model_packed_bytes(const struct v2w_model* m);
+/* Fold weight norm (w = g*v/||v||, norm over all dims but 0 -- i.e. per INPUT channel for
+ * ConvTranspose1d), spectral norm (sigma = u.(W v), eval semantics of modules.py:16) and the
+ * BN running statistics, and lay everything out in the packed format.  `packed_host` must
+ * hold v2w_model_packed_bytes() bytes.  Pure host arithmetic, replaces the per-forward
+ * weight_norm/spectral_norm pre-forward hooks of the reference. */
+int32_t v2w_model_pack(const struct v2w_model* m, const v2w_params* params, void* packed_host);
+/* Algorithmic FLOPs (2*MAC, zero polyphase blocks excluded) per input frame. */
+int64_t v2w_model_flops_per_frame(const struct v2w_model* m);
+
+/* ---- plan --------------------------------------------------------------------------- */
+int32_t v2w_plan_create(const struct v2w_model* m, int32_t batch, int32_t frames,
+                        int32_t precision, struct v2w_plan** out);
+void v2w_plan_destroy(struct v2w_plan* p);
+int64_t v2w_plan_workspace_bytes(const struct v2w_plan* p);
+int32_t v2w_plan_num_ops(const struct v2w_plan* p);
+int32_t v2w_plan_get_op(const struct v2w_plan* p, int32_t index, v2w_op_desc* out);
+/* Debug: force op `index` onto an engine (V2W_ENGINE_*). Only meaningful for TAPGEMM ops of
+ * a BF16 plan; must be called before v2w_plan_bind. */
+int32_t v2w_plan_set_engine(struct v2w_plan* p, int32_t index, int32_t engine);
+/* Attach device memory: `packed_dev` = device copy of the packed weights, `workspace_dev` =
+ * v2w_plan_workspace_bytes() bytes, both 256-byte aligned.  Builds the TMA tensor maps. */
+int32_t v2w_plan_bind(struct v2w_plan* p, const void* packed_dev, void* workspace_dev);
+
+/* Generator.forward(x, spk_emb, noise) (vec2wav/models.py:116-147), eval semantics.
+ *   x_dev     fp32 [batch, num_wv_feat, frames]  channels-first, as collate_fn_tensor emits
+ *             (vec2wav/dataset.py:212-213)
+ *   spk_dev   fp32 [batch, spk_dim]     noise_dev fp32 [batch, noise_dim]
+ *   out_dev   fp32 [batch, 1, 320*frames]
+ * Asynchronous on `stream`. `gpu_launches`, if non-NULL, receives the number of kernels
+ * enqueued. */
+int32_t v2w_forward(struct v2w_plan* p, const float* x_dev, const float* spk_dev,
+                    const float* noise_dev, float* out_dev, void* stream,
+                    int32_t* gpu_launches);
+/* Same call with HOST buffers (pinned recommended): H2D of the three inputs, the forward,
+ * D2H of the waveform, all on `stream`; returns after the stream is synchronised.  Uses
+ * staging areas inside the bound workspace. */
+int32_t v2w_forward_host(struct v2w_plan* p, const float* x_host, const float* spk_host,
+                         const float* noise_host, float* out_host, void* stream,
+                         int32_t* gpu_launches);
+
+/* ---- kernel-level entry (unit tests; the plan executor goes through the same code) -- */
+typedef struct v2w_tapgemm_args {
+  int32_t engine;              /* V2W_ENGINE_* */
+  int32_t batch, rows, cin, n_total, cmod; /* cmod: period of bias/affine columns (= cout) */
+  int32_t n_tile, n_tiles;
+  int32_t num_taps[V2W_MAX_TILES];
+  int32_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];   /* input-row offsets */
+  int32_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];   /* tap index j: weights at W[j] */
+  const void* in_act;          /* dev: bf16 or fp32 [batch,rows,cin] */
+  int32_t in_is_bf16;
+  float in_slope;
+  const void* w16;             /* dev: bf16 [taps][n_total][cin] (TC engine) */
+  const float* w32;            /* dev: fp32 [taps][cin][n_total] (SIMT engine) */
+  const float* bias;           /* dev: [cmod] or NULL */
+  const float* scale;          /* dev: [batch][cmod] or NULL */
+  const float* shift;          /* dev: [batch][cmod] or NULL */
+  const float* residual;       /* dev fp32 [batch,rows,n_total] or NULL */
+  const float* accum_in;       /* dev fp32 or NULL */
+  float out_scale;
+  float* out_f32;              /* dev or NULL */
+  void* out_bf16;              /* dev or NULL */
+  float out_slope;
+  int32_t tc_flags;            /* experiment switches of the TC kernel, see DESIGN.md */
+} v2w_tapgemm_args;
+int32_t v2w_tapgemm(const v2w_tapgemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2W_H_ */

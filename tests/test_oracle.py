@@ -1,0 +1,104 @@
+"""The oracle is pinned: both restatements reproduce what the UNMODIFIED reference produced
+(tests/golden/*.npz, written by oracle/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, ref_import, vec2wav_numpy, vec2wav_torch_cpu
+
+from helpers import assert_checksums, dropin_in_state, hparams, load_golden, t
+
+CASES = list(fixtures.GOLDEN_CASES)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_reconstruction_matches_reference(name):
+    """Seeded init + seeded re-draw + committed warm-up products == the reference's state,
+    tensor by tensor (sum and sum of squares in float64, exact)."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    assert_checksums(gen, g)
+    assert len(gen.state_dict()) == g.meta["num_keys"]
+    assert sum(p.numel() for p in gen.parameters()) == g.meta["num_params"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_cpu_port_is_bit_exact(name):
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    y = vec2wav_torch_cpu.generator_forward(gen.state_dict(), gen.h, t(g.x), t(g.spk), t(g.noise))
+    # same ATen calls in the same order; thread-count dependent summation allows a few ulp
+    assert y.shape == g.y.shape
+    np.testing.assert_allclose(y.numpy(), g.y, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
+                                  "rb2_768_stress_tiny", "rb1_1024_stress"])
+def test_numpy_restatement_fp64(name):
+    """Independent arithmetic (no ATen conv): must sit on the reference's own fp64 run."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    sd = vec2wav_numpy.state_dict_to_numpy(gen)
+    y, pre = vec2wav_numpy.generator_forward(sd, gen.h, g.x, g.spk, g.noise, return_pre_tanh=True)
+    assert y.shape == g.y.shape
+    assert np.abs(y - g.y64).max() < 2e-6          # reference fp64 (its weights are fp32-cast)
+    assert np.abs(pre - g.y_pre).max() < 2e-5 * max(1.0, np.abs(g.y_pre).max())
+    assert np.abs(y - g.y).max() < 2e-6            # reference fp32
+
+
+def test_numpy_restatement_fresh_saturated():
+    """The fresh state saturates (sigma unconverged): compare pre-tanh relatively."""
+    g = load_golden("rb2_768_fresh")
+    gen = dropin_in_state(g)
+    sd = vec2wav_numpy.state_dict_to_numpy(gen)
+    y, pre = vec2wav_numpy.generator_forward(sd, gen.h, g.x, g.spk, g.noise, return_pre_tanh=True)
+    assert (np.abs(g.y) > 0.99).mean() > 0.95
+    rel = np.abs(pre - g.y_pre).max() / np.abs(g.y_pre).max()
+    assert rel < 1e-4
+    assert np.abs(y - g.y).max() < 1e-3
+
+
+def test_remove_weight_norm_form_is_accepted():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False)
+    gen.remove_weight_norm()
+    sd = vec2wav_numpy.state_dict_to_numpy(gen)
+    assert "conv_pre.weight" in sd and "conv_pre.weight_v" not in sd
+    y = vec2wav_numpy.generator_forward(sd, gen.h, g.x, g.spk, g.noise)
+    assert np.abs(y - g.y).max() < 2e-6
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference not on this machine")
+def test_against_live_reference():
+    """In the build container: the live reference, the drop-in's autograd delegate and the
+    torch port agree bit-for-bit on a fresh seeded draw (not just on committed files)."""
+    import warnings
+    from wavthruvec_pytorch_b200 import Generator
+    models, _ = ref_import.load_reference()
+    for rb in (1, '1'):
+        h_ref = ref_import.RefHParams(resblock=rb, num_wv_feat=768)
+        h = hparams(resblock=rb, num_wv_feat=768)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = fixtures.construct(models.Generator, h_ref)
+            mine = fixtures.construct(Generator, h)
+        sd_ref, sd = ref.state_dict(), mine.state_dict()
+        assert list(sd_ref.keys()) == list(sd.keys())
+        for k in sd:
+            assert sd[k].dtype == sd_ref[k].dtype and sd[k].shape == sd_ref[k].shape, k
+            assert torch.equal(sd[k], sd_ref[k]), k
+        mine.load_state_dict(sd_ref, strict=True)
+        ref.load_state_dict(sd, strict=True)
+        x, s, n = fixtures.make_inputs(h, 2, 9, 5)
+        # train() forward: batch-stat BN + power iteration, buffers mutate identically
+        ref.train(); mine.train()
+        with torch.no_grad():
+            a, b = ref(x, s, n), mine(x, s, n)
+        assert torch.equal(a, b)
+        for k in sd:
+            assert torch.equal(mine.state_dict()[k], ref.state_dict()[k]), k
+        ref.eval()
+        with torch.no_grad():
+            a = ref(x, s, n)
+        c = vec2wav_torch_cpu.generator_forward(ref.state_dict(), h, x, s, n)
+        assert torch.equal(a, c)

@@ -1,0 +1,301 @@
+// FFMA tap-GEMM (fp32 accumulate from fp32 or bf16 activations) and the small memory-bound
+// kernels of the generator: input transpose, conditioning affine, conv_post + tanh.
+//
+// The FFMA tap-GEMM has exactly the semantics of the tcgen05 one (kernels_tc.cuh); it is the
+// engine of V2W_PREC_FP32 plans (parity bar max-abs <= 1e-4, which a single-pass tensor-core
+// format cannot meet: SURVEY.md section 7 "Hard parts 1") and the on-device cross-check for
+// the tensor-core engine.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "v2w.h"
+
+namespace v2w {
+namespace simt {
+
+constexpr int kBM = 64;        // rows per CTA
+constexpr int kKC = 16;        // channels per K-chunk
+constexpr int kThreads = 128;
+constexpr int kMaxHalo = 64;   // (num_taps-1)*dilation upper bound supported
+
+struct Params {
+  int batch, rows, cin, n_total, cmod, n_tile;
+  int16_t num_taps[V2W_MAX_TILES];
+  int16_t off_min[V2W_MAX_TILES];
+  int16_t halo[V2W_MAX_TILES];
+  int16_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int16_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  const void* in_act;
+  float in_slope;
+  const float* w32;        // [taps][cin][n_total]
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* residual;   // may alias out_f32
+  const float* accum_in;   // may alias out_f32
+  float out_scale;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  float out_slope;
+};
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ float4 load4(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// BN: columns per CTA (16, 32 or 64).  Thread layout: BN/4 column groups x 128/(BN/4) row
+// groups; each thread owns TM x 4 outputs.
+template <typename TIn, int BN>
+__global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const Params p) {
+  constexpr int CG = BN / 4;
+  constexpr int RG = kThreads / CG;
+  constexpr int TM = kBM / RG;
+  constexpr int AS = kKC + 1;  // padded row stride: conflict-free column reads
+  __shared__ float As[(kBM + kMaxHalo) * AS];
+  __shared__ __align__(16) float Ws[kKC * BN];
+
+  const int tid = threadIdx.x;
+  const int cg = tid % CG, rg = tid / CG;
+  const int q0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int b = blockIdx.z;
+  const int nt = n0 / p.n_tile;
+  const int ntaps = p.num_taps[nt];
+  const int off_min = p.off_min[nt];
+  const int a_rows = kBM + p.halo[nt];
+  const TIn* in = reinterpret_cast<const TIn*>(p.in_act) + static_cast<size_t>(b) * p.rows * p.cin;
+
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+
+  for (int c0 = 0; c0 < p.cin; c0 += kKC) {
+    __syncthreads();
+    // A halo tile: a_rows x 16 channels, 4 channels per thread-load, leaky-relu on load
+    for (int idx = tid; idx < a_rows * (kKC / 4); idx += kThreads) {
+      const int r = idx / (kKC / 4), c4 = (idx % (kKC / 4)) * 4;
+      const int row = q0 + off_min + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= 0 && row < p.rows) {
+        v = load4(in + static_cast<size_t>(row) * p.cin + c0 + c4);
+        v.x = lrelu(v.x, p.in_slope); v.y = lrelu(v.y, p.in_slope);
+        v.z = lrelu(v.z, p.in_slope); v.w = lrelu(v.w, p.in_slope);
+      }
+      float* d = As + r * AS + c4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    for (int j = 0; j < ntaps; ++j) {
+      __syncthreads();
+      const float* wsrc =
+          p.w32 + (static_cast<size_t>(p.tap_row[nt][j]) * p.cin + c0) * p.n_total + n0;
+      for (int idx = tid; idx < kKC * (BN / 4); idx += kThreads) {
+        const int kk = idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(Ws + kk * BN + c4) =
+            __ldg(reinterpret_cast<const float4*>(wsrc + static_cast<size_t>(kk) * p.n_total + c4));
+      }
+      __syncthreads();
+      const int shift = p.tap_off[nt][j] - off_min;
+      const float* arow = As + (rg * TM + shift) * AS;
+#pragma unroll
+      for (int kk = 0; kk < kKC; ++kk) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + kk * BN + cg * 4);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          const float a = arow[i * AS + kk];
+          acc[i][0] = fmaf(a, w.x, acc[i][0]);
+          acc[i][1] = fmaf(a, w.y, acc[i][1]);
+          acc[i][2] = fmaf(a, w.z, acc[i][2]);
+          acc[i][3] = fmaf(a, w.w, acc[i][3]);
+        }
+      }
+    }
+  }
+
+  const int col = n0 + cg * 4;
+  const int cb = col % p.cmod;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+  float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.scale) {
+    sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + static_cast<size_t>(b) * p.cmod + cb));
+    sh4 = __ldg(reinterpret_cast<const float4*>(p.shift + static_cast<size_t>(b) * p.cmod + cb));
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = q0 + rg * TM + i;
+    if (row >= p.rows) continue;
+    const size_t o = (static_cast<size_t>(b) * p.rows + row) * p.n_total + col;
+    float v0 = acc[i][0] + bias4.x, v1 = acc[i][1] + bias4.y, v2 = acc[i][2] + bias4.z,
+          v3 = acc[i][3] + bias4.w;
+    if (p.scale) {
+      v0 = fmaf(v0, sc4.x, sh4.x); v1 = fmaf(v1, sc4.y, sh4.y);
+      v2 = fmaf(v2, sc4.z, sh4.z); v3 = fmaf(v3, sc4.w, sh4.w);
+    }
+    if (p.residual) {
+      const float4 t = *reinterpret_cast<const float4*>(p.residual + o);
+      v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w;
+    }
+    if (p.accum_in) {
+      const float4 t = *reinterpret_cast<const float4*>(p.accum_in + o);
+      v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w;
+    }
+    if (p.out_scale != 1.0f) {
+      v0 *= p.out_scale; v1 *= p.out_scale; v2 *= p.out_scale; v3 *= p.out_scale;
+    }
+    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(v0, v1, v2, v3);
+    if (p.out_bf16) {
+      const __nv_bfloat162 h0 =
+          __floats2bfloat162_rn(lrelu(v0, p.out_slope), lrelu(v1, p.out_slope));
+      const __nv_bfloat162 h1 =
+          __floats2bfloat162_rn(lrelu(v2, p.out_slope), lrelu(v3, p.out_slope));
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.out_bf16 + o) = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x[B, C, T] fp32 (channels-first, what collate_fn_tensor emits: vec2wav/dataset.py:212-213)
+//   -> [B, T, C] channels-last, fp32 or bf16.  32x32 tiles through shared memory so that both
+// the global read (along T) and the global write (along C) are coalesced.
+// ---------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256) transpose_in_kernel(const float* __restrict__ x,
+                                                           TOut* __restrict__ y, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xb = x + static_cast<size_t>(b) * C * T;
+  TOut* yb = y + static_cast<size_t>(b) * C * T;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, t = t0 + tx;
+    tile[ty + i][tx] = (c < C && t < T) ? xb[static_cast<size_t>(c) * T + t] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int t = t0 + ty + i, c = c0 + tx;
+    if (t < T && c < C) yb[static_cast<size_t>(t) * C + c] = static_cast<TOut>(tile[tx][ty + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning affine, one CTA per (stage, utterance)   (models.py:120,131-134; modules.py:23-28)
+//   z      = fcs[i](cat(spk, noise))                       [128]
+//   g|b    = (W_orig / sigma) z + bias                     [2C]   (sigma folded at pack time)
+//   scale  = g * rsqrt(var + eps)     shift = b - scale * mean
+// so that CBN(x) = scale * x + shift, applied in the epilogue of ups[i].
+// ---------------------------------------------------------------------------------------------
+struct CondStage {
+  const float* fcw; const float* fcb; const float* snw; const float* snb;
+  const float* rstd; const float* mean;
+  float* scale; float* shift;   // [B][C]
+  int C;
+};
+struct CondParams {
+  CondStage st[V2W_MAX_STAGES];
+  const float* spk; const float* noise;
+  int spk_dim, noise_dim;
+};
+
+__global__ void __launch_bounds__(128) cond_affine_kernel(const CondParams p) {
+  extern __shared__ float sm[];
+  const CondStage& S = p.st[blockIdx.x];
+  const int b = blockIdx.y;
+  const int D = p.spk_dim + p.noise_dim;
+  float* sn = sm;            // [D]
+  float* z = sm + D;         // [128]
+  float* gb = z + 128;       // [2C]
+  for (int i = threadIdx.x; i < D; i += blockDim.x)
+    sn[i] = i < p.spk_dim ? p.spk[static_cast<size_t>(b) * p.spk_dim + i]
+                          : p.noise[static_cast<size_t>(b) * p.noise_dim + (i - p.spk_dim)];
+  __syncthreads();
+  {
+    const int t = threadIdx.x;  // blockDim.x == 128 == z channels
+    const float* w = S.fcw + static_cast<size_t>(t) * D;
+    float a = S.fcb[t];
+    for (int d = 0; d < D; ++d) a = fmaf(w[d], sn[d], a);
+    z[t] = a;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < 2 * S.C; r += blockDim.x) {
+    const float* w = S.snw + static_cast<size_t>(r) * 128;
+    float a = S.snb[r];
+    for (int t = 0; t < 128; ++t) a = fmaf(w[t], z[t], a);
+    gb[r] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < S.C; c += blockDim.x) {
+    const float sc = gb[c] * S.rstd[c];
+    S.scale[static_cast<size_t>(b) * S.C + c] = sc;
+    S.shift[static_cast<size_t>(b) * S.C + c] = gb[S.C + c] - sc * S.mean[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaky_relu(0.01) -> Conv1d(C -> 1, k = 7, pad 3) -> tanh      (models.py:143-145)
+// in: fp32 channels-last [B, L, C] (C = 16 in the reference config); out: fp32 [B, 1, L].
+// Purely memory-bound: each CTA stages 256+6 rows (float4, coalesced) and emits 256 samples.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPostRows = 256;
+constexpr int kPostK = 7;
+
+template <int C>
+__global__ void __launch_bounds__(kPostRows) conv_post_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ w,  // [7][C]
+                                                              const float* __restrict__ bias,
+                                                              float* __restrict__ y, int L,
+                                                              float in_slope) {
+  constexpr int RS = C + 1;
+  __shared__ float tile[(kPostRows + kPostK - 1) * RS];
+  __shared__ float ws[kPostK * C];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kPostRows;
+  const float* xb = x + static_cast<size_t>(b) * L * C;
+  for (int i = threadIdx.x; i < kPostK * C; i += kPostRows) ws[i] = w[i];
+  for (int idx = threadIdx.x; idx < (kPostRows + kPostK - 1) * (C / 4); idx += kPostRows) {
+    const int r = idx / (C / 4), c4 = (idx % (C / 4)) * 4;
+    const int row = t0 - (kPostK / 2) + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0 && row < L) {
+      v = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(row) * C + c4);
+      v.x = lrelu(v.x, in_slope); v.y = lrelu(v.y, in_slope);
+      v.z = lrelu(v.z, in_slope); v.w = lrelu(v.w, in_slope);
+    }
+    float* d = tile + r * RS + c4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t < L) {
+    float a = bias[0];
+#pragma unroll
+    for (int j = 0; j < kPostK; ++j) {
+      const float* r = tile + (threadIdx.x + j) * RS;
+#pragma unroll
+      for (int c = 0; c < C; ++c) a = fmaf(r[c], ws[j * C + c], a);
+    }
+    y[static_cast<size_t>(b) * L + t] = tanhf(a);
+  }
+}
+
+}  // namespace simt
+}  // namespace v2w

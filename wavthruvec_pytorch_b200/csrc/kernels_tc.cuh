@@ -1,0 +1,422 @@
+// tcgen05 / TMEM / TMA tap-GEMM for sm_100a.
+//
+//   out[b, q, n] = epilogue( sum_taps sum_c  A[b, q + off_j, c] * W[j][n][c] )
+//
+// A  : bf16 channels-last activations [B, rows, cin]  (already leaky-relu'd by the producer op)
+// W  : bf16 [taps][n_total][cin]  (K-major, like A) -- see v2w_layer_desc in include/v2w.h
+// acc: fp32 in TMEM, M = 128 time steps per tile (TMEM lane = time step), N = n_tile columns.
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer   : A halo tile once per K-chunk, W block once per (K-chunk, tap)
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma; owns the TMEM allocation
+//   warps 4-11  epilogue       : two groups of 4 warps; group g drains accumulator stage g, so the
+//                                epilogue of tile i overlaps the MMAs of tile i+1
+//
+// Halo reuse: the A tile for one K-chunk holds rows [q0 + off_min, q0 + 128 + off_max) and is loaded
+// ONCE; every tap (and every dilation) is a row-shifted view of it -- the UMMA shared-memory
+// descriptor's start address is advanced by shift * row_bytes.  With the 128B/64B/32B swizzles the
+// XOR pattern is a function of the absolute shared-memory address, so a shifted view stays
+// consistent with what TMA wrote.  (kFlagPerTap reloads A per tap instead; kept as a cross-check.)
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "v2w.h"
+
+namespace v2w {
+namespace tc {
+
+constexpr int kThreads = 384;
+constexpr int kMTile = 128;
+constexpr int kBoxRows = 32;       // rows per TMA box of A
+constexpr int kMaxStagesA = 4;
+constexpr int kMaxStagesW = 8;
+constexpr int kFlagPerTap = 1;     // reload A for every tap (no halo reuse)
+constexpr int kFlagBaseOffset = 2; // fill the descriptor's base_offset field from the address
+
+struct Params {
+  int batch, rows, cin, n_total, cmod, n_tile, n_tiles, m_tiles;
+  int kc, num_chunks;
+  int swizzle_layout;   // UMMA layout_type: 2 = 128B, 4 = 64B, 6 = 32B
+  int sbo_bytes;        // 8 rows * row bytes
+  int ra_boxes;         // TMA boxes per A fill in halo mode
+  int stages_a, stages_w;
+  int stage_a_bytes, stage_w_bytes;
+  int acc_cols;         // TMEM columns per accumulator stage
+  int flags;
+  int16_t num_taps[V2W_MAX_TILES];
+  int16_t off_min[V2W_MAX_TILES];
+  int16_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int16_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* residual;   // may alias out_f32 (element-wise in-place update)
+  const float* accum_in;   // may alias out_f32
+  float out_scale;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  float out_slope;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tm, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tm, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand in a swizzled row-major tile
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor -- start[0,14) LBO[16,30) SBO[32,46)
+//  version[46,48)=1  base_offset[49,52)  layout_type[61,64)).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes,
+                                                   uint32_t layout_type, bool base_offset_mode) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;  // LBO: unused for swizzled K-major, canonical value 1
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+  if (base_offset_mode) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, dense
+// (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_w = smem_a + p.stages_a * p.stage_a_bytes;
+  const uint32_t bars = smem_w + p.stages_w * p.stage_w_bytes;
+  // barrier block (8 B each): fullA[4] emptyA[4] fullW[8] emptyW[8] accFull[2] accEmpty[2]
+  const uint32_t full_a = bars, empty_a = bars + 32, full_w = bars + 64, empty_w = bars + 128;
+  const uint32_t acc_full = bars + 192, acc_empty = bars + 208, tmem_slot = bars + 224;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool per_tap = (p.flags & kFlagPerTap) != 0;
+  const bool base_off = (p.flags & kFlagBaseOffset) != 0;
+  const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+  const uint32_t tmem_cols = 2u * p.acc_cols;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+    for (int i = 0; i < kMaxStagesA; ++i) {
+      mbar_init(full_a + 8 * i, 1);
+      mbar_init(empty_a + 8 * i, 1);
+    }
+    for (int i = 0; i < kMaxStagesW; ++i) {
+      mbar_init(full_w + 8 * i, 1);
+      mbar_init(empty_w + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t it_a = 0, it_w = 0;
+      const uint32_t box_bytes = kBoxRows * p.kc * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int b = tile / (p.n_tiles * p.m_tiles);
+        const int ntaps = p.num_taps[nt];
+        const int q0 = mt * kMTile;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          for (int j = 0; j < ntaps; ++j) {
+            if (j == 0 || per_tap) {
+              const uint32_t s = it_a % p.stages_a, par = (it_a / p.stages_a) & 1u;
+              mbar_wait(empty_a + 8 * s, par ^ 1u);
+              const int nb = per_tap ? (kMTile / kBoxRows) : p.ra_boxes;
+              mbar_expect_tx(full_a + 8 * s, nb * box_bytes);
+              const int row0 = q0 + (per_tap ? p.tap_off[nt][j] : p.off_min[nt]);
+              const uint32_t dst = smem_a + s * p.stage_a_bytes;
+              for (int bx = 0; bx < nb; ++bx)
+                tma_load_3d(dst + bx * box_bytes, &tmA, c * p.kc, row0 + bx * kBoxRows, b,
+                            full_a + 8 * s);
+              ++it_a;
+            }
+            const uint32_t s = it_w % p.stages_w, par = (it_w / p.stages_w) & 1u;
+            mbar_wait(empty_w + 8 * s, par ^ 1u);
+            mbar_expect_tx(full_w + 8 * s, p.n_tile * p.kc * 2);
+            tma_load_2d(smem_w + s * p.stage_w_bytes, &tmW, c * p.kc,
+                        p.tap_row[nt][j] * p.n_total + nt * p.n_tile, full_w + 8 * s);
+            ++it_w;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      uint32_t it_a = 0, it_w = 0, tile_iter = 0;
+      const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile);
+      const int ksteps = p.kc / 16;
+      const uint32_t row_bytes = p.kc * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        const int nt = tile % p.n_tiles;
+        const int ntaps = p.num_taps[nt];
+        const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
+        mbar_wait(acc_empty + 8 * as, aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.acc_cols;
+        uint32_t accumulate = 0;
+        uint32_t sa = 0;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          for (int j = 0; j < ntaps; ++j) {
+            if (j == 0 || per_tap) {
+              sa = it_a % p.stages_a;
+              mbar_wait(full_a + 8 * sa, (it_a / p.stages_a) & 1u);
+            }
+            const uint32_t sw = it_w % p.stages_w;
+            mbar_wait(full_w + 8 * sw, (it_w / p.stages_w) & 1u);
+            tcgen05_fence_after();
+            const int shift = per_tap ? 0 : (p.tap_off[nt][j] - p.off_min[nt]);
+            const uint32_t a_addr = smem_a + sa * p.stage_a_bytes + shift * row_bytes;
+            const uint32_t w_addr = smem_w + sw * p.stage_w_bytes;
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t adesc =
+                  make_smem_desc(a_addr + kk * 32, p.sbo_bytes, p.swizzle_layout, base_off);
+              const uint64_t bdesc =
+                  make_smem_desc(w_addr + kk * 32, p.sbo_bytes, p.swizzle_layout, base_off);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_w + 8 * sw);
+            ++it_w;
+            if (j == ntaps - 1 || per_tap) {
+              umma_commit(empty_a + 8 * sa);
+              ++it_a;
+            }
+          }
+        }
+        umma_commit(acc_full + 8 * as);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int group = (warp - 4) >> 2;  // accumulator stage this warp drains
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may read
+    const bool pow2 = (p.cmod & (p.cmod - 1)) == 0;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      if ((tile_iter & 1u) != static_cast<uint32_t>(group)) continue;
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int b = tile / (p.n_tiles * p.m_tiles);
+      const uint32_t aph = (tile_iter >> 1) & 1u;
+      mbar_wait(acc_full + 8 * group, aph);
+      tcgen05_fence_after();
+      const int row = mt * kMTile + quarter * 32 + lane;
+      const bool valid = row < p.rows;
+      const size_t row_base = (static_cast<size_t>(b) * p.rows + row) * p.n_total;
+      const uint32_t t_base =
+          tmem_base + group * p.acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int cc = 0; cc < p.n_tile; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_base + cc, r);
+        tmem_ld_wait();
+        if (valid) {
+          const int col = nt * p.n_tile + cc;
+          const int cb = pow2 ? (col & (p.cmod - 1)) : (col % p.cmod);
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + e));
+              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+            }
+          }
+          if (p.scale) {
+            const float* sc = p.scale + static_cast<size_t>(b) * p.cmod + cb;
+            const float* sh = p.shift + static_cast<size_t>(b) * p.cmod + cb;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + e));
+              const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + e));
+              v[e] = fmaf(v[e], s4.x, h4.x);
+              v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+              v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);
+              v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+            }
+          }
+          if (p.residual) {
+            const float* rp = p.residual + row_base + col;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(rp + e);
+              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+            }
+          }
+          if (p.accum_in) {
+            const float* ap = p.accum_in + row_base + col;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(ap + e);
+              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+            }
+          }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] *= p.out_scale;
+          }
+          if (p.out_f32) {
+            float* op = p.out_f32 + row_base + col;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
+          if (p.out_bf16) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
+            op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty + 8 * group);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace tc
+}  // namespace v2w

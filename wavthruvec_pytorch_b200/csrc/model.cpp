@@ -1,0 +1,382 @@
+// Host half of libv2w: hyper-parameters -> tap-GEMM layer table, and state_dict -> packed
+// weights (weight-norm / spectral-norm / batch-norm folding).  No CUDA in this file, so it is
+// exercised by the CPU test-suite on a box without a GPU.
+//
+// Reference semantics restated here (never copied):
+//   Generator.__init__        vec2wav/models.py:78-114
+//   get_padding               vec2wav/utils.py:35-36
+//   weight_norm(dim=0)        torch.nn.utils.weight_norm as used at models.py:18-33,58-61,83,90-92,100
+//   ConditionalBatchNorm1d    vec2wav/modules.py:5-30  (eval: running stats, sigma = u.(W v))
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "common.h"
+
+namespace v2w {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+static void add_conv1d(v2w_model* m, int role, int stage, int conv_index, int cin, int cout,
+                       int k, int dil) {
+  v2w_layer_desc L;
+  std::memset(&L, 0, sizeof(L));
+  L.role = role;
+  L.stage = stage;
+  L.conv_index = conv_index;
+  L.cin = cin;
+  L.cout = cout;
+  L.up = 1;
+  L.n_total = cout;
+  L.kernel_size = k;
+  L.dilation = dil;
+  L.padding = (k * dil - dil) / 2;  // utils.py:35-36
+  L.num_taps = k;
+  for (int j = 0; j < k; ++j) {
+    L.tap_off[j] = j * dil - L.padding;
+    L.tap_mask[j] = 1u;
+  }
+  L.macs_per_row = (int64_t)k * cin * cout;
+  m->layers.push_back(L);
+}
+
+// ConvTranspose1d(cin, cout, k, stride=u, padding=(k-u)//2) as a polyphase tap-GEMM.
+//   y[t*u + kk - pad] += x[t] * w[kk]   ==>   for output row o = q*u + p:
+//   kk = u*m + p + pad with input row t = q - m, valid while 0 <= kk < k.
+static void add_convT(v2w_model* m, int stage, int conv_index, int cin, int cout, int k, int u) {
+  v2w_layer_desc L;
+  std::memset(&L, 0, sizeof(L));
+  const int pad = (k - u) / 2;  // models.py:92
+  L.role = V2W_ROLE_UPSAMPLE;
+  L.stage = stage;
+  L.conv_index = conv_index;
+  L.cin = cin;
+  L.cout = cout;
+  L.up = u;
+  L.n_total = u * cout;
+  L.kernel_size = k;
+  L.dilation = 1;
+  L.padding = pad;
+  int m_lo = 1 << 30, m_hi = -(1 << 30);
+  for (int p = 0; p < u; ++p)
+    for (int mm = -k; mm <= k; ++mm) {
+      int kk = u * mm + p + pad;
+      if (kk >= 0 && kk < k) {
+        m_lo = std::min(m_lo, mm);
+        m_hi = std::max(m_hi, mm);
+      }
+    }
+  // ascending input-row offset: offset = -m, so walk m from high to low
+  int nt = 0;
+  int64_t pairs = 0;
+  for (int mm = m_hi; mm >= m_lo; --mm) {
+    uint32_t mask = 0;
+    for (int p = 0; p < u; ++p) {
+      int kk = u * mm + p + pad;
+      if (kk >= 0 && kk < k) {
+        mask |= 1u << p;
+        ++pairs;
+      }
+    }
+    L.tap_off[nt] = -mm;
+    L.tap_mask[nt] = mask;
+    ++nt;
+  }
+  L.num_taps = nt;
+  L.macs_per_row = pairs * cin * cout;  // == k*cin*cout
+  m->layers.push_back(L);
+}
+
+}  // namespace v2w
+
+using namespace v2w;
+
+extern "C" {
+
+int32_t v2w_abi_version(void) { return V2W_ABI_VERSION; }
+
+const char* v2w_last_error(void) { return g_last_error.c_str(); }
+
+int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
+  if (!c || !out) {
+    set_error("v2w_model_create: null argument");
+    return V2W_ERR_INVALID;
+  }
+  *out = nullptr;
+  const int U = c->num_upsamples;
+  if (U < 1 || U > V2W_MAX_STAGES) {
+    set_error("num_upsamples=%d out of range [1,%d]", U, V2W_MAX_STAGES);
+    return V2W_ERR_INVALID;
+  }
+  if (c->num_kernels < 1 || c->num_kernels > V2W_MAX_KERNELS) {
+    set_error("num_kernels=%d out of range [1,%d]", c->num_kernels, V2W_MAX_KERNELS);
+    return V2W_ERR_INVALID;
+  }
+  if (c->resblock_type != 1 && c->resblock_type != 2) {
+    set_error("resblock_type must be 1 or 2 (got %d)", c->resblock_type);
+    return V2W_ERR_INVALID;
+  }
+  // ResBlock2 reads dilation[0..1], ResBlock1 all three (models.py:14,54); the constructors index
+  // them positionally, so fewer entries is an IndexError in the reference.
+  const int need_dil = c->resblock_type == 1 ? 3 : 2;
+  if (c->num_dilations < need_dil || c->num_dilations > V2W_MAX_DILATIONS) {
+    set_error("resblock_dilation_sizes rows need >= %d entries (got %d, max %d)", need_dil,
+              c->num_dilations, V2W_MAX_DILATIONS);
+    return V2W_ERR_INVALID;
+  }
+  // models.py:113 hard-codes the CBN widths 256>>i, which equals the ups[i] output width only
+  // when upsample_initial_channel == 512; anything else raises a shape error in the reference.
+  if (c->upsample_initial_channel != 512) {
+    set_error("upsample_initial_channel must be 512 (CBN widths are hard-coded 256>>i at "
+              "vec2wav/models.py:113); got %d", c->upsample_initial_channel);
+    return V2W_ERR_INVALID;
+  }
+  if (c->num_wv_feat < 16 || c->num_wv_feat % 16 != 0) {
+    set_error("num_wv_feat must be a positive multiple of 16 (got %d)", c->num_wv_feat);
+    return V2W_ERR_INVALID;
+  }
+  if (c->num_wv_feat > 64 && c->num_wv_feat % 64 != 0) {
+    set_error("num_wv_feat above 64 must be a multiple of 64 (got %d)", c->num_wv_feat);
+    return V2W_ERR_INVALID;
+  }
+  if (c->spk_dim < 1 || c->noise_dim < 0 || c->spk_dim + c->noise_dim > 4096) {
+    set_error("spk_dim/noise_dim out of range (%d, %d)", c->spk_dim, c->noise_dim);
+    return V2W_ERR_INVALID;
+  }
+  if ((c->upsample_initial_channel >> U) < 16) {
+    set_error("too many upsample stages: last stage would have %d channels (< 16)",
+              c->upsample_initial_channel >> U);
+    return V2W_ERR_INVALID;
+  }
+  if ((c->upsample_initial_channel >> U) > 32) {
+    set_error("conv_post kernel supports 16 or 32 input channels; %d stages leave %d", U,
+              c->upsample_initial_channel >> U);
+    return V2W_ERR_INVALID;
+  }
+  for (int i = 0; i < U; ++i) {
+    int k = c->upsample_kernel_sizes[i], u = c->upsample_rates[i];
+    if (u < 1 || k < u || ((k - u) & 1)) {
+      set_error("upsample stage %d: kernel %d / rate %d unsupported (need k >= u and k-u even so "
+                "that L_out == L_in*u)", i, k, u);
+      return V2W_ERR_INVALID;
+    }
+    if (u > 8) {
+      set_error("upsample rate %d > 8 unsupported", u);
+      return V2W_ERR_INVALID;
+    }
+  }
+  for (int j = 0; j < c->num_kernels; ++j) {
+    int k = c->resblock_kernel_sizes[j];
+    if (k < 1 || !(k & 1) || k > V2W_MAX_TAPS) {
+      set_error("resblock kernel size %d unsupported (odd, <= %d)", k, V2W_MAX_TAPS);
+      return V2W_ERR_INVALID;
+    }
+    for (int d = 0; d < need_dil; ++d)
+      if (c->resblock_dilation_sizes[j][d] < 1 || c->resblock_dilation_sizes[j][d] > 32) {
+        set_error("resblock dilation %d unsupported", c->resblock_dilation_sizes[j][d]);
+        return V2W_ERR_INVALID;
+      }
+  }
+
+  v2w_model* m = new (std::nothrow) v2w_model();
+  if (!m) {
+    set_error("out of memory");
+    return V2W_ERR_NOMEM;
+  }
+  m->cfg = *c;
+
+  // ---- conv index bookkeeping: conv_pre, ups[0..U), resblock convs (execution order), conv_post
+  const int convs_per_block = c->resblock_type == 1 ? 6 : 2;
+  int rb_conv_base = 1 + U;
+  add_conv1d(m, V2W_ROLE_CONV_PRE, -1, 0, c->num_wv_feat, c->upsample_initial_channel, 7, 1);
+  int ch = c->upsample_initial_channel;
+  int up_total = 1;
+  for (int i = 0; i < U; ++i) {
+    const int cin = ch;
+    ch = c->upsample_initial_channel >> (i + 1);
+    add_convT(m, i, 1 + i, cin, ch, c->upsample_kernel_sizes[i], c->upsample_rates[i]);
+    if (m->layers.back().num_taps > V2W_MAX_TAPS) {
+      set_error("upsample stage %d needs too many taps", i);
+      delete m;
+      return V2W_ERR_INVALID;
+    }
+    up_total *= c->upsample_rates[i];
+    m->stage_channels.push_back(ch);
+    m->stage_up.push_back(up_total);
+    for (int j = 0; j < c->num_kernels; ++j) {
+      const int k = c->resblock_kernel_sizes[j];
+      const int block = i * c->num_kernels + j;
+      const int base = rb_conv_base + block * convs_per_block;
+      if (c->resblock_type == 2) {
+        // ResBlock2.forward (models.py:65-70): dilations d[0], d[1]
+        for (int s = 0; s < 2; ++s)
+          add_conv1d(m, V2W_ROLE_RESBLOCK, i, base + s, ch, ch, k,
+                     c->resblock_dilation_sizes[j][s]);
+      } else {
+        // ResBlock1.forward (models.py:37-44): (convs1[s] dil d[s], convs2[s] dil 1) x 3
+        for (int s = 0; s < 3; ++s) {
+          add_conv1d(m, V2W_ROLE_RESBLOCK, i, base + 2 * s, ch, ch, k,
+                     c->resblock_dilation_sizes[j][s]);
+          add_conv1d(m, V2W_ROLE_RESBLOCK, i, base + 2 * s + 1, ch, ch, k, 1);
+        }
+      }
+    }
+  }
+  m->total_up = up_total;
+  m->num_convs = rb_conv_base + U * c->num_kernels * convs_per_block + 1;
+  add_conv1d(m, V2W_ROLE_CONV_POST, -1, m->num_convs - 1, ch, 1, 7, 1);
+
+  // ---- packed layout
+  int64_t off = 0;
+  int64_t flops = 0;
+  for (auto& L : m->layers) {
+    if (L.role != V2W_ROLE_CONV_POST) {
+      L.w16_off = off;
+      off = align_up(off + (int64_t)L.num_taps * L.n_total * L.cin * 2, 1024);
+    } else {
+      L.w16_off = -1;
+    }
+    L.w32_off = off;
+    off = align_up(off + (int64_t)L.num_taps * L.cin * L.n_total * 4, 1024);
+    L.bias_off = off;
+    off = align_up(off + (int64_t)L.cout * 4, 1024);
+    int rows_per_frame = 1;
+    if (L.role == V2W_ROLE_UPSAMPLE) rows_per_frame = L.stage == 0 ? 1 : m->stage_up[L.stage - 1];
+    else if (L.role == V2W_ROLE_RESBLOCK) rows_per_frame = m->stage_up[L.stage];
+    else if (L.role == V2W_ROLE_CONV_POST) rows_per_frame = up_total;
+    flops += 2 * L.macs_per_row * rows_per_frame;
+  }
+  const int D = c->spk_dim + c->noise_dim;
+  for (int i = 0; i < U; ++i) {
+    CondLayout cl;
+    cl.C = m->stage_channels[i];
+    cl.D = D;
+    cl.fcw = off; off = align_up(off + (int64_t)kZ * D * 4, 256);
+    cl.fcb = off; off = align_up(off + (int64_t)kZ * 4, 256);
+    cl.snw = off; off = align_up(off + (int64_t)2 * cl.C * kZ * 4, 256);
+    cl.snb = off; off = align_up(off + (int64_t)2 * cl.C * 4, 256);
+    cl.rstd = off; off = align_up(off + (int64_t)cl.C * 4, 256);
+    cl.mean = off; off = align_up(off + (int64_t)cl.C * 4, 256);
+    m->cond.push_back(cl);
+  }
+  m->packed_bytes = align_up(off, 1024);
+  m->flops_per_frame = flops;
+  *out = m;
+  return V2W_OK;
+}
+
+void v2w_model_destroy(v2w_model* m) { delete m; }
+
+int32_t v2w_model_num_layers(const v2w_model* m) { return m ? (int32_t)m->layers.size() : 0; }
+
+int32_t v2w_model_get_layer(const v2w_model* m, int32_t i, v2w_layer_desc* out) {
+  if (!m || !out || i < 0 || i >= (int32_t)m->layers.size()) {
+    set_error("v2w_model_get_layer: bad index %d", i);
+    return V2W_ERR_INVALID;
+  }
+  *out = m->layers[i];
+  return V2W_OK;
+}
+
+int32_t v2w_model_num_convs(const v2w_model* m) { return m ? m->num_convs : 0; }
+int64_t v2w_model_packed_bytes(const v2w_model* m) { return m ? m->packed_bytes : 0; }
+int64_t v2w_model_flops_per_frame(const v2w_model* m) { return m ? m->flops_per_frame : 0; }
+
+int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_host) {
+  if (!m || !P || !packed_host) {
+    set_error("v2w_model_pack: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if (P->num_convs != m->num_convs || P->num_stages != (int)m->cond.size()) {
+    set_error("v2w_model_pack: expected %d convs / %d stages, got %d / %d", m->num_convs,
+              (int)m->cond.size(), P->num_convs, P->num_stages);
+    return V2W_ERR_INVALID;
+  }
+  uint8_t* base = static_cast<uint8_t*>(packed_host);
+  std::memset(base, 0, (size_t)m->packed_bytes);
+  std::vector<float> scale;
+  for (const auto& L : m->layers) {
+    const v2w_conv_params& cp = P->convs[L.conv_index];
+    if (!cp.v || !cp.bias) {
+      set_error("v2w_model_pack: conv %d has null weight/bias", L.conv_index);
+      return V2W_ERR_INVALID;
+    }
+    const int K = L.kernel_size;
+    const bool transposed = L.role == V2W_ROLE_UPSAMPLE;
+    // weight_norm(dim=0): one norm per index of dim 0 -- Cout for Conv1d [Cout,Cin,K],
+    // Cin for ConvTranspose1d [Cin,Cout,K].
+    const int d0 = transposed ? L.cin : L.cout;
+    const int inner = (transposed ? L.cout : L.cin) * K;
+    scale.assign(d0, 1.0f);
+    if (cp.g) {
+      for (int r = 0; r < d0; ++r) {
+        double ss = 0.0;
+        const float* row = cp.v + (size_t)r * inner;
+        for (int e = 0; e < inner; ++e) ss += (double)row[e] * row[e];
+        scale[r] = (float)((double)cp.g[r] / std::sqrt(ss));
+      }
+    }
+    uint16_t* w16 = L.w16_off >= 0 ? reinterpret_cast<uint16_t*>(base + L.w16_off) : nullptr;
+    float* w32 = reinterpret_cast<float*>(base + L.w32_off);
+    float* bias = reinterpret_cast<float*>(base + L.bias_off);
+    for (int co = 0; co < L.cout; ++co) bias[co] = cp.bias[co];
+    for (int j = 0; j < L.num_taps; ++j) {
+      for (int p = 0; p < L.up; ++p) {
+        if (!(L.tap_mask[j] >> p & 1u)) continue;
+        // kernel element addressed by (tap j, phase p)
+        const int kk = transposed ? (L.up * (-L.tap_off[j]) + p + L.padding) : j;
+        for (int co = 0; co < L.cout; ++co) {
+          const int n = p * L.cout + co;
+          for (int ci = 0; ci < L.cin; ++ci) {
+            float w;
+            if (transposed) w = cp.v[((size_t)ci * L.cout + co) * K + kk] * scale[ci];
+            else w = cp.v[((size_t)co * L.cin + ci) * K + kk] * scale[co];
+            if (w16) w16[((size_t)j * L.n_total + n) * L.cin + ci] = bf16_bits(w);
+            w32[((size_t)j * L.cin + ci) * L.n_total + n] = w;
+          }
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < m->cond.size(); ++i) {
+    const CondLayout& cl = m->cond[i];
+    const v2w_cond_params& q = P->cond[i];
+    if (!q.fc_weight || !q.fc_bias || !q.sn_weight_orig || !q.sn_u || !q.sn_v || !q.sn_bias ||
+        !q.bn_mean || !q.bn_var) {
+      set_error("v2w_model_pack: cond stage %d has a null pointer", (int)i);
+      return V2W_ERR_INVALID;
+    }
+    std::memcpy(base + cl.fcw, q.fc_weight, (size_t)kZ * cl.D * 4);
+    std::memcpy(base + cl.fcb, q.fc_bias, (size_t)kZ * 4);
+    // spectral_norm in eval(): sigma = u . (W v) with the stored u, v (no power iteration)
+    double sigma = 0.0;
+    for (int r = 0; r < 2 * cl.C; ++r) {
+      double wv = 0.0;
+      for (int c2 = 0; c2 < kZ; ++c2) wv += (double)q.sn_weight_orig[(size_t)r * kZ + c2] * q.sn_v[c2];
+      sigma += (double)q.sn_u[r] * wv;
+    }
+    const float fsigma = (float)sigma;
+    float* snw = reinterpret_cast<float*>(base + cl.snw);
+    for (int e = 0; e < 2 * cl.C * kZ; ++e) snw[e] = q.sn_weight_orig[e] / fsigma;
+    std::memcpy(base + cl.snb, q.sn_bias, (size_t)2 * cl.C * 4);
+    float* rstd = reinterpret_cast<float*>(base + cl.rstd);
+    float* mean = reinterpret_cast<float*>(base + cl.mean);
+    for (int ch = 0; ch < cl.C; ++ch) {
+      rstd[ch] = 1.0f / std::sqrt(q.bn_var[ch] + kBnEps);
+      mean[ch] = q.bn_mean[ch];
+    }
+  }
+  return V2W_OK;
+}
+
+}  // extern "C"

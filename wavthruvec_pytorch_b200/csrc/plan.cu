@@ -1,0 +1,820 @@
+// Plan construction (host), device binding and the forward executor of libv2w.
+//
+// A plan turns Generator.forward (vec2wav/models.py:116-147) for one (batch, frames, precision)
+// into an ordered list of ops over a caller-provided workspace:
+//
+//   TRANSPOSE_IN   x[B,Cin,T] -> [B,T,Cin]                                  (models.py:123 input)
+//   COND_AFFINE    cat(spk,noise) -> fcs[i] -> SN-Linear -> BN fold        (models.py:120,131-134)
+//   TAPGEMM        conv_pre / ups[i] (+CBN affine) / resblock convs (+residual, +MRF sum, /3)
+//   CONV_POST      leaky_relu(0.01) -> conv_post -> tanh                    (models.py:143-145)
+//
+// Every elementwise step of the reference forward is folded into the producing GEMM's epilogue or
+// the consuming GEMM's load; see DESIGN.md for the table.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.h"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace v2w {
+
+#define V2W_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return V2W_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+struct Act {        // one logical activation tensor [B, rows, C]
+  int64_t f32 = -1;   // fp32 copy (pre-activation values)
+  int64_t bf16 = -1;  // bf16 copy of leaky_relu(value, slope)
+  float slope = 1.f;  // the activation the consumer must see
+};
+
+struct TcLaunch {
+  CUtensorMap tm_a, tm_w;
+  tc::Params prm;
+  int grid = 0;
+  int smem = 0;
+};
+
+struct Op {
+  v2w_op_desc d;
+  v2w_tapgemm_args g;   // resolved at bind time (TAPGEMM ops)
+  TcLaunch tcl;         // TC engine only
+  bool tc_ready = false;
+};
+
+}  // namespace v2w
+
+struct v2w_plan {
+  const v2w_model* model = nullptr;
+  int batch = 0, frames = 0, precision = 0;
+  std::vector<v2w::Op> ops;
+  int64_t workspace_bytes = 0;
+  // workspace offsets
+  int64_t stage_x = -1, stage_spk = -1, stage_noise = -1, stage_out = -1;
+  int64_t cond_scale[V2W_MAX_STAGES], cond_shift[V2W_MAX_STAGES];
+  int64_t xt = -1;        // transposed input
+  int64_t post_in = -1;   // fp32 input of conv_post
+  bool bound = false;
+  const uint8_t* packed = nullptr;
+  uint8_t* ws = nullptr;
+};
+
+namespace v2w {
+
+// ---------------------------------------------------------------------------------------------
+// device / driver helpers
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    V2W_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return V2W_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return V2W_OK;
+}
+
+static int sm_count(int* out) {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    V2W_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    V2W_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+      set_error("libv2w is built for sm_100a only; device %d has compute capability %d.x", dev,
+                major);
+      return V2W_ERR_CUDA;
+    }
+    V2W_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  *out = n;
+  return V2W_OK;
+}
+
+static int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tap-GEMM launchers
+// ---------------------------------------------------------------------------------------------
+static int validate_gemm(const v2w_tapgemm_args& a) {
+  if (a.batch < 1 || a.rows < 1 || a.cin < 16 || a.cin % 16 || a.n_total < 16 || a.n_total % 16 ||
+      a.n_tile < 16 || a.n_tile % 16 || a.n_tiles < 1 || a.n_tiles > V2W_MAX_TILES ||
+      a.n_tile * a.n_tiles != a.n_total || a.cmod < 16 || a.cmod % 16) {
+    set_error("tapgemm: bad shape batch=%d rows=%d cin=%d n_total=%d n_tile=%d n_tiles=%d cmod=%d",
+              a.batch, a.rows, a.cin, a.n_total, a.n_tile, a.n_tiles, a.cmod);
+    return V2W_ERR_INVALID;
+  }
+  for (int t = 0; t < a.n_tiles; ++t) {
+    if (a.num_taps[t] < 1 || a.num_taps[t] > V2W_MAX_TAPS) {
+      set_error("tapgemm: tile %d has %d taps", t, a.num_taps[t]);
+      return V2W_ERR_INVALID;
+    }
+    for (int j = 1; j < a.num_taps[t]; ++j)
+      if (a.tap_off[t][j] < a.tap_off[t][j - 1]) {
+        set_error("tapgemm: tap offsets must be ascending");
+        return V2W_ERR_INVALID;
+      }
+  }
+  if (!a.in_act || (!a.out_f32 && !a.out_bf16)) {
+    set_error("tapgemm: null input or no output");
+    return V2W_ERR_INVALID;
+  }
+  if ((a.scale == nullptr) != (a.shift == nullptr)) {
+    set_error("tapgemm: scale and shift must be given together");
+    return V2W_ERR_INVALID;
+  }
+  return V2W_OK;
+}
+
+static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
+  if (!a.in_is_bf16 || a.in_slope != 1.0f) {
+    set_error("tapgemm(TC): input must be pre-activated bf16");
+    return V2W_ERR_INVALID;
+  }
+  if (!a.w16) {
+    set_error("tapgemm(TC): w16 is null");
+    return V2W_ERR_INVALID;
+  }
+  const int kc = a.cin >= 64 ? 64 : a.cin;
+  if ((kc != 16 && kc != 32 && kc != 64) || a.cin % kc) {
+    set_error("tapgemm(TC): cin=%d unsupported (16, 32 or a multiple of 64)", a.cin);
+    return V2W_ERR_INVALID;
+  }
+  if (a.n_tile > 256) {
+    set_error("tapgemm(TC): n_tile=%d > 256", a.n_tile);
+    return V2W_ERR_INVALID;
+  }
+  tc::Params& p = L->prm;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
+  p.n_tile = a.n_tile; p.n_tiles = a.n_tiles;
+  p.m_tiles = (a.rows + tc::kMTile - 1) / tc::kMTile;
+  p.kc = kc;
+  p.num_chunks = a.cin / kc;
+  p.swizzle_layout = kc == 64 ? 2 : (kc == 32 ? 4 : 6);
+  p.sbo_bytes = 8 * kc * 2;
+  p.flags = a.tc_flags;
+  int halo_max = 0;
+  for (int t = 0; t < a.n_tiles; ++t) {
+    p.num_taps[t] = (int16_t)a.num_taps[t];
+    p.off_min[t] = (int16_t)a.tap_off[t][0];
+    halo_max = std::max(halo_max, a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0]);
+    for (int j = 0; j < a.num_taps[t]; ++j) {
+      p.tap_off[t][j] = (int16_t)a.tap_off[t][j];
+      p.tap_row[t][j] = (int16_t)a.tap_row[t][j];
+    }
+  }
+  p.ra_boxes = (tc::kMTile + halo_max + tc::kBoxRows - 1) / tc::kBoxRows;
+  p.stage_a_bytes = p.ra_boxes * tc::kBoxRows * kc * 2;
+  p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
+  const int budget = 227 * 1024 - 1024 - 256;
+  p.stages_a = 2;
+  int sw = (budget - p.stages_a * p.stage_a_bytes) / p.stage_w_bytes;
+  if (sw < 2) {
+    set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)", p.stage_a_bytes,
+              p.stage_w_bytes);
+    return V2W_ERR_INVALID;
+  }
+  p.stages_w = std::min(sw, tc::kMaxStagesW);
+  int sa = (budget - p.stages_w * p.stage_w_bytes) / p.stage_a_bytes;
+  p.stages_a = std::max(2, std::min(sa, tc::kMaxStagesA));
+  p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift;
+  p.residual = a.residual; p.accum_in = a.accum_in;
+  p.out_scale = a.out_scale; p.out_f32 = a.out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  p.out_slope = a.out_slope;
+  L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + 256 + 1024;
+
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const int64_t tiles = (int64_t)a.batch * p.m_tiles * a.n_tiles;
+  L->grid = (int)std::min<int64_t>(tiles, sms);
+
+  EncodeTiledFn enc = nullptr;
+  rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+    cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.rows * a.cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc::kBoxRows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.in_act),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r);
+      return V2W_ERR_CUDA;
+    }
+  }
+  {
+    int max_row = 0;
+    for (int t = 0; t < a.n_tiles; ++t)
+      for (int j = 0; j < a.num_taps[t]; ++j) max_row = std::max(max_row, a.tap_row[t][j]);
+    cuuint64_t dims[2] = {(cuuint64_t)a.cin, (cuuint64_t)(max_row + 1) * a.n_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&L->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.w16), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(W) failed with CUresult %d", (int)r);
+      return V2W_ERR_CUDA;
+    }
+  }
+  return V2W_OK;
+}
+
+static int launch_tc(const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  tc::tapgemm_tc_kernel<<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  V2W_CUDA(cudaGetLastError());
+  return V2W_OK;
+}
+
+template <typename TIn>
+static void launch_simt_bn(const simt::Params& p, int bn, dim3 grid, cudaStream_t st) {
+  if (bn == 64) simt::tapgemm_simt_kernel<TIn, 64><<<grid, simt::kThreads, 0, st>>>(p);
+  else if (bn == 32) simt::tapgemm_simt_kernel<TIn, 32><<<grid, simt::kThreads, 0, st>>>(p);
+  else simt::tapgemm_simt_kernel<TIn, 16><<<grid, simt::kThreads, 0, st>>>(p);
+}
+
+static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
+  if (!a.w32) {
+    set_error("tapgemm(SIMT): w32 is null");
+    return V2W_ERR_INVALID;
+  }
+  simt::Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
+  p.n_tile = a.n_tile;
+  for (int t = 0; t < a.n_tiles; ++t) {
+    p.num_taps[t] = (int16_t)a.num_taps[t];
+    p.off_min[t] = (int16_t)a.tap_off[t][0];
+    const int halo = a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0];
+    if (halo > simt::kMaxHalo) {
+      set_error("tapgemm(SIMT): halo %d > %d", halo, simt::kMaxHalo);
+      return V2W_ERR_INVALID;
+    }
+    p.halo[t] = (int16_t)halo;
+    for (int j = 0; j < a.num_taps[t]; ++j) {
+      p.tap_off[t][j] = (int16_t)a.tap_off[t][j];
+      p.tap_row[t][j] = (int16_t)a.tap_row[t][j];
+    }
+  }
+  p.in_act = a.in_act; p.in_slope = a.in_slope; p.w32 = a.w32;
+  p.bias = a.bias; p.scale = a.scale; p.shift = a.shift;
+  p.residual = a.residual; p.accum_in = a.accum_in;
+  p.out_scale = a.out_scale; p.out_f32 = a.out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  p.out_slope = a.out_slope;
+  const int bn = a.n_tile % 64 == 0 ? 64 : (a.n_tile % 32 == 0 ? 32 : 16);
+  dim3 grid((a.rows + simt::kBM - 1) / simt::kBM, a.n_total / bn, a.batch);
+  if (grid.z > 65535 || grid.y > 65535) {
+    set_error("tapgemm(SIMT): grid too large");
+    return V2W_ERR_INVALID;
+  }
+  if (a.in_is_bf16) launch_simt_bn<__nv_bfloat16>(p, bn, grid, st);
+  else launch_simt_bn<float>(p, bn, grid, st);
+  V2W_CUDA(cudaGetLastError());
+  return V2W_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+  int64_t off = 0;
+  int64_t take(int64_t bytes) {
+    int64_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  }
+};
+
+// Pick the column tile of a layer: whole phases (or a divisor of cout), <= 256 columns, minimum
+// issued MMA columns (zero polyphase blocks cost issue slots), then the largest tile; shrink while
+// the launch would leave SMs idle.
+static void choose_tiles(const v2w_layer_desc& L, int batch, int rows, v2w_op_desc* d) {
+  int best = 0;
+  int64_t best_cost = 0;
+  for (int nt = 16; nt <= 256; nt <<= 1) {
+    if (L.n_total % nt) continue;
+    if (nt % L.cout && L.cout % nt) continue;
+    int64_t cost = 0;
+    for (int t = 0; t < L.n_total / nt; ++t) {
+      const int p_lo = t * nt / L.cout, p_hi = ((t + 1) * nt - 1) / L.cout;
+      uint32_t pm = 0;
+      for (int p = p_lo; p <= p_hi; ++p) pm |= 1u << p;
+      int taps = 0;
+      for (int j = 0; j < L.num_taps; ++j) taps += (L.tap_mask[j] & pm) != 0;
+      cost += (int64_t)taps * nt;
+    }
+    if (L.n_total / nt > V2W_MAX_TILES) continue;
+    if (!best || cost < best_cost || (cost == best_cost && nt > best)) {
+      best = nt;
+      best_cost = cost;
+    }
+  }
+  const int m_tiles = (rows + 127) / 128;
+  while (best >= 64 && (int64_t)batch * m_tiles * (L.n_total / best) < 148 &&
+         L.n_total / (best / 2) <= V2W_MAX_TILES)
+    best >>= 1;
+  d->n_tile = best;
+  d->n_tiles = L.n_total / best;
+  for (int t = 0; t < d->n_tiles; ++t) {
+    const int p_lo = t * best / L.cout, p_hi = ((t + 1) * best - 1) / L.cout;
+    uint32_t pm = 0;
+    for (int p = p_lo; p <= p_hi; ++p) pm |= 1u << p;
+    int n = 0;
+    for (int j = 0; j < L.num_taps; ++j)
+      if (L.tap_mask[j] & pm) d->tap_index[t][n++] = j;
+    d->num_taps[t] = n;
+  }
+}
+
+}  // namespace v2w
+
+using namespace v2w;
+
+extern "C" {
+
+int32_t v2w_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+        major == 10)
+      ++ok;
+  }
+  return ok;
+}
+
+int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32_t precision,
+                        v2w_plan** out) {
+  if (!m || !out) {
+    set_error("v2w_plan_create: null argument");
+    return V2W_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (batch < 1 || frames < 1 || batch > 65535) {
+    set_error("v2w_plan_create: batch=%d frames=%d out of range", batch, frames);
+    return V2W_ERR_INVALID;
+  }
+  if (precision != V2W_PREC_FP32 && precision != V2W_PREC_BF16) {
+    set_error("v2w_plan_create: unknown precision %d", precision);
+    return V2W_ERR_INVALID;
+  }
+  if ((int64_t)frames * m->total_up > (1 << 30)) {
+    set_error("v2w_plan_create: %d frames is too long", frames);
+    return V2W_ERR_INVALID;
+  }
+  v2w_plan* P = new (std::nothrow) v2w_plan();
+  if (!P) {
+    set_error("out of memory");
+    return V2W_ERR_NOMEM;
+  }
+  P->model = m;
+  P->batch = batch;
+  P->frames = frames;
+  P->precision = precision;
+  const bool bf = precision == V2W_PREC_BF16;
+  const v2w_config& c = m->cfg;
+  const int U = c.num_upsamples;
+  const int B = batch, T = frames;
+  const bool force_simt = std::getenv("V2W_FORCE_SIMT") != nullptr;
+
+  Bump ws;
+  P->stage_x = ws.take((int64_t)B * c.num_wv_feat * T * 4);
+  P->stage_spk = ws.take((int64_t)B * c.spk_dim * 4);
+  P->stage_noise = ws.take((int64_t)B * std::max(1, c.noise_dim) * 4);
+  P->stage_out = ws.take((int64_t)B * T * m->total_up * 4);
+  for (int i = 0; i < U; ++i) {
+    P->cond_scale[i] = ws.take((int64_t)B * m->stage_channels[i] * 4);
+    P->cond_shift[i] = ws.take((int64_t)B * m->stage_channels[i] * 4);
+  }
+  int64_t max_e = 0;
+  for (int i = 0; i < U; ++i)
+    max_e = std::max(max_e, (int64_t)B * T * m->stage_up[i] * m->stage_channels[i]);
+  const int64_t esz = bf ? 2 : 4;
+  P->xt = ws.take((int64_t)B * T * c.num_wv_feat * esz);
+  Act pre;   // conv_pre output, leaky-relu'd for ups[0] (models.py:128)
+  pre.slope = kLreluSlope;
+  if (bf) pre.bf16 = ws.take((int64_t)B * T * c.upsample_initial_channel * 2);
+  else pre.f32 = ws.take((int64_t)B * T * c.upsample_initial_channel * 4);
+  Act x0, y1, t1;
+  x0.slope = y1.slope = t1.slope = kLreluSlope;
+  x0.f32 = ws.take(max_e * 4);
+  y1.f32 = ws.take(max_e * 4);
+  const int64_t sum_f32 = ws.take(max_e * 4);
+  if (bf) {
+    x0.bf16 = ws.take(max_e * 2);
+    y1.bf16 = ws.take(max_e * 2);
+  }
+  if (c.resblock_type == 1) {
+    if (bf) t1.bf16 = ws.take(max_e * 2);
+    else t1.f32 = ws.take(max_e * 4);
+  }
+  const int64_t next_bf16 = bf ? ws.take(max_e * 2) : -1;
+  P->workspace_bytes = ws.off;
+  P->post_in = sum_f32;
+
+  auto blank = [](int kind) {
+    Op o;
+    std::memset(&o.d, 0, sizeof(o.d));
+    std::memset(&o.g, 0, sizeof(o.g));
+    o.d.kind = kind;
+    o.d.layer = -1;
+    o.d.in_act = o.d.residual = o.d.accum_in = o.d.out_f32 = o.d.out_bf16 = -1;
+    o.d.cond_stage = -1;
+    o.d.in_slope = 1.f;
+    o.d.out_scale = 1.f;
+    o.d.out_slope = 1.f;
+    return o;
+  };
+  {
+    Op o = blank(V2W_OP_TRANSPOSE_IN);
+    o.d.batch = B; o.d.rows = T;
+    o.d.out_f32 = bf ? -1 : P->xt;
+    o.d.out_bf16 = bf ? P->xt : -1;
+    P->ops.push_back(o);
+  }
+  {
+    Op o = blank(V2W_OP_COND_AFFINE);
+    o.d.batch = B;
+    P->ops.push_back(o);
+  }
+  auto emit = [&](int layer, int rows, const Act& in, int cond_stage, int64_t residual,
+                  int64_t accum, float out_scale, const Act& out) {
+    const v2w_layer_desc& L = m->layers[layer];
+    Op o = blank(V2W_OP_TAPGEMM);
+    o.d.engine = (bf && !force_simt) ? V2W_ENGINE_TC : V2W_ENGINE_SIMT;
+    o.d.layer = layer;
+    o.d.batch = B;
+    o.d.rows = rows;
+    choose_tiles(L, B, rows, &o.d);
+    if (bf) {
+      o.d.in_act = in.bf16; o.d.in_is_bf16 = 1; o.d.in_slope = 1.f;
+      o.d.out_f32 = out.f32; o.d.out_bf16 = out.bf16; o.d.out_slope = out.slope;
+    } else {
+      o.d.in_act = in.f32; o.d.in_is_bf16 = 0; o.d.in_slope = in.slope;
+      o.d.out_f32 = out.f32; o.d.out_bf16 = -1; o.d.out_slope = 1.f;
+    }
+    o.d.cond_stage = cond_stage;
+    o.d.residual = residual;
+    o.d.accum_in = accum;
+    o.d.out_scale = out_scale;
+    o.d.flops = 2 * L.macs_per_row * (int64_t)rows * B;
+    P->ops.push_back(o);
+  };
+
+  // layer indices follow v2w_model_create's push order
+  int li = 0;
+  Act xin;  // transposed input, no activation (models.py:123)
+  xin.slope = 1.f;
+  if (bf) xin.bf16 = P->xt; else xin.f32 = P->xt;
+  emit(li++, T, xin, -1, -1, -1, 1.f, pre);
+  Act cur_in = pre;
+  int rows = T;
+  const int nk = c.num_kernels;
+  for (int i = 0; i < U; ++i) {
+    const bool last_stage = i == U - 1;
+    // x = cbns[i](ups[i](leaky_relu(x)), fcs[i](spk_noise))   (models.py:128-134)
+    emit(li++, rows, cur_in, i, -1, -1, 1.f, x0);
+    rows *= c.upsample_rates[i];
+    Act stage_out;   // x = xs / num_kernels (models.py:141), as the next consumer wants it
+    stage_out.slope = last_stage ? kLreluSlopePost : kLreluSlope;
+    stage_out.f32 = (!bf || last_stage) ? sum_f32 : -1;
+    stage_out.bf16 = (bf && !last_stage) ? next_bf16 : -1;
+    Act partial;     // running MRF sum xs (models.py:136-140)
+    partial.f32 = sum_f32;
+    for (int j = 0; j < nk; ++j) {
+      const bool last_branch = j == nk - 1;
+      const int64_t accum = j > 0 ? sum_f32 : -1;
+      const float scale = last_branch ? 1.0f / nk : 1.0f;
+      const Act& tail_out = last_branch ? stage_out : partial;
+      if (c.resblock_type == 2) {
+        // ResBlock2 (models.py:65-70): x = c(lrelu(x)) + x, twice
+        emit(li++, rows, x0, -1, x0.f32, -1, 1.f, y1);
+        emit(li++, rows, y1, -1, y1.f32, accum, scale, tail_out);
+      } else {
+        // ResBlock1 (models.py:37-44): x = c2(lrelu(c1(lrelu(x)))) + x, three times
+        Act cur = x0;
+        for (int s = 0; s < 3; ++s) {
+          emit(li++, rows, cur, -1, -1, -1, 1.f, t1);
+          if (s < 2) {
+            emit(li++, rows, t1, -1, cur.f32, -1, 1.f, y1);
+            cur = y1;
+          } else {
+            emit(li++, rows, t1, -1, cur.f32, accum, scale, tail_out);
+          }
+        }
+      }
+    }
+    cur_in = stage_out;
+  }
+  {
+    Op o = blank(V2W_OP_CONV_POST);
+    o.d.layer = li;
+    o.d.batch = B; o.d.rows = rows;
+    o.d.in_act = sum_f32;
+    o.d.in_slope = kLreluSlopePost;
+    o.d.flops = 2 * m->layers[li].macs_per_row * (int64_t)rows * B;
+    P->ops.push_back(o);
+  }
+  *out = P;
+  return V2W_OK;
+}
+
+void v2w_plan_destroy(v2w_plan* p) { delete p; }
+
+int64_t v2w_plan_workspace_bytes(const v2w_plan* p) { return p ? p->workspace_bytes : 0; }
+int32_t v2w_plan_num_ops(const v2w_plan* p) { return p ? (int32_t)p->ops.size() : 0; }
+
+int32_t v2w_plan_get_op(const v2w_plan* p, int32_t i, v2w_op_desc* out) {
+  if (!p || !out || i < 0 || i >= (int32_t)p->ops.size()) {
+    set_error("v2w_plan_get_op: bad index %d", i);
+    return V2W_ERR_INVALID;
+  }
+  *out = p->ops[i].d;
+  return V2W_OK;
+}
+
+int32_t v2w_plan_set_engine(v2w_plan* p, int32_t i, int32_t engine) {
+  if (!p || i < 0 || i >= (int32_t)p->ops.size() ||
+      (engine != V2W_ENGINE_SIMT && engine != V2W_ENGINE_TC)) {
+    set_error("v2w_plan_set_engine: bad argument");
+    return V2W_ERR_INVALID;
+  }
+  if (p->bound) {
+    set_error("v2w_plan_set_engine: plan already bound");
+    return V2W_ERR_STATE;
+  }
+  Op& o = p->ops[i];
+  if (o.d.kind != V2W_OP_TAPGEMM) {
+    set_error("v2w_plan_set_engine: op %d is not a tap-GEMM", i);
+    return V2W_ERR_INVALID;
+  }
+  if (engine == V2W_ENGINE_TC && p->precision != V2W_PREC_BF16) {
+    set_error("v2w_plan_set_engine: the tensor-core engine needs a BF16 plan");
+    return V2W_ERR_INVALID;
+  }
+  o.d.engine = engine;
+  return V2W_OK;
+}
+
+int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) {
+  if (!p || !packed_dev || !workspace_dev) {
+    set_error("v2w_plan_bind: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(packed_dev) & 255) ||
+      (reinterpret_cast<uintptr_t>(workspace_dev) & 255)) {
+    set_error("v2w_plan_bind: buffers must be 256-byte aligned");
+    return V2W_ERR_INVALID;
+  }
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  p->packed = static_cast<const uint8_t*>(packed_dev);
+  p->ws = static_cast<uint8_t*>(workspace_dev);
+  const v2w_model* m = p->model;
+  const int tc_flags = std::getenv("V2W_TC_FLAGS") ? std::atoi(std::getenv("V2W_TC_FLAGS")) : 0;
+  for (Op& o : p->ops) {
+    if (o.d.kind != V2W_OP_TAPGEMM) continue;
+    const v2w_layer_desc& L = m->layers[o.d.layer];
+    v2w_tapgemm_args& g = o.g;
+    std::memset(&g, 0, sizeof(g));
+    g.engine = o.d.engine;
+    g.batch = o.d.batch; g.rows = o.d.rows; g.cin = L.cin; g.n_total = L.n_total; g.cmod = L.cout;
+    g.n_tile = o.d.n_tile; g.n_tiles = o.d.n_tiles;
+    for (int t = 0; t < o.d.n_tiles; ++t) {
+      g.num_taps[t] = o.d.num_taps[t];
+      for (int j = 0; j < o.d.num_taps[t]; ++j) {
+        g.tap_row[t][j] = o.d.tap_index[t][j];
+        g.tap_off[t][j] = L.tap_off[o.d.tap_index[t][j]];
+      }
+    }
+    auto at = [&](int64_t off) -> uint8_t* { return off < 0 ? nullptr : p->ws + off; };
+    g.in_act = at(o.d.in_act);
+    g.in_is_bf16 = o.d.in_is_bf16;
+    g.in_slope = o.d.in_slope;
+    g.w16 = L.w16_off >= 0 ? p->packed + L.w16_off : nullptr;
+    g.w32 = reinterpret_cast<const float*>(p->packed + L.w32_off);
+    g.bias = reinterpret_cast<const float*>(p->packed + L.bias_off);
+    if (o.d.cond_stage >= 0) {
+      g.scale = reinterpret_cast<const float*>(at(p->cond_scale[o.d.cond_stage]));
+      g.shift = reinterpret_cast<const float*>(at(p->cond_shift[o.d.cond_stage]));
+    }
+    g.residual = reinterpret_cast<const float*>(at(o.d.residual));
+    g.accum_in = reinterpret_cast<const float*>(at(o.d.accum_in));
+    g.out_scale = o.d.out_scale;
+    g.out_f32 = reinterpret_cast<float*>(at(o.d.out_f32));
+    g.out_bf16 = at(o.d.out_bf16);
+    g.out_slope = o.d.out_slope;
+    g.tc_flags = tc_flags;
+    rc = validate_gemm(g);
+    if (rc) return rc;
+    o.tc_ready = false;
+    if (g.engine == V2W_ENGINE_TC) {
+      rc = prepare_tc(g, &o.tcl);
+      if (rc) return rc;
+      o.tc_ready = true;
+    }
+  }
+  p->bound = true;
+  return V2W_OK;
+}
+
+int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
+                    float* out_dev, void* stream, int32_t* gpu_launches) {
+  if (!p || !x_dev || !spk_dev || !out_dev) {
+    set_error("v2w_forward: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if (!p->bound) {
+    set_error("v2w_forward: plan is not bound to device buffers");
+    return V2W_ERR_STATE;
+  }
+  const v2w_model* m = p->model;
+  const v2w_config& c = m->cfg;
+  if (c.noise_dim > 0 && !noise_dev) {
+    set_error("v2w_forward: noise is required (vec2wav/models.py:120)");
+    return V2W_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bf = p->precision == V2W_PREC_BF16;
+  int launches = 0;
+  for (Op& o : p->ops) {
+    switch (o.d.kind) {
+      case V2W_OP_TRANSPOSE_IN: {
+        dim3 grid((p->frames + 31) / 32, (c.num_wv_feat + 31) / 32, p->batch);
+        if (bf)
+          simt::transpose_in_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+              x_dev, reinterpret_cast<__nv_bfloat16*>(p->ws + p->xt), c.num_wv_feat, p->frames);
+        else
+          simt::transpose_in_kernel<float><<<grid, 256, 0, st>>>(
+              x_dev, reinterpret_cast<float*>(p->ws + p->xt), c.num_wv_feat, p->frames);
+        V2W_CUDA(cudaGetLastError());
+        ++launches;
+        break;
+      }
+      case V2W_OP_COND_AFFINE: {
+        simt::CondParams cp;
+        std::memset(&cp, 0, sizeof(cp));
+        int cmax = 0;
+        for (size_t i = 0; i < m->cond.size(); ++i) {
+          const CondLayout& cl = m->cond[i];
+          simt::CondStage& S = cp.st[i];
+          S.fcw = reinterpret_cast<const float*>(p->packed + cl.fcw);
+          S.fcb = reinterpret_cast<const float*>(p->packed + cl.fcb);
+          S.snw = reinterpret_cast<const float*>(p->packed + cl.snw);
+          S.snb = reinterpret_cast<const float*>(p->packed + cl.snb);
+          S.rstd = reinterpret_cast<const float*>(p->packed + cl.rstd);
+          S.mean = reinterpret_cast<const float*>(p->packed + cl.mean);
+          S.scale = reinterpret_cast<float*>(p->ws + p->cond_scale[i]);
+          S.shift = reinterpret_cast<float*>(p->ws + p->cond_shift[i]);
+          S.C = cl.C;
+          cmax = std::max(cmax, cl.C);
+        }
+        cp.spk = spk_dev; cp.noise = noise_dev;
+        cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
+        const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * cmax) * 4;
+        dim3 grid((unsigned)m->cond.size(), p->batch);
+        simt::cond_affine_kernel<<<grid, 128, smem, st>>>(cp);
+        V2W_CUDA(cudaGetLastError());
+        ++launches;
+        break;
+      }
+      case V2W_OP_TAPGEMM: {
+        int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st) : launch_simt(o.g, st);
+        if (rc) return rc;
+        ++launches;
+        break;
+      }
+      case V2W_OP_CONV_POST: {
+        const v2w_layer_desc& L = m->layers[o.d.layer];
+        const float* in = reinterpret_cast<const float*>(p->ws + o.d.in_act);
+        const float* w = reinterpret_cast<const float*>(p->packed + L.w32_off);
+        const float* bias = reinterpret_cast<const float*>(p->packed + L.bias_off);
+        dim3 grid((o.d.rows + simt::kPostRows - 1) / simt::kPostRows, p->batch);
+        if (L.cin == 16)
+          simt::conv_post_kernel<16><<<grid, simt::kPostRows, 0, st>>>(in, w, bias, out_dev,
+                                                                      o.d.rows, o.d.in_slope);
+        else if (L.cin == 32)
+          simt::conv_post_kernel<32><<<grid, simt::kPostRows, 0, st>>>(in, w, bias, out_dev,
+                                                                      o.d.rows, o.d.in_slope);
+        else {
+          set_error("conv_post with %d input channels unsupported", L.cin);
+          return V2W_ERR_INVALID;
+        }
+        V2W_CUDA(cudaGetLastError());
+        ++launches;
+        break;
+      }
+      default:
+        set_error("v2w_forward: unknown op kind %d", o.d.kind);
+        return V2W_ERR_STATE;
+    }
+  }
+  if (gpu_launches) *gpu_launches = launches;
+  return V2W_OK;
+}
+
+int32_t v2w_forward_host(v2w_plan* p, const float* x_host, const float* spk_host,
+                         const float* noise_host, float* out_host, void* stream,
+                         int32_t* gpu_launches) {
+  if (!p || !x_host || !spk_host || !out_host) {
+    set_error("v2w_forward_host: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if (!p->bound) {
+    set_error("v2w_forward_host: plan is not bound to device buffers");
+    return V2W_ERR_STATE;
+  }
+  const v2w_config& c = p->model->cfg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dx = reinterpret_cast<float*>(p->ws + p->stage_x);
+  float* ds = reinterpret_cast<float*>(p->ws + p->stage_spk);
+  float* dn = reinterpret_cast<float*>(p->ws + p->stage_noise);
+  float* dout = reinterpret_cast<float*>(p->ws + p->stage_out);
+  const size_t B = p->batch;
+  V2W_CUDA(cudaMemcpyAsync(dx, x_host, B * c.num_wv_feat * p->frames * 4, cudaMemcpyHostToDevice, st));
+  V2W_CUDA(cudaMemcpyAsync(ds, spk_host, B * c.spk_dim * 4, cudaMemcpyHostToDevice, st));
+  if (c.noise_dim > 0) {
+    if (!noise_host) {
+      set_error("v2w_forward_host: noise is required (vec2wav/models.py:120)");
+      return V2W_ERR_INVALID;
+    }
+    V2W_CUDA(cudaMemcpyAsync(dn, noise_host, B * c.noise_dim * 4, cudaMemcpyHostToDevice, st));
+  }
+  int rc = v2w_forward(p, dx, ds, dn, dout, stream, gpu_launches);
+  if (rc) return rc;
+  V2W_CUDA(cudaMemcpyAsync(out_host, dout, B * p->frames * p->model->total_up * 4,
+                           cudaMemcpyDeviceToHost, st));
+  V2W_CUDA(cudaStreamSynchronize(st));
+  return V2W_OK;
+}
+
+int32_t v2w_tapgemm(const v2w_tapgemm_args* a, void* stream) {
+  if (!a) {
+    set_error("v2w_tapgemm: null argument");
+    return V2W_ERR_INVALID;
+  }
+  int rc = validate_gemm(*a);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->engine == V2W_ENGINE_TC) {
+    TcLaunch L;
+    rc = prepare_tc(*a, &L);
+    if (rc) return rc;
+    return launch_tc(L, st);
+  }
+  if (a->engine == V2W_ENGINE_SIMT) return launch_simt(*a, st);
+  set_error("v2w_tapgemm: unknown engine %d", a->engine);
+  return V2W_ERR_INVALID;
+}
+
+}  // extern "C"

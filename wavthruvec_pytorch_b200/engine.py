@@ -1,0 +1,219 @@
+"""Host side of the native generation path: parameter folding cache, plan cache, launch.
+
+PyTorch is plumbing here -- device memory (`torch.empty`), the current CUDA stream and the
+module's parameter storage; all arithmetic happens in libv2w (include/v2w.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import native
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class NativeEngine:
+    """Owns the libv2w model/plan handles of one Generator instance."""
+
+    def __init__(self, module):
+        self._module = module
+        self._lib = native.load()
+        self._cfg = native.make_config(module.h)
+        handle = C.c_void_p()
+        native.check(self._lib.v2w_model_create(C.byref(self._cfg), C.byref(handle)))
+        self._model = handle
+        self._packed: Dict[torch.device, torch.Tensor] = {}
+        self._packed_sig = None
+        self._plans: Dict[Tuple, Tuple[C.c_void_p, torch.Tensor]] = {}
+        self.last_launches = 0
+
+    def __del__(self):
+        try:
+            self._drop_plans()
+            if getattr(self, "_model", None):
+                self._lib.v2w_model_destroy(self._model)
+                self._model = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _drop_plans(self):
+        for plan, _ws in self._plans.values():
+            self._lib.v2w_plan_destroy(plan)
+        self._plans.clear()
+
+    def invalidate(self):
+        self._packed.clear()
+        self._packed_sig = None
+        self._drop_plans()
+
+    def flops_per_frame(self) -> int:
+        return int(self._lib.v2w_model_flops_per_frame(self._model))
+
+    def layers(self) -> List[native.LayerDesc]:
+        out = []
+        for i in range(self._lib.v2w_model_num_layers(self._model)):
+            d = native.LayerDesc()
+            native.check(self._lib.v2w_model_get_layer(self._model, i, C.byref(d)))
+            out.append(d)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # state_dict -> v2w_params -> packed buffer
+    # ------------------------------------------------------------------------------------------
+    def _state_tensors(self):
+        m = self._module
+        ts = []
+        for conv in m.conv_modules():
+            if hasattr(conv, "weight_v"):
+                ts += [conv.weight_v, conv.weight_g, conv.bias]
+            else:  # after remove_weight_norm()
+                ts += [conv.weight, None, conv.bias]
+        for fc, cbn in zip(m.fcs, m.cbns):
+            ts += [fc.weight, fc.bias, cbn.layer.weight_orig, cbn.layer.weight_u,
+                   cbn.layer.weight_v, cbn.layer.bias, cbn.batch_nrom.running_mean,
+                   cbn.batch_nrom.running_var]
+        return ts
+
+    def _signature(self, ts):
+        return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
+
+    def pack_host(self) -> torch.Tensor:
+        """Fold + pack on the host (v2w_model_pack); returns a uint8 CPU tensor."""
+        ts = self._state_tensors()
+        host = [None if t is None else t.detach().to("cpu", torch.float32).contiguous() for t in ts]
+        nconv = self._lib.v2w_model_num_convs(self._model)
+        nstage = self._cfg.num_upsamples
+        if len(host) != 3 * nconv + 8 * nstage:
+            raise RuntimeError("module structure does not match the native layer table")
+        convs = (native.ConvParams * nconv)()
+        for i in range(nconv):
+            v, g, b = host[3 * i: 3 * i + 3]
+            convs[i].v = _ptr(v)
+            convs[i].g = _ptr(g) if g is not None else None
+            convs[i].bias = _ptr(b)
+        cond = (native.CondParams * nstage)()
+        base = 3 * nconv
+        for i in range(nstage):
+            vals = host[base + 8 * i: base + 8 * i + 8]
+            for (name, _), t in zip(native.CondParams._fields_, vals):
+                setattr(cond[i], name, _ptr(t))
+        params = native.Params(nconv, convs, nstage, cond)
+        nbytes = int(self._lib.v2w_model_packed_bytes(self._model))
+        packed = torch.empty(nbytes, dtype=torch.uint8)
+        native.check(self._lib.v2w_model_pack(self._model, C.byref(params), packed.data_ptr()))
+        del host
+        return packed
+
+    def _packed_on(self, device: torch.device) -> torch.Tensor:
+        sig = self._signature(self._state_tensors())
+        if sig != self._packed_sig:
+            self._packed.clear()
+            self._drop_plans()   # plans hold pointers into the packed buffer
+            self._packed_sig = sig
+        buf = self._packed.get(device)
+        if buf is None:
+            buf = self.pack_host().to(device)
+            self._packed[device] = buf
+        return buf
+
+    # ------------------------------------------------------------------------------------------
+    def plan(self, batch: int, frames: int, precision: str, device: torch.device):
+        """(plan handle, workspace) for this problem size; created and bound on first use."""
+        key = (batch, frames, precision, device)
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit
+        packed = self._packed_on(device)
+        prec = native.PREC_BF16 if precision == "bf16" else native.PREC_FP32
+        handle = C.c_void_p()
+        native.check(self._lib.v2w_plan_create(self._model, batch, frames, prec, C.byref(handle)))
+        try:
+            ws_bytes = int(self._lib.v2w_plan_workspace_bytes(handle))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                native.check(self._lib.v2w_plan_bind(handle, packed.data_ptr(), ws.data_ptr()))
+        except Exception:
+            self._lib.v2w_plan_destroy(handle)
+            raise
+        self._plans[key] = (handle, ws)
+        return handle, ws
+
+    def ops(self, batch: int, frames: int, precision: str, device) -> List[native.OpDesc]:
+        handle, _ = self.plan(batch, frames, precision, torch.device(device))
+        out = []
+        for i in range(self._lib.v2w_plan_num_ops(handle)):
+            d = native.OpDesc()
+            native.check(self._lib.v2w_plan_get_op(handle, i, C.byref(d)))
+            out.append(d)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def _check_inputs(self, x, spk, noise):
+        h = self._module.h
+        if x.dim() != 3 or x.shape[1] != h.num_wv_feat:
+            raise RuntimeError(f"expected x of shape [B, {h.num_wv_feat}, T], got {tuple(x.shape)}")
+        B = x.shape[0]
+        if spk.dim() != 2 or tuple(spk.shape) != (B, h.spk_dim):
+            raise RuntimeError(f"expected spk_emb of shape [{B}, {h.spk_dim}], got {tuple(spk.shape)}")
+        if noise.dim() != 2 or tuple(noise.shape) != (B, h.noise_dim):
+            raise RuntimeError(f"expected noise of shape [{B}, {h.noise_dim}], got {tuple(noise.shape)}")
+
+    def forward(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """Device tensors in, device tensor out, asynchronous on the current stream."""
+        self._check_inputs(x, spk, noise)
+        if not x.is_cuda:
+            raise RuntimeError(
+                "the native Vec2Wav generation path runs on sm_100 GPUs only and has no CPU "
+                "fallback; move the module and inputs to a CUDA device (train() mode / autograd "
+                "use the PyTorch delegate on any device)")
+        if spk.device != x.device or noise.device != x.device:
+            raise RuntimeError("x, spk_emb and noise must live on the same device")
+        dev = x.device
+        x = x.detach().to(torch.float32).contiguous()
+        spk = spk.detach().to(torch.float32).contiguous()
+        noise = noise.detach().to(torch.float32).contiguous()
+        B, _, T = x.shape
+        handle, _ws = self.plan(B, T, self._module.precision, dev)
+        out = torch.empty((B, 1, T * self.total_upsample()), dtype=torch.float32, device=dev)
+        n = C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(),
+                                               noise.data_ptr(), out.data_ptr(),
+                                               C.c_void_p(stream), C.byref(n)))
+        self.last_launches = n.value
+        return out
+
+    def forward_host(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor,
+                     out: torch.Tensor, device) -> torch.Tensor:
+        """Host (ideally pinned) tensors in and out through v2w_forward_host: H2D, forward, D2H,
+        stream synchronised on return."""
+        self._check_inputs(x, spk, noise)
+        for t in (x, spk, noise, out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("forward_host takes contiguous fp32 CPU tensors")
+        dev = torch.device(device)
+        B, _, T = x.shape
+        if tuple(out.shape) != (B, 1, T * self.total_upsample()):
+            raise RuntimeError("out has the wrong shape")
+        handle, _ws = self.plan(B, T, self._module.precision, dev)
+        n = C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            native.check(self._lib.v2w_forward_host(handle, x.data_ptr(), spk.data_ptr(),
+                                                    noise.data_ptr(), out.data_ptr(),
+                                                    C.c_void_p(stream), C.byref(n)))
+        self.last_launches = n.value
+        return out
+
+    def total_upsample(self) -> int:
+        r = 1
+        for u in self._module.h.upsample_rates:
+            r *= int(u)
+        return r
