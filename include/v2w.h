@@ -137,6 +137,19 @@ typedef struct v2w_layer_desc {
   int64_t macs_per_row;        /* real multiply-accumulates per input row (zero blocks excluded) */
 } v2w_layer_desc;
 
+/* Where the folded conditioning parameters of one stage live in the packed buffer (byte
+ * offsets, all fp32).  snw is weight_orig already divided by sigma = u.(W v). */
+typedef struct v2w_cond_desc {
+  int32_t channels;            /* C_i */
+  int32_t in_dim;              /* spk_dim + noise_dim */
+  int64_t fcw_off;             /* [128][in_dim] */
+  int64_t fcb_off;             /* [128] */
+  int64_t snw_off;             /* [2C][128] */
+  int64_t snb_off;             /* [2C] */
+  int64_t rstd_off;            /* [C]  1/sqrt(running_var + 1e-5) */
+  int64_t mean_off;            /* [C] */
+} v2w_cond_desc;
+
 /* Kinds of op in a plan's execution list. */
 #define V2W_OP_TRANSPOSE_IN 0  /* x[B,Cin,T] fp32 -> [B,T,Cin] (fp32 or bf16) */
 #define V2W_OP_COND_AFFINE 1   /* fcs + spectral-norm Linear + BN fold -> scale/shift per (b, stage, c) */
@@ -179,6 +192,7 @@ int32_t v2w_model_create(const v2w_config* cfg, struct v2w_model** out);
 void v2w_model_destroy(struct v2w_model* m);
 int32_t v2w_model_num_layers(const struct v2w_model* m);
 int32_t v2w_model_get_layer(const struct v2w_model* m, int32_t index, v2w_layer_desc* out);
+int32_t v2w_model_get_cond(const struct v2w_model* m, int32_t stage, v2w_cond_desc* out);
 int32_t v2w_model_num_convs(const struct v2w_model* m);   /* expected v2w_params.num_convs */
 int64_t v2w_model_packed_bytes(const struct v2w_model* m);
 /* Fold weight norm (w = g*v/||v||, norm over all dims but 0 -- i.e. per INPUT channel for
@@ -220,6 +234,13 @@ int32_t v2w_forward(struct v2w_plan* p, const float* x_dev, const float* spk_dev
 int32_t v2w_forward_host(struct v2w_plan* p, const float* x_host, const float* spk_host,
                          const float* noise_host, float* out_host, void* stream,
                          int32_t* gpu_launches);
+
+/* Per-op device timing.  When enabled, v2w_forward brackets every op with CUDA events recorded
+ * on the caller's stream; after the stream has been synchronised by the caller,
+ * v2w_plan_op_time_ms returns the last forward's duration of op `index` in milliseconds
+ * (negative on error).  Used by bench.py for the live roofline numbers. */
+int32_t v2w_plan_set_profiling(struct v2w_plan* p, int32_t enabled);
+float v2w_plan_op_time_ms(struct v2w_plan* p, int32_t index);
 
 /* ---- kernel-level entry (unit tests; the plan executor goes through the same code) -- */
 typedef struct v2w_tapgemm_args {

@@ -1,0 +1,157 @@
+"""numpy interpreter of a libv2w plan (TEST INFRASTRUCTURE).
+
+Executes the op list that v2w_plan_create emits over the buffer that v2w_model_pack produced,
+with the same rounding points as the device kernels (bf16 operands where the plan says bf16,
+fp32 accumulation).  On the CPU box this validates everything except the CUDA kernels
+themselves: layer table, polyphase decomposition, weight folding/packing, tile tap lists,
+epilogue wiring and buffer lifetimes.  It also predicts the bf16 path's SNR.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from wavthruvec_pytorch_b200 import native
+
+
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest-even bf16 -> fp32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).view(np.float32)
+
+
+def lrelu(x, slope):
+    return np.where(x > 0, x, x * np.float32(slope)).astype(np.float32)
+
+
+class HostPlan:
+    """Plan created through the C-ABI on the host only (no bind, no CUDA)."""
+
+    def __init__(self, engine, batch, frames, precision):
+        self.lib = engine._lib
+        self.engine = engine
+        self.model = engine._model
+        self.precision = precision
+        h = C.c_void_p()
+        prec = native.PREC_BF16 if precision == "bf16" else native.PREC_FP32
+        native.check(self.lib.v2w_plan_create(self.model, batch, frames, prec, C.byref(h)))
+        self.handle = h
+        self.ops = []
+        for i in range(self.lib.v2w_plan_num_ops(h)):
+            d = native.OpDesc()
+            native.check(self.lib.v2w_plan_get_op(h, i, C.byref(d)))
+            self.ops.append(d)
+        self.layers = engine.layers()
+        self.workspace_bytes = int(self.lib.v2w_plan_workspace_bytes(h))
+
+    def close(self):
+        if self.handle:
+            self.lib.v2w_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+
+def _packed_views(plan: HostPlan, packed: np.ndarray):
+    lib, model = plan.lib, plan.model
+
+    def f32(off, n):
+        return packed[off: off + 4 * n].view(np.float32)
+
+    def u16(off, n):
+        return packed[off: off + 2 * n].view(np.uint16)
+
+    conds = []
+    for i in range(plan.engine._cfg.num_upsamples):
+        d = native.CondDesc()
+        native.check(lib.v2w_model_get_cond(model, i, C.byref(d)))
+        Cn, D = d.channels, d.in_dim
+        conds.append(dict(C=Cn, fcw=f32(d.fcw_off, 128 * D).reshape(128, D), fcb=f32(d.fcb_off, 128),
+                          snw=f32(d.snw_off, 2 * Cn * 128).reshape(2 * Cn, 128),
+                          snb=f32(d.snb_off, 2 * Cn), rstd=f32(d.rstd_off, Cn),
+                          mean=f32(d.mean_off, Cn)))
+    return f32, u16, conds
+
+
+def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
+    """Returns the waveform [B,1,L] (fp32).  `collect`, if a dict, receives every op's fp32
+    output keyed by op index."""
+    f32, u16, conds = _packed_views(plan, packed)
+    bf = plan.precision == "bf16"
+    ws = {}       # workspace offset -> ndarray [B, rows, C] (values as the device buffer holds them)
+    scale, shift = {}, {}
+    out = None
+    x = np.asarray(x, np.float32)
+    for idx, op in enumerate(plan.ops):
+        if op.kind == native.OP_TRANSPOSE_IN:
+            xt = np.ascontiguousarray(x.transpose(0, 2, 1))
+            if op.out_bf16 >= 0:
+                ws[op.out_bf16] = bf16_round(xt)
+            else:
+                ws[op.out_f32] = xt
+        elif op.kind == native.OP_COND_AFFINE:
+            sn = np.concatenate([spk, noise], axis=1).astype(np.float32)
+            for i, c in enumerate(conds):
+                z = sn @ c["fcw"].T + c["fcb"]
+                gb = z @ c["snw"].T + c["snb"]
+                Cn = c["C"]
+                sc = gb[:, :Cn] * c["rstd"]
+                scale[i] = sc.astype(np.float32)
+                shift[i] = (gb[:, Cn:] - sc * c["mean"]).astype(np.float32)
+        elif op.kind == native.OP_TAPGEMM:
+            L = plan.layers[op.layer]
+            # an upsample op's output row [u*Cout] is u consecutive channels-last rows [Cout]
+            A = ws[op.in_act].reshape(op.batch, op.rows, L.cin)
+            if op.in_slope != 1.0:
+                A = lrelu(A, op.in_slope)
+            if bf:     # TC engine semantics: bf16 weights [taps][n_total][cin]
+                w = u16(L.w16_off, L.num_taps * L.n_total * L.cin).astype(np.uint32) << 16
+                W = w.view(np.float32).reshape(L.num_taps, L.n_total, L.cin)
+            else:      # FFMA engine: fp32 [taps][cin][n_total]
+                W = f32(L.w32_off, L.num_taps * L.cin * L.n_total).reshape(
+                    L.num_taps, L.cin, L.n_total).transpose(0, 2, 1)
+            acc = np.zeros((op.batch, op.rows, L.n_total), np.float32)
+            for t in range(op.n_tiles):
+                cols = slice(t * op.n_tile, (t + 1) * op.n_tile)
+                for jj in range(op.num_taps[t]):
+                    j = op.tap_index[t][jj]
+                    off = L.tap_off[j]
+                    sh = np.zeros_like(A)
+                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                    if hi > lo:
+                        sh[:, lo:hi] = A[:, lo + off: hi + off]
+                    acc[:, :, cols] += sh @ W[j][cols].T
+            bias = f32(L.bias_off, L.cout)
+            n_idx = np.arange(L.n_total) % L.cout
+            v = acc + bias[n_idx]
+            if op.cond_stage >= 0:
+                v = v * scale[op.cond_stage][:, None, n_idx] + shift[op.cond_stage][:, None, n_idx]
+            if op.residual >= 0:
+                v = v + ws[op.residual].reshape(v.shape)
+            if op.accum_in >= 0:
+                v = v + ws[op.accum_in].reshape(v.shape)
+            if op.out_scale != 1.0:
+                v = v * np.float32(op.out_scale)
+            v = v.astype(np.float32)
+            if op.out_f32 >= 0:
+                ws[op.out_f32] = v
+            if op.out_bf16 >= 0:
+                ws[op.out_bf16] = bf16_round(lrelu(v, op.out_slope))
+            if collect is not None:
+                collect[idx] = v
+        elif op.kind == native.OP_CONV_POST:
+            L = plan.layers[op.layer]
+            A = lrelu(ws[op.in_act].reshape(op.batch, op.rows, L.cin), op.in_slope)
+            W = f32(L.w32_off, 7 * L.cin).reshape(7, L.cin)
+            bias = f32(L.bias_off, 1)[0]
+            Ap = np.pad(A, ((0, 0), (3, 3), (0, 0)))
+            y = np.full((op.batch, op.rows), bias, np.float32)
+            for j in range(7):
+                y += Ap[:, j: j + op.rows] @ W[j]
+            out = np.tanh(y).astype(np.float32)[:, None, :]
+        else:
+            raise AssertionError(f"unknown op kind {op.kind}")
+    return out

@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle -- needs a B200.
+
+Bars (BASELINE.json north_star): FP32 plan max-abs <= 1e-4 on the waveform; BF16 plan waveform
+SNR >= 45 dB, SNR = 10 log10(sum ref^2 / sum (ref-y)^2), on the named fixture state.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures
+from wavthruvec_pytorch_b200 import native
+
+import gemm_ref
+import plan_interp
+from helpers import dropin_in_state, hparams, load_golden, t
+
+pytestmark = pytest.mark.gpu
+
+FP32_MAX_ABS = 1e-4
+BF16_MIN_SNR_DB = 45.0
+
+
+def _native(gen, g, precision, dev="cuda:0"):
+    gen.precision = precision
+    with torch.no_grad():
+        y = gen(t(g.x).to(dev), t(g.spk).to(dev), t(g.noise).to(dev))
+    torch.cuda.synchronize()
+    assert gen.engine().last_launches > 0
+    return y.cpu().numpy()
+
+
+def test_library_sees_the_gpu():
+    assert native.load().v2w_device_count() >= 1
+
+
+# ----------------------------------------------------------------------------------------------
+# kernel level: v2w_tapgemm against float64 arithmetic
+# ----------------------------------------------------------------------------------------------
+def _gemm_case(engine, B, rows, cin, n_total, n_tile, k, d, epilogue, seed=0, flags=0):
+    rng = np.random.default_rng(seed)
+    A = plan_interp.bf16_round(rng.standard_normal((B, rows, cin)).astype(np.float32))
+    W = plan_interp.bf16_round((rng.standard_normal((k, n_total, cin)) / np.sqrt(cin * k)).astype(np.float32))
+    tiles = gemm_ref.conv_tiles(k, d, n_total // n_tile)
+    cmod = n_total
+    bias = scale = shift = resid = accum = None
+    out_scale = 1.0
+    if epilogue:
+        bias = rng.standard_normal(cmod).astype(np.float32)
+        scale = rng.standard_normal((B, cmod)).astype(np.float32)
+        shift = rng.standard_normal((B, cmod)).astype(np.float32)
+        resid = rng.standard_normal((B, rows, n_total)).astype(np.float32)
+        accum = rng.standard_normal((B, rows, n_total)).astype(np.float32)
+        out_scale = 1.0 / 3.0
+    want = gemm_ref.tapgemm_expected(A, W, tiles, n_tile, bias, scale, shift, resid, accum, out_scale, cmod)
+    o32, o16 = gemm_ref.run_tapgemm(engine, A, W, tiles, n_tile, cmod, bias, scale, shift, resid,
+                                    accum, out_scale, 0.1, tc_flags=flags)
+    tol = 2e-4 * max(1.0, np.abs(want).max())
+    assert not np.isnan(o32).any()
+    assert np.abs(o32 - want).max() < tol
+    lre = np.where(want > 0, want, 0.1 * want)
+    assert np.abs(o16 - lre).max() < 1e-2 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cin,n", [(16, 16), (32, 32), (64, 64), (128, 128), (256, 256)])
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+def test_tapgemm_simt(cin, n, k, d):
+    _gemm_case(native.ENGINE_SIMT, 2, 203, cin, n, min(n, 256), k, d, True)
+
+
+@pytest.mark.parametrize("cin,n", [(16, 16), (32, 32), (64, 64), (128, 128), (256, 256), (768, 512)])
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 3), (11, 5)])
+def test_tapgemm_tc(cin, n, k, d):
+    _gemm_case(native.ENGINE_TC, 2, 517, cin, n, min(n, 256), k, d, True)
+
+
+@pytest.mark.parametrize("rows", [1, 31, 128, 129, 1000])
+def test_tapgemm_tc_ragged_rows(rows):
+    _gemm_case(native.ENGINE_TC, 3, rows, 64, 128, 128, 7, 1, True, seed=rows)
+
+
+def test_tapgemm_tc_per_tap_cross_check():
+    """Halo-reuse (row-shifted descriptor views) and per-tap reload give the same numbers."""
+    _gemm_case(native.ENGINE_TC, 2, 300, 128, 128, 128, 11, 3, False, flags=0)
+    _gemm_case(native.ENGINE_TC, 2, 300, 128, 128, 128, 11, 3, False, flags=native.TC_FLAG_PER_TAP)
+
+
+# ----------------------------------------------------------------------------------------------
+# whole forward against the goldens written by the reference
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
+                                  "rb1_1024_stress", "rb2_768_stress_tiny"])
+def test_fp32_plan_max_abs(name):
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "fp32")
+    assert y.shape == g.y.shape
+    err = np.abs(y - g.y).max()
+    print(f"{name}: fp32 max-abs {err:.2e}")
+    assert err <= FP32_MAX_ABS
+
+
+def test_fp32_plan_fresh_state():
+    g = load_golden("rb2_768_fresh")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "fp32")
+    assert (np.abs(y) > 0.99).mean() > 0.95 and np.abs(y - g.y).max() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb2_1024_warm", "rb2_768_stress_tiny"])
+def test_bf16_plan_snr(name):
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "bf16")
+    snr = fixtures.snr_db(g.y, y)
+    print(f"{name}: bf16 SNR {snr:.1f} dB")
+    assert snr >= BF16_MIN_SNR_DB
+
+
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress"])
+def test_bf16_plan_matches_cpu_emulation(name):
+    """The device BF16 plan and the numpy interpreter round at the same points, so they agree far
+    more tightly than either agrees with fp32 -- this isolates kernel bugs from format error."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False)
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "bf16")
+    emu = plan_interp.run(plan, eng.pack_host().numpy(), g.x, g.spk, g.noise)
+    gen = gen.to("cuda:0")
+    y = _native(gen, g, "bf16")
+    snr = fixtures.snr_db(emu, y)
+    print(f"{name}: device-vs-emulation SNR {snr:.1f} dB, max-abs {np.abs(y - emu).max():.2e}")
+    assert snr >= 60.0
+
+
+def test_forward_host_equals_forward_and_is_deterministic():
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    a = _native(gen, g, "bf16")
+    b = _native(gen, g, "bf16")
+    np.testing.assert_array_equal(a, b)
+    out = torch.empty(g.y.shape, dtype=torch.float32).pin_memory()
+    gen.engine().forward_host(t(g.x).pin_memory(), t(g.spk).pin_memory(), t(g.noise).pin_memory(),
+                              out, "cuda:0")
+    np.testing.assert_array_equal(out.numpy(), a)
+
+
+@pytest.mark.parametrize("rb", [1, '1'])
+def test_full_size_against_autograd_delegate(rb):
+    """cfg-scale shapes (B=4, T=200 and a ragged T) where the numpy oracle is too slow: the FP32
+    plan against the reference-equivalent PyTorch op sequence run in fp32 on the same GPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from wavthruvec_pytorch_b200 import Generator
+    h = hparams(resblock=rb, num_wv_feat=768)
+    gen = fixtures.construct(Generator, h)
+    fixtures.redraw_variance_preserving(gen)
+    fixtures.warmup(gen, 5)
+    gen = gen.to("cuda:0").eval()
+    for B, T in ((4, 200), (3, 77)):
+        x, s, n = fixtures.make_inputs(h, B, T, 3)
+        x, s, n = x.cuda(), s.cuda(), n.cuda()
+        with torch.no_grad():
+            ref = gen._forward_autograd(x, s, n).cpu().numpy()
+            gen.precision = "fp32"
+            y32 = gen(x, s, n).cpu().numpy()
+            gen.precision = "bf16"
+            y16 = gen(x, s, n).cpu().numpy()
+        err = np.abs(y32 - ref).max()
+        snr = fixtures.snr_db(ref, y16)
+        print(f"rb={rb!r} B={B} T={T}: fp32 max-abs {err:.2e}, bf16 SNR {snr:.1f} dB")
+        assert err <= FP32_MAX_ABS
+        if rb == 1:
+            assert snr >= BF16_MIN_SNR_DB
+
+
+def test_linearity_property_of_resblock_free_path():
+    """Size-independent property: utterances are independent (eval BN, per-sample CBN), so a
+    batch equals its utterances run one by one."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    gen.precision = "bf16"
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    with torch.no_grad():
+        full = gen(x, s, n)
+        parts = torch.cat([gen(x[i:i + 1], s[i:i + 1], n[i:i + 1]) for i in range(x.shape[0])])
+    assert torch.equal(full, parts)
+
+
+def test_state_change_triggers_refold():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    a = _native(gen, g, "fp32")
+    with torch.no_grad():
+        gen.conv_post.bias.add_(0.25)
+    b = _native(gen, g, "fp32")
+    want = np.tanh(np.arctanh(np.clip(a.astype(np.float64), -0.999999, 0.999999)) + 0.25)
+    assert np.abs(b - want).max() < 1e-4
+    gen.remove_weight_norm()
+    c = _native(gen, g, "fp32")
+    assert np.abs(c - b).max() < 1e-5

@@ -1,0 +1,193 @@
+"""CPU-side tests of libv2w: ABI surface, layer table, FLOP accounting, weight folding/packing
+and the plan (executed by the numpy interpreter in plan_interp.py against the goldens).
+No compute call reaches a GPU here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, vec2wav_numpy
+from wavthruvec_pytorch_b200 import Generator, native
+
+import plan_interp
+from helpers import dropin_in_state, hparams, load_golden, t
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = (ROOT / "include" / "v2w.h").read_text()
+    declared = set(re.findall(r"\b(v2w_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = native.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libv2w.so does not export {name}"
+    assert declared == set(native.EXPORTED_SYMBOLS), declared ^ set(native.EXPORTED_SYMBOLS)
+    assert lib.v2w_abi_version() == 1
+
+
+@pytest.mark.parametrize("rb,feat,layers,flops", [
+    (1, 768, 37, 118_888_448), (1, 1024, 37, 120_723_456),
+    ('1', 768, 97, 325_326_848), ('1', 1024, 97, 327_161_856)])
+def test_layer_table_and_flops(rb, feat, layers, flops):
+    """Algorithmic FLOPs per input frame == SURVEY.md section 8(d) / BASELINE.md section 3."""
+    gen = Generator(hparams(resblock=rb, num_wv_feat=feat))
+    eng = gen.engine()
+    ls = eng.layers()
+    assert len(ls) == layers
+    assert eng.flops_per_frame() == flops
+    assert eng._lib.v2w_model_num_convs(eng._model) == len(gen.conv_modules())
+    # polyphase tap sets of the five transposed convs: (k,u) -> taps per phase
+    ups = [l for l in ls if l.role == native.ROLE_UPSAMPLE]
+    assert [(l.kernel_size, l.up, l.num_taps) for l in ups] == [
+        (11, 5, 3), (8, 4, 3), (8, 4, 3), (4, 2, 3), (4, 2, 3)]
+    l0 = ups[0]
+    per_phase = [sum((l0.tap_mask[j] >> p) & 1 for j in range(l0.num_taps)) for p in range(5)]
+    assert sorted(per_phase) == [2, 2, 2, 2, 3]
+    assert list(l0.tap_off[:3]) == [-1, 0, 1]
+
+
+@pytest.mark.parametrize("bad", [
+    dict(upsample_initial_channel=256), dict(num_wv_feat=100),
+    dict(upsample_rates=[5, 4, 4, 2, 2], upsample_kernel_sizes=[10, 8, 8, 4, 4]),
+    dict(resblock_kernel_sizes=[3, 4, 11]),
+    dict(resblock='1', resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])])
+def test_unsupported_hyperparameters_fail_loudly(bad):
+    h = hparams(**bad)
+    cfg = native.make_config(h)
+    handle = C.c_void_p()
+    rc = native.load().v2w_model_create(C.byref(cfg), C.byref(handle))
+    assert rc == -1 and not handle.value
+    assert native.last_error()
+
+
+def test_pack_matches_numpy_fold():
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    packed = eng.pack_host().numpy()
+    sd = vec2wav_numpy.state_dict_to_numpy(gen)
+    names = ["conv_pre"] + [f"ups.{i}" for i in range(5)]
+    for rb in range(15):
+        names += [f"resblocks.{rb}.convs.0", f"resblocks.{rb}.convs.1"]
+    names.append("conv_post")
+    for L in eng.layers():
+        name = names[L.conv_index]
+        w = vec2wav_numpy.effective_weight(sd, name, np.float64)
+        w32 = packed[L.w32_off: L.w32_off + 4 * L.num_taps * L.cin * L.n_total].view(
+            np.float32).reshape(L.num_taps, L.cin, L.n_total)
+        bias = packed[L.bias_off: L.bias_off + 4 * L.cout].view(np.float32)
+        np.testing.assert_array_equal(bias, sd[name + ".bias"])
+        if L.role != native.ROLE_UPSAMPLE:
+            # Conv1d [Cout,Cin,K]: tap j <-> kernel index j
+            want = w.transpose(2, 1, 0)
+            np.testing.assert_allclose(w32, want, rtol=2e-6, atol=1e-9)
+        else:
+            # ConvTranspose1d [Cin,Cout,K]: (tap j, phase p) <-> kk = u*m + p + pad, m = -off
+            u, pad = L.up, L.padding
+            total = 0.0
+            for j in range(L.num_taps):
+                for p in range(u):
+                    blk = w32[j][:, p * L.cout:(p + 1) * L.cout]
+                    kk = u * (-L.tap_off[j]) + p + pad
+                    if (L.tap_mask[j] >> p) & 1:
+                        assert 0 <= kk < L.kernel_size
+                        np.testing.assert_allclose(blk, w[:, :, kk], rtol=2e-6, atol=1e-9)
+                        total += 1
+                    else:
+                        assert not (0 <= kk < L.kernel_size)
+                        assert not blk.any()
+            assert total == L.kernel_size   # every kernel element lands exactly once
+        if L.w16_off >= 0:
+            w16 = packed[L.w16_off: L.w16_off + 2 * L.num_taps * L.n_total * L.cin].view(np.uint16)
+            back = (w16.astype(np.uint32) << 16).view(np.float32).reshape(
+                L.num_taps, L.n_total, L.cin)
+            np.testing.assert_array_equal(back, plan_interp.bf16_round(w32.transpose(0, 2, 1)))
+
+
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
+                                  "rb2_768_stress_tiny", "rb1_1024_stress"])
+def test_fp32_plan_reproduces_reference(name):
+    """Layer table + folding + packing + op wiring, executed in numpy fp32: max-abs <= 1e-5
+    against the reference output (the device FP32 plan's bar is 1e-4)."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    packed = eng.pack_host().numpy()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "fp32")
+    assert all(op.engine == native.ENGINE_SIMT for op in plan.ops if op.kind == native.OP_TAPGEMM)
+    y = plan_interp.run(plan, packed, g.x, g.spk, g.noise)
+    assert y.shape == g.y.shape
+    assert np.abs(y - g.y).max() < 1e-5
+
+
+def test_fp32_plan_fresh_state_pre_tanh():
+    g = load_golden("rb2_768_fresh")
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, 1, g.x.shape[2], "fp32")
+    y = plan_interp.run(plan, eng.pack_host().numpy(), g.x, g.spk, g.noise)
+    assert np.abs(y - g.y).max() < 1e-3      # saturated +-1: sign agreement everywhere
+
+
+@pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 45.0), ("rb2_1024_warm", 45.0)])
+def test_bf16_plan_predicted_snr(name, min_snr):
+    """Same op list with the device's bf16 rounding points (bf16 operands, fp32 accumulate,
+    fp32 residual stream): the waveform SNR bar of the bf16 path, predicted on the CPU."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "bf16")
+    y = plan_interp.run(plan, eng.pack_host().numpy(), g.x, g.spk, g.noise)
+    snr = fixtures.snr_db(g.y, y)
+    print(f"{name}: predicted bf16 SNR {snr:.1f} dB")
+    assert snr >= min_snr
+
+
+def test_plan_structure_bf16_rb2():
+    gen = Generator(hparams(resblock=1, num_wv_feat=768))
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, 16, 200, "bf16")
+    kinds = [op.kind for op in plan.ops]
+    assert kinds[0] == native.OP_TRANSPOSE_IN and kinds[1] == native.OP_COND_AFFINE
+    assert kinds[-1] == native.OP_CONV_POST
+    gemms = [op for op in plan.ops if op.kind == native.OP_TAPGEMM]
+    assert len(gemms) == 36 and all(op.engine == native.ENGINE_TC for op in gemms)
+    total = sum(op.flops for op in plan.ops)
+    assert total == eng.flops_per_frame() * 16 * 200
+    # rows double-check: stage outputs 1000, 4000, 16000, 32000, 64000
+    assert sorted({op.rows for op in gemms}) == [200, 1000, 4000, 16000, 32000, 64000]
+    # the three transposed convs with 4 or 2 phases split into phase groups with 2 taps each
+    for op in gemms:
+        L = plan.layers[op.layer]
+        if L.role == native.ROLE_UPSAMPLE and L.up in (2, 4):
+            assert all(op.num_taps[t] == 2 for t in range(op.n_tiles))
+
+
+def test_native_path_has_no_cpu_fallback():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="no CPU"):
+            gen(t(g.x), t(g.spk), t(g.noise))
+    if native.load().v2w_device_count() == 0:
+        eng = gen.engine()
+        plan = plan_interp.HostPlan(eng, 1, 4, "bf16")
+        rc = eng._lib.v2w_forward(plan.handle, 1, 1, 1, 1, None, None)
+        assert rc == -3      # not bound: state error, never a silent success
+        rc = eng._lib.v2w_plan_bind(plan.handle, 256, 256)
+        assert rc == -2      # no usable GPU
+
+
+def test_autograd_delegate_matches_reference_output():
+    """train()/autograd mode runs stock PyTorch ops in the reference's order: in eval with grad
+    enabled it reproduces the golden bit-for-bit (up to thread-order ulps)."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g)
+    with pytest.warns(RuntimeWarning):
+        y = gen(t(g.x), t(g.spk), t(g.noise))
+    assert y.requires_grad
+    np.testing.assert_allclose(y.detach().numpy(), g.y, rtol=0, atol=2e-6)

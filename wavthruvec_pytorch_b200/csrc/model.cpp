@@ -288,6 +288,18 @@ int32_t v2w_model_get_layer(const v2w_model* m, int32_t i, v2w_layer_desc* out) 
   return V2W_OK;
 }
 
+int32_t v2w_model_get_cond(const v2w_model* m, int32_t i, v2w_cond_desc* out) {
+  if (!m || !out || i < 0 || i >= (int32_t)m->cond.size()) {
+    set_error("v2w_model_get_cond: bad stage %d", i);
+    return V2W_ERR_INVALID;
+  }
+  const CondLayout& c = m->cond[i];
+  out->channels = c.C; out->in_dim = c.D;
+  out->fcw_off = c.fcw; out->fcb_off = c.fcb; out->snw_off = c.snw; out->snb_off = c.snb;
+  out->rstd_off = c.rstd; out->mean_off = c.mean;
+  return V2W_OK;
+}
+
 int32_t v2w_model_num_convs(const v2w_model* m) { return m ? m->num_convs : 0; }
 int64_t v2w_model_packed_bytes(const v2w_model* m) { return m ? m->packed_bytes : 0; }
 int64_t v2w_model_flops_per_frame(const v2w_model* m) { return m ? m->flops_per_frame : 0; }

@@ -68,6 +68,11 @@ struct v2w_plan {
   bool bound = false;
   const uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;   // ops.size() + 1 when profiling
+  ~v2w_plan() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+  }
 };
 
 namespace v2w {
@@ -687,7 +692,10 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bf = p->precision == V2W_PREC_BF16;
   int launches = 0;
+  size_t op_index = 0;
   for (Op& o : p->ops) {
+    if (p->profiling) V2W_CUDA(cudaEventRecord(p->events[op_index], st));
+    ++op_index;
     switch (o.d.kind) {
       case V2W_OP_TRANSPOSE_IN: {
         dim3 grid((p->frames + 31) / 32, (c.num_wv_feat + 31) / 32, p->batch);
@@ -759,8 +767,36 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
         return V2W_ERR_STATE;
     }
   }
+  if (p->profiling) V2W_CUDA(cudaEventRecord(p->events[op_index], st));
   if (gpu_launches) *gpu_launches = launches;
   return V2W_OK;
+}
+
+int32_t v2w_plan_set_profiling(v2w_plan* p, int32_t enabled) {
+  if (!p) {
+    set_error("v2w_plan_set_profiling: null plan");
+    return V2W_ERR_INVALID;
+  }
+  if (enabled && p->events.empty()) {
+    p->events.resize(p->ops.size() + 1);
+    for (auto& e : p->events) V2W_CUDA(cudaEventCreate(&e));
+  }
+  p->profiling = enabled != 0;
+  return V2W_OK;
+}
+
+float v2w_plan_op_time_ms(v2w_plan* p, int32_t i) {
+  if (!p || p->events.empty() || i < 0 || i >= (int32_t)p->ops.size()) {
+    set_error("v2w_plan_op_time_ms: profiling not enabled or bad index");
+    return -1.f;
+  }
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, p->events[i], p->events[i + 1]) != cudaSuccess) {
+    set_error("v2w_plan_op_time_ms: events not complete");
+    cudaGetLastError();
+    return -1.f;
+  }
+  return ms;
 }
 
 int32_t v2w_forward_host(v2w_plan* p, const float* x_host, const float* spk_host,

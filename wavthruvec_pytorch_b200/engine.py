@@ -212,6 +212,30 @@ class NativeEngine:
         self.last_launches = n.value
         return out
 
+    def profile_ops(self, x, spk, noise, reps: int = 3, before_each=None):
+        """Per-op device times (ms, mean over `reps` forwards) from CUDA events recorded by the
+        library on the launch stream.  Returns [(OpDesc, ms)]."""
+        B, _, T = x.shape
+        dev = x.device
+        handle, _ws = self.plan(B, T, self._module.precision, dev)
+        ops = self.ops(B, T, self._module.precision, dev)
+        native.check(self._lib.v2w_plan_set_profiling(handle, 1))
+        acc = [0.0] * len(ops)
+        try:
+            for _ in range(reps):
+                if before_each is not None:
+                    before_each()
+                self.forward(x, spk, noise)
+                torch.cuda.synchronize(dev)
+                for i in range(len(ops)):
+                    ms = float(self._lib.v2w_plan_op_time_ms(handle, i))
+                    if ms < 0:
+                        raise native.V2WError(-3, native.last_error())
+                    acc[i] += ms
+        finally:
+            native.check(self._lib.v2w_plan_set_profiling(handle, 0))
+        return [(op, a / reps) for op, a in zip(ops, acc)]
+
     def total_upsample(self) -> int:
         r = 1
         for u in self._module.h.upsample_rates:

@@ -87,6 +87,11 @@ class LayerDesc(C.Structure):
     ]
 
 
+class CondDesc(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("in_dim", C.c_int32)] + [
+        (n, C.c_int64) for n in ("fcw_off", "fcb_off", "snw_off", "snb_off", "rstd_off", "mean_off")]
+
+
 class OpDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("engine", C.c_int32), ("layer", C.c_int32),
@@ -128,6 +133,7 @@ _SIGNATURES = [
     ("v2w_model_destroy", None, [C.c_void_p]),
     ("v2w_model_num_layers", C.c_int32, [C.c_void_p]),
     ("v2w_model_get_layer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(LayerDesc)]),
+    ("v2w_model_get_cond", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(CondDesc)]),
     ("v2w_model_num_convs", C.c_int32, [C.c_void_p]),
     ("v2w_model_packed_bytes", C.c_int64, [C.c_void_p]),
     ("v2w_model_pack", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
@@ -146,6 +152,8 @@ _SIGNATURES = [
     ("v2w_forward_host", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
+    ("v2w_plan_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("v2w_plan_op_time_ms", C.c_float, [C.c_void_p, C.c_int32]),
     ("v2w_tapgemm", C.c_int32, [C.POINTER(TapGemmArgs), C.c_void_p]),
 ]
 
