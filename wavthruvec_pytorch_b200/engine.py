@@ -30,6 +30,9 @@ class NativeEngine:
         self._packed: Dict[torch.device, torch.Tensor] = {}
         self._packed_sig = None
         self._plans: Dict[Tuple, Tuple[C.c_void_p, torch.Tensor]] = {}
+        self._convs = None        # cached module list / tensor list for the per-call change check
+        self._tensors = None
+        self._structure = None
         self.last_launches = 0
 
     def __del__(self):
@@ -50,6 +53,7 @@ class NativeEngine:
     def invalidate(self):
         self._packed.clear()
         self._packed_sig = None
+        self._tensors = None
         self._drop_plans()
 
     def flops_per_frame(self) -> int:
@@ -110,12 +114,25 @@ class NativeEngine:
         del host
         return packed
 
-    def _packed_on(self, device: torch.device) -> torch.Tensor:
-        sig = self._signature(self._state_tensors())
+    def _refresh(self) -> None:
+        """Drop the folded weights (and the plans bound to them) when any parameter or buffer
+        changed: storage pointer or in-place version counter (optimizer step, load_state_dict,
+        manual edits), or the weight-norm structure (remove_weight_norm on any sub-block).
+        Module._apply (.to()/.cuda()/.float()) replaces buffer objects and calls invalidate().
+        The tensor list is cached because walking the module tree costs ~4x the check itself."""
+        if self._convs is None:
+            self._convs = self._module.conv_modules()
+        structure = tuple("weight_v" in c._parameters for c in self._convs)
+        if self._tensors is None or structure != self._structure:
+            self._tensors = self._state_tensors()
+            self._structure = structure
+        sig = self._signature(self._tensors)
         if sig != self._packed_sig:
             self._packed.clear()
             self._drop_plans()   # plans hold pointers into the packed buffer
             self._packed_sig = sig
+
+    def _packed_on(self, device: torch.device) -> torch.Tensor:
         buf = self._packed.get(device)
         if buf is None:
             buf = self.pack_host().to(device)
@@ -125,6 +142,7 @@ class NativeEngine:
     # ------------------------------------------------------------------------------------------
     def plan(self, batch: int, frames: int, precision: str, device: torch.device):
         """(plan handle, workspace) for this problem size; created and bound on first use."""
+        self._refresh()
         key = (batch, frames, precision, device)
         hit = self._plans.get(key)
         if hit is not None:

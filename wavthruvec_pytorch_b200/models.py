@@ -159,6 +159,12 @@ class Generator(nn.Module):
         if eng is not None:
             eng.invalidate()
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to()/.cuda()/.float(): parameter storage moves and buffer objects are replaced
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     def conv_modules(self):
         """Weight-normed convs in the order of v2w_params.convs (include/v2w.h)."""
         convs = [self.conv_pre, *self.ups]
