@@ -50,7 +50,7 @@ extern "C" {
 #define V2W_MAX_KERNELS 4     /* resblock kernel sizes per stage (reference: 3) */
 #define V2W_MAX_DILATIONS 4
 #define V2W_MAX_TAPS 16
-#define V2W_MAX_TILES 8
+#define V2W_MAX_TILES 16
 
 /* ---- precision of a plan ----------------------------------------------------------- */
 #define V2W_PREC_FP32 0  /* FFMA kernels, fp32 everywhere: parity bar max-abs <= 1e-4 */

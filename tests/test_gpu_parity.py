@@ -78,10 +78,13 @@ def test_tapgemm_tc_ragged_rows(rows):
     _gemm_case(native.ENGINE_TC, 3, rows, 64, 128, 128, 7, 1, True, seed=rows)
 
 
-def test_tapgemm_tc_per_tap_cross_check():
-    """Halo-reuse (row-shifted descriptor views) and per-tap reload give the same numbers."""
-    _gemm_case(native.ENGINE_TC, 2, 300, 128, 128, 128, 11, 3, False, flags=0)
-    _gemm_case(native.ENGINE_TC, 2, 300, 128, 128, 128, 11, 3, False, flags=native.TC_FLAG_PER_TAP)
+@pytest.mark.parametrize("msub", [1, 2, 4])
+@pytest.mark.parametrize("cin,n,rows", [(64, 64, 1100), (16, 16, 777), (128, 128, 515)])
+def test_tapgemm_tc_super_tile_heights(monkeypatch, msub, cin, n, rows):
+    """Every super-tile height (128-row sub-tiles sharing one W block) gives the same numbers,
+    including ragged last super-tiles."""
+    monkeypatch.setenv("V2W_TC_MSUB", str(msub))
+    _gemm_case(native.ENGINE_TC, 2, rows, cin, n, n, 11, 3, True, seed=msub)
 
 
 # ----------------------------------------------------------------------------------------------

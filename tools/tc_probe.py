@@ -39,6 +39,11 @@ def one(case):
     accum = rng.standard_normal((B, rows, n_total)).astype(np.float32) if full else None
     out_scale = 1.0 / 3.0 if full else 1.0
     want = gemm_ref.tapgemm_expected(A, W, tiles, n_tile, bias, scale, shift, resid, accum, out_scale, cmod)
+    import os
+    if case.get("msub"):
+        os.environ["V2W_TC_MSUB"] = str(case["msub"])
+    else:
+        os.environ.pop("V2W_TC_MSUB", None)
     engine = native.ENGINE_TC if case.get("engine", "tc") == "tc" else native.ENGINE_SIMT
     o32, o16 = gemm_ref.run_tapgemm(engine, A, W, tiles, n_tile, cmod, bias, scale, shift, resid,
                                     accum, out_scale, 0.1, tc_flags=case.get("flags", 0))
@@ -55,9 +60,11 @@ def one(case):
 def grid():
     cases = []
     base = dict(B=2, rows=300, cin=64, n_total=64, n_tile=64, k=3, d=1)
-    # descriptor-variant probe on the simplest halo case, then without halo (k=1)
-    for flags in (0, 1, 2, 3):
-        cases.append(dict(base, flags=flags, tag="variant"))
+    # super-tile heights on the simplest halo case, then without halo (k=1)
+    for msub in (1, 2, 4):
+        cases.append(dict(base, rows=1100, msub=msub, tag="msub"))
+        cases.append(dict(base, rows=1100, cin=16, n_total=16, n_tile=16, k=11, d=5, msub=msub,
+                          epilogue=True, tag="msub"))
     cases.append(dict(base, k=1, flags=0, tag="k1"))
     for cin, n in ((16, 16), (32, 32), (64, 64), (128, 128), (256, 256), (768, 512)):
         for (k, d) in ((3, 1), (7, 3), (11, 3), (11, 5)):
@@ -116,7 +123,7 @@ def main():
                 n_ok += bool(res.get("ok"))
                 c = res["case"]
                 print(f"{'OK ' if res.get('ok') else 'BAD'} {c.get('tag')} cin={c['cin']} n={c['n_total']} "
-                      f"k={c['k']} d={c['d']} rows={c['rows']} flags={c.get('flags', 0)} "
+                      f"k={c['k']} d={c['d']} rows={c['rows']} msub={c.get('msub', 0)} "
                       f"eng={c.get('engine', 'tc')} err={res.get('max_err')} err16={res.get('max_err_bf16')} "
                       f"nan={res.get('nan')} bad_rows={res.get('bad_rows')} {res.get('error', '')}",
                       flush=True)

@@ -4,19 +4,31 @@
 //
 // A  : bf16 channels-last activations [B, rows, cin]  (already leaky-relu'd by the producer op)
 // W  : bf16 [taps][n_total][cin]  (K-major, like A) -- see v2w_layer_desc in include/v2w.h
-// acc: fp32 in TMEM, M = 128 time steps per tile (TMEM lane = time step), N = n_tile columns.
+// acc: fp32 in TMEM, 128 time steps per accumulator (TMEM lane = time step), N = n_tile columns.
 //
-// Persistent, warp-specialised CTA (one per SM):
+// Persistent, warp-specialised CTA (one per SM).  A work item is a SUPER-TILE: `msub` (1, 2 or 4)
+// consecutive 128-row sub-tiles of one utterance x one column tile.  Every W block that TMA
+// brings in is used by `msub` MMAs, which divides the L2->SMEM weight traffic (64 B/clk/SM at
+// msub = 1, above what L2 sustains for all SMs) and amortises barrier round trips.
+//
 //   warp 0      TMA producer   : A halo tile once per K-chunk, W block once per (K-chunk, tap)
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma; owns the TMEM allocation
+//   warp 1      MMA issuer     : owns the TMEM allocation; one elected lane issues tcgen05.mma
 //   warps 4-11  epilogue       : two groups of 4 warps; group g drains accumulator stage g, so the
-//                                epilogue of tile i overlaps the MMAs of tile i+1
+//                                epilogue of super-tile i overlaps the MMAs of super-tile i+1
 //
-// Halo reuse: the A tile for one K-chunk holds rows [q0 + off_min, q0 + 128 + off_max) and is loaded
-// ONCE; every tap (and every dilation) is a row-shifted view of it -- the UMMA shared-memory
-// descriptor's start address is advanced by shift * row_bytes.  With the 128B/64B/32B swizzles the
-// XOR pattern is a function of the absolute shared-memory address, so a shifted view stays
-// consistent with what TMA wrote.  (kFlagPerTap reloads A per tap instead; kept as a cross-check.)
+// Role loops are warp-uniform (all 32 lanes walk the loop, `elect.sync` picks the issuing lane):
+// issuing uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR) from inside a divergent
+// `if (lane == 0)` region makes ptxas wrap each of them in a BRA.U.ANY waterfall loop, and the
+// round-1 profile showed the single issuing thread instruction-bound at ~900 clk per step.
+// Stage indices and phase bits are running counters (no div/mod in the loops); K-chunk width is
+// a template parameter.
+//
+// Halo reuse: the A tile for one K-chunk holds rows [q0 + off_min, q0 + 128*msub + off_max) and is
+// loaded ONCE; every tap (and every dilation) is a row-shifted view of it -- the UMMA shared-memory
+// descriptor's start address is advanced by shift * row_bytes.  Measured on B200 (tools/tc_probe.py):
+// with the 128B/64B/32B swizzles the XOR pattern is a function of the absolute shared-memory
+// address, so a shifted view is consistent with what TMA wrote, and the descriptor's base_offset
+// field must stay 0 (filling it from the address gives wrong results).
 #pragma once
 
 #include <cuda.h>
@@ -31,24 +43,22 @@ namespace tc {
 
 constexpr int kThreads = 384;
 constexpr int kMTile = 128;
-constexpr int kBoxRows = 32;       // rows per TMA box of A
 constexpr int kMaxStagesA = 4;
 constexpr int kMaxStagesW = 8;
-constexpr int kFlagPerTap = 1;     // reload A for every tap (no halo reuse)
-constexpr int kFlagBaseOffset = 2; // fill the descriptor's base_offset field from the address
+constexpr int kMaxSub = 4;
 
 struct Params {
-  int batch, rows, cin, n_total, cmod, n_tile, n_tiles, m_tiles;
-  int kc, num_chunks;
-  int swizzle_layout;   // UMMA layout_type: 2 = 128B, 4 = 64B, 6 = 32B
-  int sbo_bytes;        // 8 rows * row bytes
-  int ra_boxes;         // TMA boxes per A fill in halo mode
+  int batch, rows, cin, n_total, cmod, n_tile, n_tiles;
+  int msub;             // 128-row sub-tiles per super-tile
+  int s_tiles;          // super-tiles per utterance
+  int num_chunks;
+  int box_rows;         // rows per TMA box of A
   int stages_a, stages_w;
   int stage_a_bytes, stage_w_bytes;
-  int acc_cols;         // TMEM columns per accumulator stage
-  int flags;
+  int acc_cols;         // TMEM columns per accumulator (per sub-tile)
   int16_t num_taps[V2W_MAX_TILES];
   int16_t off_min[V2W_MAX_TILES];
+  int16_t halo[V2W_MAX_TILES];
   int16_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
   int16_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
   const float* bias;
@@ -67,6 +77,18 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -170,19 +192,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory descriptor, K-major operand in a swizzled row-major tile
-// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor -- start[0,14) LBO[16,30) SBO[32,46)
-//  version[46,48)=1  base_offset[49,52)  layout_type[61,64)).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes,
-                                                   uint32_t layout_type, bool base_offset_mode) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;  // LBO: unused for swizzled K-major, canonical value 1
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-  if (base_offset_mode) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
-  d |= static_cast<uint64_t>(layout_type) << 61;
-  return d;
+// Upper 32 bits of the UMMA shared-memory descriptor of a K-major operand in a swizzled
+// row-major tile (cute/arch/mma_sm100_desc.hpp SmemDescriptor: SBO[32,46) version[46,48)=1
+// base_offset[49,52)=0 layout_type[61,64)); the lower word is (address >> 4) | LBO(=1) << 16.
+template <int KC>
+__device__ __forceinline__ uint32_t smem_desc_hi() {
+  constexpr uint32_t sbo = 8 * KC * 2;                          // 8 rows of one swizzle span
+  constexpr uint32_t layout = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);  // 128B / 64B / 32B swizzle
+  return (sbo >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t hi, uint32_t saddr) {
+  return (static_cast<uint64_t>(hi) << 32) | ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
 }
 
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, dense
@@ -199,12 +219,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
+  uint32_t s = 0, ph = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++s == n) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ Params p) {
+  constexpr int kRowBytes = KC * 2;
+  constexpr int kKSteps = KC / 16;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
@@ -216,10 +249,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool per_tap = (p.flags & kFlagPerTap) != 0;
-  const bool base_off = (p.flags & kFlagBaseOffset) != 0;
-  const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
-  const uint32_t tmem_cols = 2u * p.acc_cols;
+  const int tiles_per_b = p.s_tiles * p.n_tiles;
+  const int total_tiles = p.batch * tiles_per_b;
+  const uint32_t stage_cols = p.msub * p.acc_cols;   // TMEM columns per accumulator stage
+  const uint32_t tmem_cols = 2u * stage_cols;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -248,88 +281,91 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      uint32_t it_a = 0, it_w = 0;
-      const uint32_t box_bytes = kBoxRows * p.kc * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = (tile / p.n_tiles) % p.m_tiles;
-        const int b = tile / (p.n_tiles * p.m_tiles);
-        const int ntaps = p.num_taps[nt];
-        const int q0 = mt * kMTile;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          for (int j = 0; j < ntaps; ++j) {
-            if (j == 0 || per_tap) {
-              const uint32_t s = it_a % p.stages_a, par = (it_a / p.stages_a) & 1u;
-              mbar_wait(empty_a + 8 * s, par ^ 1u);
-              const int nb = per_tap ? (kMTile / kBoxRows) : p.ra_boxes;
-              mbar_expect_tx(full_a + 8 * s, nb * box_bytes);
-              const int row0 = q0 + (per_tap ? p.tap_off[nt][j] : p.off_min[nt]);
-              const uint32_t dst = smem_a + s * p.stage_a_bytes;
-              for (int bx = 0; bx < nb; ++bx)
-                tma_load_3d(dst + bx * box_bytes, &tmA, c * p.kc, row0 + bx * kBoxRows, b,
-                            full_a + 8 * s);
-              ++it_a;
-            }
-            const uint32_t s = it_w % p.stages_w, par = (it_w / p.stages_w) & 1u;
-            mbar_wait(empty_w + 8 * s, par ^ 1u);
-            mbar_expect_tx(full_w + 8 * s, p.n_tile * p.kc * 2);
-            tma_load_2d(smem_w + s * p.stage_w_bytes, &tmW, c * p.kc,
-                        p.tap_row[nt][j] * p.n_total + nt * p.n_tile, full_w + 8 * s);
-            ++it_w;
+    Ring ra, rw;
+    const uint32_t box_bytes = p.box_rows * kRowBytes;
+    const uint32_t w_bytes = p.n_tile * kRowBytes;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_b;
+      const int rem = tile - b * tiles_per_b;
+      const int st = rem / p.n_tiles;
+      const int nt = rem - st * p.n_tiles;
+      const int ntaps = p.num_taps[nt];
+      const int q0 = st * p.msub * kMTile;
+      const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
+      const int nbox = (nsub * kMTile + p.halo[nt] + p.box_rows - 1) / p.box_rows;
+      const int row0 = q0 + p.off_min[nt];
+      const int wcol = nt * p.n_tile;
+      for (int c = 0; c < p.num_chunks; ++c) {
+        mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t bar = full_a + 8 * ra.s;
+          mbar_expect_tx(bar, nbox * box_bytes);
+          const uint32_t dst = smem_a + ra.s * p.stage_a_bytes;
+          for (int bx = 0; bx < nbox; ++bx)
+            tma_load_3d(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+        }
+        __syncwarp();
+        ra.advance(p.stages_a);
+        for (int j = 0; j < ntaps; ++j) {
+          mbar_wait(empty_w + 8 * rw.s, rw.ph ^ 1u);
+          if (elect_one()) {
+            const uint32_t bar = full_w + 8 * rw.s;
+            mbar_expect_tx(bar, w_bytes);
+            tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
+                        p.tap_row[nt][j] * p.n_total + wcol, bar);
           }
+          __syncwarp();
+          rw.advance(p.stages_w);
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      uint32_t it_a = 0, it_w = 0, tile_iter = 0;
-      const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile);
-      const int ksteps = p.kc / 16;
-      const uint32_t row_bytes = p.kc * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-        const int nt = tile % p.n_tiles;
-        const int ntaps = p.num_taps[nt];
-        const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
-        mbar_wait(acc_empty + 8 * as, aph ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.acc_cols;
-        uint32_t accumulate = 0;
-        uint32_t sa = 0;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          for (int j = 0; j < ntaps; ++j) {
-            if (j == 0 || per_tap) {
-              sa = it_a % p.stages_a;
-              mbar_wait(full_a + 8 * sa, (it_a / p.stages_a) & 1u);
+    Ring ra, rw;
+    uint32_t tile_iter = 0;
+    const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile);
+    const uint32_t dhi = smem_desc_hi<KC>();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int b = tile / tiles_per_b;
+      const int rem = tile - b * tiles_per_b;
+      const int st = rem / p.n_tiles;
+      const int nt = rem - st * p.n_tiles;
+      const int ntaps = p.num_taps[nt];
+      const int off_min = p.off_min[nt];
+      const int q0 = st * p.msub * kMTile;
+      const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
+      const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
+      mbar_wait(acc_empty + 8 * as, aph ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + as * stage_cols;
+      for (int c = 0; c < p.num_chunks; ++c) {
+        mbar_wait(full_a + 8 * ra.s, ra.ph);
+        const uint32_t a_stage = smem_a + ra.s * p.stage_a_bytes;
+        for (int j = 0; j < ntaps; ++j) {
+          mbar_wait(full_w + 8 * rw.s, rw.ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = a_stage + (p.tap_off[nt][j] - off_min) * kRowBytes;
+            const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
+            const uint32_t acc0 = (c | j) != 0;
+            for (int m = 0; m < nsub; ++m) {
+              const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
+              const uint64_t bd = smem_desc(dhi, w_addr);
+#pragma unroll
+              for (int kk = 0; kk < kKSteps; ++kk)
+                umma_bf16(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
+                          acc0 | (kk != 0));
             }
-            const uint32_t sw = it_w % p.stages_w;
-            mbar_wait(full_w + 8 * sw, (it_w / p.stages_w) & 1u);
-            tcgen05_fence_after();
-            const int shift = per_tap ? 0 : (p.tap_off[nt][j] - p.off_min[nt]);
-            const uint32_t a_addr = smem_a + sa * p.stage_a_bytes + shift * row_bytes;
-            const uint32_t w_addr = smem_w + sw * p.stage_w_bytes;
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t adesc =
-                  make_smem_desc(a_addr + kk * 32, p.sbo_bytes, p.swizzle_layout, base_off);
-              const uint64_t bdesc =
-                  make_smem_desc(w_addr + kk * 32, p.sbo_bytes, p.swizzle_layout, base_off);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(empty_w + 8 * sw);
-            ++it_w;
-            if (j == ntaps - 1 || per_tap) {
-              umma_commit(empty_a + 8 * sa);
-              ++it_a;
-            }
+            umma_commit(empty_w + 8 * rw.s);
+            if (j == ntaps - 1) umma_commit(empty_a + 8 * ra.s);
+            if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit(acc_full + 8 * as);
           }
+          __syncwarp();
+          rw.advance(p.stages_w);
         }
-        umma_commit(acc_full + 8 * as);
+        ra.advance(p.stages_a);
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
     const int group = (warp - 4) >> 2;  // accumulator stage this warp drains
@@ -338,81 +374,96 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       if ((tile_iter & 1u) != static_cast<uint32_t>(group)) continue;
-      const int nt = tile % p.n_tiles;
-      const int mt = (tile / p.n_tiles) % p.m_tiles;
-      const int b = tile / (p.n_tiles * p.m_tiles);
+      const int b = tile / tiles_per_b;
+      const int rem = tile - b * tiles_per_b;
+      const int st = rem / p.n_tiles;
+      const int nt = rem - st * p.n_tiles;
+      const int q0 = st * p.msub * kMTile;
+      const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const uint32_t aph = (tile_iter >> 1) & 1u;
       mbar_wait(acc_full + 8 * group, aph);
       tcgen05_fence_after();
-      const int row = mt * kMTile + quarter * 32 + lane;
-      const bool valid = row < p.rows;
-      const size_t row_base = (static_cast<size_t>(b) * p.rows + row) * p.n_total;
-      const uint32_t t_base =
-          tmem_base + group * p.acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int cc = 0; cc < p.n_tile; cc += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_base + cc, r);
-        tmem_ld_wait();
-        if (valid) {
+      const uint32_t t_lane = tmem_base + group * stage_cols +
+                              (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int m = 0; m < nsub; ++m) {
+        const int row = q0 + m * kMTile + quarter * 32 + lane;
+        const bool valid = row < p.rows;
+        const size_t row_base = (static_cast<size_t>(b) * p.rows + row) * p.n_total;
+        for (int cc = 0; cc < p.n_tile; cc += 16) {
           const int col = nt * p.n_tile + cc;
-          const int cb = pow2 ? (col & (p.cmod - 1)) : (col % p.cmod);
-          float v[16];
+          // issue the global reads first so that they overlap the TMEM load
+          float4 res[4], acc[4];
+          if (valid && p.residual) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + row_base + col);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-          if (p.bias) {
+            for (int e = 0; e < 4; ++e) res[e] = rp[e];
+          }
+          if (valid && p.accum_in) {
+            const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + col);
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + e));
-              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+            for (int e = 0; e < 4; ++e) acc[e] = ap[e];
+          }
+          uint32_t r[16];
+          tmem_ld16(t_lane + m * p.acc_cols + cc, r);
+          tmem_ld_wait();
+          if (valid) {
+            const int cb = pow2 ? (col & (p.cmod - 1)) : (col % p.cmod);
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+            if (p.bias) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + e));
+                v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+              }
             }
-          }
-          if (p.scale) {
-            const float* sc = p.scale + static_cast<size_t>(b) * p.cmod + cb;
-            const float* sh = p.shift + static_cast<size_t>(b) * p.cmod + cb;
+            if (p.scale) {
+              const float* sc = p.scale + static_cast<size_t>(b) * p.cmod + cb;
+              const float* sh = p.shift + static_cast<size_t>(b) * p.cmod + cb;
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + e));
-              const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + e));
-              v[e] = fmaf(v[e], s4.x, h4.x);
-              v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
-              v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);
-              v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+              for (int e = 0; e < 16; e += 4) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + e));
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + e));
+                v[e] = fmaf(v[e], s4.x, h4.x);
+                v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);
+                v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+              }
             }
-          }
-          if (p.residual) {
-            const float* rp = p.residual + row_base + col;
+            if (p.residual) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(rp + e);
-              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+              for (int e = 0; e < 4; ++e) {
+                v[4 * e] += res[e].x; v[4 * e + 1] += res[e].y;
+                v[4 * e + 2] += res[e].z; v[4 * e + 3] += res[e].w;
+              }
             }
-          }
-          if (p.accum_in) {
-            const float* ap = p.accum_in + row_base + col;
+            if (p.accum_in) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(ap + e);
-              v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+              for (int e = 0; e < 4; ++e) {
+                v[4 * e] += acc[e].x; v[4 * e + 1] += acc[e].y;
+                v[4 * e + 2] += acc[e].z; v[4 * e + 3] += acc[e].w;
+              }
             }
-          }
-          if (p.out_scale != 1.0f) {
+            if (p.out_scale != 1.0f) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] *= p.out_scale;
-          }
-          if (p.out_f32) {
-            float* op = p.out_f32 + row_base + col;
+              for (int e = 0; e < 16; ++e) v[e] *= p.out_scale;
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + col);
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              *reinterpret_cast<float4*>(op + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          }
-          if (p.out_bf16) {
-            uint32_t h[8];
+              for (int e = 0; e < 4; ++e)
+                op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            }
+            if (p.out_bf16) {
+              uint32_t h[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
-            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
-            op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              for (int e = 0; e < 8; ++e)
+                h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
+              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
+              op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            }
           }
         }
       }

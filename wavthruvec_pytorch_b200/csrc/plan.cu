@@ -44,6 +44,7 @@ struct TcLaunch {
   tc::Params prm;
   int grid = 0;
   int smem = 0;
+  int kc = 64;
 };
 
 struct Op {
@@ -176,52 +177,63 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     set_error("tapgemm(TC): n_tile=%d > 256", a.n_tile);
     return V2W_ERR_INVALID;
   }
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
   tc::Params& p = L->prm;
   std::memset(&p, 0, sizeof(p));
   p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
   p.n_tile = a.n_tile; p.n_tiles = a.n_tiles;
-  p.m_tiles = (a.rows + tc::kMTile - 1) / tc::kMTile;
-  p.kc = kc;
   p.num_chunks = a.cin / kc;
-  p.swizzle_layout = kc == 64 ? 2 : (kc == 32 ? 4 : 6);
-  p.sbo_bytes = 8 * kc * 2;
-  p.flags = a.tc_flags;
   int halo_max = 0;
   for (int t = 0; t < a.n_tiles; ++t) {
     p.num_taps[t] = (int16_t)a.num_taps[t];
     p.off_min[t] = (int16_t)a.tap_off[t][0];
-    halo_max = std::max(halo_max, a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0]);
+    const int halo = a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0];
+    p.halo[t] = (int16_t)halo;
+    halo_max = std::max(halo_max, halo);
     for (int j = 0; j < a.num_taps[t]; ++j) {
       p.tap_off[t][j] = (int16_t)a.tap_off[t][j];
       p.tap_row[t][j] = (int16_t)a.tap_row[t][j];
     }
   }
-  p.ra_boxes = (tc::kMTile + halo_max + tc::kBoxRows - 1) / tc::kBoxRows;
-  p.stage_a_bytes = p.ra_boxes * tc::kBoxRows * kc * 2;
-  p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
-  const int budget = 227 * 1024 - 1024 - 256;
-  p.stages_a = 2;
-  int sw = (budget - p.stages_a * p.stage_a_bytes) / p.stage_w_bytes;
-  if (sw < 2) {
-    set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)", p.stage_a_bytes,
-              p.stage_w_bytes);
-    return V2W_ERR_INVALID;
-  }
-  p.stages_w = std::min(sw, tc::kMaxStagesW);
-  int sa = (budget - p.stages_w * p.stage_w_bytes) / p.stage_a_bytes;
-  p.stages_a = std::max(2, std::min(sa, tc::kMaxStagesA));
   p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
+  p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
+  // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
+  // columns) and shared memory allow, while keeping >= 2 work items per SM.
+  const int budget = 227 * 1024 - 1024 - 256;
+  const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
+  int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
+  if (forced >= 1 && forced <= msub) msub = forced;
+  for (;; msub >>= 1) {
+    p.msub = msub;
+    p.box_rows = msub == 1 ? 32 : 64;
+    const int boxes = (msub * tc::kMTile + halo_max + p.box_rows - 1) / p.box_rows;
+    p.stage_a_bytes = boxes * p.box_rows * kc * 2;
+    p.s_tiles = (a.rows + msub * tc::kMTile - 1) / (msub * tc::kMTile);
+    const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
+    const bool fits = 2 * p.stage_a_bytes + 3 * p.stage_w_bytes <= budget;
+    if (msub == 1 || (fits && (tiles >= 2 * sms || forced))) {
+      if (!fits) {
+        set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)",
+                  p.stage_a_bytes, p.stage_w_bytes);
+        return V2W_ERR_INVALID;
+      }
+      break;
+    }
+  }
+  p.stages_a = 2;
+  p.stages_w = std::min((budget - 2 * p.stage_a_bytes) / p.stage_w_bytes, tc::kMaxStagesW);
+  p.stages_a = std::max(2, std::min((budget - p.stages_w * p.stage_w_bytes) / p.stage_a_bytes,
+                                    tc::kMaxStagesA));
   p.bias = a.bias; p.scale = a.scale; p.shift = a.shift;
   p.residual = a.residual; p.accum_in = a.accum_in;
   p.out_scale = a.out_scale; p.out_f32 = a.out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_slope = a.out_slope;
+  L->kc = kc;
   L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + 256 + 1024;
-
-  int sms = 0;
-  int rc = sm_count(&sms);
-  if (rc) return rc;
-  const int64_t tiles = (int64_t)a.batch * p.m_tiles * a.n_tiles;
+  const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
   L->grid = (int)std::min<int64_t>(tiles, sms);
 
   EncodeTiledFn enc = nullptr;
@@ -233,7 +245,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   {
     cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
     cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.rows * a.cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)tc::kBoxRows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.in_act),
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -265,11 +277,20 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
 static int launch_tc(const TcLaunch& L, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel,
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<32>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  tc::tapgemm_tc_kernel<<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  if (L.kc == 64)
+    tc::tapgemm_tc_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  else if (L.kc == 32)
+    tc::tapgemm_tc_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  else
+    tc::tapgemm_tc_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
   V2W_CUDA(cudaGetLastError());
   return V2W_OK;
 }
@@ -334,13 +355,14 @@ struct Bump {
   }
 };
 
-// Pick the column tile of a layer: whole phases (or a divisor of cout), <= 256 columns, minimum
-// issued MMA columns (zero polyphase blocks cost issue slots), then the largest tile; shrink while
-// the launch would leave SMs idle.
+// Pick the column tile of a layer: whole phases (or a divisor of cout), <= 128 columns (so that
+// two 128-row sub-tiles share every W block: see kernels_tc.cuh), minimum issued MMA columns
+// (zero polyphase blocks cost issue slots), then the largest tile; shrink while the launch would
+// leave SMs idle.
 static void choose_tiles(const v2w_layer_desc& L, int batch, int rows, v2w_op_desc* d) {
   int best = 0;
   int64_t best_cost = 0;
-  for (int nt = 16; nt <= 256; nt <<= 1) {
+  for (int nt = 16; nt <= 128; nt <<= 1) {
     if (L.n_total % nt) continue;
     if (nt % L.cout && L.cout % nt) continue;
     int64_t cost = 0;

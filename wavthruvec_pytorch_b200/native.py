@@ -15,7 +15,7 @@ MAX_STAGES = 8
 MAX_KERNELS = 4
 MAX_DILATIONS = 4
 MAX_TAPS = 16
-MAX_TILES = 8
+MAX_TILES = 16
 
 PREC_FP32 = 0
 PREC_BF16 = 1
