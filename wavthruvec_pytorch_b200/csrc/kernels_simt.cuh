@@ -216,34 +216,48 @@ struct CondParams {
   int spk_dim, noise_dim;
 };
 
-__global__ void __launch_bounds__(128) cond_affine_kernel(const CondParams p) {
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kCondThreads = 256;
+
+// One warp per output row, lanes stride the (contiguous) weight row: coalesced reads + shuffle
+// reduction.  The first version walked one row per thread (uncoalesced) and took 70 us for what
+// is 0.4 MFLOP per utterance.
+__global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondParams p) {
   extern __shared__ float sm[];
   const CondStage& S = p.st[blockIdx.x];
   const int b = blockIdx.y;
   const int D = p.spk_dim + p.noise_dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kCondThreads / 32;
   float* sn = sm;            // [D]
   float* z = sm + D;         // [128]
   float* gb = z + 128;       // [2C]
-  for (int i = threadIdx.x; i < D; i += blockDim.x)
+  for (int i = threadIdx.x; i < D; i += kCondThreads)
     sn[i] = i < p.spk_dim ? p.spk[static_cast<size_t>(b) * p.spk_dim + i]
                           : p.noise[static_cast<size_t>(b) * p.noise_dim + (i - p.spk_dim)];
   __syncthreads();
-  {
-    const int t = threadIdx.x;  // blockDim.x == 128 == z channels
+  for (int t = warp; t < 128; t += kWarps) {
     const float* w = S.fcw + static_cast<size_t>(t) * D;
-    float a = S.fcb[t];
-    for (int d = 0; d < D; ++d) a = fmaf(w[d], sn[d], a);
-    z[t] = a;
+    float a = 0.f;
+    for (int d = lane; d < D; d += 32) a = fmaf(__ldg(w + d), sn[d], a);
+    a = warp_sum(a);
+    if (lane == 0) z[t] = a + S.fcb[t];
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < 2 * S.C; r += blockDim.x) {
-    const float* w = S.snw + static_cast<size_t>(r) * 128;
-    float a = S.snb[r];
-    for (int t = 0; t < 128; ++t) a = fmaf(w[t], z[t], a);
-    gb[r] = a;
+  for (int r = warp; r < 2 * S.C; r += kWarps) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(S.snw + static_cast<size_t>(r) * 128) + lane);
+    const float4 z4 = *reinterpret_cast<const float4*>(z + 4 * lane);
+    float a = w4.x * z4.x + w4.y * z4.y + w4.z * z4.z + w4.w * z4.w;
+    a = warp_sum(a);
+    if (lane == 0) gb[r] = a + S.snb[r];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < S.C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < S.C; c += kCondThreads) {
     const float sc = gb[c] * S.rstd[c];
     S.scale[static_cast<size_t>(b) * S.C + c] = sc;
     S.shift[static_cast<size_t>(b) * S.C + c] = gb[S.C + c] - sc * S.mean[c];
@@ -253,47 +267,59 @@ __global__ void __launch_bounds__(128) cond_affine_kernel(const CondParams p) {
 // ---------------------------------------------------------------------------------------------
 // leaky_relu(0.01) -> Conv1d(C -> 1, k = 7, pad 3) -> tanh      (models.py:143-145)
 // in: fp32 channels-last [B, L, C] (C = 16 in the reference config); out: fp32 [B, 1, L].
-// Purely memory-bound: each CTA stages 256+6 rows (float4, coalesced) and emits 256 samples.
+// Purely memory-bound.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPostRows = 256;
+constexpr int kPostThreads = 256;
 constexpr int kPostK = 7;
+constexpr int kPostOut = kPostThreads - (kPostK - 1);   // outputs per CTA (250)
 
 template <int C>
-__global__ void __launch_bounds__(kPostRows) conv_post_kernel(const float* __restrict__ x,
-                                                              const float* __restrict__ w,  // [7][C]
-                                                              const float* __restrict__ bias,
-                                                              float* __restrict__ y, int L,
-                                                              float in_slope) {
-  constexpr int RS = C + 1;
-  __shared__ float tile[(kPostRows + kPostK - 1) * RS];
-  __shared__ float ws[kPostK * C];
+struct PostWeights {      // by-value kernel parameter: FFMA reads it straight from the constant bank
+  float w[kPostK][C];
+  float bias;
+};
+
+// One thread per input row: 64 B (C = 16) contiguous per thread => a warp reads 2 KB contiguous.
+// Each thread forms the 7 tap partial sums of its row (weights are constant-bank operands, no
+// shared-memory traffic), the partials meet through shared memory (7 floats per row instead of
+// the 112 LDS per output of the first version) and thread t adds the 7 partials of output t.
+template <int C>
+__global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const float* __restrict__ x,
+                                                                 const PostWeights<C> pw,
+                                                                 float* __restrict__ y, int L,
+                                                                 float in_slope) {
+  __shared__ float part[kPostK][kPostThreads + 1];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kPostRows;
-  const float* xb = x + static_cast<size_t>(b) * L * C;
-  for (int i = threadIdx.x; i < kPostK * C; i += kPostRows) ws[i] = w[i];
-  for (int idx = threadIdx.x; idx < (kPostRows + kPostK - 1) * (C / 4); idx += kPostRows) {
-    const int r = idx / (C / 4), c4 = (idx % (C / 4)) * 4;
-    const int row = t0 - (kPostK / 2) + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row >= 0 && row < L) {
-      v = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(row) * C + c4);
-      v.x = lrelu(v.x, in_slope); v.y = lrelu(v.y, in_slope);
-      v.z = lrelu(v.z, in_slope); v.w = lrelu(v.w, in_slope);
+  const int t0 = blockIdx.x * kPostOut;
+  const int row = t0 - (kPostK / 2) + threadIdx.x;   // input row owned by this thread
+  float a[C];
+  if (row >= 0 && row < L) {
+    const float4* src = reinterpret_cast<const float4*>(x + (static_cast<size_t>(b) * L + row) * C);
+#pragma unroll
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 v = __ldg(src + c4);
+      a[4 * c4] = lrelu(v.x, in_slope); a[4 * c4 + 1] = lrelu(v.y, in_slope);
+      a[4 * c4 + 2] = lrelu(v.z, in_slope); a[4 * c4 + 3] = lrelu(v.w, in_slope);
     }
-    float* d = tile + r * RS + c4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kPostK; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s = fmaf(a[c], pw.w[j][c], s);
+    part[j][threadIdx.x] = s;
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t < L) {
-    float a = bias[0];
+  if (threadIdx.x < kPostOut && t < L) {
+    // y[t] = bias + sum_j w[j] . x[t + j - 3]; input row t + j - 3 is owned by thread tid + j
+    float s = pw.bias;
 #pragma unroll
-    for (int j = 0; j < kPostK; ++j) {
-      const float* r = tile + (threadIdx.x + j) * RS;
-#pragma unroll
-      for (int c = 0; c < C; ++c) a = fmaf(r[c], ws[j * C + c], a);
-    }
-    y[static_cast<size_t>(b) * L + t] = tanhf(a);
+    for (int j = 0; j < kPostK; ++j) s += part[j][threadIdx.x + j];
+    y[static_cast<size_t>(b) * L + t] = tanhf(s);
   }
 }
 

@@ -69,6 +69,8 @@ struct v2w_plan {
   bool bound = false;
   const uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
+  std::vector<float> post_w;   // host copy of conv_post's folded weights [7][C] (kernel parameter)
+  float post_bias = 0.f;
   bool profiling = false;
   std::vector<cudaEvent_t> events;   // ops.size() + 1 when profiling
   ~v2w_plan() {
@@ -691,6 +693,14 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       o.tc_ready = true;
     }
   }
+  {
+    // conv_post's 7 x C weights travel as a by-value kernel parameter (constant bank operands)
+    const v2w_layer_desc& L = m->layers.back();
+    p->post_w.assign((size_t)L.num_taps * L.cin, 0.f);
+    V2W_CUDA(cudaMemcpy(p->post_w.data(), p->packed + L.w32_off, p->post_w.size() * 4,
+                        cudaMemcpyDeviceToHost));
+    V2W_CUDA(cudaMemcpy(&p->post_bias, p->packed + L.bias_off, 4, cudaMemcpyDeviceToHost));
+  }
   p->bound = true;
   return V2W_OK;
 }
@@ -753,7 +763,7 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
         cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
         const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * cmax) * 4;
         dim3 grid((unsigned)m->cond.size(), p->batch);
-        simt::cond_affine_kernel<<<grid, 128, smem, st>>>(cp);
+        simt::cond_affine_kernel<<<grid, simt::kCondThreads, smem, st>>>(cp);
         V2W_CUDA(cudaGetLastError());
         ++launches;
         break;
@@ -767,16 +777,20 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
       case V2W_OP_CONV_POST: {
         const v2w_layer_desc& L = m->layers[o.d.layer];
         const float* in = reinterpret_cast<const float*>(p->ws + o.d.in_act);
-        const float* w = reinterpret_cast<const float*>(p->packed + L.w32_off);
-        const float* bias = reinterpret_cast<const float*>(p->packed + L.bias_off);
-        dim3 grid((o.d.rows + simt::kPostRows - 1) / simt::kPostRows, p->batch);
-        if (L.cin == 16)
-          simt::conv_post_kernel<16><<<grid, simt::kPostRows, 0, st>>>(in, w, bias, out_dev,
-                                                                      o.d.rows, o.d.in_slope);
-        else if (L.cin == 32)
-          simt::conv_post_kernel<32><<<grid, simt::kPostRows, 0, st>>>(in, w, bias, out_dev,
-                                                                      o.d.rows, o.d.in_slope);
-        else {
+        dim3 grid((o.d.rows + simt::kPostOut - 1) / simt::kPostOut, p->batch);
+        if (L.cin == 16) {
+          simt::PostWeights<16> pw;
+          std::memcpy(pw.w, p->post_w.data(), sizeof(pw.w));
+          pw.bias = p->post_bias;
+          simt::conv_post_kernel<16><<<grid, simt::kPostThreads, 0, st>>>(in, pw, out_dev, o.d.rows,
+                                                                         o.d.in_slope);
+        } else if (L.cin == 32) {
+          simt::PostWeights<32> pw;
+          std::memcpy(pw.w, p->post_w.data(), sizeof(pw.w));
+          pw.bias = p->post_bias;
+          simt::conv_post_kernel<32><<<grid, simt::kPostThreads, 0, st>>>(in, pw, out_dev, o.d.rows,
+                                                                         o.d.in_slope);
+        } else {
           set_error("conv_post with %d input channels unsupported", L.cin);
           return V2W_ERR_INVALID;
         }
