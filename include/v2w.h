@@ -150,11 +150,36 @@ typedef struct v2w_cond_desc {
   int64_t mean_off;            /* [C] */
 } v2w_cond_desc;
 
+/* Fused multi-receptive-field stage (kernels_fused.cuh).  All resblocks of one stage run in one
+ * kernel on 256-row windows: per branch conv1 -> (bias, +x, leaky-relu, bf16) -> shared memory ->
+ * conv2, all conv2 outputs plus ONE extra convolution `sum` (taps = per-offset sums of the conv1
+ * weights) accumulate in a single TMEM accumulator.  Weight taps are stored in issue order. */
+#define V2W_FUSED_MAX_SEG 12
+#define V2W_FUSED_MAX_TAPS 80
+#define V2W_FUSED_SEG_CONV1 0
+#define V2W_FUSED_SEG_SUM 1
+#define V2W_FUSED_SEG_CONV2 2
+typedef struct v2w_fused_desc {
+  int32_t ok;                  /* 0: this stage is executed as separate tap-GEMM ops */
+  int32_t channels, num_branches;
+  int32_t first_layer;         /* layer index of branch 0's first conv (2 layers per branch) */
+  int32_t hc, h1, rc;          /* conv2 halo, conv1 halo, central rows per 256-row window */
+  int32_t a0_boxes;            /* 64-row TMA boxes per input tile */
+  int32_t num_segments, num_taps;
+  int16_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];
+  int16_t seg_ntaps[V2W_FUSED_MAX_SEG], seg_first[V2W_FUSED_MAX_SEG];
+  int16_t shift[V2W_FUSED_MAX_TAPS];   /* operand row of the tap inside its input tile */
+  int16_t offset[V2W_FUSED_MAX_TAPS];  /* time offset of the tap (rows) */
+  int64_t w_off;               /* packed: bf16 [num_taps][channels][channels] (n, c), issue order */
+  int64_t bsum_off;            /* packed: fp32 [channels] = sum_j (b1_j + b2_j) */
+} v2w_fused_desc;
+
 /* Kinds of op in a plan's execution list. */
 #define V2W_OP_TRANSPOSE_IN 0  /* x[B,Cin,T] fp32 -> [B,T,Cin] (fp32 or bf16) */
 #define V2W_OP_COND_AFFINE 1   /* fcs + spectral-norm Linear + BN fold -> scale/shift per (b, stage, c) */
 #define V2W_OP_TAPGEMM 2
 #define V2W_OP_CONV_POST 3     /* lrelu(0.01) -> Conv1d(16->1,k7) -> tanh */
+#define V2W_OP_MRF_FUSED 4     /* one whole multi-receptive-field stage (ResBlock2, C <= 64) */
 
 #define V2W_ENGINE_SIMT 0      /* FFMA tap-GEMM */
 #define V2W_ENGINE_TC 1        /* tcgen05 / TMEM / TMA tap-GEMM */
@@ -179,6 +204,7 @@ typedef struct v2w_op_desc {
   int64_t out_bf16;            /* bf16 leaky_relu(result, out_slope): the next conv's operand */
   float out_slope;
   int64_t flops;               /* 2 * real MACs of this op (0 for non-GEMM ops) */
+  int32_t stage;               /* upsample stage of an MRF_FUSED op, else -1 */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -193,6 +219,7 @@ void v2w_model_destroy(struct v2w_model* m);
 int32_t v2w_model_num_layers(const struct v2w_model* m);
 int32_t v2w_model_get_layer(const struct v2w_model* m, int32_t index, v2w_layer_desc* out);
 int32_t v2w_model_get_cond(const struct v2w_model* m, int32_t stage, v2w_cond_desc* out);
+int32_t v2w_model_get_fused(const struct v2w_model* m, int32_t stage, v2w_fused_desc* out);
 int32_t v2w_model_num_convs(const struct v2w_model* m);   /* expected v2w_params.num_convs */
 int64_t v2w_model_packed_bytes(const struct v2w_model* m);
 /* Fold weight norm (w = g*v/||v||, norm over all dims but 0 -- i.e. per INPUT channel for

@@ -142,6 +142,47 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                 ws[op.out_bf16] = bf16_round(lrelu(v, op.out_slope))
             if collect is not None:
                 collect[idx] = v
+        elif op.kind == native.OP_MRF_FUSED:
+            F = native.FusedDesc()
+            native.check(plan.lib.v2w_model_get_fused(plan.model, op.stage, C.byref(F)))
+            assert F.ok
+            Cn, nb = F.channels, F.num_branches
+            A0 = ws[op.in_act].reshape(op.batch, op.rows, Cn)
+            X0 = ws[op.residual].reshape(op.batch, op.rows, Cn)
+            w = u16(F.w_off, F.num_taps * Cn * Cn).astype(np.uint32) << 16
+            Wf = w.view(np.float32).reshape(F.num_taps, Cn, Cn)      # [tap][n][c]
+            bsum = f32(F.bsum_off, Cn)
+
+            def conv(A, first, ntaps):
+                acc = np.zeros((op.batch, op.rows, Cn), np.float32)
+                for t in range(first, first + ntaps):
+                    off = F.offset[t]
+                    sh = np.zeros_like(A)
+                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                    if hi > lo:
+                        sh[:, lo:hi] = A[:, lo + off: hi + off]
+                    acc += sh @ Wf[t].T
+                return acc
+
+            T2 = np.zeros((op.batch, op.rows, Cn), np.float32)
+            A1 = {}
+            for sgi in range(F.num_segments):
+                typ, j = F.seg_type[sgi], F.seg_branch[sgi]
+                first, nt = F.seg_first[sgi], F.seg_ntaps[sgi]
+                if typ == native.SEG_CONV1:
+                    b1 = f32(plan.layers[F.first_layer + 2 * j].bias_off, Cn)
+                    A1[j] = bf16_round(lrelu(conv(A0, first, nt) + b1 + X0, 0.1))
+                elif typ == native.SEG_SUM:
+                    T2 += conv(A0, first, nt)
+                else:
+                    T2 += conv(A1[j], first, nt)
+            v = ((T2 + bsum + np.float32(nb) * X0) * np.float32(op.out_scale)).astype(np.float32)
+            if op.out_f32 >= 0:
+                ws[op.out_f32] = v
+            if op.out_bf16 >= 0:
+                ws[op.out_bf16] = bf16_round(lrelu(v, op.out_slope))
+            if collect is not None:
+                collect[idx] = v
         elif op.kind == native.OP_CONV_POST:
             L = plan.layers[op.layer]
             A = lrelu(ws[op.in_act].reshape(op.batch, op.rows, L.cin), op.in_slope)

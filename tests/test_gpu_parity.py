@@ -138,6 +138,27 @@ def test_bf16_plan_matches_cpu_emulation(name, min_snr):
     assert snr >= min_snr
 
 
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb2_768_stress_tiny", "rb2_1024_warm"])
+def test_fused_stage_kernel_matches_separate_tapgemms(monkeypatch, name):
+    """kernels_fused.cuh (whole MRF stage on-chip) against the six separate tap-GEMM launches it
+    replaces, on the device: they differ only by the rounding of the summed conv1 weights."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    fused = _native(gen, g, "bf16")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    assert sum(op.kind == native.OP_MRF_FUSED for op in ops) == 3
+    monkeypatch.setenv("V2W_NO_FUSE", "1")
+    gen.invalidate()
+    plain = _native(gen, g, "bf16")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    assert sum(op.kind == native.OP_MRF_FUSED for op in ops) == 0
+    snr = fixtures.snr_db(plain, fused)
+    print(f"{name}: fused vs unfused on device {snr:.1f} dB; vs reference "
+          f"{fixtures.snr_db(g.y, fused):.1f} / {fixtures.snr_db(g.y, plain):.1f} dB")
+    assert snr >= 55.0
+    assert fixtures.snr_db(g.y, fused) >= BF16_MIN_SNR_DB
+
+
 def test_forward_host_equals_forward_and_is_deterministic():
     g = load_golden("rb2_768_stress")
     gen = dropin_in_state(g, cache=False).to("cuda:0")

@@ -133,6 +133,21 @@ def test_fp32_plan_fresh_state_pre_tanh():
     assert np.abs(y - g.y).max() < 1e-3      # saturated +-1: sign agreement everywhere
 
 
+def test_fused_and_unfused_plans_agree(monkeypatch):
+    """The fused-stage op (conv_sum trick, on-chip intermediates) is the same arithmetic as the
+    six separate tap-GEMMs up to the rounding of the summed conv1 weights."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    packed = eng.pack_host().numpy()
+    fused = plan_interp.run(plan_interp.HostPlan(eng, 2, 24, "bf16"), packed, g.x, g.spk, g.noise)
+    monkeypatch.setenv("V2W_NO_FUSE", "1")
+    plain = plan_interp.run(plan_interp.HostPlan(eng, 2, 24, "bf16"), packed, g.x, g.spk, g.noise)
+    snr = fixtures.snr_db(plain, fused)
+    print(f"fused vs unfused (emulated): {snr:.1f} dB")
+    assert snr > 60.0
+
+
 @pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 45.0), ("rb2_1024_warm", 45.0)])
 def test_bf16_plan_predicted_snr(name, min_snr):
     """Same op list with the device's bf16 rounding points (bf16 operands, fp32 accumulate,
@@ -147,9 +162,10 @@ def test_bf16_plan_predicted_snr(name, min_snr):
     assert snr >= min_snr
 
 
-def test_plan_structure_bf16_rb2():
+def test_plan_structure_bf16_rb2(monkeypatch):
     gen = Generator(hparams(resblock=1, num_wv_feat=768))
     eng = gen.engine()
+    monkeypatch.setenv("V2W_NO_FUSE", "1")
     plan = plan_interp.HostPlan(eng, 16, 200, "bf16")
     kinds = [op.kind for op in plan.ops]
     assert kinds[0] == native.OP_TRANSPOSE_IN and kinds[1] == native.OP_COND_AFFINE
@@ -160,6 +176,17 @@ def test_plan_structure_bf16_rb2():
     assert total == eng.flops_per_frame() * 16 * 200
     # rows double-check: stage outputs 1000, 4000, 16000, 32000, 64000
     assert sorted({op.rows for op in gemms}) == [200, 1000, 4000, 16000, 32000, 64000]
+    # default plan: the three C <= 64 stages collapse into one fused op each, same FLOP total
+    monkeypatch.delenv("V2W_NO_FUSE")
+    fplan = plan_interp.HostPlan(eng, 16, 200, "bf16")
+    fused = [op for op in fplan.ops if op.kind == native.OP_MRF_FUSED]
+    assert [op.stage for op in fused] == [2, 3, 4] and [op.n_tile for op in fused] == [64, 32, 16]
+    assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 18
+    assert sum(op.flops for op in fplan.ops) == total
+    F = native.FusedDesc()
+    native.check(eng._lib.v2w_model_get_fused(eng._model, 2, C.byref(F)))
+    assert (F.ok, F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments) == (1, 15, 5, 226, 5, 53, 7)
+    assert list(F.seg_type[:7]) == [0, 0, 1, 2, 0, 2, 2] and list(F.seg_ntaps[:7]) == [3, 7, 11, 3, 11, 7, 11]
     # the three transposed convs with 4 or 2 phases split into phase groups with 2 taps each
     for op in gemms:
         L = plan.layers[op.layer]

@@ -48,6 +48,7 @@ struct v2w_model {
   v2w_config cfg;
   std::vector<v2w_layer_desc> layers;
   std::vector<v2w::CondLayout> cond;
+  std::vector<v2w_fused_desc> fused;   // per stage; ok == 0 when not fusable
   std::vector<int> stage_channels;  // C_i
   std::vector<int> stage_up;        // cumulative upsampling AFTER stage i
   int total_up = 1;

@@ -1,0 +1,342 @@
+// Fused multi-receptive-field stage for C <= 64 (ResBlock2):  one kernel computes
+//
+//     x_out = (1/nk) * sum_j  ResBlock2_j(x)            (vec2wav/models.py:65-70,135-141)
+//
+// for a 226-row tile without the intermediates ever leaving the SM.  Unfused, one stage moves
+// ~74 B per output element through HBM (six convs x [bf16 operand + fp32 residual in, fp32 + bf16
+// out]); fused it is ~10 B (bf16 A0 + fp32 X0 in, bf16 or fp32 out), which turns the C <= 64 stages
+// from HBM-bound into MMA-bound.
+//
+// Algebra (per branch j: conv1_j dilation d0, conv2_j dilation d1_j; A0 = bf16(lrelu(X0))):
+//     Y1_j  = conv1_j(A0) + b1_j + X0                       (fp32)
+//     A1_j  = bf16(lrelu(Y1_j)), zero outside [0, L)        (stays in shared memory)
+//     out_j = conv2_j(A1_j) + b2_j + Y1_j
+//     sum_j out_j = [ sum_j conv2_j(A1_j) + conv_sum(A0) ] + sum_j (b1_j + b2_j) + nk * X0
+// where conv_sum is ONE convolution whose taps are the per-offset sums of the conv1_j weights
+// (built at pack time).  Everything in brackets accumulates in a single TMEM accumulator T2; the
+// only per-branch epilogue is T1_j -> A1_j.
+//
+// Geometry: window = 256 rows (two 128-lane accumulators) = central rows [q0c, q0c + rc) plus hc rows
+// of halo per side (hc = max_j d1_j (k_j - 1)/2 = 15, rc = 226).  conv1_j is evaluated on the whole
+// window (its output feeds conv2's halo), conv_sum and conv2_j on the 256 rows starting at q0c (the
+// last 2*hc of them are discarded).  A0 tile = window + h1 rows per side (h1 = d0 (kmax - 1)/2).
+//
+// Roles: warp 0 TMA producer (A0 tile, double buffered across tiles; weight taps streamed in issue
+// order through an 8-deep ring), warp 1 MMA issuer, warps 4-11 epilogue (thread = window row).
+// T1 and A1 are double buffered across branches so that conv1_{j+1} overlaps the epilogue of
+// branch j and conv2_j overlaps the epilogue of branch j+1.
+#pragma once
+
+#include "kernels_tc.cuh"
+
+namespace v2w {
+namespace fused {
+
+using namespace v2w::tc;
+
+constexpr int kWin = 256;          // window rows per tile
+constexpr int kBoxRows = 64;
+constexpr int kMaxSeg = 12;
+constexpr int kMaxTaps = 80;
+constexpr int kSegConv1 = 0, kSegSum = 1, kSegConv2 = 2;
+
+struct Segment {
+  int16_t type, branch, ntaps, first;
+};
+
+struct Params {
+  int batch, rows, tiles_per_b;
+  int rc, hc, h1;               // central rows per tile, conv2 halo, conv1 halo
+  int a0_boxes;                 // TMA boxes (64 rows) per A0 tile
+  int nseg, nbranch, ntaps_total;
+  int stages_w, stage_w_bytes;
+  Segment seg[kMaxSeg];
+  int16_t shift[kMaxTaps];      // operand row (sub-tile 0) of each tap inside its A tile
+  const float* x0;              // fp32 [B, L, C]
+  const float* bias1[V2W_MAX_KERNELS];
+  const float* bsum;            // sum_j (b1_j + b2_j)
+  float mid_slope;              // leaky-relu between the convs of a block (0.1)
+  float res_scale;              // nk: multiplier of X0 in the final sum
+  float out_scale;              // 1/nk
+  float out_slope;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ Params p) {
+  constexpr int kRowBytes = C * 2;
+  constexpr int kKSteps = C / 16;
+  constexpr int kAccCols = C < 32 ? 32 : C;
+  constexpr uint32_t kT1Cols = 2 * kAccCols;             // two sub-tiles
+  constexpr uint32_t kTmemCols = C == 64 ? 512 : 256;    // 2 x T1 + T2, rounded to a power of two
+  constexpr uint32_t kA1Bytes = kWin * kRowBytes;
+  constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
+  constexpr uint32_t kWBytes = C * kRowBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a0_bytes = p.a0_boxes * kBoxBytes;
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_a1 = smem_a0 + 2 * a0_bytes;
+  const uint32_t smem_w = smem_a1 + 2 * kA1Bytes;
+  const uint32_t bars = smem_w + p.stages_w * p.stage_w_bytes;
+  // barriers: a0_full[2] a0_empty[2] w_full[8] w_empty[8] t1_full[2] t1_empty[2] a1_full[2]
+  //           a1_empty[2] t2_full t2_empty
+  const uint32_t a0_full = bars, a0_empty = bars + 16, w_full = bars + 32, w_empty = bars + 96;
+  const uint32_t t1_full = bars + 160, t1_empty = bars + 176, a1_full = bars + 192;
+  const uint32_t a1_empty = bars + 208, t2_full = bars + 224, t2_empty = bars + 232;
+  const uint32_t tmem_slot = bars + 240;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batch * p.tiles_per_b;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a0_full + 8 * i, 1);
+      mbar_init(a0_empty + 8 * i, 1);
+      mbar_init(t1_full + 8 * i, 1);
+      mbar_init(t1_empty + 8 * i, 256);
+      mbar_init(a1_full + 8 * i, 256);
+      mbar_init(a1_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < kMaxStagesW; ++i) {
+      mbar_init(w_full + 8 * i, 1);
+      mbar_init(w_empty + 8 * i, 1);
+    }
+    mbar_init(t2_full, 1);
+    mbar_init(t2_empty, 256);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const uint32_t tmem_t2 = tmem_base + 2 * kT1Cols;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    Ring rw;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int b = tile / p.tiles_per_b;
+      const int ti = tile - b * p.tiles_per_b;
+      const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the A0 tile
+      const uint32_t buf = tile_iter & 1u, ph = (tile_iter >> 1) & 1u;
+      mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t bar = a0_full + 8 * buf;
+        mbar_expect_tx(bar, p.a0_boxes * kBoxBytes);
+        for (int bx = 0; bx < p.a0_boxes; ++bx)
+          tma_load_3d(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b,
+                      bar);
+      }
+      __syncwarp();
+      for (int t = 0; t < p.ntaps_total; ++t) {
+        mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t bar = w_full + 8 * rw.s;
+          mbar_expect_tx(bar, kWBytes);
+          tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, 0, t * C, bar);
+        }
+        __syncwarp();
+        rw.advance(p.stages_w);
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    Ring rw;
+    uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
+    const uint32_t idesc = make_idesc_bf16(kMTile, C);
+    const uint32_t dhi = smem_desc_hi<C>();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const uint32_t buf = tile_iter & 1u;
+      mbar_wait(a0_full + 8 * buf, (tile_iter >> 1) & 1u);
+      const uint32_t a0 = smem_a0 + buf * a0_bytes;
+      for (int s = 0; s < p.nseg; ++s) {
+        const Segment sg = p.seg[s];
+        uint32_t d_tmem, a_tile, slot = 0;
+        if (sg.type == kSegConv1) {
+          slot = n1 & 1u;
+          mbar_wait(t1_empty + 8 * slot, ((n1 >> 1) & 1u) ^ 1u);
+          d_tmem = tmem_base + slot * kT1Cols;
+          a_tile = a0;
+        } else if (sg.type == kSegSum) {
+          mbar_wait(t2_empty, (tile_iter & 1u) ^ 1u);
+          d_tmem = tmem_t2;
+          a_tile = a0;
+        } else {
+          slot = n2 & 1u;
+          mbar_wait(a1_full + 8 * slot, (n2 >> 1) & 1u);
+          d_tmem = tmem_t2;
+          a_tile = smem_a1 + slot * kA1Bytes;
+        }
+        tcgen05_fence_after();
+        const bool last_seg = s == p.nseg - 1;
+        for (int t = 0; t < sg.ntaps; ++t) {
+          mbar_wait(w_full + 8 * rw.s, rw.ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = a_tile + p.shift[sg.first + t] * kRowBytes;
+            const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
+            const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
+              const uint64_t bd = smem_desc(dhi, w_addr);
+#pragma unroll
+              for (int kk = 0; kk < kKSteps; ++kk)
+                umma_bf16(d_tmem + m * kAccCols, ad + 2 * kk, bd + 2 * kk, idesc, acc0 | (kk != 0));
+            }
+            umma_commit(w_empty + 8 * rw.s);
+            if (t == sg.ntaps - 1) {
+              if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
+              if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
+              if (last_seg) {
+                umma_commit(t2_full);
+                umma_commit(a0_empty + 8 * buf);
+              }
+            }
+          }
+          __syncwarp();
+          rw.advance(p.stages_w);
+        }
+        if (sg.type == kSegConv1) ++n1;
+        if (sg.type == kSegConv2) ++n2;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int sub = (warp - 4) >> 2;              // which 128-row accumulator
+    const int quarter = warp & 3;                 // TMEM lane quarter
+    const int i = sub * kMTile + quarter * 32 + lane;   // window row of this thread
+    const uint32_t t_lane = (static_cast<uint32_t>(quarter * 32) << 16) + sub * kAccCols;
+    const uint32_t swz = C == 64 ? (i & 7) : (C == 32 ? ((i >> 1) & 3) : ((i >> 2) & 1));
+    uint32_t tile_iter = 0, e1 = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+      const int b = tile / p.tiles_per_b;
+      const int ti = tile - b * p.tiles_per_b;
+      const int q0c = ti * p.rc;
+      // ---- per branch: T1 -> A1 = bf16(lrelu(conv1 + b1 + X0)) in shared memory ----
+      {
+        const int gr = q0c - p.hc + i;
+        const bool valid = gr >= 0 && gr < p.rows;
+        const float* xrow = p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
+        for (int j = 0; j < p.nbranch; ++j, ++e1) {
+          const uint32_t slot = e1 & 1u, ph = (e1 >> 1) & 1u;
+          mbar_wait(t1_full + 8 * slot, ph);
+          mbar_wait(a1_empty + 8 * slot, ph ^ 1u);
+          tcgen05_fence_after();
+          const uint32_t a1_row = smem_a1 + slot * kA1Bytes + i * kRowBytes;
+          const float* b1 = p.bias1[j];
+#pragma unroll
+          for (int cc = 0; cc < C; cc += 16) {
+            float4 xr[4];
+            if (valid) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = *reinterpret_cast<const float4*>(xrow + cc + 4 * e);
+            }
+            uint32_t r[16];
+            tmem_ld16(tmem_base + slot * kT1Cols + t_lane + cc, r);
+            tmem_ld_wait();
+            uint32_t h[8];
+            if (valid) {
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + cc + 4 * e));
+                v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
+                v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
+                v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;
+                v[4 * e + 3] = __uint_as_float(r[4 * e + 3]) + bb.w + xr[e].w;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                h[e] = pack_bf16x2(lrelu(v[2 * e], p.mid_slope), lrelu(v[2 * e + 1], p.mid_slope));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h[e] = 0u;   // conv2's zero padding outside [0, L)
+            }
+            const uint32_t q = cc >> 3;               // 16-byte chunk index within the row
+            st_shared_v4(a1_row + ((q ^ swz) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(a1_row + (((q + 1) ^ swz) << 4), h[4], h[5], h[6], h[7]);
+          }
+          fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
+          tcgen05_fence_before();
+          mbar_arrive(a1_full + 8 * slot);
+          mbar_arrive(t1_empty + 8 * slot);
+        }
+      }
+      // ---- final: out = (T2 + bsum + nk * X0) / nk ----
+      {
+        mbar_wait(t2_full, tile_iter & 1u);
+        tcgen05_fence_after();
+        const int gr = q0c + i;
+        const bool valid = i < p.rc && gr < p.rows;
+        const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
+#pragma unroll
+        for (int cc = 0; cc < C; cc += 16) {
+          float4 xr[4];
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              xr[e] = *reinterpret_cast<const float4*>(p.x0 + row_base + cc + 4 * e);
+          }
+          uint32_t r[16];
+          tmem_ld16(tmem_t2 + t_lane + cc, r);
+          tmem_ld_wait();
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bsum + cc + 4 * e));
+              v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x) * p.out_scale;
+              v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y) * p.out_scale;
+              v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z) * p.out_scale;
+              v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w) * p.out_scale;
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            }
+            if (p.out_bf16) {
+              uint32_t h[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
+              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + cc);
+              op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(t2_empty);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace fused
+}  // namespace v2w

@@ -97,6 +97,67 @@ static void add_convT(v2w_model* m, int stage, int conv_index, int cin, int cout
   m->layers.push_back(L);
 }
 
+// Decide whether stage `i` can run as one fused kernel and lay out its tap program.
+// `first_layer` = index of branch 0's first conv in m->layers.
+static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_layer) {
+  v2w_fused_desc F;
+  std::memset(&F, 0, sizeof(F));
+  const v2w_config& c = m->cfg;
+  const int C = m->stage_channels[i];
+  const int nb = c.num_kernels;
+  F.channels = C;
+  F.num_branches = nb;
+  F.first_layer = first_layer;
+  if (c.resblock_type != 2 || (C != 16 && C != 32 && C != 64)) return F;
+  const int d0 = c.resblock_dilation_sizes[0][0];
+  int kmax = 0, hc = 0, total = 0;
+  for (int j = 0; j < nb; ++j) {
+    if (c.resblock_dilation_sizes[j][0] != d0) return F;   // conv_sum needs aligned conv1 taps
+    const int k = c.resblock_kernel_sizes[j];
+    kmax = std::max(kmax, k);
+    hc = std::max(hc, c.resblock_dilation_sizes[j][1] * (k - 1) / 2);
+    total += 2 * k;
+  }
+  const int h1 = d0 * (kmax - 1) / 2;
+  total += kmax;
+  const int rc = 256 - 2 * hc;
+  const int a0_rows = 256 + hc + 2 * h1;
+  if (rc < 64 || a0_rows > 64 * 7 || total > V2W_FUSED_MAX_TAPS || 2 * nb + 1 > V2W_FUSED_MAX_SEG)
+    return F;
+  F.hc = hc; F.h1 = h1; F.rc = rc;
+  F.a0_boxes = (a0_rows + 63) / 64;
+  // issue order: c1_0, c1_1, SUM, then c2_j interleaved with c1_{j+2}
+  int nseg = 0, ntap = 0;
+  auto push = [&](int type, int j) {
+    const int k = type == V2W_FUSED_SEG_SUM ? kmax : c.resblock_kernel_sizes[j];
+    const int dil = type == V2W_FUSED_SEG_CONV2 ? c.resblock_dilation_sizes[j][1] : d0;
+    F.seg_type[nseg] = (int16_t)type;
+    F.seg_branch[nseg] = (int16_t)j;
+    F.seg_ntaps[nseg] = (int16_t)k;
+    F.seg_first[nseg] = (int16_t)ntap;
+    for (int t = 0; t < k; ++t) {
+      const int off = (t - (k - 1) / 2) * dil;
+      F.offset[ntap] = (int16_t)off;
+      F.shift[ntap] = (int16_t)(type == V2W_FUSED_SEG_CONV1 ? h1 + off
+                                : type == V2W_FUSED_SEG_SUM ? hc + h1 + off
+                                                            : hc + off);
+      ++ntap;
+    }
+    ++nseg;
+  };
+  push(V2W_FUSED_SEG_CONV1, 0);
+  if (nb > 1) push(V2W_FUSED_SEG_CONV1, 1);
+  push(V2W_FUSED_SEG_SUM, -1);
+  for (int j = 0; j < nb; ++j) {
+    push(V2W_FUSED_SEG_CONV2, j);
+    if (j + 2 < nb) push(V2W_FUSED_SEG_CONV1, j + 2);
+  }
+  F.num_segments = nseg;
+  F.num_taps = ntap;
+  F.ok = 1;
+  return F;
+}
+
 }  // namespace v2w
 
 using namespace v2w;
@@ -213,6 +274,7 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
     up_total *= c->upsample_rates[i];
     m->stage_channels.push_back(ch);
     m->stage_up.push_back(up_total);
+    m->fused.push_back(plan_fused_stage(m, i, (int)m->layers.size()));
     for (int j = 0; j < c->num_kernels; ++j) {
       const int k = c->resblock_kernel_sizes[j];
       const int block = i * c->num_kernels + j;
@@ -269,6 +331,13 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
     cl.mean = off; off = align_up(off + (int64_t)cl.C * 4, 256);
     m->cond.push_back(cl);
   }
+  for (auto& F : m->fused) {
+    if (!F.ok) continue;
+    F.w_off = off;
+    off = align_up(off + (int64_t)F.num_taps * F.channels * F.channels * 2, 1024);
+    F.bsum_off = off;
+    off = align_up(off + (int64_t)F.channels * 4, 1024);
+  }
   m->packed_bytes = align_up(off, 1024);
   m->flops_per_frame = flops;
   *out = m;
@@ -297,6 +366,15 @@ int32_t v2w_model_get_cond(const v2w_model* m, int32_t i, v2w_cond_desc* out) {
   out->channels = c.C; out->in_dim = c.D;
   out->fcw_off = c.fcw; out->fcb_off = c.fcb; out->snw_off = c.snw; out->snb_off = c.snb;
   out->rstd_off = c.rstd; out->mean_off = c.mean;
+  return V2W_OK;
+}
+
+int32_t v2w_model_get_fused(const v2w_model* m, int32_t i, v2w_fused_desc* out) {
+  if (!m || !out || i < 0 || i >= (int32_t)m->fused.size()) {
+    set_error("v2w_model_get_fused: bad stage %d", i);
+    return V2W_ERR_INVALID;
+  }
+  *out = m->fused[i];
   return V2W_OK;
 }
 
@@ -386,6 +464,42 @@ int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_hos
     for (int ch = 0; ch < cl.C; ++ch) {
       rstd[ch] = 1.0f / std::sqrt(q.bn_var[ch] + kBnEps);
       mean[ch] = q.bn_mean[ch];
+    }
+  }
+  // fused stages: tap matrices in issue order, from the folded fp32 weights packed above
+  for (const auto& F : m->fused) {
+    if (!F.ok) continue;
+    const int C = F.channels;
+    uint16_t* wf = reinterpret_cast<uint16_t*>(base + F.w_off);
+    float* bsum = reinterpret_cast<float*>(base + F.bsum_off);
+    for (int ch = 0; ch < C; ++ch) bsum[ch] = 0.f;
+    for (int j = 0; j < 2 * F.num_branches; ++j) {
+      const float* bl = reinterpret_cast<const float*>(base + m->layers[F.first_layer + j].bias_off);
+      for (int ch = 0; ch < C; ++ch) bsum[ch] += bl[ch];
+    }
+    std::vector<float> acc((size_t)C * C);
+    for (int s = 0; s < F.num_segments; ++s) {
+      for (int t = 0; t < F.seg_ntaps[s]; ++t) {
+        const int tap = F.seg_first[s] + t;
+        std::fill(acc.begin(), acc.end(), 0.f);
+        // layers contributing to this tap: one conv, or every conv1 that has this offset
+        for (int j = 0; j < F.num_branches; ++j) {
+          int li;
+          if (F.seg_type[s] == V2W_FUSED_SEG_SUM) li = F.first_layer + 2 * j;
+          else if (F.seg_branch[s] == j) li = F.first_layer + 2 * j + (F.seg_type[s] == V2W_FUSED_SEG_CONV2);
+          else continue;
+          const v2w_layer_desc& L = m->layers[li];
+          int lt = -1;
+          for (int q = 0; q < L.num_taps; ++q)
+            if (L.tap_off[q] == F.offset[tap]) lt = q;
+          if (lt < 0) continue;   // this branch's kernel does not reach that offset
+          const float* w32 = reinterpret_cast<const float*>(base + L.w32_off) + (size_t)lt * C * C;
+          for (int ci = 0; ci < C; ++ci)
+            for (int n = 0; n < C; ++n) acc[(size_t)n * C + ci] += w32[(size_t)ci * C + n];
+        }
+        uint16_t* dst = wf + (size_t)tap * C * C;
+        for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = bf16_bits(acc[e]);
+      }
     }
   }
   return V2W_OK;

@@ -21,6 +21,7 @@
 #include "common.h"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fused.cuh"
 
 namespace v2w {
 
@@ -47,10 +48,19 @@ struct TcLaunch {
   int kc = 64;
 };
 
+struct FusedLaunch {
+  CUtensorMap tm_a, tm_w;
+  fused::Params prm;
+  int grid = 0;
+  int smem = 0;
+  int channels = 0;
+};
+
 struct Op {
   v2w_op_desc d;
   v2w_tapgemm_args g;   // resolved at bind time (TAPGEMM ops)
   TcLaunch tcl;         // TC engine only
+  FusedLaunch fl;       // MRF_FUSED ops
   bool tc_ready = false;
 };
 
@@ -346,6 +356,107 @@ static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fused MRF stage launcher
+// ---------------------------------------------------------------------------------------------
+static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_op_desc& d,
+                         const uint8_t* packed, uint8_t* ws, FusedLaunch* L) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const int C = F.channels;
+  fused::Params& p = L->prm;
+  std::memset(&p, 0, sizeof(p));
+  p.batch = d.batch; p.rows = d.rows;
+  p.tiles_per_b = (d.rows + F.rc - 1) / F.rc;
+  p.rc = F.rc; p.hc = F.hc; p.h1 = F.h1; p.a0_boxes = F.a0_boxes;
+  p.nseg = F.num_segments; p.nbranch = F.num_branches; p.ntaps_total = F.num_taps;
+  for (int s = 0; s < F.num_segments; ++s) {
+    p.seg[s].type = F.seg_type[s]; p.seg[s].branch = F.seg_branch[s];
+    p.seg[s].ntaps = F.seg_ntaps[s]; p.seg[s].first = F.seg_first[s];
+  }
+  for (int t = 0; t < F.num_taps; ++t) p.shift[t] = F.shift[t];
+  p.stage_w_bytes = (int)align_up((int64_t)C * C * 2, 1024);
+  const int a0_bytes = F.a0_boxes * fused::kBoxRows * C * 2;
+  const int a1_bytes = fused::kWin * C * 2;
+  const int budget = 227 * 1024 - 1024 - 256;
+  const int left = budget - 2 * a0_bytes - 2 * a1_bytes;
+  p.stages_w = std::min(left / p.stage_w_bytes, tc::kMaxStagesW);
+  if (p.stages_w < 2) {
+    set_error("fused stage: does not fit shared memory");
+    return V2W_ERR_INVALID;
+  }
+  p.x0 = reinterpret_cast<const float*>(ws + d.residual);
+  for (int j = 0; j < F.num_branches; ++j)
+    p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * j].bias_off);
+  p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
+  p.mid_slope = kLreluSlope;
+  p.res_scale = (float)F.num_branches;
+  p.out_scale = d.out_scale;
+  p.out_slope = d.out_slope;
+  p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
+  p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
+  L->channels = C;
+  L->smem = 2 * a0_bytes + 2 * a1_bytes + p.stages_w * p.stage_w_bytes + 256 + 1024;
+  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
+
+  EncodeTiledFn enc = nullptr;
+  rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const CUtensorMapSwizzle swz = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)d.rows, (cuuint64_t)d.batch};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)d.rows * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)fused::kBoxRows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ws + d.in_act, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(fused A) failed with CUresult %d", (int)r);
+      return V2W_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)F.num_taps * C};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)C};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&L->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<uint8_t*>(packed + F.w_off), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(fused W) failed with CUresult %d", (int)r);
+      return V2W_ERR_CUDA;
+    }
+  }
+  return V2W_OK;
+}
+
+static int launch_fused(const FusedLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<64>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<32>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<16>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (L.channels == 64)
+    fused::mrf_stage_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  else if (L.channels == 32)
+    fused::mrf_stage_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  else
+    fused::mrf_stage_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  V2W_CUDA(cudaGetLastError());
+  return V2W_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // plan construction
 // ---------------------------------------------------------------------------------------------
 struct Bump {
@@ -454,6 +565,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   const int U = c.num_upsamples;
   const int B = batch, T = frames;
   const bool force_simt = std::getenv("V2W_FORCE_SIMT") != nullptr;
+  const bool no_fuse = std::getenv("V2W_NO_FUSE") != nullptr;
 
   Bump ws;
   P->stage_x = ws.take((int64_t)B * c.num_wv_feat * T * 4);
@@ -498,6 +610,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     o.d.layer = -1;
     o.d.in_act = o.d.residual = o.d.accum_in = o.d.out_f32 = o.d.out_bf16 = -1;
     o.d.cond_stage = -1;
+    o.d.stage = -1;
     o.d.in_slope = 1.f;
     o.d.out_scale = 1.f;
     o.d.out_slope = 1.f;
@@ -559,6 +672,27 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     stage_out.bf16 = (bf && !last_stage) ? next_bf16 : -1;
     Act partial;     // running MRF sum xs (models.py:136-140)
     partial.f32 = sum_f32;
+    if (bf && !force_simt && !no_fuse && m->fused[i].ok) {
+      // whole stage in one kernel (kernels_fused.cuh)
+      Op o = blank(V2W_OP_MRF_FUSED);
+      o.d.engine = V2W_ENGINE_TC;
+      o.d.layer = li;
+      o.d.stage = i;
+      o.d.batch = B;
+      o.d.rows = rows;
+      o.d.n_tile = m->stage_channels[i];
+      o.d.n_tiles = 1;
+      o.d.in_act = x0.bf16; o.d.in_is_bf16 = 1;
+      o.d.residual = x0.f32;
+      o.d.out_scale = 1.0f / nk;
+      o.d.out_f32 = stage_out.f32; o.d.out_bf16 = stage_out.bf16; o.d.out_slope = stage_out.slope;
+      for (int q = 0; q < 2 * nk; ++q)
+        o.d.flops += 2 * m->layers[li + q].macs_per_row * (int64_t)rows * B;
+      P->ops.push_back(o);
+      li += 2 * nk;
+      cur_in = stage_out;
+      continue;
+    }
     for (int j = 0; j < nk; ++j) {
       const bool last_branch = j == nk - 1;
       const int64_t accum = j > 0 ? sum_f32 : -1;
@@ -652,6 +786,11 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   const v2w_model* m = p->model;
   const int tc_flags = std::getenv("V2W_TC_FLAGS") ? std::atoi(std::getenv("V2W_TC_FLAGS")) : 0;
   for (Op& o : p->ops) {
+    if (o.d.kind == V2W_OP_MRF_FUSED) {
+      rc = prepare_fused(m, m->fused[o.d.stage], o.d, p->packed, p->ws, &o.fl);
+      if (rc) return rc;
+      continue;
+    }
     if (o.d.kind != V2W_OP_TAPGEMM) continue;
     const v2w_layer_desc& L = m->layers[o.d.layer];
     v2w_tapgemm_args& g = o.g;
@@ -770,6 +909,12 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
       }
       case V2W_OP_TAPGEMM: {
         int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st) : launch_simt(o.g, st);
+        if (rc) return rc;
+        ++launches;
+        break;
+      }
+      case V2W_OP_MRF_FUSED: {
+        int rc = launch_fused(o.fl, st);
         if (rc) return rc;
         ++launches;
         break;

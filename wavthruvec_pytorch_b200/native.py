@@ -21,7 +21,9 @@ PREC_FP32 = 0
 PREC_BF16 = 1
 ENGINE_SIMT = 0
 ENGINE_TC = 1
-OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST = 0, 1, 2, 3
+OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED = 0, 1, 2, 3, 4
+FUSED_MAX_SEG, FUSED_MAX_TAPS = 12, 80
+SEG_CONV1, SEG_SUM, SEG_CONV2 = 0, 1, 2
 ROLE_CONV_PRE, ROLE_UPSAMPLE, ROLE_RESBLOCK, ROLE_CONV_POST = 0, 1, 2, 3
 TC_FLAG_PER_TAP = 1
 TC_FLAG_BASE_OFFSET = 2
@@ -104,6 +106,19 @@ class OpDesc(C.Structure):
         ("residual", C.c_int64), ("accum_in", C.c_int64), ("out_scale", C.c_float),
         ("out_f32", C.c_int64), ("out_bf16", C.c_int64), ("out_slope", C.c_float),
         ("flops", C.c_int64),
+        ("stage", C.c_int32),
+    ]
+
+
+class FusedDesc(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int32), ("channels", C.c_int32), ("num_branches", C.c_int32),
+        ("first_layer", C.c_int32), ("hc", C.c_int32), ("h1", C.c_int32), ("rc", C.c_int32),
+        ("a0_boxes", C.c_int32), ("num_segments", C.c_int32), ("num_taps", C.c_int32),
+        ("seg_type", C.c_int16 * FUSED_MAX_SEG), ("seg_branch", C.c_int16 * FUSED_MAX_SEG),
+        ("seg_ntaps", C.c_int16 * FUSED_MAX_SEG), ("seg_first", C.c_int16 * FUSED_MAX_SEG),
+        ("shift", C.c_int16 * FUSED_MAX_TAPS), ("offset", C.c_int16 * FUSED_MAX_TAPS),
+        ("w_off", C.c_int64), ("bsum_off", C.c_int64),
     ]
 
 
@@ -134,6 +149,7 @@ _SIGNATURES = [
     ("v2w_model_num_layers", C.c_int32, [C.c_void_p]),
     ("v2w_model_get_layer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(LayerDesc)]),
     ("v2w_model_get_cond", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(CondDesc)]),
+    ("v2w_model_get_fused", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FusedDesc)]),
     ("v2w_model_num_convs", C.c_int32, [C.c_void_p]),
     ("v2w_model_packed_bytes", C.c_int64, [C.c_void_p]),
     ("v2w_model_pack", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
