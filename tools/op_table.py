@@ -69,6 +69,11 @@ def main():
                              tflops=op.flops / ms / 1e9, gbs=by / ms / 1e6, mb=by / 1e6,
                              resid=op.residual >= 0, accum=op.accum_in >= 0,
                              f32=op.out_f32 >= 0, b16=op.out_bf16 >= 0))
+        elif op.kind == native.OP_MRF_FUSED:
+            C = op.n_tile
+            by = op.batch * op.rows * C * (2 + 4 + (4 if op.out_f32 >= 0 else 0) + (2 if op.out_bf16 >= 0 else 0))
+            rows.append(dict(i=i, kind="fused", stage=op.stage, cin=C, rows=op.rows, ms=ms,
+                             tflops=op.flops / ms / 1e9, gbs=by / ms / 1e6, mb=by / 1e6))
         else:
             rows.append(dict(i=i, kind={0: "transpose", 1: "cond", 3: "post"}[op.kind], ms=ms))
     for r in rows:
@@ -77,6 +82,9 @@ def main():
                   f"k={r['k']:2d} d={r['d']} up={r['up']} rows={r['rows']:6d} tile={r['n_tile']:3d} "
                   f"taps={r['taps']} {r['ms'] * 1e3:8.1f} us {r['tflops']:7.1f} TF/s "
                   f"{r['gbs']:7.0f} GB/s ({r['mb']:.0f} MB)")
+        elif r["kind"] == "fused":
+            print(f"{r['i']:3d} FUSED MRF stage {r['stage']} C={r['cin']:3d} rows={r['rows']:6d} "
+                  f"{r['ms'] * 1e3:8.1f} us {r['tflops']:7.1f} TF/s {r['gbs']:7.0f} GB/s ({r['mb']:.0f} MB)")
         else:
             print(f"{r['i']:3d} {r['kind']:9s} {r['ms'] * 1e3:8.1f} us")
     print(f"total {tot:.3f} ms for {batch * frames / 50:.0f} audio-s -> {batch * frames / 50 / tot * 1e3:.0f} audio-s/s")

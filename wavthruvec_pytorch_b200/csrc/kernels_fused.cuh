@@ -21,10 +21,15 @@
 // window (its output feeds conv2's halo), conv_sum and conv2_j on the 256 rows starting at q0c (the
 // last 2*hc of them are discarded).  A0 tile = window + h1 rows per side (h1 = d0 (kmax - 1)/2).
 //
-// Roles: warp 0 TMA producer (A0 tile, double buffered across tiles; weight taps streamed in issue
-// order through an 8-deep ring), warp 1 MMA issuer, warps 4-11 epilogue (thread = window row).
-// T1 and A1 are double buffered across branches so that conv1_{j+1} overlaps the epilogue of
-// branch j and conv2_j overlaps the epilogue of branch j+1.
+// Roles: warp 0 TMA producer (A0 tile, double buffered across tiles; weight taps), warp 1 MMA
+// issuer, warps 4-11 epilogue (thread = window row).  T1 and A1 are double buffered across branches
+// so that conv1_{j+1} overlaps the epilogue of branch j and conv2_j overlaps the epilogue of branch
+// j+1; T2 is double buffered across tiles so that the final epilogue overlaps the next tile.
+//
+// Weights: for C <= 32 all taps of the stage (53 x C x C bf16 = 27 / 106 KB) are loaded ONCE per
+// CTA and stay resident; the MMA loop then has no per-tap barrier at all.  The first version
+// streamed every tap through an 8-deep ring and measured ~430 clk per tap at C = 16 (ring round
+// trip = TMA latency / 8) against ~16 clk of MMA work.  C = 64 (424 KB of taps) still streams.
 #pragma once
 
 #include "kernels_tc.cuh"
@@ -50,6 +55,7 @@ struct Params {
   int a0_boxes;                 // TMA boxes (64 rows) per A0 tile
   int nseg, nbranch, ntaps_total;
   int stages_w, stage_w_bytes;
+  int w_region_bytes;           // bytes of the weight region (ring or resident block)
   Segment seg[kMaxSeg];
   int16_t shift[kMaxTaps];      // operand row (sub-tile 0) of each tap inside its A tile
   const float* x0;              // fp32 [B, L, C]
@@ -77,8 +83,9 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kRowBytes = C * 2;
   constexpr int kKSteps = C / 16;
   constexpr int kAccCols = C < 32 ? 32 : C;
+  constexpr bool kResident = C <= 32;                    // weights stay in shared memory
   constexpr uint32_t kT1Cols = 2 * kAccCols;             // two sub-tiles
-  constexpr uint32_t kTmemCols = C == 64 ? 512 : 256;    // 2 x T1 + T2, rounded to a power of two
+  constexpr uint32_t kTmemCols = 8 * kAccCols;           // 2 x T1 + 2 x T2 (512 / 256 / 256)
   constexpr uint32_t kA1Bytes = kWin * kRowBytes;
   constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
   constexpr uint32_t kWBytes = C * kRowBytes;
@@ -89,13 +96,13 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_a1 = smem_a0 + 2 * a0_bytes;
   const uint32_t smem_w = smem_a1 + 2 * kA1Bytes;
-  const uint32_t bars = smem_w + p.stages_w * p.stage_w_bytes;
+  const uint32_t bars = smem_w + p.w_region_bytes;
   // barriers: a0_full[2] a0_empty[2] w_full[8] w_empty[8] t1_full[2] t1_empty[2] a1_full[2]
   //           a1_empty[2] t2_full t2_empty
   const uint32_t a0_full = bars, a0_empty = bars + 16, w_full = bars + 32, w_empty = bars + 96;
   const uint32_t t1_full = bars + 160, t1_empty = bars + 176, a1_full = bars + 192;
-  const uint32_t a1_empty = bars + 208, t2_full = bars + 224, t2_empty = bars + 232;
-  const uint32_t tmem_slot = bars + 240;
+  const uint32_t a1_empty = bars + 208, t2_full = bars + 224, t2_empty = bars + 240;
+  const uint32_t w_all = bars + 256, tmem_slot = bars + 264;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,8 +123,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(w_full + 8 * i, 1);
       mbar_init(w_empty + 8 * i, 1);
     }
-    mbar_init(t2_full, 1);
-    mbar_init(t2_empty, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(t2_full + 8 * i, 1);
+      mbar_init(t2_empty + 8 * i, 256);
+    }
+    mbar_init(w_all, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -127,12 +137,20 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-  const uint32_t tmem_t2 = tmem_base + 2 * kT1Cols;
+  const uint32_t tmem_t2 = tmem_base + 2 * kT1Cols;   // T2[slot] = tmem_t2 + slot * kT1Cols
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     Ring rw;
     uint32_t tile_iter = 0;
+    if (kResident) {
+      if (elect_one()) {
+        mbar_expect_tx(w_all, p.ntaps_total * kWBytes);
+        for (int t = 0; t < p.ntaps_total; ++t)
+          tma_load_2d(smem_w + t * kWBytes, &tmW, 0, t * C, w_all);
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
@@ -147,7 +165,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                       bar);
       }
       __syncwarp();
-      for (int t = 0; t < p.ntaps_total; ++t) {
+      for (int t = 0; !kResident && t < p.ntaps_total; ++t) {
         mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
         if (elect_one()) {
           const uint32_t bar = w_full + 8 * rw.s;
@@ -164,8 +182,10 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
     const uint32_t idesc = make_idesc_bf16(kMTile, C);
     const uint32_t dhi = smem_desc_hi<C>();
+    if (kResident) mbar_wait(w_all, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const uint32_t buf = tile_iter & 1u;
+      const uint32_t t2s = tile_iter & 1u, t2ph = (tile_iter >> 1) & 1u;
       mbar_wait(a0_full + 8 * buf, (tile_iter >> 1) & 1u);
       const uint32_t a0 = smem_a0 + buf * a0_bytes;
       for (int s = 0; s < p.nseg; ++s) {
@@ -177,23 +197,26 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           d_tmem = tmem_base + slot * kT1Cols;
           a_tile = a0;
         } else if (sg.type == kSegSum) {
-          mbar_wait(t2_empty, (tile_iter & 1u) ^ 1u);
-          d_tmem = tmem_t2;
+          mbar_wait(t2_empty + 8 * t2s, t2ph ^ 1u);
+          d_tmem = tmem_t2 + t2s * kT1Cols;
           a_tile = a0;
         } else {
           slot = n2 & 1u;
           mbar_wait(a1_full + 8 * slot, (n2 >> 1) & 1u);
-          d_tmem = tmem_t2;
+          d_tmem = tmem_t2 + t2s * kT1Cols;
           a_tile = smem_a1 + slot * kA1Bytes;
         }
         tcgen05_fence_after();
         const bool last_seg = s == p.nseg - 1;
         for (int t = 0; t < sg.ntaps; ++t) {
-          mbar_wait(w_full + 8 * rw.s, rw.ph);
-          tcgen05_fence_after();
+          if (!kResident) {
+            mbar_wait(w_full + 8 * rw.s, rw.ph);
+            tcgen05_fence_after();
+          }
           if (elect_one()) {
             const uint32_t a_addr = a_tile + p.shift[sg.first + t] * kRowBytes;
-            const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
+            const uint32_t w_addr = kResident ? smem_w + (sg.first + t) * kWBytes
+                                              : smem_w + rw.s * p.stage_w_bytes;
             const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -203,18 +226,18 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int kk = 0; kk < kKSteps; ++kk)
                 umma_bf16(d_tmem + m * kAccCols, ad + 2 * kk, bd + 2 * kk, idesc, acc0 | (kk != 0));
             }
-            umma_commit(w_empty + 8 * rw.s);
+            if (!kResident) umma_commit(w_empty + 8 * rw.s);
             if (t == sg.ntaps - 1) {
               if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
               if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
               if (last_seg) {
-                umma_commit(t2_full);
+                umma_commit(t2_full + 8 * t2s);
                 umma_commit(a0_empty + 8 * buf);
               }
             }
           }
           __syncwarp();
-          rw.advance(p.stages_w);
+          if (!kResident) rw.advance(p.stages_w);
         }
         if (sg.type == kSegConv1) ++n1;
         if (sg.type == kSegConv2) ++n2;
@@ -237,6 +260,14 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c - p.hc + i;
         const bool valid = gr >= 0 && gr < p.rows;
         const float* xrow = p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
+        // C <= 32: this row of X0 is the same for every branch -> read it once per tile, before
+        // the first accumulator is even ready, so that no global latency sits between MMAs.
+        constexpr int kXc = kResident ? C / 4 : 1;
+        float4 xc[kXc];
+        if (kResident && valid) {
+#pragma unroll
+          for (int e = 0; e < kXc; ++e) xc[e] = __ldg(reinterpret_cast<const float4*>(xrow) + e);
+        }
         for (int j = 0; j < p.nbranch; ++j, ++e1) {
           const uint32_t slot = e1 & 1u, ph = (e1 >> 1) & 1u;
           mbar_wait(t1_full + 8 * slot, ph);
@@ -249,7 +280,9 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float4 xr[4];
             if (valid) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xr[e] = *reinterpret_cast<const float4*>(xrow + cc + 4 * e);
+              for (int e = 0; e < 4; ++e)
+                xr[e] = kResident ? xc[(kResident ? cc / 4 : 0) + e]
+                                  : *reinterpret_cast<const float4*>(xrow + cc + 4 * e);
             }
             uint32_t r[16];
             tmem_ld16(tmem_base + slot * kT1Cols + t_lane + cc, r);
@@ -284,21 +317,30 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk ----
       {
-        mbar_wait(t2_full, tile_iter & 1u);
-        tcgen05_fence_after();
+        const uint32_t t2s = tile_iter & 1u, t2ph = (tile_iter >> 1) & 1u;
         const int gr = q0c + i;
         const bool valid = i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
+        constexpr int kXc = kResident ? C / 4 : 1;
+        float4 xc[kXc];
+        if (kResident && valid) {   // issued before the wait: overlaps the last conv2 MMAs
+#pragma unroll
+          for (int e = 0; e < kXc; ++e)
+            xc[e] = __ldg(reinterpret_cast<const float4*>(p.x0 + row_base) + e);
+        }
+        mbar_wait(t2_full + 8 * t2s, t2ph);
+        tcgen05_fence_after();
 #pragma unroll
         for (int cc = 0; cc < C; cc += 16) {
           float4 xr[4];
           if (valid) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              xr[e] = *reinterpret_cast<const float4*>(p.x0 + row_base + cc + 4 * e);
+              xr[e] = kResident ? xc[(kResident ? cc / 4 : 0) + e]
+                                : *reinterpret_cast<const float4*>(p.x0 + row_base + cc + 4 * e);
           }
           uint32_t r[16];
-          tmem_ld16(tmem_t2 + t_lane + cc, r);
+          tmem_ld16(tmem_t2 + t2s * kT1Cols + t_lane + cc, r);
           tmem_ld_wait();
           if (valid) {
             float v[16];
@@ -328,7 +370,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(t2_empty);
+        mbar_arrive(t2_empty + 8 * t2s);
       }
     }
   }

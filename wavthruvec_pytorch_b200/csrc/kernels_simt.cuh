@@ -222,11 +222,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-constexpr int kCondThreads = 256;
+constexpr int kCondThreads = 512;
 
 // One warp per output row, lanes stride the (contiguous) weight row: coalesced reads + shuffle
-// reduction.  The first version walked one row per thread (uncoalesced) and took 70 us for what
-// is 0.4 MFLOP per utterance.
+// reduction, four rows in flight per warp.  The op is pure latency (0.4 MFLOP per utterance, and
+// in the benchmark its weights come from DRAM after the L2 flush): the first version walked one
+// row per thread (uncoalesced, 70 us), the second one row per warp at a time (still 70 us: one
+// dependent DRAM round trip per row).
 __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondParams p) {
   extern __shared__ float sm[];
   const CondStage& S = p.st[blockIdx.x];
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondPar
   const int D = p.spk_dim + p.noise_dim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = kCondThreads / 32;
+  constexpr int kRows = 4;   // rows per warp pass
   float* sn = sm;            // [D]
   float* z = sm + D;         // [128]
   float* gb = z + 128;       // [2C]
@@ -241,20 +244,35 @@ __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondPar
     sn[i] = i < p.spk_dim ? p.spk[static_cast<size_t>(b) * p.spk_dim + i]
                           : p.noise[static_cast<size_t>(b) * p.noise_dim + (i - p.spk_dim)];
   __syncthreads();
-  for (int t = warp; t < 128; t += kWarps) {
-    const float* w = S.fcw + static_cast<size_t>(t) * D;
-    float a = 0.f;
-    for (int d = lane; d < D; d += 32) a = fmaf(__ldg(w + d), sn[d], a);
-    a = warp_sum(a);
-    if (lane == 0) z[t] = a + S.fcb[t];
+  for (int t0 = warp * kRows; t0 < 128; t0 += kWarps * kRows) {
+    float a[kRows] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = lane; d < D; d += 32) {
+      float w[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) w[r] = __ldg(S.fcw + static_cast<size_t>(t0 + r) * D + d);
+      const float x = sn[d];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) a[r] = fmaf(w[r], x, a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float v = warp_sum(a[r]);
+      if (lane == 0) z[t0 + r] = v + S.fcb[t0 + r];
+    }
   }
   __syncthreads();
-  for (int r = warp; r < 2 * S.C; r += kWarps) {
-    const float4 w4 = __ldg(reinterpret_cast<const float4*>(S.snw + static_cast<size_t>(r) * 128) + lane);
-    const float4 z4 = *reinterpret_cast<const float4*>(z + 4 * lane);
-    float a = w4.x * z4.x + w4.y * z4.y + w4.z * z4.z + w4.w * z4.w;
-    a = warp_sum(a);
-    if (lane == 0) gb[r] = a + S.snb[r];
+  const float4 z4 = *reinterpret_cast<const float4*>(z + 4 * lane);
+  for (int r0 = warp * kRows; r0 < 2 * S.C; r0 += kWarps * kRows) {
+    float4 w4[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      w4[r] = __ldg(reinterpret_cast<const float4*>(S.snw + static_cast<size_t>(r0 + r) * 128) + lane);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float v = w4[r].x * z4.x + w4[r].y * z4.y + w4[r].z * z4.z + w4[r].w * z4.w;
+      v = warp_sum(v);
+      if (lane == 0) gb[r0 + r] = v + S.snb[r0 + r];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < S.C; c += kCondThreads) {

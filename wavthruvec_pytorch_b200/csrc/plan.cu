@@ -380,10 +380,22 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   const int a1_bytes = fused::kWin * C * 2;
   const int budget = 227 * 1024 - 1024 - 256;
   const int left = budget - 2 * a0_bytes - 2 * a1_bytes;
-  p.stages_w = std::min(left / p.stage_w_bytes, tc::kMaxStagesW);
-  if (p.stages_w < 2) {
-    set_error("fused stage: does not fit shared memory");
-    return V2W_ERR_INVALID;
+  int w_bytes_total;
+  if (C <= 32) {
+    // resident weights: every tap of the stage lives in shared memory (kernels_fused.cuh)
+    p.stages_w = 1;
+    w_bytes_total = (int)align_up((int64_t)F.num_taps * C * C * 2, 1024);
+    if (w_bytes_total > left) {
+      set_error("fused stage: resident weights (%d B) do not fit shared memory", w_bytes_total);
+      return V2W_ERR_INVALID;
+    }
+  } else {
+    p.stages_w = std::min(left / p.stage_w_bytes, tc::kMaxStagesW);
+    if (p.stages_w < 2) {
+      set_error("fused stage: does not fit shared memory");
+      return V2W_ERR_INVALID;
+    }
+    w_bytes_total = p.stages_w * p.stage_w_bytes;
   }
   p.x0 = reinterpret_cast<const float*>(ws + d.residual);
   for (int j = 0; j < F.num_branches; ++j)
@@ -396,7 +408,8 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
   p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
   L->channels = C;
-  L->smem = 2 * a0_bytes + 2 * a1_bytes + p.stages_w * p.stage_w_bytes + 256 + 1024;
+  p.w_region_bytes = w_bytes_total;
+  L->smem = 2 * a0_bytes + 2 * a1_bytes + w_bytes_total + 512 + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
 
   EncodeTiledFn enc = nullptr;
