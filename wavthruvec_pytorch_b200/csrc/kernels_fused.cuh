@@ -45,8 +45,12 @@ constexpr int kMaxSeg = 12;
 constexpr int kMaxTaps = 80;
 constexpr int kSegConv1 = 0, kSegSum = 1, kSegConv2 = 2;
 
+// 32-bit fields on purpose: with four packed int16 ptxas (12.9) merged the constant-bank loads
+// of a dynamically indexed p.seg[s] and then read `first` from an unrelated register whenever
+// the array sat at a 4-byte (not 8-byte) aligned parameter offset -- wrong taps, no diagnostics
+// (profiles/r01_ptxas_param_miscompile.md).
 struct Segment {
-  int16_t type, branch, ntaps, first;
+  int type, branch, ntaps, first;
 };
 
 struct Params {
@@ -57,7 +61,7 @@ struct Params {
   int stages_w, stage_w_bytes;
   int w_region_bytes;           // bytes of the weight region (ring or resident block)
   Segment seg[kMaxSeg];
-  int16_t shift[kMaxTaps];      // operand row (sub-tile 0) of each tap inside its A tile
+  int shift[kMaxTaps];          // operand row (sub-tile 0) of each tap inside its A tile
   const float* x0;              // fp32 [B, L, C]
   const float* bias1[V2W_MAX_KERNELS];
   const float* bsum;            // sum_j (b1_j + b2_j)
@@ -208,36 +212,47 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tcgen05_fence_after();
         const bool last_seg = s == p.nseg - 1;
-        for (int t = 0; t < sg.ntaps; ++t) {
-          if (!kResident) {
-            mbar_wait(w_full + 8 * rw.s, rw.ph);
-            tcgen05_fence_after();
-          }
-          if (elect_one()) {
-            const uint32_t a_addr = a_tile + p.shift[sg.first + t] * kRowBytes;
-            const uint32_t w_addr = kResident ? smem_w + (sg.first + t) * kWBytes
-                                              : smem_w + rw.s * p.stage_w_bytes;
+        // One elected lane issues the whole segment: per tap only two descriptor words change
+        // (A: row shift inside the tile, W: next tap matrix), everything else is loop-invariant.
+        if (elect_one()) {
+          const uint32_t a_lo = ((a_tile & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t w0 = kResident ? smem_w + sg.first * kWBytes : 0u;
+          Ring r = rw;   // the elected lane walks a private copy; all lanes advance `rw` below
+          for (int t = 0; t < sg.ntaps; ++t) {
+            uint32_t w_addr;
+            if (kResident) {
+              w_addr = w0 + t * kWBytes;
+            } else {
+              mbar_wait(w_full + 8 * r.s, r.ph);
+              tcgen05_fence_after();
+              w_addr = smem_w + r.s * p.stage_w_bytes;
+            }
+            const uint32_t a_t = a_lo + p.shift[sg.first + t] * (kRowBytes >> 4);
+            const uint64_t bd = smem_desc(dhi, w_addr);
             const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-              const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
-              const uint64_t bd = smem_desc(dhi, w_addr);
+              const uint64_t ad =
+                  (static_cast<uint64_t>(dhi) << 32) | (a_t + m * ((kMTile * kRowBytes) >> 4));
 #pragma unroll
               for (int kk = 0; kk < kKSteps; ++kk)
                 umma_bf16(d_tmem + m * kAccCols, ad + 2 * kk, bd + 2 * kk, idesc, acc0 | (kk != 0));
             }
-            if (!kResident) umma_commit(w_empty + 8 * rw.s);
-            if (t == sg.ntaps - 1) {
-              if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
-              if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
-              if (last_seg) {
-                umma_commit(t2_full + 8 * t2s);
-                umma_commit(a0_empty + 8 * buf);
-              }
+            if (!kResident) {
+              umma_commit(w_empty + 8 * r.s);
+              r.advance(p.stages_w);
             }
           }
-          __syncwarp();
-          if (!kResident) rw.advance(p.stages_w);
+          if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
+          if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
+          if (last_seg) {
+            umma_commit(t2_full + 8 * t2s);
+            umma_commit(a0_empty + 8 * buf);
+          }
+        }
+        __syncwarp();
+        if (!kResident) {
+          for (int t = 0; t < sg.ntaps; ++t) rw.advance(p.stages_w);
         }
         if (sg.type == kSegConv1) ++n1;
         if (sg.type == kSegConv2) ++n2;
@@ -260,11 +275,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c - p.hc + i;
         const bool valid = gr >= 0 && gr < p.rows;
         const float* xrow = p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        // C <= 32: this row of X0 is the same for every branch -> read it once per tile, before
-        // the first accumulator is even ready, so that no global latency sits between MMAs.
-        constexpr int kXc = kResident ? C / 4 : 1;
+        // This row of X0 is the same for every branch -> read it once per tile, before the first
+        // accumulator is even ready, so that no global latency sits between the MMAs.
+        constexpr int kXc = C / 4;
         float4 xc[kXc];
-        if (kResident && valid) {
+        if (valid) {
 #pragma unroll
           for (int e = 0; e < kXc; ++e) xc[e] = __ldg(reinterpret_cast<const float4*>(xrow) + e);
         }
@@ -280,9 +295,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float4 xr[4];
             if (valid) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                xr[e] = kResident ? xc[(kResident ? cc / 4 : 0) + e]
-                                  : *reinterpret_cast<const float4*>(xrow + cc + 4 * e);
+              for (int e = 0; e < 4; ++e) xr[e] = xc[cc / 4 + e];
             }
             uint32_t r[16];
             tmem_ld16(tmem_base + slot * kT1Cols + t_lane + cc, r);
@@ -321,9 +334,9 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c + i;
         const bool valid = i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        constexpr int kXc = kResident ? C / 4 : 1;
+        constexpr int kXc = C / 4;
         float4 xc[kXc];
-        if (kResident && valid) {   // issued before the wait: overlaps the last conv2 MMAs
+        if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
           for (int e = 0; e < kXc; ++e)
             xc[e] = __ldg(reinterpret_cast<const float4*>(p.x0 + row_base) + e);
@@ -335,9 +348,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float4 xr[4];
           if (valid) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              xr[e] = kResident ? xc[(kResident ? cc / 4 : 0) + e]
-                                : *reinterpret_cast<const float4*>(p.x0 + row_base + cc + 4 * e);
+            for (int e = 0; e < 4; ++e) xr[e] = xc[cc / 4 + e];
           }
           uint32_t r[16];
           tmem_ld16(tmem_t2 + t2s * kT1Cols + t_lane + cc, r);

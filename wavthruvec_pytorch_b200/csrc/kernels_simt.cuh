@@ -23,11 +23,11 @@ constexpr int kMaxHalo = 64;   // (num_taps-1)*dilation upper bound supported
 
 struct Params {
   int batch, rows, cin, n_total, cmod, n_tile;
-  int16_t num_taps[V2W_MAX_TILES];
-  int16_t off_min[V2W_MAX_TILES];
-  int16_t halo[V2W_MAX_TILES];
-  int16_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
-  int16_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int num_taps[V2W_MAX_TILES];
+  int off_min[V2W_MAX_TILES];
+  int halo[V2W_MAX_TILES];
+  int tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
   const void* in_act;
   float in_slope;
   const float* w32;        // [taps][cin][n_total]

@@ -56,11 +56,13 @@ struct Params {
   int stages_a, stages_w;
   int stage_a_bytes, stage_w_bytes;
   int acc_cols;         // TMEM columns per accumulator (per sub-tile)
-  int16_t num_taps[V2W_MAX_TILES];
-  int16_t off_min[V2W_MAX_TILES];
-  int16_t halo[V2W_MAX_TILES];
-  int16_t tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
-  int16_t tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  // 32-bit entries on purpose: see the note at fused::Segment (ptxas merges 16-bit loads of
+  // dynamically indexed parameter arrays incorrectly at some alignments).
+  int num_taps[V2W_MAX_TILES];
+  int off_min[V2W_MAX_TILES];
+  int halo[V2W_MAX_TILES];
+  int tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
   const float* bias;
   const float* scale;
   const float* shift;

@@ -199,14 +199,14 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   p.num_chunks = a.cin / kc;
   int halo_max = 0;
   for (int t = 0; t < a.n_tiles; ++t) {
-    p.num_taps[t] = (int16_t)a.num_taps[t];
-    p.off_min[t] = (int16_t)a.tap_off[t][0];
+    p.num_taps[t] = a.num_taps[t];
+    p.off_min[t] = a.tap_off[t][0];
     const int halo = a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0];
-    p.halo[t] = (int16_t)halo;
+    p.halo[t] = halo;
     halo_max = std::max(halo_max, halo);
     for (int j = 0; j < a.num_taps[t]; ++j) {
-      p.tap_off[t][j] = (int16_t)a.tap_off[t][j];
-      p.tap_row[t][j] = (int16_t)a.tap_row[t][j];
+      p.tap_off[t][j] = a.tap_off[t][j];
+      p.tap_row[t][j] = a.tap_row[t][j];
     }
   }
   p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
@@ -324,17 +324,17 @@ static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
   p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
   p.n_tile = a.n_tile;
   for (int t = 0; t < a.n_tiles; ++t) {
-    p.num_taps[t] = (int16_t)a.num_taps[t];
-    p.off_min[t] = (int16_t)a.tap_off[t][0];
+    p.num_taps[t] = a.num_taps[t];
+    p.off_min[t] = a.tap_off[t][0];
     const int halo = a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0];
     if (halo > simt::kMaxHalo) {
       set_error("tapgemm(SIMT): halo %d > %d", halo, simt::kMaxHalo);
       return V2W_ERR_INVALID;
     }
-    p.halo[t] = (int16_t)halo;
+    p.halo[t] = halo;
     for (int j = 0; j < a.num_taps[t]; ++j) {
-      p.tap_off[t][j] = (int16_t)a.tap_off[t][j];
-      p.tap_row[t][j] = (int16_t)a.tap_row[t][j];
+      p.tap_off[t][j] = a.tap_off[t][j];
+      p.tap_row[t][j] = a.tap_row[t][j];
     }
   }
   p.in_act = a.in_act; p.in_slope = a.in_slope; p.w32 = a.w32;
@@ -579,6 +579,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   const int B = batch, T = frames;
   const bool force_simt = std::getenv("V2W_FORCE_SIMT") != nullptr;
   const bool no_fuse = std::getenv("V2W_NO_FUSE") != nullptr;
+  const int fuse_mask = std::getenv("V2W_FUSE_MASK") ? std::atoi(std::getenv("V2W_FUSE_MASK")) : -1;
 
   Bump ws;
   P->stage_x = ws.take((int64_t)B * c.num_wv_feat * T * 4);
@@ -685,7 +686,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     stage_out.bf16 = (bf && !last_stage) ? next_bf16 : -1;
     Act partial;     // running MRF sum xs (models.py:136-140)
     partial.f32 = sum_f32;
-    if (bf && !force_simt && !no_fuse && m->fused[i].ok) {
+    if (bf && !force_simt && !no_fuse && m->fused[i].ok && ((fuse_mask >> i) & 1)) {
       // whole stage in one kernel (kernels_fused.cuh)
       Op o = blank(V2W_OP_MRF_FUSED);
       o.d.engine = V2W_ENGINE_TC;

@@ -28,7 +28,8 @@ ROLE_CONV_PRE, ROLE_UPSAMPLE, ROLE_RESBLOCK, ROLE_CONV_POST = 0, 1, 2, 3
 TC_FLAG_PER_TAP = 1
 TC_FLAG_BASE_OFFSET = 2
 
-LIB_PATH = Path(__file__).resolve().parent / "libv2w.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("V2W_LIB") or (Path(__file__).resolve().parent / "libv2w.so"))
 
 
 class NativeLibraryError(RuntimeError):
