@@ -87,6 +87,12 @@ def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2):
     import torch
     from oracle import fixtures, vec2wav_torch_cpu
     from wavthruvec_pytorch_b200 import Generator
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use every core this process may run on
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     h = make_hparams(args, feat)
     gen = fixtures.construct(Generator, h).eval()
     sd = {k: v.detach() for k, v in gen.state_dict().items()}
