@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--resblock", default="2", choices=["1", "2"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -296,7 +296,7 @@ def run_native_arm(args):
         value = world * audio_per_step / (ms_per_step * 1e-3)
         e2e_value = world * audio_per_step / (e2e_s / e2e_steps)
         peak_tf, peak_gbs, peak_src = measured_peaks()
-        gemm = [(op, ms) for op, ms in prof if op.kind == native.OP_TAPGEMM]
+        gemm = [(op, ms) for op, ms in prof if op.kind in (native.OP_TAPGEMM, native.OP_MRF_FUSED)]
         gemm_flops = sum(op.flops for op, _ in gemm)
         gemm_ms = sum(ms for _, ms in gemm)
         all_ms = sum(ms for _, ms in prof)
@@ -312,7 +312,7 @@ def run_native_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(args, batch, frames, feat),
                        "per_gpu_batch": batch, "l2": "flushed with a 256 MB write before every step",
                        "precision": args.precision, "sharding": f"dp{world} (independent utterances)"},
@@ -323,7 +323,7 @@ def run_native_arm(args):
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "tapgemm_tc_kernel" if args.precision == "bf16" else "tapgemm_simt_kernel",
+                         "kernel": "tapgemm_simt_kernel" if args.precision == "fp32" else "tapgemm_tc_kernel + mrf_stage_kernel",
                          "launches": len(gemm), "gemm_ms_per_step": gemm_ms,
                          "all_ops_ms_per_step": all_ms,
                          "algorithmic_gflop_per_step": gemm_flops / 1e9},

@@ -55,6 +55,13 @@ extern "C" {
 /* ---- precision of a plan ----------------------------------------------------------- */
 #define V2W_PREC_FP32 0  /* FFMA kernels, fp32 everywhere: parity bar max-abs <= 1e-4 */
 #define V2W_PREC_BF16 1  /* tcgen05 bf16 x bf16 -> fp32 (TMEM), fp32 residual stream: SNR >= 45 dB */
+#define V2W_PREC_FP16 2  /* same kernels with fp16 operands (3 more mantissa bits, same tensor rate;
+                            activations are clamped to +-65504).  Needed by ResBlock1 to reach 45 dB. */
+
+/* 16-bit operand format of a packed weight buffer */
+#define V2W_HALF_BF16 0
+#define V2W_HALF_FP16 1
+#define V2W_PACKED_HEADER_BYTES 1024   /* {uint32 magic 'V2WP', abi, half_format} then zeros */
 
 /* Hyper-parameters.  Replaces the attribute bag `h` of Generator.__init__
  * (vec2wav/models.py:78-114; values in vec2wav/hparams.py:26-27,30,40-44,51). */
@@ -228,6 +235,11 @@ int64_t v2w_model_packed_bytes(const struct v2w_model* m);
  * hold v2w_model_packed_bytes() bytes.  Pure host arithmetic, replaces the per-forward
  * weight_norm/spectral_norm pre-forward hooks of the reference. */
 int32_t v2w_model_pack(const struct v2w_model* m, const v2w_params* params, void* packed_host);
+/* Same with an explicit 16-bit operand format (v2w_model_pack == V2W_HALF_BF16).  A BF16 plan must be
+ * bound to a V2W_HALF_BF16 buffer and an FP16 plan to a V2W_HALF_FP16 one (checked in v2w_plan_bind;
+ * an FP32 plan accepts either). */
+int32_t v2w_model_pack_half(const struct v2w_model* m, const v2w_params* params, void* packed_host,
+                            int32_t half_format);
 /* Algorithmic FLOPs (2*MAC, zero polyphase blocks excluded) per input frame. */
 int64_t v2w_model_flops_per_frame(const struct v2w_model* m);
 
@@ -291,7 +303,7 @@ typedef struct v2w_tapgemm_args {
   float* out_f32;              /* dev or NULL */
   void* out_bf16;              /* dev or NULL */
   float out_slope;
-  int32_t tc_flags;            /* experiment switches of the TC kernel, see DESIGN.md */
+  int32_t tc_flags;            /* TC engine: bit 8 (0x100) = 16-bit operands are fp16 instead of bf16 */
 } v2w_tapgemm_args;
 int32_t v2w_tapgemm(const v2w_tapgemm_args* args, void* stream);
 

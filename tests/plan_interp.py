@@ -22,6 +22,11 @@ def bf16_round(a: np.ndarray) -> np.ndarray:
     return ((u + r) & 0xFFFF0000).view(np.float32)
 
 
+def fp16_round(a: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest-even fp16 (clamped to the finite range like the kernels) -> fp32."""
+    return np.clip(np.asarray(a, np.float32), -65504.0, 65504.0).astype(np.float16).astype(np.float32)
+
+
 def lrelu(x, slope):
     return np.where(x > 0, x, x * np.float32(slope)).astype(np.float32)
 
@@ -35,7 +40,7 @@ class HostPlan:
         self.model = engine._model
         self.precision = precision
         h = C.c_void_p()
-        prec = native.PREC_BF16 if precision == "bf16" else native.PREC_FP32
+        prec = native.PRECISIONS[precision]
         native.check(self.lib.v2w_plan_create(self.model, batch, frames, prec, C.byref(h)))
         self.handle = h
         self.ops = []
@@ -80,7 +85,16 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
     """Returns the waveform [B,1,L] (fp32).  `collect`, if a dict, receives every op's fp32
     output keyed by op index."""
     f32, u16, conds = _packed_views(plan, packed)
-    bf = plan.precision == "bf16"
+    bf = plan.precision in ("bf16", "fp16")
+    half = fp16_round if plan.precision == "fp16" else bf16_round
+    hdr = packed[:12].view(np.uint32)
+    assert hdr[0] == 0x50573256 and (not bf or hdr[2] == (1 if plan.precision == "fp16" else 0)), \
+        "packed buffer format does not match the plan precision"
+
+    def half_to_f32(bits):      # packed 16-bit weights -> fp32
+        if plan.precision == "fp16":
+            return bits.view(np.float16).astype(np.float32)
+        return (bits.astype(np.uint32) << 16).view(np.float32)
     ws = {}       # workspace offset -> ndarray [B, rows, C] (values as the device buffer holds them)
     scale, shift = {}, {}
     out = None
@@ -89,7 +103,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
         if op.kind == native.OP_TRANSPOSE_IN:
             xt = np.ascontiguousarray(x.transpose(0, 2, 1))
             if op.out_bf16 >= 0:
-                ws[op.out_bf16] = bf16_round(xt)
+                ws[op.out_bf16] = half(xt)
             else:
                 ws[op.out_f32] = xt
         elif op.kind == native.OP_COND_AFFINE:
@@ -108,8 +122,8 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             if op.in_slope != 1.0:
                 A = lrelu(A, op.in_slope)
             if bf:     # TC engine semantics: bf16 weights [taps][n_total][cin]
-                w = u16(L.w16_off, L.num_taps * L.n_total * L.cin).astype(np.uint32) << 16
-                W = w.view(np.float32).reshape(L.num_taps, L.n_total, L.cin)
+                W = half_to_f32(u16(L.w16_off, L.num_taps * L.n_total * L.cin)).reshape(
+                    L.num_taps, L.n_total, L.cin)
             else:      # FFMA engine: fp32 [taps][cin][n_total]
                 W = f32(L.w32_off, L.num_taps * L.cin * L.n_total).reshape(
                     L.num_taps, L.cin, L.n_total).transpose(0, 2, 1)
@@ -139,7 +153,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             if op.out_f32 >= 0:
                 ws[op.out_f32] = v
             if op.out_bf16 >= 0:
-                ws[op.out_bf16] = bf16_round(lrelu(v, op.out_slope))
+                ws[op.out_bf16] = half(lrelu(v, op.out_slope))
             if collect is not None:
                 collect[idx] = v
         elif op.kind == native.OP_MRF_FUSED:
@@ -149,8 +163,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             Cn, nb = F.channels, F.num_branches
             A0 = ws[op.in_act].reshape(op.batch, op.rows, Cn)
             X0 = ws[op.residual].reshape(op.batch, op.rows, Cn)
-            w = u16(F.w_off, F.num_taps * Cn * Cn).astype(np.uint32) << 16
-            Wf = w.view(np.float32).reshape(F.num_taps, Cn, Cn)      # [tap][n][c]
+            Wf = half_to_f32(u16(F.w_off, F.num_taps * Cn * Cn)).reshape(F.num_taps, Cn, Cn)  # [tap][n][c]
             bsum = f32(F.bsum_off, Cn)
 
             def conv(A, first, ntaps):
@@ -171,7 +184,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                 first, nt = F.seg_first[sgi], F.seg_ntaps[sgi]
                 if typ == native.SEG_CONV1:
                     b1 = f32(plan.layers[F.first_layer + 2 * j].bias_off, Cn)
-                    A1[j] = bf16_round(lrelu(conv(A0, first, nt) + b1 + X0, 0.1))
+                    A1[j] = half(lrelu(conv(A0, first, nt) + b1 + X0, 0.1))
                 elif typ == native.SEG_SUM:
                     T2 += conv(A0, first, nt)
                 else:
@@ -180,7 +193,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             if op.out_f32 >= 0:
                 ws[op.out_f32] = v
             if op.out_bf16 >= 0:
-                ws[op.out_bf16] = bf16_round(lrelu(v, op.out_slope))
+                ws[op.out_bf16] = half(lrelu(v, op.out_slope))
             if collect is not None:
                 collect[idx] = v
         elif op.kind == native.OP_CONV_POST:

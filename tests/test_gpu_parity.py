@@ -119,6 +119,34 @@ def test_bf16_plan_snr(name):
     assert snr >= BF16_MIN_SNR_DB
 
 
+@pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress", "rb2_768_stress"])
+def test_fp16_plan_snr(name):
+    """fp16 operands: the 16-bit tensor-core path that ResBlock1 needs (and the 'auto' default
+    for it); bf16 operands give 40.8 dB on rb1_768_stress."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    if g.overrides.get("resblock") == '1':
+        assert gen.precision == "fp16"      # 'auto'
+    y = _native(gen, g, "fp16")
+    snr = fixtures.snr_db(g.y, y)
+    print(f"{name}: fp16 SNR {snr:.1f} dB")
+    assert snr >= BF16_MIN_SNR_DB + 5.0
+
+
+def test_bind_rejects_mismatched_operand_format():
+    import ctypes as C
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    eng = gen.engine()
+    packed = eng.pack_host(native.HALF_BF16).to("cuda:0")
+    handle = C.c_void_p()
+    native.check(eng._lib.v2w_plan_create(eng._model, 1, 4, native.PREC_FP16, C.byref(handle)))
+    ws = torch.empty(int(eng._lib.v2w_plan_workspace_bytes(handle)), dtype=torch.uint8, device="cuda:0")
+    rc = eng._lib.v2w_plan_bind(handle, packed.data_ptr(), ws.data_ptr())
+    assert rc == -1 and "bf16" in native.last_error()
+    eng._lib.v2w_plan_destroy(handle)
+
+
 @pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 60.0), ("rb1_768_stress", 42.0)])
 def test_bf16_plan_matches_cpu_emulation(name, min_snr):
     """The device BF16 plan and the numpy interpreter round at the same points; what separates
@@ -192,10 +220,14 @@ def test_full_size_against_autograd_delegate(rb):
             y32 = gen(x, s, n).cpu().numpy()
             gen.precision = "bf16"
             y16 = gen(x, s, n).cpu().numpy()
+            gen.precision = "fp16"
+            yh = gen(x, s, n).cpu().numpy()
         err = np.abs(y32 - ref).max()
         snr = fixtures.snr_db(ref, y16)
-        print(f"rb={rb!r} B={B} T={T}: fp32 max-abs {err:.2e}, bf16 SNR {snr:.1f} dB")
+        snr_h = fixtures.snr_db(ref, yh)
+        print(f"rb={rb!r} B={B} T={T}: fp32 max-abs {err:.2e}, bf16 SNR {snr:.1f} dB, fp16 SNR {snr_h:.1f} dB")
         assert err <= FP32_MAX_ABS
+        assert snr_h >= BF16_MIN_SNR_DB
         if rb == 1:
             assert snr >= BF16_MIN_SNR_DB
 

@@ -26,6 +26,31 @@ static inline uint16_t bf16_bits(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// round-to-nearest-even fp32 -> IEEE fp16 bit pattern (overflow saturates to +-65504)
+static inline uint16_t fp16_bits(float f) {
+  uint32_t u;
+  __builtin_memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);          // NaN
+  if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);         // >= 65520 -> max finite
+  if (u < 0x38800000u) {                                           // subnormal or zero in fp16
+    if (u < 0x33000000u) return (uint16_t)sign;                    // < 2^-25 -> 0
+    const uint32_t shift = 126u - (u >> 23);                       // 14 .. 24
+    const uint32_t mant = (u & 0x7fffffu) | 0x800000u;
+    uint32_t h = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((u - 0x38000000u) >> 13);
+  const uint32_t rem = u & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
+
+constexpr uint32_t kPackedMagic = 0x50573256u;  // "V2WP"
+
 constexpr int kZ = 128;          // z_channels of ConditionalBatchNorm1d (modules.py:9)
 constexpr float kBnEps = 1e-5f;  // nn.BatchNorm1d default eps (modules.py:14)
 constexpr float kLreluSlope = 0.1f;      // LRELU_SLOPE (models.py:10)

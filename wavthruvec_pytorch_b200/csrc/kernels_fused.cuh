@@ -60,6 +60,7 @@ struct Params {
   int nseg, nbranch, ntaps_total;
   int stages_w, stage_w_bytes;
   int w_region_bytes;           // bytes of the weight region (ring or resident block)
+  int fp16;                     // 16-bit operand format: 0 = bf16, 1 = fp16
   Segment seg[kMaxSeg];
   int shift[kMaxTaps];          // operand row (sub-tile 0) of each tap inside its A tile
   const float* x0;              // fp32 [B, L, C]
@@ -184,7 +185,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ====================================== MMA issuer ======================================
     Ring rw;
     uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
-    const uint32_t idesc = make_idesc_bf16(kMTile, C);
+    const uint32_t idesc = make_idesc_bf16(kMTile, C, p.fp16);
     const uint32_t dhi = smem_desc_hi<C>();
     if (kResident) mbar_wait(w_all, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
@@ -313,7 +314,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                h[e] = pack_bf16x2(lrelu(v[2 * e], p.mid_slope), lrelu(v[2 * e + 1], p.mid_slope));
+                h[e] = pack_half2(lrelu(v[2 * e], p.mid_slope), lrelu(v[2 * e + 1], p.mid_slope),
+                                  p.fp16);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) h[e] = 0u;   // conv2's zero padding outside [0, L)
@@ -373,7 +375,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t h[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
+                h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
+                                  p.fp16);
               uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + cc);
               op[0] = make_uint4(h[0], h[1], h[2], h[3]);
               op[1] = make_uint4(h[4], h[5], h[6], h[7]);

@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -175,6 +176,11 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const Params p) 
 //   -> [B, T, C] channels-last, fp32 or bf16.  32x32 tiles through shared memory so that both
 // the global read (along T) and the global write (along C) are coalesced.
 // ---------------------------------------------------------------------------------------------
+template <typename TOut> __device__ __forceinline__ TOut cvt_out(float v) { return static_cast<TOut>(v); }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+
 template <typename TOut>
 __global__ void __launch_bounds__(256) transpose_in_kernel(const float* __restrict__ x,
                                                            TOut* __restrict__ y, int C, int T) {
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int t = t0 + ty + i, c = c0 + tx;
-    if (t < T && c < C) yb[static_cast<size_t>(t) * C + c] = static_cast<TOut>(tile[tx][ty + i]);
+    if (t < T && c < C) yb[static_cast<size_t>(t) * C + c] = cvt_out<TOut>(tile[tx][ty + i]);
   }
 }
 

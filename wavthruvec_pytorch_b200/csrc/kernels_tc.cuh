@@ -33,6 +33,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,6 +57,7 @@ struct Params {
   int stages_a, stages_w;
   int stage_a_bytes, stage_w_bytes;
   int acc_cols;         // TMEM columns per accumulator (per sub-tile)
+  int fp16;             // 16-bit operand format: 0 = bf16, 1 = fp16
   // 32-bit entries on purpose: see the note at fused::Segment (ptxas merges 16-bit loads of
   // dynamically indexed parameter arrays incorrectly at some alignments).
   int num_taps[V2W_MAX_TILES];
@@ -207,10 +209,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t hi, uint32_t saddr) {
   return (static_cast<uint64_t>(hi) << 32) | ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
 }
 
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, dense
-// (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
-__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// kind::f16 instruction descriptor: D = F32, A = B = BF16 (format 1) or F16 (format 0), both
+// K-major, dense (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int fp16 = 0) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -219,6 +222,16 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// two fp32 -> one packed pair of 16-bit operands (bf16, or fp16 clamped to the finite range)
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi, int fp16) {
+  if (fp16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
 }
 
 struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
@@ -325,7 +338,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ====================================== MMA issuer ======================================
     Ring ra, rw;
     uint32_t tile_iter = 0;
-    const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile);
+    const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile, p.fp16);
     const uint32_t dhi = smem_desc_hi<KC>();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int b = tile / tiles_per_b;
@@ -461,7 +474,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               uint32_t h[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                h[e] = pack_bf16x2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope));
+                h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
+                                  p.fp16);
               uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
               op[0] = make_uint4(h[0], h[1], h[2], h[3]);
               op[1] = make_uint4(h[4], h[5], h[6], h[7]);

@@ -298,8 +298,8 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
   m->num_convs = rb_conv_base + U * c->num_kernels * convs_per_block + 1;
   add_conv1d(m, V2W_ROLE_CONV_POST, -1, m->num_convs - 1, ch, 1, 7, 1);
 
-  // ---- packed layout
-  int64_t off = 0;
+  // ---- packed layout (after the format header)
+  int64_t off = V2W_PACKED_HEADER_BYTES;
   int64_t flops = 0;
   for (auto& L : m->layers) {
     if (L.role != V2W_ROLE_CONV_POST) {
@@ -383,10 +383,21 @@ int64_t v2w_model_packed_bytes(const v2w_model* m) { return m ? m->packed_bytes 
 int64_t v2w_model_flops_per_frame(const v2w_model* m) { return m ? m->flops_per_frame : 0; }
 
 int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_host) {
+  return v2w_model_pack_half(m, P, packed_host, V2W_HALF_BF16);
+}
+
+int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packed_host,
+                            int32_t half_format) {
   if (!m || !P || !packed_host) {
     set_error("v2w_model_pack: null argument");
     return V2W_ERR_INVALID;
   }
+  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16) {
+    set_error("v2w_model_pack: unknown 16-bit format %d", half_format);
+    return V2W_ERR_INVALID;
+  }
+  const bool f16 = half_format == V2W_HALF_FP16;
+  auto half_bits = [f16](float w) { return f16 ? fp16_bits(w) : bf16_bits(w); };
   if (P->num_convs != m->num_convs || P->num_stages != (int)m->cond.size()) {
     set_error("v2w_model_pack: expected %d convs / %d stages, got %d / %d", m->num_convs,
               (int)m->cond.size(), P->num_convs, P->num_stages);
@@ -394,6 +405,10 @@ int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_hos
   }
   uint8_t* base = static_cast<uint8_t*>(packed_host);
   std::memset(base, 0, (size_t)m->packed_bytes);
+  {
+    uint32_t hdr[3] = {kPackedMagic, V2W_ABI_VERSION, (uint32_t)half_format};
+    std::memcpy(base, hdr, sizeof(hdr));
+  }
   std::vector<float> scale;
   for (const auto& L : m->layers) {
     const v2w_conv_params& cp = P->convs[L.conv_index];
@@ -431,7 +446,7 @@ int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_hos
             float w;
             if (transposed) w = cp.v[((size_t)ci * L.cout + co) * K + kk] * scale[ci];
             else w = cp.v[((size_t)co * L.cin + ci) * K + kk] * scale[co];
-            if (w16) w16[((size_t)j * L.n_total + n) * L.cin + ci] = bf16_bits(w);
+            if (w16) w16[((size_t)j * L.n_total + n) * L.cin + ci] = half_bits(w);
             w32[((size_t)j * L.cin + ci) * L.n_total + n] = w;
           }
         }
@@ -498,7 +513,7 @@ int32_t v2w_model_pack(const v2w_model* m, const v2w_params* P, void* packed_hos
             for (int n = 0; n < C; ++n) acc[(size_t)n * C + ci] += w32[(size_t)ci * C + n];
         }
         uint16_t* dst = wf + (size_t)tap * C * C;
-        for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = bf16_bits(acc[e]);
+        for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = half_bits(acc[e]);
       }
     }
   }

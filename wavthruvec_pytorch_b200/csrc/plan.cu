@@ -210,6 +210,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     }
   }
   p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
+  p.fp16 = (a.tc_flags & 0x100) ? 1 : 0;   // V2W_TC_FLAG_FP16
   p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
@@ -259,7 +260,8 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.rows * a.cin * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.in_act),
+    CUresult r = enc(&L->tm_a, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     const_cast<void*>(a.in_act),
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -275,7 +277,8 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     cuuint64_t strides[1] = {(cuuint64_t)a.cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&L->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.w16), dims,
+    CUresult r = enc(&L->tm_w, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(a.w16), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -359,7 +362,7 @@ static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
 // fused MRF stage launcher
 // ---------------------------------------------------------------------------------------------
 static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_op_desc& d,
-                         const uint8_t* packed, uint8_t* ws, FusedLaunch* L) {
+                         const uint8_t* packed, uint8_t* ws, bool fp16, FusedLaunch* L) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
@@ -409,6 +412,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
   L->channels = C;
   p.w_region_bytes = w_bytes_total;
+  p.fp16 = fp16 ? 1 : 0;
   L->smem = 2 * a0_bytes + 2 * a1_bytes + w_bytes_total + 512 + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
 
@@ -423,7 +427,8 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)d.rows * C * 2};
     cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)fused::kBoxRows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ws + d.in_act, dims, strides,
+    CUresult r = enc(&L->tm_a, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     ws + d.in_act, dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -436,7 +441,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
     cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)C};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&L->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+    CUresult r = enc(&L->tm_w, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      const_cast<uint8_t*>(packed + F.w_off), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -556,7 +561,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     set_error("v2w_plan_create: batch=%d frames=%d out of range", batch, frames);
     return V2W_ERR_INVALID;
   }
-  if (precision != V2W_PREC_FP32 && precision != V2W_PREC_BF16) {
+  if (precision != V2W_PREC_FP32 && precision != V2W_PREC_BF16 && precision != V2W_PREC_FP16) {
     set_error("v2w_plan_create: unknown precision %d", precision);
     return V2W_ERR_INVALID;
   }
@@ -573,7 +578,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   P->batch = batch;
   P->frames = frames;
   P->precision = precision;
-  const bool bf = precision == V2W_PREC_BF16;
+  const bool bf = precision != V2W_PREC_FP32;   // 16-bit tensor-core operands (bf16 or fp16)
   const v2w_config& c = m->cfg;
   const int U = c.num_upsamples;
   const int B = batch, T = frames;
@@ -646,7 +651,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
                   int64_t accum, float out_scale, const Act& out) {
     const v2w_layer_desc& L = m->layers[layer];
     Op o = blank(V2W_OP_TAPGEMM);
-    o.d.engine = (bf && !force_simt) ? V2W_ENGINE_TC : V2W_ENGINE_SIMT;
+    o.d.engine = (bf && (!force_simt || precision == V2W_PREC_FP16)) ? V2W_ENGINE_TC : V2W_ENGINE_SIMT;
     o.d.layer = layer;
     o.d.batch = B;
     o.d.rows = rows;
@@ -774,8 +779,12 @@ int32_t v2w_plan_set_engine(v2w_plan* p, int32_t i, int32_t engine) {
     set_error("v2w_plan_set_engine: op %d is not a tap-GEMM", i);
     return V2W_ERR_INVALID;
   }
-  if (engine == V2W_ENGINE_TC && p->precision != V2W_PREC_BF16) {
-    set_error("v2w_plan_set_engine: the tensor-core engine needs a BF16 plan");
+  if (engine == V2W_ENGINE_TC && p->precision == V2W_PREC_FP32) {
+    set_error("v2w_plan_set_engine: the tensor-core engine needs a BF16/FP16 plan");
+    return V2W_ERR_INVALID;
+  }
+  if (engine == V2W_ENGINE_SIMT && p->precision == V2W_PREC_FP16) {
+    set_error("v2w_plan_set_engine: the FFMA engine reads fp32 or bf16 activations, not fp16");
     return V2W_ERR_INVALID;
   }
   o.d.engine = engine;
@@ -798,10 +807,25 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   p->packed = static_cast<const uint8_t*>(packed_dev);
   p->ws = static_cast<uint8_t*>(workspace_dev);
   const v2w_model* m = p->model;
-  const int tc_flags = std::getenv("V2W_TC_FLAGS") ? std::atoi(std::getenv("V2W_TC_FLAGS")) : 0;
+  {
+    uint32_t hdr[3] = {0, 0, 0};
+    V2W_CUDA(cudaMemcpy(hdr, packed_dev, sizeof(hdr), cudaMemcpyDeviceToHost));
+    if (hdr[0] != kPackedMagic || hdr[1] != V2W_ABI_VERSION) {
+      set_error("v2w_plan_bind: packed_dev is not a v2w_model_pack buffer of this ABI");
+      return V2W_ERR_INVALID;
+    }
+    const int want = p->precision == V2W_PREC_FP16 ? V2W_HALF_FP16 : V2W_HALF_BF16;
+    if (p->precision != V2W_PREC_FP32 && (int)hdr[2] != want) {
+      set_error("v2w_plan_bind: packed weights hold %s operands but the plan computes in %s",
+                hdr[2] == V2W_HALF_FP16 ? "fp16" : "bf16", want == V2W_HALF_FP16 ? "fp16" : "bf16");
+      return V2W_ERR_INVALID;
+    }
+  }
+  const int tc_flags = p->precision == V2W_PREC_FP16 ? 0x100 : 0;
   for (Op& o : p->ops) {
     if (o.d.kind == V2W_OP_MRF_FUSED) {
-      rc = prepare_fused(m, m->fused[o.d.stage], o.d, p->packed, p->ws, &o.fl);
+      rc = prepare_fused(m, m->fused[o.d.stage], o.d, p->packed, p->ws,
+                         p->precision == V2W_PREC_FP16, &o.fl);
       if (rc) return rc;
       continue;
     }
@@ -875,7 +899,7 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
     return V2W_ERR_INVALID;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool bf = p->precision == V2W_PREC_BF16;
+  const bool bf = p->precision != V2W_PREC_FP32;
   int launches = 0;
   size_t op_index = 0;
   for (Op& o : p->ops) {
@@ -884,7 +908,10 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
     switch (o.d.kind) {
       case V2W_OP_TRANSPOSE_IN: {
         dim3 grid((p->frames + 31) / 32, (c.num_wv_feat + 31) / 32, p->batch);
-        if (bf)
+        if (p->precision == V2W_PREC_FP16)
+          simt::transpose_in_kernel<__half><<<grid, 256, 0, st>>>(
+              x_dev, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames);
+        else if (bf)
           simt::transpose_in_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
               x_dev, reinterpret_cast<__nv_bfloat16*>(p->ws + p->xt), c.num_wv_feat, p->frames);
         else

@@ -27,7 +27,7 @@ class NativeEngine:
         handle = C.c_void_p()
         native.check(self._lib.v2w_model_create(C.byref(self._cfg), C.byref(handle)))
         self._model = handle
-        self._packed: Dict[torch.device, torch.Tensor] = {}
+        self._packed: Dict[Tuple, torch.Tensor] = {}     # (device, 16-bit format) -> packed weights
         self._packed_sig = None
         self._plans: Dict[Tuple, Tuple[C.c_void_p, torch.Tensor]] = {}
         self._convs = None        # cached module list / tensor list for the per-call change check
@@ -87,8 +87,8 @@ class NativeEngine:
     def _signature(self, ts):
         return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
 
-    def pack_host(self) -> torch.Tensor:
-        """Fold + pack on the host (v2w_model_pack); returns a uint8 CPU tensor."""
+    def pack_host(self, half_format: int = native.HALF_BF16) -> torch.Tensor:
+        """Fold + pack on the host (v2w_model_pack_half); returns a uint8 CPU tensor."""
         ts = self._state_tensors()
         host = [None if t is None else t.detach().to("cpu", torch.float32).contiguous() for t in ts]
         nconv = self._lib.v2w_model_num_convs(self._model)
@@ -110,7 +110,8 @@ class NativeEngine:
         params = native.Params(nconv, convs, nstage, cond)
         nbytes = int(self._lib.v2w_model_packed_bytes(self._model))
         packed = torch.empty(nbytes, dtype=torch.uint8)
-        native.check(self._lib.v2w_model_pack(self._model, C.byref(params), packed.data_ptr()))
+        native.check(self._lib.v2w_model_pack_half(self._model, C.byref(params), packed.data_ptr(),
+                                                   half_format))
         del host
         return packed
 
@@ -132,11 +133,11 @@ class NativeEngine:
             self._drop_plans()   # plans hold pointers into the packed buffer
             self._packed_sig = sig
 
-    def _packed_on(self, device: torch.device) -> torch.Tensor:
-        buf = self._packed.get(device)
+    def _packed_on(self, device: torch.device, half_format: int) -> torch.Tensor:
+        buf = self._packed.get((device, half_format))
         if buf is None:
-            buf = self.pack_host().to(device)
-            self._packed[device] = buf
+            buf = self.pack_host(half_format).to(device)
+            self._packed[(device, half_format)] = buf
         return buf
 
     # ------------------------------------------------------------------------------------------
@@ -147,8 +148,8 @@ class NativeEngine:
         hit = self._plans.get(key)
         if hit is not None:
             return hit
-        packed = self._packed_on(device)
-        prec = native.PREC_BF16 if precision == "bf16" else native.PREC_FP32
+        prec = native.PRECISIONS[precision]
+        packed = self._packed_on(device, native.HALF_FP16 if precision == "fp16" else native.HALF_BF16)
         handle = C.c_void_p()
         native.check(self._lib.v2w_plan_create(self._model, batch, frames, prec, C.byref(handle)))
         try:

@@ -133,14 +133,20 @@ class Generator(nn.Module):
     # ------------------------------------------------------------------------------------------
     @property
     def precision(self) -> str:
-        """'bf16' (tcgen05, default) or 'fp32' (FFMA); also settable via $V2W_PRECISION."""
+        """Arithmetic of the native path: 'bf16' / 'fp16' (tcgen05 with 16-bit operands, fp32
+        accumulation and fp32 residual stream) or 'fp32' (FFMA).  Default 'auto' (also via
+        $V2W_PRECISION): bf16 for ResBlock2; fp16 for ResBlock1, whose 97-conv chain does not reach
+        the 45 dB waveform-SNR bar with bf16 operands."""
         import os
-        return (self._precision or os.environ.get("V2W_PRECISION", "bf16")).lower()
+        value = (self._precision or os.environ.get("V2W_PRECISION", "auto")).lower()
+        if value == "auto":
+            value = "fp16" if self.h.resblock == '1' else "bf16"
+        return value
 
     @precision.setter
     def precision(self, value: str) -> None:
-        if value not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if value not in ("auto", "bf16", "fp16", "fp32"):
+            raise ValueError("precision must be 'auto', 'bf16', 'fp16' or 'fp32'")
         self._precision = value
 
     def engine(self):

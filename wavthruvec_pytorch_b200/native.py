@@ -19,6 +19,11 @@ MAX_TILES = 16
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_FP16 = 2
+HALF_BF16, HALF_FP16 = 0, 1
+PACKED_HEADER_BYTES = 1024
+TC_FLAG_FP16 = 0x100
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
 OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED = 0, 1, 2, 3, 4
@@ -154,6 +159,7 @@ _SIGNATURES = [
     ("v2w_model_num_convs", C.c_int32, [C.c_void_p]),
     ("v2w_model_packed_bytes", C.c_int64, [C.c_void_p]),
     ("v2w_model_pack", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
+    ("v2w_model_pack_half", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32]),
     ("v2w_model_flops_per_frame", C.c_int64, [C.c_void_p]),
     ("v2w_plan_create", C.c_int32,
      [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
