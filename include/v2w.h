@@ -175,6 +175,7 @@ typedef struct v2w_fused_desc {
   int32_t num_segments, num_taps;
   int16_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];
   int16_t seg_ntaps[V2W_FUSED_MAX_SEG], seg_first[V2W_FUSED_MAX_SEG];
+  int16_t seg_flags[V2W_FUSED_MAX_SEG];  /* bit0: last reader of the input tile, bit1: last segment */
   int16_t shift[V2W_FUSED_MAX_TAPS];   /* operand row of the tap inside its input tile */
   int16_t offset[V2W_FUSED_MAX_TAPS];  /* time offset of the tap (rows) */
   int64_t w_off;               /* packed: bf16 [num_taps][channels][channels] (n, c), issue order */
@@ -186,7 +187,7 @@ typedef struct v2w_fused_desc {
 #define V2W_OP_COND_AFFINE 1   /* fcs + spectral-norm Linear + BN fold -> scale/shift per (b, stage, c) */
 #define V2W_OP_TAPGEMM 2
 #define V2W_OP_CONV_POST 3     /* lrelu(0.01) -> Conv1d(16->1,k7) -> tanh */
-#define V2W_OP_MRF_FUSED 4     /* one whole multi-receptive-field stage (ResBlock2, C <= 64) */
+#define V2W_OP_MRF_FUSED 4     /* one whole multi-receptive-field stage (ResBlock2, C <= 128) */
 
 #define V2W_ENGINE_SIMT 0      /* FFMA tap-GEMM */
 #define V2W_ENGINE_TC 1        /* tcgen05 / TMEM / TMA tap-GEMM */

@@ -174,7 +174,7 @@ def test_fused_stage_kernel_matches_separate_tapgemms(monkeypatch, name):
     gen = dropin_in_state(g, cache=False).to("cuda:0")
     fused = _native(gen, g, "bf16")
     ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
-    assert sum(op.kind == native.OP_MRF_FUSED for op in ops) == 3
+    assert sum(op.kind == native.OP_MRF_FUSED for op in ops) == 4
     monkeypatch.setenv("V2W_NO_FUSE", "1")
     gen.invalidate()
     plain = _native(gen, g, "bf16")

@@ -224,13 +224,20 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     monkeypatch.delenv("V2W_NO_FUSE")
     fplan = plan_interp.HostPlan(eng, 16, 200, "bf16")
     fused = [op for op in fplan.ops if op.kind == native.OP_MRF_FUSED]
-    assert [op.stage for op in fused] == [2, 3, 4] and [op.n_tile for op in fused] == [64, 32, 16]
-    assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 18
+    assert [op.stage for op in fused] == [1, 2, 3, 4]
+    assert [op.n_tile for op in fused] == [128, 64, 32, 16]
+    assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 12
     assert sum(op.flops for op in fplan.ops) == total
     F = native.FusedDesc()
     native.check(eng._lib.v2w_model_get_fused(eng._model, 2, C.byref(F)))
     assert (F.ok, F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments) == (1, 15, 5, 226, 5, 53, 7)
     assert list(F.seg_type[:7]) == [0, 0, 1, 2, 0, 2, 2] and list(F.seg_ntaps[:7]) == [3, 7, 11, 3, 11, 7, 11]
+    assert list(F.seg_flags[:7]) == [0, 0, 0, 0, 1, 0, 2]
+    # C = 128 is single buffered: conv_sum right behind conv1_0, then conv2_j / conv1_{j+1}
+    native.check(eng._lib.v2w_model_get_fused(eng._model, 1, C.byref(F)))
+    assert F.ok and F.channels == 128
+    assert list(F.seg_type[:7]) == [0, 1, 2, 0, 2, 0, 2] and list(F.seg_branch[:7]) == [0, -1, 0, 1, 1, 2, 2]
+    assert list(F.seg_flags[:7]) == [0, 0, 0, 0, 0, 1, 2]
     # the three transposed convs with 4 or 2 phases split into phase groups with 2 taps each
     for op in gemms:
         L = plan.layers[op.layer]

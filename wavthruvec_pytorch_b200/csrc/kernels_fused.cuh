@@ -1,15 +1,15 @@
-// Fused multi-receptive-field stage for C <= 64 (ResBlock2):  one kernel computes
+// Fused multi-receptive-field stage for C <= 128 (ResBlock2):  one kernel computes
 //
 //     x_out = (1/nk) * sum_j  ResBlock2_j(x)            (vec2wav/models.py:65-70,135-141)
 //
 // for a 226-row tile without the intermediates ever leaving the SM.  Unfused, one stage moves
-// ~74 B per output element through HBM (six convs x [bf16 operand + fp32 residual in, fp32 + bf16
-// out]); fused it is ~10 B (bf16 A0 + fp32 X0 in, bf16 or fp32 out), which turns the C <= 64 stages
-// from HBM-bound into MMA-bound.
+// ~74 B per output element through HBM (six convs x [16-bit operand + fp32 residual in, fp32 +
+// 16-bit out]); fused it is ~10 B (A0 + fp32 X0 in, 16-bit or fp32 out), which turns these stages
+// from HBM-/L1-bound into MMA-bound.
 //
-// Algebra (per branch j: conv1_j dilation d0, conv2_j dilation d1_j; A0 = bf16(lrelu(X0))):
+// Algebra (per branch j: conv1_j dilation d0, conv2_j dilation d1_j; A0 = half(lrelu(X0))):
 //     Y1_j  = conv1_j(A0) + b1_j + X0                       (fp32)
-//     A1_j  = bf16(lrelu(Y1_j)), zero outside [0, L)        (stays in shared memory)
+//     A1_j  = half(lrelu(Y1_j)), zero outside [0, L)        (stays in shared memory)
 //     out_j = conv2_j(A1_j) + b2_j + Y1_j
 //     sum_j out_j = [ sum_j conv2_j(A1_j) + conv_sum(A0) ] + sum_j (b1_j + b2_j) + nk * X0
 // where conv_sum is ONE convolution whose taps are the per-offset sums of the conv1_j weights
@@ -20,16 +20,21 @@
 // of halo per side (hc = max_j d1_j (k_j - 1)/2 = 15, rc = 226).  conv1_j is evaluated on the whole
 // window (its output feeds conv2's halo), conv_sum and conv2_j on the 256 rows starting at q0c (the
 // last 2*hc of them are discarded).  A0 tile = window + h1 rows per side (h1 = d0 (kmax - 1)/2).
+// Channels are processed in K-chunks of 64 (one 128-byte swizzle span); C = 128 has two.
 //
-// Roles: warp 0 TMA producer (A0 tile, double buffered across tiles; weight taps), warp 1 MMA
-// issuer, warps 4-11 epilogue (thread = window row).  T1 and A1 are double buffered across branches
-// so that conv1_{j+1} overlaps the epilogue of branch j and conv2_j overlaps the epilogue of branch
-// j+1; T2 is double buffered across tiles so that the final epilogue overlaps the next tile.
+// Roles: warp 0 TMA producer (A0 tile, weight taps), warp 1 MMA issuer (one elected lane issues a
+// whole segment), warps 4-11 epilogue (thread = window row).
 //
-// Weights: for C <= 32 all taps of the stage (53 x C x C bf16 = 27 / 106 KB) are loaded ONCE per
-// CTA and stay resident; the MMA loop then has no per-tap barrier at all.  The first version
-// streamed every tap through an 8-deep ring and measured ~430 clk per tap at C = 16 (ring round
-// trip = TMA latency / 8) against ~16 clk of MMA work.  C = 64 (424 KB of taps) still streams.
+// Buffering (kSlots): for C <= 64 T1/A1 are double buffered across branches (conv1_{j+1} overlaps the
+// epilogue of branch j, conv2_j overlaps the epilogue of branch j+1) and A0/T2 across tiles.  C = 128
+// fills TMEM (T1 256 + T2 256 columns) and shared memory (A0 80 KB + A1 64 KB + weight ring 64 KB),
+// so everything is single buffered there and the segment order puts conv_sum behind conv1_0 to cover
+// the first epilogue.  The segment program comes from the host (model.cpp plan_fused_stage).
+//
+// Weights: for C <= 32 all taps of the stage (53 x C x C x 2 B = 27 / 106 KB) are loaded ONCE per
+// CTA and stay resident; the MMA loop then has no per-tap barrier at all.  (The first version
+// streamed every tap through an 8-deep ring and measured ~430 clk per tap at C = 16 against ~16 clk
+// of MMA work.)  C >= 64 streams (tap, K-chunk) blocks through a ring.
 #pragma once
 
 #include "kernels_tc.cuh"
@@ -44,19 +49,21 @@ constexpr int kBoxRows = 64;
 constexpr int kMaxSeg = 12;
 constexpr int kMaxTaps = 80;
 constexpr int kSegConv1 = 0, kSegSum = 1, kSegConv2 = 2;
+constexpr int kSegFlagReleaseA0 = 1;   // last reader of the A0 tile
+constexpr int kSegFlagLast = 2;        // last segment of the tile
 
 // 32-bit fields on purpose: with four packed int16 ptxas (12.9) merged the constant-bank loads
 // of a dynamically indexed p.seg[s] and then read `first` from an unrelated register whenever
 // the array sat at a 4-byte (not 8-byte) aligned parameter offset -- wrong taps, no diagnostics
 // (profiles/r01_ptxas_param_miscompile.md).
 struct Segment {
-  int type, branch, ntaps, first;
+  int type, branch, ntaps, first, flags;
 };
 
 struct Params {
   int batch, rows, tiles_per_b;
   int rc, hc, h1;               // central rows per tile, conv2 halo, conv1 halo
-  int a0_boxes;                 // TMA boxes (64 rows) per A0 tile
+  int a0_boxes;                 // TMA boxes (64 rows) per A0 tile and K-chunk
   int nseg, nbranch, ntaps_total;
   int stages_w, stage_w_bytes;
   int w_region_bytes;           // bytes of the weight region (ring or resident block)
@@ -74,6 +81,24 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
+template <int C>
+struct Cfg {
+  static constexpr int kKC = C < 64 ? C : 64;            // channels per K-chunk
+  static constexpr int kChunks = C / kKC;
+  static constexpr int kRowBytes = kKC * 2;
+  static constexpr int kKSteps = kKC / 16;
+  static constexpr int kAccCols = C < 32 ? 32 : C;       // TMEM columns per 128-row accumulator
+  static constexpr bool kResident = C <= 32;             // weights stay in shared memory
+  static constexpr int kSlots = C <= 64 ? 2 : 1;         // buffering depth of A0 / T1 / A1 / T2
+  static constexpr bool kCacheX0 = C <= 32;              // keep the thread's X0 row in registers
+  static constexpr uint32_t kT1Cols = 2 * kAccCols;      // two sub-tiles
+  static constexpr uint32_t kTmemCols = 2 * kSlots * kT1Cols;   // 512 / 512 / 256 / 256
+  static constexpr uint32_t kA1ChunkBytes = kWin * kRowBytes;
+  static constexpr uint32_t kA1Bytes = kChunks * kA1ChunkBytes;
+  static constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
+  static constexpr uint32_t kWBytes = C * kRowBytes;     // one (tap, K-chunk) block
+};
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
@@ -85,25 +110,20 @@ template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ Params p) {
-  constexpr int kRowBytes = C * 2;
-  constexpr int kKSteps = C / 16;
-  constexpr int kAccCols = C < 32 ? 32 : C;
-  constexpr bool kResident = C <= 32;                    // weights stay in shared memory
-  constexpr uint32_t kT1Cols = 2 * kAccCols;             // two sub-tiles
-  constexpr uint32_t kTmemCols = 8 * kAccCols;           // 2 x T1 + 2 x T2 (512 / 256 / 256)
-  constexpr uint32_t kA1Bytes = kWin * kRowBytes;
-  constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
-  constexpr uint32_t kWBytes = C * kRowBytes;
+  using K = Cfg<C>;
+  constexpr int kRowBytes = K::kRowBytes;
+  constexpr int kSlots = K::kSlots;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a0_bytes = p.a0_boxes * kBoxBytes;
+  const uint32_t a0_chunk_bytes = p.a0_boxes * K::kBoxBytes;
+  const uint32_t a0_bytes = K::kChunks * a0_chunk_bytes;
   const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_a1 = smem_a0 + 2 * a0_bytes;
-  const uint32_t smem_w = smem_a1 + 2 * kA1Bytes;
+  const uint32_t smem_a1 = smem_a0 + kSlots * a0_bytes;
+  const uint32_t smem_w = smem_a1 + kSlots * K::kA1Bytes;
   const uint32_t bars = smem_w + p.w_region_bytes;
   // barriers: a0_full[2] a0_empty[2] w_full[8] w_empty[8] t1_full[2] t1_empty[2] a1_full[2]
-  //           a1_empty[2] t2_full t2_empty
+  //           a1_empty[2] t2_full[2] t2_empty[2] w_all
   const uint32_t a0_full = bars, a0_empty = bars + 16, w_full = bars + 32, w_empty = bars + 96;
   const uint32_t t1_full = bars + 160, t1_empty = bars + 176, a1_full = bars + 192;
   const uint32_t a1_empty = bars + 208, t2_full = bars + 224, t2_empty = bars + 240;
@@ -123,36 +143,34 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(t1_empty + 8 * i, 256);
       mbar_init(a1_full + 8 * i, 256);
       mbar_init(a1_empty + 8 * i, 1);
+      mbar_init(t2_full + 8 * i, 1);
+      mbar_init(t2_empty + 8 * i, 256);
     }
     for (int i = 0; i < kMaxStagesW; ++i) {
       mbar_init(w_full + 8 * i, 1);
       mbar_init(w_empty + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(t2_full + 8 * i, 1);
-      mbar_init(t2_empty + 8 * i, 256);
-    }
     mbar_init(w_all, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_slot, K::kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-  const uint32_t tmem_t2 = tmem_base + 2 * kT1Cols;   // T2[slot] = tmem_t2 + slot * kT1Cols
+  const uint32_t tmem_t2 = tmem_base + kSlots * K::kT1Cols;   // T2[slot] = tmem_t2 + slot * kT1Cols
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     Ring rw;
     uint32_t tile_iter = 0;
-    if (kResident) {
+    if (K::kResident) {
       if (elect_one()) {
-        mbar_expect_tx(w_all, p.ntaps_total * kWBytes);
+        mbar_expect_tx(w_all, p.ntaps_total * K::kWBytes);
         for (int t = 0; t < p.ntaps_total; ++t)
-          tma_load_2d(smem_w + t * kWBytes, &tmW, 0, t * C, w_all);
+          tma_load_2d(smem_w + t * K::kWBytes, &tmW, 0, t * C, w_all);
       }
       __syncwarp();
     }
@@ -160,25 +178,30 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
       const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the A0 tile
-      const uint32_t buf = tile_iter & 1u, ph = (tile_iter >> 1) & 1u;
+      const uint32_t buf = tile_iter % kSlots, ph = (tile_iter / kSlots) & 1u;
       mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
       if (elect_one()) {
         const uint32_t bar = a0_full + 8 * buf;
-        mbar_expect_tx(bar, p.a0_boxes * kBoxBytes);
-        for (int bx = 0; bx < p.a0_boxes; ++bx)
-          tma_load_3d(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b,
-                      bar);
+        mbar_expect_tx(bar, K::kChunks * p.a0_boxes * K::kBoxBytes);
+        for (int c = 0; c < K::kChunks; ++c)
+          for (int bx = 0; bx < p.a0_boxes; ++bx)
+            tma_load_3d(smem_a0 + buf * a0_bytes + c * a0_chunk_bytes + bx * K::kBoxBytes, &tmA,
+                        c * K::kKC, row0 + bx * kBoxRows, b, bar);
       }
       __syncwarp();
-      for (int t = 0; !kResident && t < p.ntaps_total; ++t) {
-        mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
-        if (elect_one()) {
-          const uint32_t bar = w_full + 8 * rw.s;
-          mbar_expect_tx(bar, kWBytes);
-          tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, 0, t * C, bar);
+      if (!K::kResident) {
+        for (int t = 0; t < p.ntaps_total; ++t) {
+          for (int c = 0; c < K::kChunks; ++c) {
+            mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t bar = w_full + 8 * rw.s;
+              mbar_expect_tx(bar, K::kWBytes);
+              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * K::kKC, t * C, bar);
+            }
+            __syncwarp();
+            rw.advance(p.stages_w);
+          }
         }
-        __syncwarp();
-        rw.advance(p.stages_w);
       }
     }
   } else if (warp == 1) {
@@ -186,74 +209,76 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     Ring rw;
     uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
     const uint32_t idesc = make_idesc_bf16(kMTile, C, p.fp16);
-    const uint32_t dhi = smem_desc_hi<C>();
-    if (kResident) mbar_wait(w_all, 0);
+    const uint32_t dhi = smem_desc_hi<K::kKC>();
+    if (K::kResident) mbar_wait(w_all, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-      const uint32_t buf = tile_iter & 1u;
-      const uint32_t t2s = tile_iter & 1u, t2ph = (tile_iter >> 1) & 1u;
-      mbar_wait(a0_full + 8 * buf, (tile_iter >> 1) & 1u);
+      const uint32_t buf = tile_iter % kSlots, tph = (tile_iter / kSlots) & 1u;
+      mbar_wait(a0_full + 8 * buf, tph);
       const uint32_t a0 = smem_a0 + buf * a0_bytes;
       for (int s = 0; s < p.nseg; ++s) {
         const Segment sg = p.seg[s];
-        uint32_t d_tmem, a_tile, slot = 0;
+        uint32_t d_tmem, a_tile, a_chunk_bytes, slot = 0;
         if (sg.type == kSegConv1) {
-          slot = n1 & 1u;
-          mbar_wait(t1_empty + 8 * slot, ((n1 >> 1) & 1u) ^ 1u);
-          d_tmem = tmem_base + slot * kT1Cols;
+          slot = n1 % kSlots;
+          mbar_wait(t1_empty + 8 * slot, ((n1 / kSlots) & 1u) ^ 1u);
+          d_tmem = tmem_base + slot * K::kT1Cols;
           a_tile = a0;
+          a_chunk_bytes = a0_chunk_bytes;
         } else if (sg.type == kSegSum) {
-          mbar_wait(t2_empty + 8 * t2s, t2ph ^ 1u);
-          d_tmem = tmem_t2 + t2s * kT1Cols;
+          mbar_wait(t2_empty + 8 * buf, tph ^ 1u);
+          d_tmem = tmem_t2 + buf * K::kT1Cols;
           a_tile = a0;
+          a_chunk_bytes = a0_chunk_bytes;
         } else {
-          slot = n2 & 1u;
-          mbar_wait(a1_full + 8 * slot, (n2 >> 1) & 1u);
-          d_tmem = tmem_t2 + t2s * kT1Cols;
-          a_tile = smem_a1 + slot * kA1Bytes;
+          slot = n2 % kSlots;
+          mbar_wait(a1_full + 8 * slot, (n2 / kSlots) & 1u);
+          d_tmem = tmem_t2 + buf * K::kT1Cols;
+          a_tile = smem_a1 + slot * K::kA1Bytes;
+          a_chunk_bytes = K::kA1ChunkBytes;
         }
         tcgen05_fence_after();
-        const bool last_seg = s == p.nseg - 1;
         // One elected lane issues the whole segment: per tap only two descriptor words change
         // (A: row shift inside the tile, W: next tap matrix), everything else is loop-invariant.
         if (elect_one()) {
           const uint32_t a_lo = ((a_tile & 0x3FFFFu) >> 4) | (1u << 16);
-          const uint32_t w0 = kResident ? smem_w + sg.first * kWBytes : 0u;
           Ring r = rw;   // the elected lane walks a private copy; all lanes advance `rw` below
           for (int t = 0; t < sg.ntaps; ++t) {
-            uint32_t w_addr;
-            if (kResident) {
-              w_addr = w0 + t * kWBytes;
-            } else {
-              mbar_wait(w_full + 8 * r.s, r.ph);
-              tcgen05_fence_after();
-              w_addr = smem_w + r.s * p.stage_w_bytes;
-            }
             const uint32_t a_t = a_lo + p.shift[sg.first + t] * (kRowBytes >> 4);
-            const uint64_t bd = smem_desc(dhi, w_addr);
-            const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              const uint64_t ad =
-                  (static_cast<uint64_t>(dhi) << 32) | (a_t + m * ((kMTile * kRowBytes) >> 4));
+            for (int c = 0; c < K::kChunks; ++c) {
+              uint32_t w_addr;
+              if (K::kResident) {
+                w_addr = smem_w + (sg.first + t) * K::kWBytes;
+              } else {
+                mbar_wait(w_full + 8 * r.s, r.ph);
+                tcgen05_fence_after();
+                w_addr = smem_w + r.s * p.stage_w_bytes;
+              }
+              const uint64_t bd = smem_desc(dhi, w_addr);
+              const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0) || (c != 0);
 #pragma unroll
-              for (int kk = 0; kk < kKSteps; ++kk)
-                umma_bf16(d_tmem + m * kAccCols, ad + 2 * kk, bd + 2 * kk, idesc, acc0 | (kk != 0));
-            }
-            if (!kResident) {
-              umma_commit(w_empty + 8 * r.s);
-              r.advance(p.stages_w);
+              for (int m = 0; m < 2; ++m) {
+                const uint64_t ad = (static_cast<uint64_t>(dhi) << 32) |
+                                    (a_t + ((c * a_chunk_bytes + m * (kMTile * kRowBytes)) >> 4));
+#pragma unroll
+                for (int kk = 0; kk < K::kKSteps; ++kk)
+                  umma_bf16(d_tmem + m * K::kAccCols, ad + 2 * kk, bd + 2 * kk, idesc,
+                            acc0 | (kk != 0));
+              }
+              if (!K::kResident) {
+                umma_commit(w_empty + 8 * r.s);
+                r.advance(p.stages_w);
+              }
             }
           }
           if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
           if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
-          if (last_seg) {
-            umma_commit(t2_full + 8 * t2s);
-            umma_commit(a0_empty + 8 * buf);
-          }
+          if (sg.flags & kSegFlagReleaseA0) umma_commit(a0_empty + 8 * buf);
+          if (sg.flags & kSegFlagLast) umma_commit(t2_full + 8 * buf);
         }
         __syncwarp();
-        if (!kResident) {
-          for (int t = 0; t < sg.ntaps; ++t) rw.advance(p.stages_w);
+        if (!K::kResident) {
+          for (int t = 0; t < sg.ntaps * K::kChunks; ++t) rw.advance(p.stages_w);
         }
         if (sg.type == kSegConv1) ++n1;
         if (sg.type == kSegConv2) ++n2;
@@ -264,42 +289,56 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int sub = (warp - 4) >> 2;              // which 128-row accumulator
     const int quarter = warp & 3;                 // TMEM lane quarter
     const int i = sub * kMTile + quarter * 32 + lane;   // window row of this thread
-    const uint32_t t_lane = (static_cast<uint32_t>(quarter * 32) << 16) + sub * kAccCols;
-    const uint32_t swz = C == 64 ? (i & 7) : (C == 32 ? ((i >> 1) & 3) : ((i >> 2) & 1));
+    const uint32_t t_lane = (static_cast<uint32_t>(quarter * 32) << 16) + sub * K::kAccCols;
+    const uint32_t swz = K::kKC == 64 ? (i & 7) : (K::kKC == 32 ? ((i >> 1) & 3) : ((i >> 2) & 1));
+    constexpr int kNC = C / 16;                   // 16-column chunks per row
+    constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
       const int q0c = ti * p.rc;
-      // ---- per branch: T1 -> A1 = bf16(lrelu(conv1 + b1 + X0)) in shared memory ----
+      // ---- per branch: T1 -> A1 = half(lrelu(conv1 + b1 + X0)) in shared memory ----
       {
         const int gr = q0c - p.hc + i;
         const bool valid = gr >= 0 && gr < p.rows;
-        const float* xrow = p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        // This row of X0 is the same for every branch -> read it once per tile, before the first
-        // accumulator is even ready, so that no global latency sits between the MMAs.
-        constexpr int kXc = C / 4;
+        const float4* xrow = reinterpret_cast<const float4*>(
+            p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
         float4 xc[kXc];
-        if (valid) {
+        if constexpr (K::kCacheX0) if (valid) {
+          // this row of X0 is the same for every branch: read it once per tile, before the first
+          // accumulator is even ready, so that no global latency sits between the MMAs
 #pragma unroll
-          for (int e = 0; e < kXc; ++e) xc[e] = __ldg(reinterpret_cast<const float4*>(xrow) + e);
+          for (int e = 0; e < kXc; ++e) xc[e] = __ldg(xrow + e);
         }
         for (int j = 0; j < p.nbranch; ++j, ++e1) {
-          const uint32_t slot = e1 & 1u, ph = (e1 >> 1) & 1u;
+          const uint32_t slot = e1 % kSlots, ph = (e1 / kSlots) & 1u;
+          if constexpr (!K::kCacheX0) if (valid) {   // look-ahead: chunks 0 and 1, before the waits
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e);
+          }
           mbar_wait(t1_full + 8 * slot, ph);
           mbar_wait(a1_empty + 8 * slot, ph ^ 1u);
           tcgen05_fence_after();
-          const uint32_t a1_row = smem_a1 + slot * kA1Bytes + i * kRowBytes;
+          const uint32_t a1_row = smem_a1 + slot * K::kA1Bytes + i * kRowBytes;
           const float* b1 = p.bias1[j];
 #pragma unroll
-          for (int cc = 0; cc < C; cc += 16) {
+          for (int ci = 0; ci < kNC; ++ci) {
+            const int cc = ci * 16;
             float4 xr[4];
-            if (valid) {
+            if constexpr (K::kCacheX0) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xr[e] = xc[cc / 4 + e];
+              for (int e = 0; e < 4; ++e) xr[e] = xc[ci * 4 + e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
+              if (valid && ci + 2 < kNC) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (ci + 2) * 4 + e);
+              }
             }
             uint32_t r[16];
-            tmem_ld16(tmem_base + slot * kT1Cols + t_lane + cc, r);
+            tmem_ld16(tmem_base + slot * K::kT1Cols + t_lane + cc, r);
             tmem_ld_wait();
             uint32_t h[8];
             if (valid) {
@@ -320,9 +359,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) h[e] = 0u;   // conv2's zero padding outside [0, L)
             }
-            const uint32_t q = cc >> 3;               // 16-byte chunk index within the row
-            st_shared_v4(a1_row + ((q ^ swz) << 4), h[0], h[1], h[2], h[3]);
-            st_shared_v4(a1_row + (((q + 1) ^ swz) << 4), h[4], h[5], h[6], h[7]);
+            // column cc lives in K-chunk cc / kKC; q = 16-byte unit inside the chunk's row
+            const uint32_t dst = a1_row + (cc / K::kKC) * K::kA1ChunkBytes;
+            const uint32_t q = (cc % K::kKC) >> 3;
+            st_shared_v4(dst + ((q ^ swz) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(dst + (((q + 1) ^ swz) << 4), h[4], h[5], h[6], h[7]);
           }
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
           tcgen05_fence_before();
@@ -332,28 +373,35 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk ----
       {
-        const uint32_t t2s = tile_iter & 1u, t2ph = (tile_iter >> 1) & 1u;
+        const uint32_t t2s = tile_iter % kSlots, t2ph = (tile_iter / kSlots) & 1u;
         const int gr = q0c + i;
         const bool valid = i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        constexpr int kXc = C / 4;
+        const float4* xrow = reinterpret_cast<const float4*>(p.x0 + row_base);
         float4 xc[kXc];
         if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
-          for (int e = 0; e < kXc; ++e)
-            xc[e] = __ldg(reinterpret_cast<const float4*>(p.x0 + row_base) + e);
+          for (int e = 0; e < (K::kCacheX0 ? kXc : 8); ++e) xc[e] = __ldg(xrow + e);
         }
         mbar_wait(t2_full + 8 * t2s, t2ph);
         tcgen05_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < C; cc += 16) {
+        for (int ci = 0; ci < kNC; ++ci) {
+          const int cc = ci * 16;
           float4 xr[4];
-          if (valid) {
+          if constexpr (K::kCacheX0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xr[e] = xc[cc / 4 + e];
+            for (int e = 0; e < 4; ++e) xr[e] = xc[ci * 4 + e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
+            if (valid && ci + 2 < kNC) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (ci + 2) * 4 + e);
+            }
           }
           uint32_t r[16];
-          tmem_ld16(tmem_t2 + t2s * kT1Cols + t_lane + cc, r);
+          tmem_ld16(tmem_t2 + t2s * K::kT1Cols + t_lane + cc, r);
           tmem_ld_wait();
           if (valid) {
             float v[16];
@@ -391,7 +439,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
 }
 
 }  // namespace fused

@@ -108,7 +108,7 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   F.channels = C;
   F.num_branches = nb;
   F.first_layer = first_layer;
-  if (c.resblock_type != 2 || (C != 16 && C != 32 && C != 64)) return F;
+  if (c.resblock_type != 2 || (C != 16 && C != 32 && C != 64 && C != 128)) return F;
   const int d0 = c.resblock_dilation_sizes[0][0];
   int kmax = 0, hc = 0, total = 0;
   for (int j = 0; j < nb; ++j) {
@@ -126,7 +126,9 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
     return F;
   F.hc = hc; F.h1 = h1; F.rc = rc;
   F.a0_boxes = (a0_rows + 63) / 64;
-  // issue order: c1_0, c1_1, SUM, then c2_j interleaved with c1_{j+2}
+  // issue order with double-buffered T1/A1 (C <= 64): c1_0, c1_1, SUM, then c2_j, c1_{j+2};
+  // single-buffered (C = 128):                            c1_0, SUM, then c2_j, c1_{j+1}
+  const int slots = C <= 64 ? 2 : 1;
   int nseg = 0, ntap = 0;
   auto push = [&](int type, int j) {
     const int k = type == V2W_FUSED_SEG_SUM ? kmax : c.resblock_kernel_sizes[j];
@@ -146,12 +148,17 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
     ++nseg;
   };
   push(V2W_FUSED_SEG_CONV1, 0);
-  if (nb > 1) push(V2W_FUSED_SEG_CONV1, 1);
+  if (slots == 2 && nb > 1) push(V2W_FUSED_SEG_CONV1, 1);
   push(V2W_FUSED_SEG_SUM, -1);
   for (int j = 0; j < nb; ++j) {
     push(V2W_FUSED_SEG_CONV2, j);
-    if (j + 2 < nb) push(V2W_FUSED_SEG_CONV1, j + 2);
+    if (j + slots < nb) push(V2W_FUSED_SEG_CONV1, j + slots);
   }
+  int last_a0 = 0;
+  for (int s = 0; s < nseg; ++s)
+    if (F.seg_type[s] != V2W_FUSED_SEG_CONV2) last_a0 = s;
+  F.seg_flags[last_a0] |= 1;
+  F.seg_flags[nseg - 1] |= 2;
   F.num_segments = nseg;
   F.num_taps = ntap;
   F.ok = 1;

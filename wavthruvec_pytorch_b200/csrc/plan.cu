@@ -376,13 +376,16 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   for (int s = 0; s < F.num_segments; ++s) {
     p.seg[s].type = F.seg_type[s]; p.seg[s].branch = F.seg_branch[s];
     p.seg[s].ntaps = F.seg_ntaps[s]; p.seg[s].first = F.seg_first[s];
+    p.seg[s].flags = F.seg_flags[s];
   }
   for (int t = 0; t < F.num_taps; ++t) p.shift[t] = F.shift[t];
-  p.stage_w_bytes = (int)align_up((int64_t)C * C * 2, 1024);
+  const int kc = C < 64 ? C : 64;        // K-chunk (fused::Cfg<C>)
+  const int slots = C <= 64 ? 2 : 1;
+  p.stage_w_bytes = (int)align_up((int64_t)C * kc * 2, 1024);   // one (tap, K-chunk) block
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * C * 2;
   const int a1_bytes = fused::kWin * C * 2;
-  const int budget = 227 * 1024 - 1024 - 256;
-  const int left = budget - 2 * a0_bytes - 2 * a1_bytes;
+  const int budget = 227 * 1024 - 1024 - 512;
+  const int left = budget - slots * (a0_bytes + a1_bytes);
   int w_bytes_total;
   if (C <= 32) {
     // resident weights: every tap of the stage lives in shared memory (kernels_fused.cuh)
@@ -413,19 +416,19 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   L->channels = C;
   p.w_region_bytes = w_bytes_total;
   p.fp16 = fp16 ? 1 : 0;
-  L->smem = 2 * a0_bytes + 2 * a1_bytes + w_bytes_total + 512 + 1024;
+  L->smem = slots * (a0_bytes + a1_bytes) + w_bytes_total + 512 + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
 
   EncodeTiledFn enc = nullptr;
   rc = get_encode_fn(&enc);
   if (rc) return rc;
-  const CUtensorMapSwizzle swz = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                    : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B);
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)d.rows, (cuuint64_t)d.batch};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)d.rows * C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)fused::kBoxRows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)fused::kBoxRows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&L->tm_a, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                      ws + d.in_act, dims, strides,
@@ -439,7 +442,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)F.num_taps * C};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)C};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L->tm_w, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      const_cast<uint8_t*>(packed + F.w_off), dims, strides, box, estr,
@@ -456,6 +459,8 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
 static int launch_fused(const FusedLaunch& L, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<64>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<32>,
@@ -464,7 +469,9 @@ static int launch_fused(const FusedLaunch& L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (L.channels == 64)
+  if (L.channels == 128)
+    fused::mrf_stage_kernel<128><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+  else if (L.channels == 64)
     fused::mrf_stage_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
   else if (L.channels == 32)
     fused::mrf_stage_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);

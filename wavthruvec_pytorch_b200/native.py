@@ -123,6 +123,7 @@ class FusedDesc(C.Structure):
         ("a0_boxes", C.c_int32), ("num_segments", C.c_int32), ("num_taps", C.c_int32),
         ("seg_type", C.c_int16 * FUSED_MAX_SEG), ("seg_branch", C.c_int16 * FUSED_MAX_SEG),
         ("seg_ntaps", C.c_int16 * FUSED_MAX_SEG), ("seg_first", C.c_int16 * FUSED_MAX_SEG),
+        ("seg_flags", C.c_int16 * FUSED_MAX_SEG),
         ("shift", C.c_int16 * FUSED_MAX_TAPS), ("offset", C.c_int16 * FUSED_MAX_TAPS),
         ("w_off", C.c_int64), ("bsum_off", C.c_int64),
     ]
