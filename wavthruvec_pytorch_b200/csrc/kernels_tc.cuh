@@ -47,6 +47,10 @@ constexpr int kMTile = 128;
 constexpr int kMaxStagesA = 4;
 constexpr int kMaxStagesW = 8;
 constexpr int kMaxSub = 4;
+// Output staging per epilogue warp: 2 x (32 rows x 16 fp32 = 2 KB) + 2 x (32 rows x 16 half = 1 KB)
+constexpr int kStageYBytes = 2048, kStageHBytes = 1024;
+constexpr int kStageWarpBytes = 2 * kStageYBytes + 2 * kStageHBytes;
+constexpr int kStageBytes = 8 * kStageWarpBytes;   // 48 KB
 
 struct Params {
   int batch, rows, cin, n_total, cmod, n_tile, n_tiles;
@@ -58,6 +62,7 @@ struct Params {
   int stage_a_bytes, stage_w_bytes;
   int acc_cols;         // TMEM columns per accumulator (per sub-tile)
   int fp16;             // 16-bit operand format: 0 = bf16, 1 = fp16
+  int tma_out;          // outputs leave through shared-memory staging + TMA stores
   // 32-bit entries on purpose: see the note at fused::Segment (ptxas merges 16-bit loads of
   // dynamically indexed parameter arrays incorrectly at some alignments).
   int num_taps[V2W_MAX_TILES];
@@ -156,6 +161,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tm, int c0
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tm)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                              uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                "r"(cols)
@@ -250,6 +278,7 @@ struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
 template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmH,
                   const __grid_constant__ Params p) {
   constexpr int kRowBytes = KC * 2;
   constexpr int kKSteps = KC / 16;
@@ -261,6 +290,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // barrier block (8 B each): fullA[4] emptyA[4] fullW[8] emptyW[8] accFull[2] accEmpty[2]
   const uint32_t full_a = bars, empty_a = bars + 32, full_w = bars + 64, empty_w = bars + 128;
   const uint32_t acc_full = bars + 192, acc_empty = bars + 208, tmem_slot = bars + 224;
+  const uint32_t stage_base = bars + 1024;   // 1024-aligned: bars is, by construction
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -386,6 +416,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int group = (warp - 4) >> 2;  // accumulator stage this warp drains
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const bool pow2 = (p.cmod & (p.cmod - 1)) == 0;
+    const uint32_t ybuf = stage_base + (warp - 4) * kStageWarpBytes;
+    const uint32_t hbuf = ybuf + 2 * kStageYBytes;
+    uint32_t sbuf = 0;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       if ((tile_iter & 1u) != static_cast<uint32_t>(group)) continue;
@@ -401,7 +434,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t t_lane = tmem_base + group * stage_cols +
                               (static_cast<uint32_t>(quarter * 32) << 16);
       for (int m = 0; m < nsub; ++m) {
-        const int row = q0 + m * kMTile + quarter * 32 + lane;
+        const int row0w = q0 + m * kMTile + quarter * 32;   // first row of this warp's slab
+        const int row = row0w + lane;
         const bool valid = row < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + row) * p.n_total;
         for (int cc = 0; cc < p.n_tile; cc += 16) {
@@ -464,28 +498,70 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] *= p.out_scale;
             }
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + col);
+            if (p.tma_out) {
+              // own row -> staging tile in the TMA swizzle layout (64B / 32B swizzle: conflict-free)
+              if (p.out_f32) {
+                const uint32_t yb = ybuf + sbuf * kStageYBytes + lane * 64;
+                const uint32_t sw = (lane >> 1) & 3;
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-            }
-            if (p.out_bf16) {
-              uint32_t h[8];
+                for (int e = 0; e < 4; ++e)
+                  st_shared_v4u(yb + ((e ^ sw) << 4), __float_as_uint(v[4 * e]),
+                                __float_as_uint(v[4 * e + 1]), __float_as_uint(v[4 * e + 2]),
+                                __float_as_uint(v[4 * e + 3]));
+              }
+              if (p.out_bf16) {
+                uint32_t h[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
-                                  p.fp16);
-              uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
-              op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-              op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                for (int e = 0; e < 8; ++e)
+                  h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
+                                    p.fp16);
+                const uint32_t hb = hbuf + sbuf * kStageHBytes + lane * 32;
+                const uint32_t sw = (lane >> 2) & 1;
+                st_shared_v4u(hb + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
+                st_shared_v4u(hb + ((1 ^ sw) << 4), h[4], h[5], h[6], h[7]);
+              }
+            } else {
+              if (p.out_f32) {
+                float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + col);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+              }
+              if (p.out_bf16) {
+                uint32_t h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
+                                    p.fp16);
+                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
+                op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              }
             }
+          }
+          if (p.tma_out) {
+            // every lane's rows are in shared memory -> one lane hands the 32-row slab to TMA.
+            // Rows past the utterance end are clipped by the 3-D tensor map.  Double buffered:
+            // before the warp moves on, the store issued one chunk earlier has finished READING
+            // its buffer (the one the next chunk writes).
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && row0w < p.rows) {
+              const int col = nt * p.n_tile + cc;
+              if (p.out_f32) tma_store_3d(&tmY, ybuf + sbuf * kStageYBytes, col, row0w, b);
+              if (p.out_bf16) tma_store_3d(&tmH, hbuf + sbuf * kStageHBytes, col, row0w, b);
+              tma_store_commit();
+              tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            sbuf ^= 1u;
           }
         }
       }
       tcgen05_fence_before();
       mbar_arrive(acc_empty + 8 * group);
     }
+    if (p.tma_out && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();

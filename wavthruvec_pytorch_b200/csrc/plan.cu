@@ -41,7 +41,7 @@ struct Act {        // one logical activation tensor [B, rows, C]
 };
 
 struct TcLaunch {
-  CUtensorMap tm_a, tm_w;
+  CUtensorMap tm_a, tm_w, tm_y, tm_h;
   tc::Params prm;
   int grid = 0;
   int smem = 0;
@@ -214,7 +214,9 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
-  const int budget = 227 * 1024 - 1024 - 256;
+  p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
+  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0);   // barriers (+ output staging)
+  const int budget = 227 * 1024 - 1024 - tail_bytes;
   const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
   int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
   if (forced >= 1 && forced <= msub) msub = forced;
@@ -245,7 +247,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_slope = a.out_slope;
   L->kc = kc;
-  L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + 256 + 1024;
+  L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + tail_bytes + 1024;
   const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
   L->grid = (int)std::min<int64_t>(tiles, sms);
 
@@ -286,6 +288,35 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
       return V2W_ERR_CUDA;
     }
   }
+  std::memset(&L->tm_y, 0, sizeof(L->tm_y));
+  std::memset(&L->tm_h, 0, sizeof(L->tm_h));
+  if (p.tma_out) {
+    // output slabs: 32 rows x 16 columns per epilogue warp and chunk (kernels_tc.cuh)
+    cuuint64_t dims[3] = {(cuuint64_t)a.n_total, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (a.out_f32) {
+      cuuint64_t strides[2] = {(cuuint64_t)a.n_total * 4, (cuuint64_t)a.rows * a.n_total * 4};
+      CUresult r = enc(&L->tm_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out_f32, dims, strides, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out f32) failed with CUresult %d", (int)r);
+        return V2W_ERR_CUDA;
+      }
+    }
+    if (a.out_bf16) {
+      cuuint64_t strides[2] = {(cuuint64_t)a.n_total * 2, (cuuint64_t)a.rows * a.n_total * 2};
+      CUresult r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                       3, a.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out 16-bit) failed with CUresult %d", (int)r);
+        return V2W_ERR_CUDA;
+      }
+    }
+  }
   return V2W_OK;
 }
 
@@ -301,11 +332,11 @@ static int launch_tc(const TcLaunch& L, cudaStream_t st) {
     attr_set = true;
   }
   if (L.kc == 64)
-    tc::tapgemm_tc_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    tc::tapgemm_tc_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
   else if (L.kc == 32)
-    tc::tapgemm_tc_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    tc::tapgemm_tc_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
   else
-    tc::tapgemm_tc_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    tc::tapgemm_tc_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
   V2W_CUDA(cudaGetLastError());
   return V2W_OK;
 }
