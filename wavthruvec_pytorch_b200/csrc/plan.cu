@@ -524,35 +524,37 @@ struct Bump {
   }
 };
 
-// Pick the column tile of a layer: whole phases (or a divisor of cout), <= 128 columns (so that
-// two 128-row sub-tiles share every W block: see kernels_tc.cuh), minimum issued MMA columns
-// (zero polyphase blocks cost issue slots), then the largest tile; shrink while the launch would
-// leave SMs idle.
+// Pick the column tile of a layer.  Candidates: whole phase groups (or divisors of cout) of 16..256
+// columns.  Cost model from the round-1 measurements: one M=128, K=16 MMA costs ~(64 + N/2) clk
+// (shared-memory operand delivery ~64 B/clk: profiles/r01_notes.md), so a tile costs
+// taps * (128 + n_tile) units and the launch takes ceil(tiles / SMs) rounds of it.  Zero polyphase
+// blocks count as issued taps.  Ties go to the larger tile (fewer A re-reads).
 static void choose_tiles(const v2w_layer_desc& L, int batch, int rows, v2w_op_desc* d) {
   int best = 0;
-  int64_t best_cost = 0;
-  for (int nt = 16; nt <= 128; nt <<= 1) {
+  double best_cost = 0;
+  const int nt_max = std::getenv("V2W_NTILE_MAX") ? std::atoi(std::getenv("V2W_NTILE_MAX")) : 256;
+  const int sms = 148;
+  const int m_tiles = (rows + 127) / 128;
+  for (int nt = 16; nt <= nt_max; nt <<= 1) {
     if (L.n_total % nt) continue;
     if (nt % L.cout && L.cout % nt) continue;
-    int64_t cost = 0;
-    for (int t = 0; t < L.n_total / nt; ++t) {
+    const int n_tiles = L.n_total / nt;
+    if (n_tiles > V2W_MAX_TILES) continue;
+    int64_t taps_sum = 0;
+    for (int t = 0; t < n_tiles; ++t) {
       const int p_lo = t * nt / L.cout, p_hi = ((t + 1) * nt - 1) / L.cout;
       uint32_t pm = 0;
       for (int p = p_lo; p <= p_hi; ++p) pm |= 1u << p;
-      int taps = 0;
-      for (int j = 0; j < L.num_taps; ++j) taps += (L.tap_mask[j] & pm) != 0;
-      cost += (int64_t)taps * nt;
+      for (int j = 0; j < L.num_taps; ++j) taps_sum += (L.tap_mask[j] & pm) != 0;
     }
-    if (L.n_total / nt > V2W_MAX_TILES) continue;
+    const int64_t tiles = (int64_t)batch * m_tiles * n_tiles;
+    const double rounds = (double)((tiles + sms - 1) / sms);
+    const double cost = rounds * ((double)taps_sum / n_tiles) * (128 + nt);
     if (!best || cost < best_cost || (cost == best_cost && nt > best)) {
       best = nt;
       best_cost = cost;
     }
   }
-  const int m_tiles = (rows + 127) / 128;
-  while (best >= 64 && (int64_t)batch * m_tiles * (L.n_total / best) < 148 &&
-         L.n_total / (best / 2) <= V2W_MAX_TILES)
-    best >>= 1;
   d->n_tile = best;
   d->n_tiles = L.n_total / best;
   for (int t = 0; t < d->n_tiles; ++t) {
