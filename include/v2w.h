@@ -275,6 +275,20 @@ int32_t v2w_forward_host(struct v2w_plan* p, const float* x_host, const float* s
                          const float* noise_host, float* out_host, void* stream,
                          int32_t* gpu_launches);
 
+/* Pipelined generation from HOST buffers (throughput API): up to two steps in flight on three
+ * library-owned streams -- H2D of step i+1 and D2H of step i-1 overlap the kernels of step i.
+ * Staging buffers are owned by the pipeline (cudaMalloc).  Every submitted step still copies its
+ * inputs from the host and its whole waveform back; only the overlap differs from
+ * v2w_forward_host.  Host buffers must stay valid (and should be pinned) until v2w_pipeline_wait
+ * returns; the same buffers may be passed to successive submits. */
+struct v2w_pipeline;
+int32_t v2w_pipeline_create(struct v2w_plan* p, struct v2w_pipeline** out);
+int32_t v2w_pipeline_submit(struct v2w_pipeline* q, const float* x_host, const float* spk_host,
+                            const float* noise_host, float* out_host);
+/* Blocks until every submitted step has landed in its out_host; returns kernels launched so far. */
+int32_t v2w_pipeline_wait(struct v2w_pipeline* q, int64_t* gpu_launches);
+void v2w_pipeline_destroy(struct v2w_pipeline* q);
+
 /* Per-op device timing.  When enabled, v2w_forward brackets every op with CUDA events recorded
  * on the caller's stream; after the stream has been synchronised by the caller,
  * v2w_plan_op_time_ms returns the last forward's duration of op `index` in milliseconds

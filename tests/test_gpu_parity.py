@@ -199,6 +199,33 @@ def test_forward_host_equals_forward_and_is_deterministic():
     np.testing.assert_array_equal(out.numpy(), a)
 
 
+def test_host_pipeline_matches_blocking_calls():
+    """v2w_pipeline_*: five steps with DIFFERENT inputs in flight two at a time; each step's
+    waveform must equal the blocking device call on the same inputs (slot reuse, event order)."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    B, _, T = g.x.shape
+    rng = np.random.default_rng(5)
+    steps = []
+    for i in range(5):
+        x = t(g.x * (0.5 + 0.25 * i) + rng.standard_normal(g.x.shape).astype(np.float32) * 0.1)
+        steps.append((x.pin_memory(), t(np.roll(g.spk, i, axis=1)).pin_memory(),
+                      t(np.roll(g.noise, -i, axis=1)).pin_memory(),
+                      torch.zeros(g.y.shape, dtype=torch.float32).pin_memory()))
+    pipe = gen.engine().host_pipeline(B, T, "cuda:0")
+    for x, s, n, o in steps:
+        pipe.submit(x, s, n, o)
+    launches = pipe.wait()
+    assert launches == 5 * len(gen.engine().ops(B, T, gen.precision, "cuda:0"))
+    for x, s, n, o in steps:
+        with torch.no_grad():
+            want = gen(x.cuda(), s.cuda(), n.cuda()).cpu().numpy()
+        np.testing.assert_array_equal(o.numpy(), want)
+    with pytest.raises(RuntimeError):
+        pipe.submit(steps[0][0][:, :, :-1].contiguous(), *steps[0][1:])
+    pipe.close()
+
+
 @pytest.mark.parametrize("rb", [1, '1'])
 def test_full_size_against_autograd_delegate(rb):
     """cfg-scale shapes (B=4, T=200 and a ragged T) where the numpy oracle is too slow: the FP32

@@ -16,8 +16,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libv2w.so"
 SOURCES = [CSRC / "model.cpp", CSRC / "plan.cu"]
-HEADERS = [CSRC / "common.h", CSRC / "kernels_simt.cuh", CSRC / "kernels_tc.cuh",
-           REPO_ROOT / "include" / "v2w.h"]
+HEADERS = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "v2w.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",

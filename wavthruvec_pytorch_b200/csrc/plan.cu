@@ -1096,6 +1096,131 @@ int32_t v2w_forward_host(v2w_plan* p, const float* x_host, const float* spk_host
   return V2W_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pipelined host API
+// ---------------------------------------------------------------------------------------------
+struct v2w_pipeline {
+  v2w_plan* plan = nullptr;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  float *x[2] = {nullptr, nullptr}, *spk[2] = {nullptr, nullptr}, *noise[2] = {nullptr, nullptr};
+  float* out[2] = {nullptr, nullptr};
+  cudaEvent_t in_ready[2], run_done[2], out_done[2];
+  bool events = false;
+  int64_t step = 0, launches = 0;
+  size_t x_bytes = 0, spk_bytes = 0, noise_bytes = 0, out_bytes = 0;
+};
+
+void v2w_pipeline_destroy(v2w_pipeline* q) {
+  if (!q) return;
+  if (q->s_run) cudaStreamSynchronize(q->s_run);
+  if (q->s_out) cudaStreamSynchronize(q->s_out);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(q->x[i]); cudaFree(q->spk[i]); cudaFree(q->noise[i]); cudaFree(q->out[i]);
+    if (q->events) {
+      cudaEventDestroy(q->in_ready[i]); cudaEventDestroy(q->run_done[i]); cudaEventDestroy(q->out_done[i]);
+    }
+  }
+  if (q->s_in) cudaStreamDestroy(q->s_in);
+  if (q->s_run) cudaStreamDestroy(q->s_run);
+  if (q->s_out) cudaStreamDestroy(q->s_out);
+  delete q;
+}
+
+int32_t v2w_pipeline_create(v2w_plan* p, v2w_pipeline** out) {
+  if (!p || !out) {
+    set_error("v2w_pipeline_create: null argument");
+    return V2W_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (!p->bound) {
+    set_error("v2w_pipeline_create: plan is not bound to device buffers");
+    return V2W_ERR_STATE;
+  }
+  v2w_pipeline* q = new (std::nothrow) v2w_pipeline();
+  if (!q) {
+    set_error("out of memory");
+    return V2W_ERR_NOMEM;
+  }
+  q->plan = p;
+  const v2w_config& c = p->model->cfg;
+  const size_t B = p->batch;
+  q->x_bytes = B * c.num_wv_feat * p->frames * 4;
+  q->spk_bytes = B * c.spk_dim * 4;
+  q->noise_bytes = B * (size_t)std::max(1, c.noise_dim) * 4;
+  q->out_bytes = B * p->frames * p->model->total_up * 4;
+  auto fail = [&](cudaError_t e, const char* what) {
+    set_error("v2w_pipeline_create: %s failed: %s", what, cudaGetErrorString(e));
+    v2w_pipeline_destroy(q);
+    return V2W_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+  if ((e = cudaStreamCreateWithFlags(&q->s_run, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+  if ((e = cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+  for (int i = 0; i < 2; ++i) {
+    if ((e = cudaMalloc(&q->x[i], q->x_bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&q->spk[i], q->spk_bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&q->noise[i], q->noise_bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&q->out[i], q->out_bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&q->in_ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&q->run_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&q->out_done[i], cudaEventDisableTiming);
+  }
+  q->events = true;
+  *out = q;
+  return V2W_OK;
+}
+
+int32_t v2w_pipeline_submit(v2w_pipeline* q, const float* x_host, const float* spk_host,
+                            const float* noise_host, float* out_host) {
+  if (!q || !x_host || !spk_host || !out_host) {
+    set_error("v2w_pipeline_submit: null argument");
+    return V2W_ERR_INVALID;
+  }
+  const v2w_config& c = q->plan->model->cfg;
+  if (c.noise_dim > 0 && !noise_host) {
+    set_error("v2w_pipeline_submit: noise is required (vec2wav/models.py:120)");
+    return V2W_ERR_INVALID;
+  }
+  const int s = (int)(q->step & 1);
+  // input slot s was last read by the kernels of step-2, output slot s by the D2H of step-2
+  if (q->step >= 2) {
+    V2W_CUDA(cudaStreamWaitEvent(q->s_in, q->run_done[s], 0));
+    V2W_CUDA(cudaStreamWaitEvent(q->s_run, q->out_done[s], 0));
+  }
+  V2W_CUDA(cudaMemcpyAsync(q->x[s], x_host, q->x_bytes, cudaMemcpyHostToDevice, q->s_in));
+  V2W_CUDA(cudaMemcpyAsync(q->spk[s], spk_host, q->spk_bytes, cudaMemcpyHostToDevice, q->s_in));
+  if (c.noise_dim > 0)
+    V2W_CUDA(cudaMemcpyAsync(q->noise[s], noise_host, (size_t)q->plan->batch * c.noise_dim * 4,
+                             cudaMemcpyHostToDevice, q->s_in));
+  V2W_CUDA(cudaEventRecord(q->in_ready[s], q->s_in));
+  V2W_CUDA(cudaStreamWaitEvent(q->s_run, q->in_ready[s], 0));
+  int32_t n = 0;
+  int rc = v2w_forward(q->plan, q->x[s], q->spk[s], q->noise[s], q->out[s], q->s_run, &n);
+  if (rc) return rc;
+  q->launches += n;
+  V2W_CUDA(cudaEventRecord(q->run_done[s], q->s_run));
+  V2W_CUDA(cudaStreamWaitEvent(q->s_out, q->run_done[s], 0));
+  V2W_CUDA(cudaMemcpyAsync(out_host, q->out[s], q->out_bytes, cudaMemcpyDeviceToHost, q->s_out));
+  V2W_CUDA(cudaEventRecord(q->out_done[s], q->s_out));
+  ++q->step;
+  return V2W_OK;
+}
+
+int32_t v2w_pipeline_wait(v2w_pipeline* q, int64_t* gpu_launches) {
+  if (!q) {
+    set_error("v2w_pipeline_wait: null argument");
+    return V2W_ERR_INVALID;
+  }
+  V2W_CUDA(cudaStreamSynchronize(q->s_in));
+  V2W_CUDA(cudaStreamSynchronize(q->s_run));
+  V2W_CUDA(cudaStreamSynchronize(q->s_out));
+  if (gpu_launches) *gpu_launches = q->launches;
+  return V2W_OK;
+}
+
 int32_t v2w_tapgemm(const v2w_tapgemm_args* a, void* stream) {
   if (!a) {
     set_error("v2w_tapgemm: null argument");

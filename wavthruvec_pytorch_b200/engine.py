@@ -231,6 +231,13 @@ class NativeEngine:
         self.last_launches = n.value
         return out
 
+    def host_pipeline(self, batch: int, frames: int, device) -> "HostPipeline":
+        """Streaming generation from pinned host buffers (v2w_pipeline_*): copies of neighbouring
+        steps overlap the kernels of the current one."""
+        dev = torch.device(device)
+        handle, _ws = self.plan(batch, frames, self._module.precision, dev)
+        return HostPipeline(self, handle, batch, frames, dev)
+
     def profile_ops(self, x, spk, noise, reps: int = 3, before_each=None):
         """Per-op device times (ms, mean over `reps` forwards) from CUDA events recorded by the
         library on the launch stream.  Returns [(OpDesc, ms)]."""
@@ -260,3 +267,51 @@ class NativeEngine:
         for u in self._module.h.upsample_rates:
             r *= int(u)
         return r
+
+
+class HostPipeline:
+    """Handle on a v2w_pipeline.  `submit` is asynchronous; `wait` drains and returns the number of
+    kernels launched.  Host tensors must be contiguous fp32 CPU tensors (pinned for overlap) and
+    stay alive until `wait` returns."""
+
+    def __init__(self, engine: NativeEngine, plan_handle, batch, frames, device):
+        self._engine = engine
+        self._lib = engine._lib
+        self._device = device
+        self._shape = (batch, frames)
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            native.check(self._lib.v2w_pipeline_create(plan_handle, C.byref(handle)))
+        self._handle = handle
+        self._keep = []
+
+    def submit(self, x, spk, noise, out) -> None:
+        self._engine._check_inputs(x, spk, noise)
+        for t in (x, spk, noise, out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("HostPipeline takes contiguous fp32 CPU tensors")
+        B, T = self._shape
+        if x.shape[0] != B or x.shape[2] != T or tuple(out.shape) != (B, 1, T * self._engine.total_upsample()):
+            raise RuntimeError("tensor shapes do not match the pipeline's plan")
+        self._keep.append((x, spk, noise, out))
+        with torch.cuda.device(self._device):
+            native.check(self._lib.v2w_pipeline_submit(self._handle, x.data_ptr(), spk.data_ptr(),
+                                                       noise.data_ptr(), out.data_ptr()))
+
+    def wait(self) -> int:
+        n = C.c_int64(0)
+        with torch.cuda.device(self._device):
+            native.check(self._lib.v2w_pipeline_wait(self._handle, C.byref(n)))
+        self._keep.clear()
+        return int(n.value)
+
+    def close(self) -> None:
+        if self._handle:
+            self._lib.v2w_pipeline_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

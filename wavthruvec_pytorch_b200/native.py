@@ -176,6 +176,10 @@ _SIGNATURES = [
     ("v2w_forward_host", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
+    ("v2w_pipeline_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("v2w_pipeline_submit", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("v2w_pipeline_wait", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ("v2w_pipeline_destroy", None, [C.c_void_p]),
     ("v2w_plan_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("v2w_plan_op_time_ms", C.c_float, [C.c_void_p, C.c_int32]),
     ("v2w_tapgemm", C.c_int32, [C.POINTER(TapGemmArgs), C.c_void_p]),
