@@ -157,28 +157,53 @@ typedef struct v2w_cond_desc {
   int64_t mean_off;            /* [C] */
 } v2w_cond_desc;
 
-/* Fused multi-receptive-field stage (kernels_fused.cuh).  All resblocks of one stage run in one
- * kernel on 256-row windows: per branch conv1 -> (bias, +x, leaky-relu, bf16) -> shared memory ->
- * conv2, all conv2 outputs plus ONE extra convolution `sum` (taps = per-offset sums of the conv1
- * weights) accumulate in a single TMEM accumulator.  Weight taps are stored in issue order. */
-#define V2W_FUSED_MAX_SEG 12
-#define V2W_FUSED_MAX_TAPS 80
+/* Fused multi-receptive-field stage (kernels_fused.cuh, kernels_stacked.cuh).  All resblocks of one
+ * stage run in one kernel on 256-row windows: per branch conv1 -> (bias, +x, leaky-relu, 16-bit) ->
+ * shared memory -> conv2; all conv2 outputs plus ONE extra convolution `sum` (taps = per-offset
+ * sums of the conv1 weights) accumulate in a single TMEM accumulator T2.
+ *
+ * The stage is described as a program of SEGMENTS; a segment is a run of MMA ENTRIES (one entry =
+ * one operand row shift and one weight block) into one accumulator range.
+ *
+ *  plain program (C = 128): every entry is one C x C tap matrix, segment types say what it feeds.
+ *  stacked program (C <= 64): the conv1 taps of all branches that share a time offset, and the
+ *    `sum` tap of that offset, are ONE entry whose weight block stacks them along N -- the operand
+ *    tile is read once for up to four tap matrices.  TMEM columns of a 128-row sub-tile are
+ *    [T2 | T1_{nb-1} | ... | T1_0] (C columns each) with branches sorted by kernel size, so the
+ *    blocks sharing an offset are always a contiguous column range [seg_dcol, seg_dcol + seg_n).
+ *    Phase-A segments (CONV1 / SUM, read the input tile) come first, then the phase-B segments
+ *    (CONV2, read A1) of the same tile. */
+#define V2W_FUSED_MAX_SEG 16
+#define V2W_FUSED_MAX_TAPS 96
 #define V2W_FUSED_SEG_CONV1 0
 #define V2W_FUSED_SEG_SUM 1
 #define V2W_FUSED_SEG_CONV2 2
+/* wait / commit bits of a stacked segment */
+#define V2W_FUSED_BIT_T1(j) (1 << (j))       /* accumulator of branch slot j (wait: free, commit: complete) */
+#define V2W_FUSED_BIT_T2 (1 << 4)
+#define V2W_FUSED_BIT_A0 (1 << 5)            /* wait: input tile landed; commit: input tile no longer read */
+#define V2W_FUSED_BIT_A1(j) (1 << (8 + (j))) /* wait: A1 of slot j written; commit: no longer read */
 typedef struct v2w_fused_desc {
   int32_t ok;                  /* 0: this stage is executed as separate tap-GEMM ops */
   int32_t channels, num_branches;
   int32_t first_layer;         /* layer index of branch 0's first conv (2 layers per branch) */
   int32_t hc, h1, rc;          /* conv2 halo, conv1 halo, central rows per 256-row window */
   int32_t a0_boxes;            /* 64-row TMA boxes per input tile */
-  int32_t num_segments, num_taps;
-  int16_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];
-  int16_t seg_ntaps[V2W_FUSED_MAX_SEG], seg_first[V2W_FUSED_MAX_SEG];
-  int16_t seg_flags[V2W_FUSED_MAX_SEG];  /* bit0: last reader of the input tile, bit1: last segment */
-  int16_t shift[V2W_FUSED_MAX_TAPS];   /* operand row of the tap inside its input tile */
-  int16_t offset[V2W_FUSED_MAX_TAPS];  /* time offset of the tap (rows) */
-  int64_t w_off;               /* packed: bf16 [num_taps][channels][channels] (n, c), issue order */
+  int32_t num_segments, num_taps;      /* num_taps = MMA entries */
+  int32_t stacked;
+  int32_t order[V2W_MAX_KERNELS];      /* stacked: model branch that runs as slot j */
+  int32_t t_bufs, a0_bufs;             /* stacked: accumulator sets / input tiles in flight */
+  int32_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];   /* branch: slot of a CONV2 */
+  int32_t seg_ntaps[V2W_FUSED_MAX_SEG], seg_first[V2W_FUSED_MAX_SEG];
+  int32_t seg_flags[V2W_FUSED_MAX_SEG];  /* plain: bit0 last reader of the input tile, bit1 last segment */
+  int32_t seg_dcol[V2W_FUSED_MAX_SEG], seg_n[V2W_FUSED_MAX_SEG];    /* accumulator columns / MMA N */
+  int32_t seg_acc[V2W_FUSED_MAX_SEG];    /* 0: the first MMA of the segment overwrites */
+  int32_t seg_wait[V2W_FUSED_MAX_SEG], seg_commit[V2W_FUSED_MAX_SEG];
+  int32_t shift[V2W_FUSED_MAX_TAPS];   /* operand row of the entry relative to its tile / window */
+  int32_t offset[V2W_FUSED_MAX_TAPS];  /* time offset of the entry (rows) */
+  int32_t w_row[V2W_FUSED_MAX_TAPS];   /* first row of the entry's block in the weight matrix */
+  int32_t w_rows;              /* rows of the weight matrix */
+  int64_t w_off;               /* packed: 16-bit [w_rows][channels] (n, c), entries in issue order */
   int64_t bsum_off;            /* packed: fp32 [channels] = sum_j (b1_j + b2_j) */
 } v2w_fused_desc;
 

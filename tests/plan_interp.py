@@ -163,32 +163,49 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             Cn, nb = F.channels, F.num_branches
             A0 = ws[op.in_act].reshape(op.batch, op.rows, Cn)
             X0 = ws[op.residual].reshape(op.batch, op.rows, Cn)
-            Wf = half_to_f32(u16(F.w_off, F.num_taps * Cn * Cn)).reshape(F.num_taps, Cn, Cn)  # [tap][n][c]
+            Wf = half_to_f32(u16(F.w_off, F.w_rows * Cn)).reshape(F.w_rows, Cn)  # [row = n][c]
             bsum = f32(F.bsum_off, Cn)
 
-            def conv(A, first, ntaps):
-                acc = np.zeros((op.batch, op.rows, Cn), np.float32)
-                for t in range(first, first + ntaps):
-                    off = F.offset[t]
-                    sh = np.zeros_like(A)
-                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
-                    if hi > lo:
-                        sh[:, lo:hi] = A[:, lo + off: hi + off]
-                    acc += sh @ Wf[t].T
-                return acc
+            def tap(A, ent, blk):
+                """One C x C block of entry `ent` applied at the entry's time offset."""
+                off = F.offset[ent]
+                W = Wf[F.w_row[ent] + blk * Cn: F.w_row[ent] + (blk + 1) * Cn]
+                sh = np.zeros_like(A)
+                lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                if hi > lo:
+                    sh[:, lo:hi] = A[:, lo + off: hi + off]
+                return sh @ W.T
 
+            # accumulators: T1 per branch SLOT (stacked: sorted by kernel size, F.order), T2
             T2 = np.zeros((op.batch, op.rows, Cn), np.float32)
-            A1 = {}
-            for sgi in range(F.num_segments):
-                typ, j = F.seg_type[sgi], F.seg_branch[sgi]
-                first, nt = F.seg_first[sgi], F.seg_ntaps[sgi]
-                if typ == native.SEG_CONV1:
-                    b1 = f32(plan.layers[F.first_layer + 2 * j].bias_off, Cn)
-                    A1[j] = half(lrelu(conv(A0, first, nt) + b1 + X0, 0.1))
-                elif typ == native.SEG_SUM:
-                    T2 += conv(A0, first, nt)
-                else:
-                    T2 += conv(A1[j], first, nt)
+            T1 = [np.zeros((op.batch, op.rows, Cn), np.float32) for _ in range(nb)]
+            segs = range(F.num_segments)
+            for sgi in segs:       # everything that reads A0
+                typ = F.seg_type[sgi]
+                if typ == native.SEG_CONV2:
+                    continue
+                for t in range(F.seg_first[sgi], F.seg_first[sgi] + F.seg_ntaps[sgi]):
+                    for blk in range(F.seg_n[sgi] // Cn):
+                        if typ == native.SEG_SUM:
+                            T2 += tap(A0, t, blk)
+                        elif not F.stacked:
+                            T1[F.seg_branch[sgi]] += tap(A0, t, blk)
+                        else:
+                            col = F.seg_dcol[sgi] // Cn + blk    # [T2 | T1_{nb-1} | ... | T1_0]
+                            if col == 0:
+                                T2 += tap(A0, t, blk)
+                            else:
+                                T1[nb - col] += tap(A0, t, blk)
+            A1 = []
+            for j in range(nb):
+                br = F.order[j] if F.stacked else j
+                b1 = f32(plan.layers[F.first_layer + 2 * br].bias_off, Cn)
+                A1.append(half(lrelu(T1[j] + b1 + X0, 0.1)))
+            for sgi in segs:
+                if F.seg_type[sgi] != native.SEG_CONV2:
+                    continue
+                for t in range(F.seg_first[sgi], F.seg_first[sgi] + F.seg_ntaps[sgi]):
+                    T2 += tap(A1[F.seg_branch[sgi]], t, 0)
             v = ((T2 + bsum + np.float32(nb) * X0) * np.float32(op.out_scale)).astype(np.float32)
             if op.out_f32 >= 0:
                 ws[op.out_f32] = v

@@ -230,12 +230,29 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     assert sum(op.flops for op in fplan.ops) == total
     F = native.FusedDesc()
     native.check(eng._lib.v2w_model_get_fused(eng._model, 2, C.byref(F)))
-    assert (F.ok, F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments) == (1, 15, 5, 226, 5, 53, 7)
-    assert list(F.seg_type[:7]) == [0, 0, 1, 2, 0, 2, 2] and list(F.seg_ntaps[:7]) == [3, 7, 11, 3, 11, 7, 11]
-    assert list(F.seg_flags[:7]) == [0, 0, 0, 0, 1, 0, 2]
-    # C = 128 is single buffered: conv_sum right behind conv1_0, then conv2_j / conv1_{j+1}
+    # C = 64: stacked program, one accumulator set, `sum` of the first offset group split off
+    T1, T2, A0, A1 = (lambda j: 1 << j), 1 << 4, 1 << 5, (lambda j: 1 << (8 + j))
+    assert (F.ok, F.stacked, F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments) == (1, 1, 15, 5, 226, 5, 35, 7)
+    assert (F.t_bufs, F.a0_bufs, list(F.order[:3]), F.w_rows) == (1, 1, [0, 1, 2], 53 * 64)
+    assert list(F.seg_type[:7]) == [0, 1, 0, 0, 2, 2, 2] and list(F.seg_ntaps[:7]) == [3, 3, 4, 4, 3, 7, 11]
+    assert list(F.seg_dcol[:7]) == [64, 0, 0, 0, 0, 0, 0] and list(F.seg_n[:7]) == [192, 64, 192, 128, 64, 64, 64]
+    assert list(F.seg_acc[:7]) == [0, 0, 1, 1, 1, 1, 1]
+    assert list(F.seg_wait[:7]) == [T1(2) | A0, T2, 0, 0, A1(0), A1(1), A1(2)]
+    assert list(F.seg_commit[:7]) == [T1(0), 0, T1(1), T1(2) | A0, A1(0), A1(1), A1(2) | T2]
+    assert [F.offset[t] for t in range(14)] == [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]
+    assert [F.shift[t] for t in range(14)] == [5 + o for o in [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]]
+    assert [F.shift[t] for t in range(14, 17)] == [-3, 0, 3] and F.shift[24] == -15 and F.shift[34] == 15
+    # C <= 32: two accumulator sets, `sum` stacked into every group (N = 4C, 3C, 2C)
+    native.check(eng._lib.v2w_model_get_fused(eng._model, 3, C.byref(F)))
+    assert (F.ok, F.stacked, F.channels, F.t_bufs, F.a0_bufs, F.num_taps, F.num_segments) == (1, 1, 32, 2, 2, 32, 6)
+    assert list(F.seg_n[:6]) == [128, 96, 64, 32, 32, 32] and list(F.seg_dcol[:6]) == [0] * 6
+    assert list(F.seg_wait[:6]) == [T2 | A0, 0, 0, A1(0), A1(1), A1(2)]
+    assert F.w_rows == 53 * 32
+    # C = 128 does not stack (N <= 256, TMEM): plain program, single buffered: conv_sum right
+    # behind conv1_0, then conv2_j / conv1_{j+1}
     native.check(eng._lib.v2w_model_get_fused(eng._model, 1, C.byref(F)))
-    assert F.ok and F.channels == 128
+    assert F.ok and F.channels == 128 and not F.stacked
+    assert (F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments, F.w_rows) == (15, 5, 226, 5, 53, 7, 53 * 128)
     assert list(F.seg_type[:7]) == [0, 1, 2, 0, 2, 0, 2] and list(F.seg_branch[:7]) == [0, -1, 0, 1, 1, 2, 2]
     assert list(F.seg_flags[:7]) == [0, 0, 0, 0, 0, 1, 2]
     # transposed convs: column tiles are whole phase groups; a tile issues 2 taps when its phases

@@ -43,7 +43,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/ into wavthruvec_pytorch_b200/libv2w.so; no-op when up to date."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC)]
+    extra = os.environ.get("V2W_NVCC_EXTRA", "").split()   # e.g. -DV2W_TRACE (developer builds)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC)]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     tmp = LIB_PATH.with_suffix(".so.tmp")

@@ -140,11 +140,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(a0_full + 8 * i, 1);
       mbar_init(a0_empty + 8 * i, 1);
       mbar_init(t1_full + 8 * i, 1);
-      mbar_init(t1_empty + 8 * i, 256);
-      mbar_init(a1_full + 8 * i, 256);
+      mbar_init(t1_empty + 8 * i, 8);
+      mbar_init(a1_full + 8 * i, 8);
       mbar_init(a1_empty + 8 * i, 1);
       mbar_init(t2_full + 8 * i, 1);
-      mbar_init(t2_empty + 8 * i, 256);
+      mbar_init(t2_empty + 8 * i, 8);
     }
     for (int i = 0; i < kMaxStagesW; ++i) {
       mbar_init(w_full + 8 * i, 1);
@@ -367,8 +367,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
           tcgen05_fence_before();
-          mbar_arrive(a1_full + 8 * slot);
-          mbar_arrive(t1_empty + 8 * slot);
+          __syncwarp();
+          if (lane == 0) {              // one arrival per warp
+            mbar_arrive(a1_full + 8 * slot);
+            mbar_arrive(t1_empty + 8 * slot);
+          }
         }
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk ----
@@ -432,7 +435,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(t2_empty + 8 * t2s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t2_empty + 8 * t2s);
       }
     }
   }

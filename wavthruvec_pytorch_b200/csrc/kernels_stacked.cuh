@@ -1,0 +1,486 @@
+// Fused multi-receptive-field stage for C <= 64 (ResBlock2), N-stacked:  same algebra as
+// kernels_fused.cuh,
+//
+//     sum_j out_j = [ sum_j conv2_j(A1_j) + conv_sum(A0) ] + sum_j (b1_j + b2_j) + nk * X0
+//     A1_j = half(lrelu(conv1_j(A0) + b1_j + X0))                  (vec2wav/models.py:65-70,135-141)
+//
+// but the tensor-core work is laid out for what actually bounds it at small C.  One
+// tcgen05.mma (M = 128, K = 16) streams its 4 KB A operand from shared memory at ~64 B/clk, i.e.
+// ~64 clk per MMA however small N is: at N = C = 16..64 the tensor pipe idles behind operand
+// delivery (measured: the first fused kernel ran C = 32 at 96 % of that 64-clk bound).  Every conv1
+// of the stage, and conv_sum, read the SAME input tile at the same row shifts, so the taps that share
+// a time offset are issued as ONE MMA whose B operand stacks their weight matrices along N
+// (N up to 4C): 11 entries instead of 21 + 11 for kernel sizes 3/7/11.  That needs
+//   * one row alignment for every accumulator: window row i <-> time q0c - hc + i for T1 AND T2
+//     (conv2 then reads A1 rows i + off, off in [-hc, hc]; rows it cannot see are the discarded
+//     halo rows i < hc, i >= hc + rc of the window);
+//   * TMEM columns [T2 | T1_{nb-1} | ... | T1_0] per 128-row sub-tile with branch slots sorted by
+//     kernel size, so the blocks sharing an offset are a contiguous column range starting at 0.
+//
+// The MMA warp interprets a host-built program (model.cpp plan_stacked, include/v2w.h): segments of
+// entries with wait / commit bit masks, phase-A segments (read the input tile) first, then the
+// phase-B segments (conv2, read A1).  C <= 32 has two accumulator sets (tile k+1's conv1 never
+// waits for tile k's final epilogue), C = 64 fills TMEM with one.  (Issuing conv1 of tile k+1
+// AHEAD of conv2 of tile k was measured 20-25 % slower: with one A1 buffer per branch the
+// epilogue of tile k+1 then waits for conv2_j(k) and the two sides ping-pong.)
+//
+// The epilogue is latency-, not throughput-bound: what matters is that nothing it waits for is a
+// cold global load.  For C <= 32 a thread keeps its fp32 X0 row in registers for all passes of a
+// tile and fetches the NEXT tile's row one tile ahead.
+//
+// Roles: warp 0 weight producer (resident block once for C <= 32, ring for C = 64), warp 2 input
+// tile producer, warp 1 MMA issuer, warps 4-11 epilogue (thread = window row).
+#pragma once
+
+#include "kernels_fused.cuh"
+
+// Developer timeline (build with V2W_NVCC_EXTRA=-DV2W_TRACE): CTA 0 prints SM-clock stamps of its MMA
+// warp and of epilogue warp 4 for the first tiles.  Compiled out otherwise.
+#ifdef V2W_TRACE
+#define V2W_TR_DECL long long tr_t[96]; int tr_tag[96]; int tr_n = 0; const long long tr_base = clock64();
+#ifndef V2W_TR_K0
+#define V2W_TR_K0 30
+#endif
+#define V2W_TR(tag) do { if (blockIdx.x == 0 && tr_n < 96 && (tag) >= V2W_TR_K0 * 100 && (tag) < (V2W_TR_K0 + 2) * 100) { tr_tag[tr_n] = (tag); tr_t[tr_n++] = clock64() - tr_base; } } while (0)
+#define V2W_TR_DUMP(name) do { if (blockIdx.x == 0 && lane == 0) for (int q = 0; q < tr_n; ++q) \
+    printf("TR %s %d %d %lld\n", name, q, tr_tag[q], tr_t[q]); } while (0)
+#else
+#define V2W_TR_DECL
+#define V2W_TR(tag) do { } while (0)
+#define V2W_TR_DUMP(name) do { } while (0)
+#endif
+
+namespace v2w {
+namespace stacked {
+
+using namespace v2w::tc;
+using fused::kBoxRows;
+using fused::kWin;
+using fused::st_shared_v4;
+
+constexpr int kMaxSeg = V2W_FUSED_MAX_SEG;
+constexpr int kMaxEnt = V2W_FUSED_MAX_TAPS;
+constexpr int kBitT2 = V2W_FUSED_BIT_T2, kBitA0 = V2W_FUSED_BIT_A0;
+
+// 32-bit fields only (profiles/r01_ptxas_param_miscompile.md)
+struct Segment {
+  int phase;        // 0: reads the input tile (conv1 / sum), 1: reads an A1 slot (conv2)
+  int src;          // phase 1: A1 slot
+  int dcol, n;      // accumulator columns inside a sub-tile, MMA N
+  int count, first; // entries
+  int acc;          // 0: the first MMA overwrites the accumulator
+  int wait, commit; // V2W_FUSED_BIT_*
+  uint32_t idesc;   // tcgen05 instruction descriptor (M = 128, N = n, operand format)
+};
+
+struct Params {
+  int batch, rows, tiles_per_b;
+  int rc, hc, h1;
+  int a0_boxes;
+  int nseg, nbranch, nent;
+  int t_bufs, a0_bufs;
+  int sub_cols, tile_cols, tmem_cols;
+  int stages_w, stage_w_bytes, w_region_bytes;
+  int w_blocks;                 // resident: C-row blocks of the weight matrix
+  int fp16;
+  Segment seg[kMaxSeg];
+  int a_off16[kMaxEnt];         // operand row shift of the entry in 16-byte units (negative for conv2 taps < 0)
+  int w_off16[kMaxEnt];         // resident weights: offset of the entry's block in 16-byte units
+  int w_row[kMaxEnt];           // first row of the entry's weight block (TMA coordinate)
+  const float* x0;              // fp32 [B, L, C]
+  const float* bias1[V2W_MAX_KERNELS];   // by slot
+  const float* bsum;
+  float mid_slope, res_scale, out_scale, out_slope;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ Params p) {
+  constexpr int kRowBytes = C * 2;              // one K-chunk: the whole channel dimension
+  constexpr int kKSteps = C / 16;
+  constexpr bool kResident = C <= 32;
+  constexpr bool kCacheX0 = C <= 32;
+  constexpr uint32_t kA1Bytes = kWin * kRowBytes;
+  constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
+  constexpr uint32_t kWBlockBytes = C * kRowBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a0_bytes = p.a0_boxes * kBoxBytes;
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_a1 = smem_a0 + p.a0_bufs * a0_bytes;
+  const uint32_t smem_w = smem_a1 + p.nbranch * kA1Bytes;
+  const uint32_t bars = smem_w + p.w_region_bytes;
+  const uint32_t a0_full = bars, a0_empty = bars + 16, w_full = bars + 32, w_empty = bars + 96;
+  const uint32_t t1_full = bars + 160, t1_empty = bars + 224;     // [t_buf][slot]
+  const uint32_t t2_full = bars + 288, t2_empty = bars + 304;     // [t_buf]
+  const uint32_t a1_full = bars + 320, a1_empty = bars + 352;     // [slot]
+  const uint32_t w_all = bars + 384, tmem_slot = bars + 392;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batch * p.tiles_per_b;
+  const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a0_full + 8 * i, 1);
+      mbar_init(a0_empty + 8 * i, 1);
+      mbar_init(t2_full + 8 * i, 1);
+      mbar_init(t2_empty + 8 * i, 8);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(w_full + 8 * i, 1);
+      mbar_init(w_empty + 8 * i, 1);
+      mbar_init(t1_full + 8 * i, 1);
+      mbar_init(t1_empty + 8 * i, 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(a1_full + 8 * i, 8);
+      mbar_init(a1_empty + 8 * i, 1);
+    }
+    mbar_init(w_all, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // =================================== weight producer ====================================
+    if (kResident) {
+      if (elect_one()) {
+        mbar_expect_tx(w_all, p.w_blocks * kWBlockBytes);
+        for (int t = 0; t < p.w_blocks; ++t)
+          tma_load_2d(smem_w + t * kWBlockBytes, &tmW, 0, t * C, w_all);
+      }
+      __syncwarp();
+    } else {
+      Ring rw;
+      for (int it = 0; it < n_my; ++it) {
+        for (int s = 0; s < p.nseg; ++s) {
+          const Segment sg = p.seg[s];
+          for (int t = 0; t < sg.count; ++t) {
+            mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
+            if (elect_one()) {
+              const uint32_t bar = w_full + 8 * rw.s;
+              const uint32_t dst = smem_w + rw.s * p.stage_w_bytes;
+              const int row = p.w_row[sg.first + t];
+              mbar_expect_tx(bar, sg.n * kRowBytes);
+              for (int q = 0; q < sg.n / C; ++q)
+                tma_load_2d(dst + q * kWBlockBytes, &tmW, 0, row + q * C, bar);
+            }
+            __syncwarp();
+            rw.advance(p.stages_w);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================= input tile producer ==================================
+    for (int k = 0; k < n_my; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int b = tile / p.tiles_per_b;
+      const int ti = tile - b * p.tiles_per_b;
+      const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the input tile
+      const uint32_t buf = k % p.a0_bufs, ph = (k / p.a0_bufs) & 1u;
+      mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
+      if (elect_one()) {
+        const uint32_t bar = a0_full + 8 * buf;
+        mbar_expect_tx(bar, p.a0_boxes * kBoxBytes);
+        for (int bx = 0; bx < p.a0_boxes; ++bx)
+          tma_load_3d(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b, bar);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    Ring rw;
+    V2W_TR_DECL
+#ifdef V2W_TRACE
+    unsigned long long tr_g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
+#endif
+    const uint32_t dhi = smem_desc_hi<C>();
+    if (kResident) mbar_wait(w_all, 0);
+    // This warp's instruction latency is what bounds the small-C stages (a tile is 64 MMAs at
+    // C = 16), so everything that can be is precomputed: per-entry descriptor offsets and the
+    // instruction descriptor come from the host, buffer indices are bit operations, and only
+    // the barriers a segment names are touched.
+    const uint32_t tmask = p.t_bufs - 1, amask = p.a0_bufs - 1;     // depths are 1 or 2
+    const uint32_t w_lo = (smem_w & 0x3FFFFu) >> 4;
+    constexpr uint32_t kSubLo = (kMTile * kRowBytes) >> 4;           // second 128-row sub-tile
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t k = it;          // CTA-local tile ordinal
+      const uint32_t tb = k & tmask, tph = (k >> tmask) & 1u;
+      const uint32_t ab = k & amask, aph = (k >> amask) & 1u;
+      const uint32_t a0_lo = ((smem_a0 + ab * a0_bytes) & 0x3FFFFu) >> 4;
+      for (int s = 0; s < p.nseg; ++s) {
+        const Segment sg = p.seg[s];
+        for (uint32_t w = sg.wait; w; w &= w - 1) {
+          const int bit = __ffs(w) - 1;
+          if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), tph ^ 1u);
+          else if (bit == 4) mbar_wait(t2_empty + 8 * tb, tph ^ 1u);
+          else if (bit == 5) mbar_wait(a0_full + 8 * ab, aph);
+          else mbar_wait(a1_full + 8 * (bit - 8), k & 1u);
+        }
+        tcgen05_fence_after();
+        V2W_TR(k * 100 + s * 2);
+        // One elected lane issues the whole segment.
+        if (elect_one()) {
+          const uint32_t a_lo = sg.phase ? ((smem_a1 + sg.src * kA1Bytes) & 0x3FFFFu) >> 4 : a0_lo;
+          const uint32_t d_tmem = tmem_base + tb * p.tile_cols + sg.dcol;
+          const uint32_t d_tmem1 = d_tmem + p.sub_cols;
+          const uint32_t idesc = sg.idesc;
+          Ring r = rw;   // private copy; all lanes advance `rw` below
+          for (int t = 0; t < sg.count; ++t) {
+            const int e = sg.first + t;
+            // 14-bit start-address fields; conv2 entries reach up to hc rows before their tile
+            const uint32_t ad_lo = ((a_lo + p.a_off16[e]) & 0x3FFFu) | (1u << 16);
+            const uint32_t ad1_lo = ((a_lo + p.a_off16[e] + kSubLo) & 0x3FFFu) | (1u << 16);
+            uint32_t bd_lo;
+            if (kResident) {
+              bd_lo = (w_lo + p.w_off16[e]) | (1u << 16);
+            } else {
+              mbar_wait(w_full + 8 * r.s, r.ph);
+              tcgen05_fence_after();
+              bd_lo = (w_lo + ((r.s * p.stage_w_bytes) >> 4)) | (1u << 16);
+            }
+            const uint64_t hi = static_cast<uint64_t>(dhi) << 32;
+            const uint32_t acc0 = sg.acc | (t != 0);
+#pragma unroll
+            for (int kk = 0; kk < kKSteps; ++kk)
+              umma_bf16(d_tmem, (hi | ad_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+#pragma unroll
+            for (int kk = 0; kk < kKSteps; ++kk)
+              umma_bf16(d_tmem1, (hi | ad1_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+            if (!kResident) {
+              umma_commit(w_empty + 8 * r.s);
+              r.advance(p.stages_w);
+            }
+          }
+          for (uint32_t w = sg.commit; w; w &= w - 1) {
+            const int bit = __ffs(w) - 1;
+            if (bit < 4) umma_commit(t1_full + 8 * (tb * 4 + bit));
+            else if (bit == 4) umma_commit(t2_full + 8 * tb);
+            else if (bit == 5) umma_commit(a0_empty + 8 * ab);
+            else umma_commit(a1_empty + 8 * (bit - 8));
+          }
+        }
+        __syncwarp();
+        V2W_TR(k * 100 + s * 2 + 1);
+        if (!kResident) {
+          for (int t = 0; t < sg.count; ++t) rw.advance(p.stages_w);
+        }
+      }
+    }
+    V2W_TR_DUMP("mma");
+#ifdef V2W_TRACE
+    if (lane == 0 && (blockIdx.x % 21) == 0) {
+      unsigned long long g1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+      printf("TRC cta %d tiles %d clocks %lld ns %llu\n", (int)blockIdx.x, n_my, clock64() - tr_base, g1 - tr_g0);
+    }
+#endif
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int sub = (warp - 4) >> 2;              // which 128-row accumulator
+    const int quarter = warp & 3;                 // TMEM lane quarter
+    const int i = sub * kMTile + quarter * 32 + lane;   // window row of this thread
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + sub * p.sub_cols;
+    const uint32_t swz = C == 64 ? (i & 7) : (C == 32 ? ((i >> 1) & 3) : ((i >> 2) & 1));
+    constexpr int kNC = C / 16;                   // 16-column chunks per row
+    constexpr int kXc = kCacheX0 ? C / 4 : 8;     // cached row, or a 2-chunk look-ahead window
+    constexpr int kPair = kNC >= 2 ? 2 : 1;
+    const bool central = i >= p.hc && i < p.hc + p.rc;
+    // fp32 X0 row of tile `k` for this thread (clamped to a valid row; `valid` says whether it counts)
+    auto row_of = [&](int k, bool& valid) -> const float4* {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int b = tile / p.tiles_per_b;
+      const int ti = tile - b * p.tiles_per_b;
+      const int gr = ti * p.rc - p.hc + i;
+      valid = gr >= 0 && gr < p.rows;
+      return reinterpret_cast<const float4*>(
+          p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
+    };
+    float4 xn[kCacheX0 ? kXc : 1];     // C <= 32: the next tile's row, fetched one tile ahead
+    if constexpr (kCacheX0) {
+      bool v;
+      const float4* x = row_of(0, v);
+#pragma unroll
+      for (int e = 0; e < kXc; ++e) xn[e] = __ldg(x + e);
+    }
+    V2W_TR_DECL
+    float4 xc[kXc];
+    if constexpr (!kCacheX0) {         // C = 64: chunks 0 and 1 of the first pass
+      bool v;
+      const float4* x = row_of(0, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xc[e] = __ldg(x + e);
+    }
+    for (int k = 0; k < n_my; ++k) {
+      bool valid, next_valid = false;
+      const float4* xrow = row_of(k, valid);
+      const float4* xnext = k + 1 < n_my ? row_of(k + 1, next_valid) : xrow;
+      const uint32_t tb = k % p.t_bufs, tph = (k / p.t_bufs) & 1u;
+      if constexpr (kCacheX0) {
+#pragma unroll
+        for (int e = 0; e < kXc; ++e) xc[e] = xn[e];
+        if (k + 1 < n_my) {
+#pragma unroll
+          for (int e = 0; e < kXc; ++e) xn[e] = __ldg(xnext + e);
+        }
+      }
+      // ---- per slot: T1 -> A1 = half(lrelu(conv1 + b1 + X0)) in shared memory ----
+      for (int j = 0; j < p.nbranch; ++j) {
+        V2W_TR(k * 100 + j * 10);
+        mbar_wait(t1_full + 8 * (tb * 4 + j), tph);
+        V2W_TR(k * 100 + j * 10 + 1);
+        mbar_wait(a1_empty + 8 * j, (k & 1u) ^ 1u);
+        tcgen05_fence_after();
+        V2W_TR(k * 100 + j * 10 + 2);
+        const uint32_t a1_row = smem_a1 + j * kA1Bytes + i * kRowBytes;
+        const uint32_t t1 = t_row + tb * p.tile_cols + (p.nbranch - j) * C;
+        const float* b1 = p.bias1[j];
+#pragma unroll
+        for (int cp = 0; cp < kNC; cp += kPair) {
+          // two 16-column chunks per TMEM round trip
+          uint32_t rr[kPair][16];
+#pragma unroll
+          for (int u = 0; u < kPair; ++u) tmem_ld16(t1 + (cp + u) * 16, rr[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < kPair; ++u) {
+            const int ci = cp + u;
+            const int cc = ci * 16;
+            const uint32_t (&r)[16] = rr[u];
+            float4 xr[4];
+            if constexpr (kCacheX0) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = xc[ci * 4 + e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
+              // C = 64: a two-chunk window that runs ahead of the consumer -- past the end of
+              // this pass it wraps to chunks 0, 1 of the next pass (same row, L1/L2 hits)
+              const int nc = ci + 2 < kNC ? ci + 2 : ci + 2 - kNC;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + nc * 4 + e);
+            }
+            uint32_t h[8];
+            if (valid) {
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + cc + 4 * e));
+                v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
+                v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
+                v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;
+                v[4 * e + 3] = __uint_as_float(r[4 * e + 3]) + bb.w + xr[e].w;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                h[e] = pack_half2(lrelu(v[2 * e], p.mid_slope), lrelu(v[2 * e + 1], p.mid_slope), p.fp16);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h[e] = 0u;   // conv2's zero padding outside [0, L)
+            }
+            const uint32_t q = cc >> 3;            // 16-byte unit inside the row
+            st_shared_v4(a1_row + ((q ^ swz) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(a1_row + (((q + 1) ^ swz) << 4), h[4], h[5], h[6], h[7]);
+          }
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {              // one arrival per warp: 256 arrivals serialise on the barrier
+          mbar_arrive(a1_full + 8 * j);
+          mbar_arrive(t1_empty + 8 * (tb * 4 + j));
+        }
+        V2W_TR(k * 100 + j * 10 + 3);
+      }
+      // ---- final: out = (T2 + bsum + nk * X0) / nk on the central rows of the window ----
+      {
+        const bool out_valid = valid && central;
+        const size_t row_base = reinterpret_cast<const float*>(xrow) - p.x0;
+        V2W_TR(k * 100 + 50);
+        mbar_wait(t2_full + 8 * tb, tph);
+        tcgen05_fence_after();
+        V2W_TR(k * 100 + 51);
+        const uint32_t t2 = t_row + tb * p.tile_cols;
+#pragma unroll
+        for (int cp = 0; cp < kNC; cp += kPair) {
+          uint32_t rr[kPair][16];
+#pragma unroll
+          for (int u = 0; u < kPair; ++u) tmem_ld16(t2 + (cp + u) * 16, rr[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < kPair; ++u) {
+            const int ci = cp + u;
+            const int cc = ci * 16;
+            const uint32_t (&r)[16] = rr[u];
+            float4 xr[4];
+            if constexpr (kCacheX0) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = xc[ci * 4 + e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
+              // past the end of the tile's last pass the window moves on to the next tile's row
+              const float4* src = ci + 2 < kNC ? xrow + (ci + 2) * 4 : xnext + (ci + 2 - kNC) * 4;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e);
+            }
+            if (out_valid) {
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bsum + cc + 4 * e));
+                v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x) * p.out_scale;
+                v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y) * p.out_scale;
+                v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z) * p.out_scale;
+                v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w) * p.out_scale;
+              }
+              if (p.out_f32) {
+                float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+              }
+              if (p.out_bf16) {
+                uint32_t h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope), p.fp16);
+                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + cc);
+                op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t2_empty + 8 * tb);
+        V2W_TR(k * 100 + 52);
+      }
+    }
+    if (warp == 4) V2W_TR_DUMP("epi");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace stacked
+}  // namespace v2w

@@ -312,7 +312,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, 128);
+      mbar_init(acc_empty + 8 * i, 4);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -559,7 +559,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(acc_empty + 8 * group);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * group);   // one arrival per warp
     }
     if (p.tma_out && lane == 0) tma_store_wait_all();
   }

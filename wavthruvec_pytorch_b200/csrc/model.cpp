@@ -9,6 +9,7 @@
 //   ConditionalBatchNorm1d    vec2wav/modules.py:5-30  (eval: running stats, sigma = u.(W v))
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -97,7 +98,99 @@ static void add_convT(v2w_model* m, int stage, int conv_index, int cin, int cout
   m->layers.push_back(L);
 }
 
-// Decide whether stage `i` can run as one fused kernel and lay out its tap program.
+// Stacked program (C <= 64): see include/v2w.h.  Branch slots are sorted by kernel size so that the
+// set of branches whose conv1 reaches time offset o is always a suffix {jmin..nb-1}; with the TMEM
+// column order [T2 | T1_{nb-1} | ... | T1_0] that suffix plus the `sum` block is columns
+// [0, (nb - jmin + 1) C).  `split_sum`: the first offset group feeds T1 only (columns [C, (nb+1) C))
+// and its `sum` taps run as a separate N = C segment -- T2 is then not touched by the first MMAs of
+// a tile, which takes the previous tile's final epilogue off the tensor pipe's critical path.
+static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
+  const v2w_config& c = m->cfg;
+  const int C = F.channels, nb = F.num_branches;
+  const int d0 = c.resblock_dilation_sizes[0][0];
+  if (C > 64 || (nb + 1) * C > 256 || 2 * (nb + 1) * C > 512) return false;
+  int split_sum = C == 64 ? 1 : 0;
+  if (const char* e = std::getenv("V2W_FUSED_SPLIT_SUM")) split_sum = std::atoi(e) != 0;
+  // slots by ascending kernel size (stable)
+  int order[V2W_MAX_KERNELS];
+  for (int j = 0; j < nb; ++j) order[j] = j;
+  std::stable_sort(order, order + nb, [&](int a, int b) {
+    return c.resblock_kernel_sizes[a] < c.resblock_kernel_sizes[b];
+  });
+  int r[V2W_MAX_KERNELS];
+  int hc = 0, entries = 0;
+  for (int j = 0; j < nb; ++j) {
+    const int k = c.resblock_kernel_sizes[order[j]];
+    r[j] = (k - 1) / 2;
+    hc = std::max(hc, c.resblock_dilation_sizes[order[j]][1] * r[j]);
+    entries += k;
+  }
+  const int h1 = d0 * r[nb - 1];
+  entries += 2 * r[nb - 1] + 1 + (split_sum ? 2 * r[0] + 1 : 0);
+  const int rc = 256 - 2 * hc;
+  const int a0_rows = 256 + 2 * h1;
+  if (rc < 64 || a0_rows > 64 * 7 || entries > V2W_FUSED_MAX_TAPS || 2 * nb + 2 > V2W_FUSED_MAX_SEG)
+    return false;
+  F.stacked = 1;
+  for (int j = 0; j < nb; ++j) F.order[j] = order[j];
+  F.hc = hc; F.h1 = h1; F.rc = rc;
+  F.a0_boxes = (a0_rows + 63) / 64;
+  F.t_bufs = 4 * (nb + 1) * C <= 512 ? 2 : 1;
+  F.a0_bufs = F.t_bufs;
+  int nseg = 0, nent = 0, wrow = 0;
+  auto begin = [&](int type, int branch, int dcol, int n, int acc, int wait, int commit) {
+    F.seg_type[nseg] = type; F.seg_branch[nseg] = branch;
+    F.seg_dcol[nseg] = dcol; F.seg_n[nseg] = n; F.seg_acc[nseg] = acc;
+    F.seg_wait[nseg] = wait; F.seg_commit[nseg] = commit;
+    F.seg_first[nseg] = nent; F.seg_ntaps[nseg] = 0;
+  };
+  auto entry = [&](int off, int shift) {
+    F.offset[nent] = off; F.shift[nent] = shift; F.w_row[nent] = wrow;
+    wrow += F.seg_n[nseg];
+    ++nent; ++F.seg_ntaps[nseg];
+  };
+  // phase A: offset groups g_j = { r[j-1] < |t| <= r[j] }, group 0 first (T1_0 completes first)
+  int last_a = -1;
+  for (int j = 0; j < nb; ++j) {
+    const int lo = j == 0 ? -1 : r[j - 1];
+    if (r[j] == lo) {                      // same kernel size as the previous slot: no new offsets
+      F.seg_commit[last_a] |= V2W_FUSED_BIT_T1(j);
+      continue;
+    }
+    const bool first = j == 0;
+    const int nblk = nb - j + ((first && split_sum) ? 0 : 1);
+    // The epilogue drains T1_0 .. T1_{nb-1}, then T2, in that order: "the last one is free" implies
+    // the earlier ones are, so the first segment of a tile names ONE accumulator barrier.
+    begin(V2W_FUSED_SEG_CONV1, -1, (first && split_sum) ? C : 0, nblk * C, first ? 0 : 1,
+          first ? (V2W_FUSED_BIT_A0 | (split_sum ? V2W_FUSED_BIT_T1(nb - 1) : V2W_FUSED_BIT_T2)) : 0,
+          V2W_FUSED_BIT_T1(j));
+    for (int t = -r[j]; t <= r[j]; ++t)
+      if (std::abs(t) > lo) entry(t * d0, h1 + t * d0);
+    last_a = nseg++;
+    if (first && split_sum) {
+      begin(V2W_FUSED_SEG_SUM, -1, 0, C, 0, V2W_FUSED_BIT_T2, 0);
+      for (int t = -r[0]; t <= r[0]; ++t) entry(t * d0, h1 + t * d0);
+      last_a = nseg++;
+    }
+  }
+  F.seg_commit[last_a] |= V2W_FUSED_BIT_A0;
+  // phase B: conv2 of every slot out of its A1 buffer
+  for (int j = 0; j < nb; ++j) {
+    const int d1 = c.resblock_dilation_sizes[order[j]][1];
+    begin(V2W_FUSED_SEG_CONV2, j, 0, C, 1, V2W_FUSED_BIT_A1(j),
+          V2W_FUSED_BIT_A1(j) | (j == nb - 1 ? V2W_FUSED_BIT_T2 : 0));
+    for (int t = -r[j]; t <= r[j]; ++t) entry(t * d1, t * d1);
+    ++nseg;
+  }
+  F.num_segments = nseg;
+  F.num_taps = nent;
+  F.w_rows = wrow;
+  F.ok = 1;
+  (void)i;
+  return true;
+}
+
+// Decide whether stage `i` can run as one fused kernel and lay out its program.
 // `first_layer` = index of branch 0's first conv in m->layers.
 static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_layer) {
   v2w_fused_desc F;
@@ -108,6 +201,7 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   F.channels = C;
   F.num_branches = nb;
   F.first_layer = first_layer;
+  for (int j = 0; j < nb; ++j) F.order[j] = j;
   if (c.resblock_type != 2 || (C != 16 && C != 32 && C != 64 && C != 128)) return F;
   const int d0 = c.resblock_dilation_sizes[0][0];
   int kmax = 0, hc = 0, total = 0;
@@ -118,6 +212,8 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
     hc = std::max(hc, c.resblock_dilation_sizes[j][1] * (k - 1) / 2);
     total += 2 * k;
   }
+  const char* no_stack = std::getenv("V2W_FUSED_NO_STACK");
+  if (!(no_stack && std::atoi(no_stack)) && plan_stacked(m, i, F)) return F;
   const int h1 = d0 * (kmax - 1) / 2;
   total += kmax;
   const int rc = 256 - 2 * hc;
@@ -133,16 +229,18 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   auto push = [&](int type, int j) {
     const int k = type == V2W_FUSED_SEG_SUM ? kmax : c.resblock_kernel_sizes[j];
     const int dil = type == V2W_FUSED_SEG_CONV2 ? c.resblock_dilation_sizes[j][1] : d0;
-    F.seg_type[nseg] = (int16_t)type;
-    F.seg_branch[nseg] = (int16_t)j;
-    F.seg_ntaps[nseg] = (int16_t)k;
-    F.seg_first[nseg] = (int16_t)ntap;
+    F.seg_type[nseg] = type;
+    F.seg_branch[nseg] = j;
+    F.seg_ntaps[nseg] = k;
+    F.seg_first[nseg] = ntap;
+    F.seg_n[nseg] = C;
     for (int t = 0; t < k; ++t) {
       const int off = (t - (k - 1) / 2) * dil;
-      F.offset[ntap] = (int16_t)off;
-      F.shift[ntap] = (int16_t)(type == V2W_FUSED_SEG_CONV1 ? h1 + off
-                                : type == V2W_FUSED_SEG_SUM ? hc + h1 + off
-                                                            : hc + off);
+      F.offset[ntap] = off;
+      F.shift[ntap] = type == V2W_FUSED_SEG_CONV1 ? h1 + off
+                      : type == V2W_FUSED_SEG_SUM ? hc + h1 + off
+                                                  : hc + off;
+      F.w_row[ntap] = ntap * C;
       ++ntap;
     }
     ++nseg;
@@ -161,6 +259,7 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   F.seg_flags[nseg - 1] |= 2;
   F.num_segments = nseg;
   F.num_taps = ntap;
+  F.w_rows = ntap * C;
   F.ok = 1;
   return F;
 }
@@ -341,7 +440,7 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
   for (auto& F : m->fused) {
     if (!F.ok) continue;
     F.w_off = off;
-    off = align_up(off + (int64_t)F.num_taps * F.channels * F.channels * 2, 1024);
+    off = align_up(off + (int64_t)F.w_rows * F.channels * 2, 1024);
     F.bsum_off = off;
     off = align_up(off + (int64_t)F.channels * 4, 1024);
   }
@@ -499,28 +598,43 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
       const float* bl = reinterpret_cast<const float*>(base + m->layers[F.first_layer + j].bias_off);
       for (int ch = 0; ch < C; ++ch) bsum[ch] += bl[ch];
     }
+    // weight matrix [w_rows][C]: per entry one C x C block (n, c) per accumulator block it feeds
     std::vector<float> acc((size_t)C * C);
+    const int nb = F.num_branches;
     for (int s = 0; s < F.num_segments; ++s) {
+      const int type = F.seg_type[s];
+      const int nblk = F.seg_n[s] / C;
       for (int t = 0; t < F.seg_ntaps[s]; ++t) {
-        const int tap = F.seg_first[s] + t;
-        std::fill(acc.begin(), acc.end(), 0.f);
-        // layers contributing to this tap: one conv, or every conv1 that has this offset
-        for (int j = 0; j < F.num_branches; ++j) {
-          int li;
-          if (F.seg_type[s] == V2W_FUSED_SEG_SUM) li = F.first_layer + 2 * j;
-          else if (F.seg_branch[s] == j) li = F.first_layer + 2 * j + (F.seg_type[s] == V2W_FUSED_SEG_CONV2);
-          else continue;
-          const v2w_layer_desc& L = m->layers[li];
-          int lt = -1;
-          for (int q = 0; q < L.num_taps; ++q)
-            if (L.tap_off[q] == F.offset[tap]) lt = q;
-          if (lt < 0) continue;   // this branch's kernel does not reach that offset
-          const float* w32 = reinterpret_cast<const float*>(base + L.w32_off) + (size_t)lt * C * C;
-          for (int ci = 0; ci < C; ++ci)
-            for (int n = 0; n < C; ++n) acc[(size_t)n * C + ci] += w32[(size_t)ci * C + n];
+        const int ent = F.seg_first[s] + t;
+        for (int q = 0; q < nblk; ++q) {
+          // which conv feeds block q: -1 = sum of all conv1, else model branch `br`, conv `which`
+          int br = -1, which = 0;
+          if (type == V2W_FUSED_SEG_CONV2) {
+            br = F.stacked ? F.order[F.seg_branch[s]] : F.seg_branch[s];
+            which = 1;
+          } else if (type == V2W_FUSED_SEG_CONV1) {
+            if (F.stacked) {
+              const int col = F.seg_dcol[s] / C + q;       // 0 = T2 (sum), c = T1 of slot nb - c
+              br = col == 0 ? -1 : F.order[nb - col];
+            } else {
+              br = F.seg_branch[s];
+            }
+          }
+          std::fill(acc.begin(), acc.end(), 0.f);
+          for (int j = 0; j < nb; ++j) {
+            if (br >= 0 && br != j) continue;
+            const v2w_layer_desc& L = m->layers[F.first_layer + 2 * j + which];
+            int lt = -1;
+            for (int u = 0; u < L.num_taps; ++u)
+              if (L.tap_off[u] == F.offset[ent]) lt = u;
+            if (lt < 0) continue;   // this branch's kernel does not reach that offset
+            const float* w32 = reinterpret_cast<const float*>(base + L.w32_off) + (size_t)lt * C * C;
+            for (int ci = 0; ci < C; ++ci)
+              for (int n = 0; n < C; ++n) acc[(size_t)n * C + ci] += w32[(size_t)ci * C + n];
+          }
+          uint16_t* dst = wf + ((size_t)F.w_row[ent] + (size_t)q * C) * C;
+          for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = half_bits(acc[e]);
         }
-        uint16_t* dst = wf + (size_t)tap * C * C;
-        for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = half_bits(acc[e]);
       }
     }
   }

@@ -22,6 +22,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_stacked.cuh"
 
 namespace v2w {
 
@@ -50,7 +51,9 @@ struct TcLaunch {
 
 struct FusedLaunch {
   CUtensorMap tm_a, tm_w;
-  fused::Params prm;
+  fused::Params prm;       // plain program (kernels_fused.cuh)
+  stacked::Params sprm;    // stacked program (kernels_stacked.cuh)
+  bool stacked = false;
   int grid = 0;
   int smem = 0;
   int channels = 0;
@@ -392,12 +395,95 @@ static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // fused MRF stage launcher
 // ---------------------------------------------------------------------------------------------
+static int encode_fused_maps(const v2w_fused_desc& F, const v2w_op_desc& d, const uint8_t* packed,
+                             uint8_t* ws, bool fp16, int kc, FusedLaunch* L);
+
+// Stacked program (C <= 64): buffering depths and the shared-memory / TMEM layout of
+// kernels_stacked.cuh.
+static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2w_op_desc& d,
+                           const uint8_t* packed, uint8_t* ws, bool fp16, int sms, FusedLaunch* L) {
+  const int C = F.channels, nb = F.num_branches;
+  stacked::Params& p = L->sprm;
+  std::memset(&p, 0, sizeof(p));
+  L->stacked = true;
+  L->channels = C;
+  p.batch = d.batch; p.rows = d.rows;
+  p.tiles_per_b = (d.rows + F.rc - 1) / F.rc;
+  p.rc = F.rc; p.hc = F.hc; p.h1 = F.h1; p.a0_boxes = F.a0_boxes;
+  p.nseg = F.num_segments; p.nbranch = nb; p.nent = F.num_taps;
+  p.t_bufs = F.t_bufs; p.a0_bufs = F.a0_bufs;
+  p.sub_cols = (nb + 1) * C;
+  p.tile_cols = 2 * p.sub_cols;
+  int cols = 32;
+  while (cols < p.t_bufs * p.tile_cols) cols *= 2;
+  if (cols > 512) {
+    set_error("fused stage: accumulators (%d columns) exceed tensor memory", p.t_bufs * p.tile_cols);
+    return V2W_ERR_INVALID;
+  }
+  p.tmem_cols = cols;
+  int max_n = 0;
+  for (int s = 0; s < F.num_segments; ++s) {
+    stacked::Segment& g = p.seg[s];
+    g.phase = F.seg_type[s] == V2W_FUSED_SEG_CONV2;
+    g.src = g.phase ? F.seg_branch[s] : 0;
+    g.dcol = F.seg_dcol[s]; g.n = F.seg_n[s];
+    g.count = F.seg_ntaps[s]; g.first = F.seg_first[s];
+    g.acc = F.seg_acc[s]; g.wait = F.seg_wait[s]; g.commit = F.seg_commit[s];
+    // tcgen05 instruction descriptor, kind::f16: D fp32, A/B bf16 (1) or fp16 (0), K-major, M = 128
+    const uint32_t fmt = fp16 ? 0u : 1u;
+    g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.n >> 3) << 17) | ((128u >> 4) << 24);
+    max_n = std::max(max_n, g.n);
+  }
+  const int row_bytes = C * 2;
+  for (int t = 0; t < F.num_taps; ++t) {
+    p.a_off16[t] = F.shift[t] * row_bytes / 16;
+    p.w_off16[t] = F.w_row[t] * row_bytes / 16;
+    p.w_row[t] = F.w_row[t];
+  }
+  const int a0_bytes = F.a0_boxes * fused::kBoxRows * row_bytes;
+  const int a1_bytes = fused::kWin * row_bytes;
+  const int budget = 227 * 1024 - 1024 - 512;
+  const int left = budget - p.a0_bufs * a0_bytes - nb * a1_bytes;
+  if (C <= 32) {
+    p.stages_w = 1;
+    p.w_blocks = F.w_rows / C;
+    p.w_region_bytes = (int)align_up((int64_t)F.w_rows * row_bytes, 1024);
+    if (p.w_region_bytes > left) {
+      set_error("fused stage: resident weights (%d B) do not fit shared memory", p.w_region_bytes);
+      return V2W_ERR_INVALID;
+    }
+  } else {
+    p.stage_w_bytes = (int)align_up((int64_t)max_n * row_bytes, 1024);
+    p.stages_w = std::min(left / p.stage_w_bytes, tc::kMaxStagesW);
+    if (p.stages_w < 2) {
+      set_error("fused stage: does not fit shared memory");
+      return V2W_ERR_INVALID;
+    }
+    p.w_region_bytes = p.stages_w * p.stage_w_bytes;
+  }
+  p.x0 = reinterpret_cast<const float*>(ws + d.residual);
+  for (int j = 0; j < nb; ++j)
+    p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * F.order[j]].bias_off);
+  p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
+  p.mid_slope = kLreluSlope;
+  p.res_scale = (float)nb;
+  p.out_scale = d.out_scale;
+  p.out_slope = d.out_slope;
+  p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
+  p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
+  p.fp16 = fp16 ? 1 : 0;
+  L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + 1024;
+  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
+  return encode_fused_maps(F, d, packed, ws, fp16, C, L);
+}
+
 static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_op_desc& d,
                          const uint8_t* packed, uint8_t* ws, bool fp16, FusedLaunch* L) {
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int C = F.channels;
+  if (F.stacked) return prepare_stacked(m, F, d, packed, ws, fp16, sms, L);
   fused::Params& p = L->prm;
   std::memset(&p, 0, sizeof(p));
   p.batch = d.batch; p.rows = d.rows;
@@ -450,8 +536,14 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   L->smem = slots * (a0_bytes + a1_bytes) + w_bytes_total + 512 + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
 
+  return encode_fused_maps(F, d, packed, ws, fp16, kc, L);
+}
+
+static int encode_fused_maps(const v2w_fused_desc& F, const v2w_op_desc& d, const uint8_t* packed,
+                             uint8_t* ws, bool fp16, int kc, FusedLaunch* L) {
+  const int C = F.channels;
   EncodeTiledFn enc = nullptr;
-  rc = get_encode_fn(&enc);
+  int rc = get_encode_fn(&enc);
   if (rc) return rc;
   const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                           : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -471,7 +563,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
     }
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)F.num_taps * C};
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)F.w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)C};
     cuuint32_t estr[2] = {1, 1};
@@ -498,7 +590,23 @@ static int launch_fused(const FusedLaunch& L, cudaStream_t st) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<32>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  if (L.stacked) {
+    if (L.channels == 64)
+      stacked::mrf_stacked_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+    else if (L.channels == 32)
+      stacked::mrf_stacked_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+    else
+      stacked::mrf_stacked_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+    V2W_CUDA(cudaGetLastError());
+    return V2W_OK;
   }
   if (L.channels == 128)
     fused::mrf_stage_kernel<128><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);

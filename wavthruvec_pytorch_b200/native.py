@@ -27,7 +27,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
 OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED = 0, 1, 2, 3, 4
-FUSED_MAX_SEG, FUSED_MAX_TAPS = 12, 80
+FUSED_MAX_SEG, FUSED_MAX_TAPS = 16, 96
 SEG_CONV1, SEG_SUM, SEG_CONV2 = 0, 1, 2
 ROLE_CONV_PRE, ROLE_UPSAMPLE, ROLE_RESBLOCK, ROLE_CONV_POST = 0, 1, 2, 3
 TC_FLAG_PER_TAP = 1
@@ -121,10 +121,15 @@ class FusedDesc(C.Structure):
         ("ok", C.c_int32), ("channels", C.c_int32), ("num_branches", C.c_int32),
         ("first_layer", C.c_int32), ("hc", C.c_int32), ("h1", C.c_int32), ("rc", C.c_int32),
         ("a0_boxes", C.c_int32), ("num_segments", C.c_int32), ("num_taps", C.c_int32),
-        ("seg_type", C.c_int16 * FUSED_MAX_SEG), ("seg_branch", C.c_int16 * FUSED_MAX_SEG),
-        ("seg_ntaps", C.c_int16 * FUSED_MAX_SEG), ("seg_first", C.c_int16 * FUSED_MAX_SEG),
-        ("seg_flags", C.c_int16 * FUSED_MAX_SEG),
-        ("shift", C.c_int16 * FUSED_MAX_TAPS), ("offset", C.c_int16 * FUSED_MAX_TAPS),
+        ("stacked", C.c_int32), ("order", C.c_int32 * 4), ("t_bufs", C.c_int32), ("a0_bufs", C.c_int32),
+        ("seg_type", C.c_int32 * FUSED_MAX_SEG), ("seg_branch", C.c_int32 * FUSED_MAX_SEG),
+        ("seg_ntaps", C.c_int32 * FUSED_MAX_SEG), ("seg_first", C.c_int32 * FUSED_MAX_SEG),
+        ("seg_flags", C.c_int32 * FUSED_MAX_SEG),
+        ("seg_dcol", C.c_int32 * FUSED_MAX_SEG), ("seg_n", C.c_int32 * FUSED_MAX_SEG),
+        ("seg_acc", C.c_int32 * FUSED_MAX_SEG),
+        ("seg_wait", C.c_int32 * FUSED_MAX_SEG), ("seg_commit", C.c_int32 * FUSED_MAX_SEG),
+        ("shift", C.c_int32 * FUSED_MAX_TAPS), ("offset", C.c_int32 * FUSED_MAX_TAPS),
+        ("w_row", C.c_int32 * FUSED_MAX_TAPS), ("w_rows", C.c_int32),
         ("w_off", C.c_int64), ("bsum_off", C.c_int64),
     ]
 
