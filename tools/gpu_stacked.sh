@@ -4,9 +4,9 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/pytest_stacked.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_stacked.log
 tail -n 4 gpurun_out/pytest_stacked.log
 for v in ${VARIANTS:-default lag1 nostack}; do
-  unset V2W_FUSED_SPLIT_SUM V2W_FUSED_NO_STACK V2W_FUSED_LAG
+  unset V2W_FUSED_SPLIT_SUM V2W_FUSED_NO_STACK V2W_FUSED_MMA_WARPS
   case $v in
-    lag1) export V2W_FUSED_LAG=1;;
+    mma1) export V2W_FUSED_MMA_WARPS=1;;
     split0) export V2W_FUSED_SPLIT_SUM=0;;
     split1) export V2W_FUSED_SPLIT_SUM=1;;
     nostack) export V2W_FUSED_NO_STACK=1;;

@@ -2,7 +2,7 @@
 import sys
 
 def main(path):
-    lines = [l.split() for l in open(path) if l.startswith('TR')]
+    lines = [l.split() for l in open(path) if l.startswith('TR ')]
     kern, cur, seen = [], {'mma': [], 'epi': []}, {'mma': -1, 'epi': -1}
     for _, name, q, tag, t in lines:
         q = int(q)

@@ -79,6 +79,7 @@ struct Params {
   int a0_boxes;
   int nseg, nbranch, nent;
   int t_bufs, a0_bufs;
+  int mma_warps;                // 1, or 2 (alternate tiles; needs t_bufs == a0_bufs == 2, resident weights)
   int sub_cols, tile_cols, tmem_cols;
   int stages_w, stage_w_bytes, w_region_bytes;
   int w_blocks;                 // resident: C-row blocks of the weight matrix
@@ -117,8 +118,9 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t a0_full = bars, a0_empty = bars + 16, w_full = bars + 32, w_empty = bars + 96;
   const uint32_t t1_full = bars + 160, t1_empty = bars + 224;     // [t_buf][slot]
   const uint32_t t2_full = bars + 288, t2_empty = bars + 304;     // [t_buf]
-  const uint32_t a1_full = bars + 320, a1_empty = bars + 352;     // [slot]
-  const uint32_t w_all = bars + 384, tmem_slot = bars + 392;
+  const uint32_t a1_full = bars + 320;                            // [t_buf][slot]: one waiter each
+  const uint32_t a1_empty = bars + 384;                           // [slot]
+  const uint32_t w_all = bars + 416, tmem_slot = bars + 424;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,6 +144,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(a1_full + 8 * i, 8);
+      mbar_init(a1_full + 8 * (4 + i), 8);
       mbar_init(a1_empty + 8 * i, 1);
     }
     mbar_init(w_all, 1);
@@ -202,8 +205,13 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 3 && p.mma_warps == 2)) {
     // ====================================== MMA issuer ======================================
+    // With two accumulator sets (C <= 32) warps 1 and 3 take alternate tiles: each thread's
+    // tcgen05.commit covers exactly its own tile's MMAs, the sets and input buffers are indexed by
+    // tile parity, and a1_full is per (set, slot) so that each barrier has ONE waiter that sees its
+    // phases in order (a parity wait can only tell a phase from its neighbour: a warp waiting for
+    // tile k+1's A1 on a barrier shared with tile k would pass on tile k-1's phase).
     Ring rw;
     V2W_TR_DECL
 #ifdef V2W_TRACE
@@ -219,7 +227,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmask = p.t_bufs - 1, amask = p.a0_bufs - 1;     // depths are 1 or 2
     const uint32_t w_lo = (smem_w & 0x3FFFFu) >> 4;
     constexpr uint32_t kSubLo = (kMTile * kRowBytes) >> 4;           // second 128-row sub-tile
-    for (int it = 0; it < n_my; ++it) {
+    for (int it = (warp == 3 ? 1 : 0); it < n_my; it += p.mma_warps) {
       const uint32_t k = it;          // CTA-local tile ordinal
       const uint32_t tb = k & tmask, tph = (k >> tmask) & 1u;
       const uint32_t ab = k & amask, aph = (k >> amask) & 1u;
@@ -231,7 +239,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), tph ^ 1u);
           else if (bit == 4) mbar_wait(t2_empty + 8 * tb, tph ^ 1u);
           else if (bit == 5) mbar_wait(a0_full + 8 * ab, aph);
-          else mbar_wait(a1_full + 8 * (bit - 8), k & 1u);
+          else mbar_wait(a1_full + 8 * (tb * 4 + bit - 8), tph);
         }
         tcgen05_fence_after();
         V2W_TR(k * 100 + s * 2);
@@ -283,9 +291,9 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-    V2W_TR_DUMP("mma");
+    if (warp == 1) V2W_TR_DUMP("mma");
 #ifdef V2W_TRACE
-    if (lane == 0 && (blockIdx.x % 21) == 0) {
+    if (warp == 1 && lane == 0 && (blockIdx.x % 21) == 0) {
       unsigned long long g1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
       printf("TRC cta %d tiles %d clocks %lld ns %llu\n", (int)blockIdx.x, n_my, clock64() - tr_base, g1 - tr_g0);
@@ -403,7 +411,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {              // one arrival per warp: 256 arrivals serialise on the barrier
-          mbar_arrive(a1_full + 8 * j);
+          mbar_arrive(a1_full + 8 * (tb * 4 + j));
           mbar_arrive(t1_empty + 8 * (tb * 4 + j));
         }
         V2W_TR(k * 100 + j * 10 + 3);

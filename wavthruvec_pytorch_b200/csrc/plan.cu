@@ -412,6 +412,8 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   p.rc = F.rc; p.hc = F.hc; p.h1 = F.h1; p.a0_boxes = F.a0_boxes;
   p.nseg = F.num_segments; p.nbranch = nb; p.nent = F.num_taps;
   p.t_bufs = F.t_bufs; p.a0_bufs = F.a0_bufs;
+  p.mma_warps = (F.t_bufs == 2 && F.a0_bufs == 2 && C <= 32) ? 2 : 1;
+  if (const char* e = std::getenv("V2W_FUSED_MMA_WARPS")) p.mma_warps = std::min(p.mma_warps, std::max(1, std::atoi(e)));
   p.sub_cols = (nb + 1) * C;
   p.tile_cols = 2 * p.sub_cols;
   int cols = 32;
