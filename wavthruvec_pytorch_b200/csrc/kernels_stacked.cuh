@@ -96,6 +96,14 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -152,6 +160,14 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  // biases of every pass in shared memory ([slot][C], then bsum[C]): an LDS broadcast in the
+  // epilogue instead of an L1 round trip on its critical path
+  const uint32_t smem_bias = bars + 512;
+  for (int t = threadIdx.x; t < (p.nbranch + 1) * C; t += kThreads) {
+    const int j = t / C, ch = t - j * C;
+    const float v = j < p.nbranch ? p.bias1[j][ch] : p.bsum[ch];
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_bias + 4 * t), "f"(v) : "memory");
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -358,7 +374,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         V2W_TR(k * 100 + j * 10 + 2);
         const uint32_t a1_row = smem_a1 + j * kA1Bytes + i * kRowBytes;
         const uint32_t t1 = t_row + tb * p.tile_cols + (p.nbranch - j) * C;
-        const float* b1 = p.bias1[j];
+        const uint32_t b1 = smem_bias + j * (C * 4);
 #pragma unroll
         for (int cp = 0; cp < kNC; cp += kPair) {
           // two 16-column chunks per TMEM round trip
@@ -389,7 +405,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float v[16];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + cc + 4 * e));
+                const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
                 v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
                 v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
                 v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;
@@ -452,7 +468,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float v[16];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bsum + cc + 4 * e));
+                const float4 bb = ld_shared_f4(smem_bias + (p.nbranch * C + cc + 4 * e) * 4);
                 v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x) * p.out_scale;
                 v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y) * p.out_scale;
                 v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z) * p.out_scale;

@@ -444,7 +444,7 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   }
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * row_bytes;
   const int a1_bytes = fused::kWin * row_bytes;
-  const int budget = 227 * 1024 - 1024 - 512;
+  const int budget = 227 * 1024 - 1024 - 512 - (nb + 1) * C * 4;
   const int left = budget - p.a0_bufs * a0_bytes - nb * a1_bytes;
   if (C <= 32) {
     p.stages_w = 1;
@@ -474,7 +474,8 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
   p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
   p.fp16 = fp16 ? 1 : 0;
-  L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + 1024;
+  // + barriers (512) + bias table + 1 KB alignment slack
+  L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + (nb + 1) * C * 4 + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
   return encode_fused_maps(F, d, packed, ws, fp16, C, L);
 }
