@@ -182,7 +182,7 @@ typedef struct v2w_cond_desc {
 #define V2W_FUSED_BIT_T1(j) (1 << (j))       /* accumulator of branch slot j (wait: free, commit: complete) */
 #define V2W_FUSED_BIT_T2 (1 << 4)
 #define V2W_FUSED_BIT_A0 (1 << 5)            /* wait: input tile landed; commit: input tile no longer read */
-#define V2W_FUSED_BIT_A1(j) (1 << (8 + (j))) /* wait: A1 of slot j written; commit: no longer read */
+#define V2W_FUSED_BIT_A1(j) (1 << (8 + (j))) /* wait only: A1 of slot j written */
 typedef struct v2w_fused_desc {
   int32_t ok;                  /* 0: this stage is executed as separate tap-GEMM ops */
   int32_t channels, num_branches;

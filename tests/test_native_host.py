@@ -238,7 +238,7 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     assert list(F.seg_dcol[:7]) == [64, 0, 0, 0, 0, 0, 0] and list(F.seg_n[:7]) == [192, 64, 192, 128, 64, 64, 64]
     assert list(F.seg_acc[:7]) == [0, 0, 1, 1, 1, 1, 1]
     assert list(F.seg_wait[:7]) == [T1(2) | A0, T2, 0, 0, A1(0), A1(1), A1(2)]
-    assert list(F.seg_commit[:7]) == [T1(0), 0, T1(1), T1(2) | A0, A1(0), A1(1), A1(2) | T2]
+    assert list(F.seg_commit[:7]) == [T1(0), 0, T1(1), T1(2) | A0, 0, 0, T2]
     assert [F.offset[t] for t in range(14)] == [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]
     assert [F.shift[t] for t in range(14)] == [5 + o for o in [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]]
     assert [F.shift[t] for t in range(14, 17)] == [-3, 0, 3] and F.shift[24] == -15 and F.shift[34] == 15

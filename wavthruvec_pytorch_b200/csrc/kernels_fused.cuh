@@ -106,6 +106,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -155,6 +163,15 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, K::kTmemCols);
+  // conv1 biases in shared memory ([branch][C]): an LDS broadcast in the per-branch epilogue
+  // instead of an L1 round trip on its critical path (bsum stays in global memory: C = 128 needs
+  // every remaining byte for the fifth weight stage)
+  const uint32_t smem_bias = bars + 512;
+  for (int t = threadIdx.x; t < p.nbranch * C; t += kThreads) {
+    const int j = t / C, ch = t - j * C;
+    const float v = p.bias1[j][ch];
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_bias + 4 * t), "f"(v) : "memory");
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -321,7 +338,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(a1_empty + 8 * slot, ph ^ 1u);
           tcgen05_fence_after();
           const uint32_t a1_row = smem_a1 + slot * K::kA1Bytes + i * kRowBytes;
-          const float* b1 = p.bias1[j];
+          const uint32_t b1 = smem_bias + j * (C * 4);
 #pragma unroll
           for (int ci = 0; ci < kNC; ++ci) {
             const int cc = ci * 16;
@@ -345,7 +362,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float v[16];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + cc + 4 * e));
+                const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
                 v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
                 v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
                 v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;

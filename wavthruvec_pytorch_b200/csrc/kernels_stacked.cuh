@@ -96,13 +96,7 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr));
-  return v;
-}
+using fused::ld_shared_f4;
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -127,7 +121,6 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t t1_full = bars + 160, t1_empty = bars + 224;     // [t_buf][slot]
   const uint32_t t2_full = bars + 288, t2_empty = bars + 304;     // [t_buf]
   const uint32_t a1_full = bars + 320;                            // [t_buf][slot]: one waiter each
-  const uint32_t a1_empty = bars + 384;                           // [slot]
   const uint32_t w_all = bars + 416, tmem_slot = bars + 424;
 
   const int warp = threadIdx.x >> 5;
@@ -153,7 +146,6 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int i = 0; i < 4; ++i) {
       mbar_init(a1_full + 8 * i, 8);
       mbar_init(a1_full + 8 * (4 + i), 8);
-      mbar_init(a1_empty + 8 * i, 1);
     }
     mbar_init(w_all, 1);
     fence_barrier_init();
@@ -296,8 +288,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int bit = __ffs(w) - 1;
             if (bit < 4) umma_commit(t1_full + 8 * (tb * 4 + bit));
             else if (bit == 4) umma_commit(t2_full + 8 * tb);
-            else if (bit == 5) umma_commit(a0_empty + 8 * ab);
-            else umma_commit(a1_empty + 8 * (bit - 8));
+            else umma_commit(a0_empty + 8 * ab);
           }
         }
         __syncwarp();
@@ -369,7 +360,8 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         V2W_TR(k * 100 + j * 10);
         mbar_wait(t1_full + 8 * (tb * 4 + j), tph);
         V2W_TR(k * 100 + j * 10 + 1);
-        mbar_wait(a1_empty + 8 * j, (k & 1u) ^ 1u);
+        // A1_j is free: this thread has already seen t2_full of the previous tile (final pass
+        // below), whose commit covers every conv2 MMA that read the A1 buffers.
         tcgen05_fence_after();
         V2W_TR(k * 100 + j * 10 + 2);
         const uint32_t a1_row = smem_a1 + j * kA1Bytes + i * kRowBytes;

@@ -177,8 +177,9 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
   // phase B: conv2 of every slot out of its A1 buffer
   for (int j = 0; j < nb; ++j) {
     const int d1 = c.resblock_dilation_sizes[order[j]][1];
-    begin(V2W_FUSED_SEG_CONV2, j, 0, C, 1, V2W_FUSED_BIT_A1(j),
-          V2W_FUSED_BIT_A1(j) | (j == nb - 1 ? V2W_FUSED_BIT_T2 : 0));
+    // no per-slot "A1 no longer read" commit: the epilogue overwrites A1 only after it has seen the
+    // tile's T2 complete, and that commit covers every conv2 MMA
+    begin(V2W_FUSED_SEG_CONV2, j, 0, C, 1, V2W_FUSED_BIT_A1(j), j == nb - 1 ? V2W_FUSED_BIT_T2 : 0);
     for (int t = -r[j]; t <= r[j]; ++t) entry(t * d1, t * d1);
     ++nseg;
   }

@@ -504,7 +504,8 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   p.stage_w_bytes = (int)align_up((int64_t)C * kc * 2, 1024);   // one (tap, K-chunk) block
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * C * 2;
   const int a1_bytes = fused::kWin * C * 2;
-  const int budget = 227 * 1024 - 1024 - 512;
+  const int bias_bytes = F.num_branches * C * 4;
+  const int budget = 227 * 1024 - 1024 - 512 - bias_bytes;
   const int left = budget - slots * (a0_bytes + a1_bytes);
   int w_bytes_total;
   if (C <= 32) {
@@ -536,7 +537,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   L->channels = C;
   p.w_region_bytes = w_bytes_total;
   p.fp16 = fp16 ? 1 : 0;
-  L->smem = slots * (a0_bytes + a1_bytes) + w_bytes_total + 512 + 1024;
+  L->smem = slots * (a0_bytes + a1_bytes) + w_bytes_total + 512 + bias_bytes + 1024;
   L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
 
   return encode_fused_maps(F, d, packed, ws, fp16, kc, L);
