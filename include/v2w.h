@@ -300,6 +300,26 @@ int32_t v2w_forward_host(struct v2w_plan* p, const float* x_host, const float* s
                          const float* noise_host, float* out_host, void* stream,
                          int32_t* gpu_launches);
 
+/* Variable-length batch.  The reference zero-pads features to the longest
+ * utterance of a batch (vec2wav/dataset.py:212, utils.py:60-77) and generates the padded tail too.
+ * Here utterance b has row_offsets[b+1] - row_offsets[b] frames (1 .. plan frames); features are ONE
+ * packed time-major buffer x_rows[sum frames][num_wv_feat] (a dataset item's layout,
+ * dataset.py:181-187, concatenated) and the waveforms come back un-padded in ONE packed buffer:
+ * utterance b owns samples [row_offsets[b] * up, row_offsets[b+1] * up), up = total upsampling.
+ * out_format: V2W_OUT_F32 (float) or V2W_OUT_PCM16 (int16 = round(clamp(y * 32768)), MAX_WAV_VALUE of
+ * dataset.py:13).  `row_offsets_host` is a HOST array of batch + 1 ints (validated; passed to the kernels
+ * by value, so the call is fully asynchronous; at most 512 utterances per call).  Values of every valid sample equal those of the padded forward: the caller only has
+ * to pick plan frames >= longest utterance + v2w_model_halo_frames() (or the longest utterance of
+ * the reference batch, whichever is smaller) -- the receptive field does not reach further. */
+#define V2W_OUT_F32 0
+#define V2W_OUT_PCM16 1
+int32_t v2w_forward_ragged(struct v2w_plan* p, const float* x_rows_dev, const int32_t* row_offsets_host,
+                           const float* spk_dev, const float* noise_dev, void* out_packed_dev,
+                           int32_t out_format, void* stream, int32_t* gpu_launches);
+/* Input frames past an utterance's end that can influence its last valid output sample (right
+ * receptive field of conv_pre .. conv_post, in frames, rounded up). */
+int32_t v2w_model_halo_frames(const struct v2w_model* m);
+
 /* Pipelined generation from HOST buffers (throughput API): up to two steps in flight on three
  * library-owned streams -- H2D of step i+1 and D2H of step i-1 overlap the kernels of step i.
  * Staging buffers are owned by the pipeline (cudaMalloc).  Every submitted step still copies its

@@ -61,6 +61,8 @@ struct Segment {
 };
 
 struct Params {
+  const int* row_limit;         // variable-length batches: see tc::Params
+  int rows_per_frame;
   int batch, rows, tiles_per_b;
   int rc, hc, h1;               // central rows per tile, conv2 halo, conv1 halo
   int a0_boxes;                 // TMA boxes (64 rows) per A0 tile and K-chunk
@@ -191,11 +193,13 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, ti * p.rc)) continue;
       const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the A0 tile
       const uint32_t buf = tile_iter % kSlots, ph = (tile_iter / kSlots) & 1u;
+      ++tile_iter;   // processed tiles only (every role counts the same way)
       mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
       if (elect_one()) {
         const uint32_t bar = a0_full + 8 * buf;
@@ -228,8 +232,13 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t idesc = make_idesc_bf16(kMTile, C, p.fp16);
     const uint32_t dhi = smem_desc_hi<K::kKC>();
     if (K::kResident) mbar_wait(w_all, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      {
+        const int b = tile / p.tiles_per_b;
+        if (tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc)) continue;
+      }
       const uint32_t buf = tile_iter % kSlots, tph = (tile_iter / kSlots) & 1u;
+      ++tile_iter;
       mbar_wait(a0_full + 8 * buf, tph);
       const uint32_t a0 = smem_a0 + buf * a0_bytes;
       for (int s = 0; s < p.nseg; ++s) {
@@ -311,10 +320,12 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kNC = C / 16;                   // 16-column chunks per row
     constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
       const int q0c = ti * p.rc;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0c)) continue;
+      const uint32_t tile_it = tile_iter++;
       // ---- per branch: T1 -> A1 = half(lrelu(conv1 + b1 + X0)) in shared memory ----
       {
         const int gr = q0c - p.hc + i;
@@ -393,7 +404,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk ----
       {
-        const uint32_t t2s = tile_iter % kSlots, t2ph = (tile_iter / kSlots) & 1u;
+        const uint32_t t2s = tile_it % kSlots, t2ph = (tile_it / kSlots) & 1u;
         const int gr = q0c + i;
         const bool valid = i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;

@@ -23,6 +23,8 @@ constexpr int kThreads = 128;
 constexpr int kMaxHalo = 64;   // (num_taps-1)*dilation upper bound supported
 
 struct Params {
+  const int* row_limit;   // variable-length batches: frames utterance b needs (nullptr = all)
+  int rows_per_frame;
   int batch, rows, cin, n_total, cmod, n_tile;
   int num_taps[V2W_MAX_TILES];
   int off_min[V2W_MAX_TILES];
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const Params p) 
   const int q0 = blockIdx.x * kBM;
   const int n0 = blockIdx.y * BN;
   const int b = blockIdx.z;
+  if (p.row_limit != nullptr && q0 >= __ldg(p.row_limit + b) * p.rows_per_frame) return;   // whole CTA
   const int nt = n0 / p.n_tile;
   const int ntaps = p.num_taps[nt];
   const int off_min = p.off_min[nt];
@@ -179,6 +182,40 @@ __global__ void __launch_bounds__(kThreads) tapgemm_simt_kernel(const Params p) 
 template <typename TOut> __device__ __forceinline__ TOut cvt_out(float v) { return static_cast<TOut>(v); }
 template <> __device__ __forceinline__ __half cvt_out<__half>(float v) {
   return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+
+constexpr int kMaxRaggedBatch = 512;
+struct RaggedOffsets {          // by-value kernel parameter (constant bank): no upload, no sync
+  int off[kMaxRaggedBatch + 1];
+};
+
+// Variable-length input: features arrive as packed time-major rows [sum_b T_b, C] -- the
+// layout a dataset item already has (vec2wav/dataset.py:181-187) -- and utterance b owns rows
+// [off[b], off[b + 1]).  Writes the padded channels-last activation y[b][t][:] for t < T with zeros
+// past the utterance's end: the zero padding of collate_fn_tensor (dataset.py:212) without the
+// [B, C, T] detour and its two transposes.
+template <typename TOut>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x,
+                                                          const RaggedOffsets ro,
+                                                          TOut* __restrict__ y, int C, int T,
+                                                          int* __restrict__ row_limit, int halo) {
+  const int b = blockIdx.y;
+  const int first = ro.off[b];
+  const int len = ro.off[b + 1] - first;
+  // frames of utterance b that later kernels have to compute: its own plus the generator's right
+  // receptive field (rows past that cannot reach a valid sample; their tiles are skipped)
+  if (blockIdx.x == 0 && threadIdx.x == 0) row_limit[b] = min(len + halo, T);
+  const int c4n = C >> 2;
+  const int t0 = blockIdx.x * 8;
+  for (int i = threadIdx.x; i < 8 * c4n; i += 256) {
+    const int t = t0 + i / c4n, c4 = i % c4n;
+    if (t >= T) break;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len) v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<size_t>(first) + t) * C) + c4);
+    TOut* dst = y + (static_cast<size_t>(b) * T + t) * C + 4 * c4;
+    dst[0] = cvt_out<TOut>(v.x); dst[1] = cvt_out<TOut>(v.y);
+    dst[2] = cvt_out<TOut>(v.z); dst[3] = cvt_out<TOut>(v.w);
+  }
 }
 
 template <typename TOut>
@@ -303,6 +340,17 @@ struct PostWeights {      // by-value kernel parameter: FFMA reads it straight f
   float bias;
 };
 
+// Output addressing of conv_post.  Padded: y[b][t] fp32, every t < L.  Ragged (variable-length
+// batches): utterance b owns samples [off[b] * up, off[b + 1] * up) of ONE packed buffer;
+// samples of the padded tail are computed but not stored.  pcm16: round(clamp(y * 32768))
+// (MAX_WAV_VALUE, vec2wav/dataset.py:13).
+struct PostOut {
+  float* y;
+  int ragged;          // 0 = padded layout
+  int up;              // samples per input frame
+  int pcm16;
+};
+
 // One thread per input row: 64 B (C = 16) contiguous per thread => a warp reads 2 KB contiguous.
 // Each thread forms the 7 tap partial sums of its row (weights are constant-bank operands, no
 // shared-memory traffic), the partials meet through shared memory (7 floats per row instead of
@@ -310,11 +358,13 @@ struct PostWeights {      // by-value kernel parameter: FFMA reads it straight f
 template <int C>
 __global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const float* __restrict__ x,
                                                                  const PostWeights<C> pw,
-                                                                 float* __restrict__ y, int L,
+                                                                 const PostOut po,
+                                                                 const RaggedOffsets ro, int L,
                                                                  float in_slope) {
   __shared__ float part[kPostK][kPostThreads + 1];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kPostOut;
+  if (po.ragged && t0 >= (ro.off[b + 1] - ro.off[b]) * po.up) return;   // nothing valid in this block
   const int row = t0 - (kPostK / 2) + threadIdx.x;   // input row owned by this thread
   float a[C];
   if (row >= 0 && row < L) {
@@ -343,7 +393,21 @@ __global__ void __launch_bounds__(kPostThreads) conv_post_kernel(const float* __
     float s = pw.bias;
 #pragma unroll
     for (int j = 0; j < kPostK; ++j) s += part[j][threadIdx.x + j];
-    y[static_cast<size_t>(b) * L + t] = tanhf(s);
+    const float v = tanhf(s);
+    if (!po.ragged) {
+      po.y[static_cast<size_t>(b) * L + t] = v;
+    } else {
+      const int first = ro.off[b];
+      const int valid = (ro.off[b + 1] - first) * po.up;
+      if (t < valid) {
+        const size_t o = static_cast<size_t>(first) * po.up + t;
+        if (po.pcm16)
+          reinterpret_cast<short*>(po.y)[o] =
+              static_cast<short>(__float2int_rn(fminf(fmaxf(v * 32768.f, -32768.f), 32767.f)));
+        else
+          po.y[o] = v;
+      }
+    }
   }
 }
 

@@ -74,6 +74,8 @@ struct Segment {
 };
 
 struct Params {
+  const int* row_limit;         // variable-length batches: see tc::Params
+  int rows_per_frame;
   int batch, rows, tiles_per_b;
   int rc, hc, h1;
   int a0_boxes;
@@ -127,6 +129,17 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.tiles_per_b;
   const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Variable-length batches: first local tile index >= kt whose rows some utterance still needs.
+  // Every role walks the same sequence  kt = live(0), live(kt + 1), ...  and numbers the tiles it
+  // meets k = 0, 1, ... (buffer indices and barrier phases follow k, addresses follow kt).
+  auto live = [&](int kt) {
+    for (; kt < n_my; ++kt) {
+      const int tile = blockIdx.x + kt * gridDim.x;
+      const int b = tile / p.tiles_per_b;
+      if (!tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc)) break;
+    }
+    return kt;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -177,7 +190,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       __syncwarp();
     } else {
       Ring rw;
-      for (int it = 0; it < n_my; ++it) {
+      for (int kt = live(0); kt < n_my; kt = live(kt + 1)) {
         for (int s = 0; s < p.nseg; ++s) {
           const Segment sg = p.seg[s];
           for (int t = 0; t < sg.count; ++t) {
@@ -198,8 +211,8 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 2) {
     // ================================= input tile producer ==================================
-    for (int k = 0; k < n_my; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+    for (int kt = live(0), k = 0; kt < n_my; kt = live(kt + 1), ++k) {
+      const int tile = blockIdx.x + kt * gridDim.x;
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
       const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the input tile
@@ -235,8 +248,9 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmask = p.t_bufs - 1, amask = p.a0_bufs - 1;     // depths are 1 or 2
     const uint32_t w_lo = (smem_w & 0x3FFFFu) >> 4;
     constexpr uint32_t kSubLo = (kMTile * kRowBytes) >> 4;           // second 128-row sub-tile
-    for (int it = (warp == 3 ? 1 : 0); it < n_my; it += p.mma_warps) {
-      const uint32_t k = it;          // CTA-local tile ordinal
+    for (int kt = live(0), kk = 0; kt < n_my; kt = live(kt + 1), ++kk) {
+      if (p.mma_warps == 2 && (kk & 1) != (warp == 3 ? 1 : 0)) continue;
+      const uint32_t k = kk;          // ordinal of this tile among the CTA's live tiles
       const uint32_t tb = k & tmask, tph = (k >> tmask) & 1u;
       const uint32_t ab = k & amask, aph = (k >> amask) & 1u;
       const uint32_t a0_lo = ((smem_a0 + ab * a0_bytes) & 0x3FFFFu) >> 4;
@@ -318,8 +332,8 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int kPair = kNC >= 2 ? 2 : 1;
     const bool central = i >= p.hc && i < p.hc + p.rc;
     // fp32 X0 row of tile `k` for this thread (clamped to a valid row; `valid` says whether it counts)
-    auto row_of = [&](int k, bool& valid) -> const float4* {
-      const int tile = blockIdx.x + k * gridDim.x;
+    auto row_of = [&](int kt, bool& valid) -> const float4* {
+      const int tile = blockIdx.x + kt * gridDim.x;
       const int b = tile / p.tiles_per_b;
       const int ti = tile - b * p.tiles_per_b;
       const int gr = ti * p.rc - p.hc + i;
@@ -330,7 +344,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     float4 xn[kCacheX0 ? kXc : 1];     // C <= 32: the next tile's row, fetched one tile ahead
     if constexpr (kCacheX0) {
       bool v;
-      const float4* x = row_of(0, v);
+      const float4* x = row_of(min(live(0), n_my - 1), v);
 #pragma unroll
       for (int e = 0; e < kXc; ++e) xn[e] = __ldg(x + e);
     }
@@ -338,19 +352,20 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     float4 xc[kXc];
     if constexpr (!kCacheX0) {         // C = 64: chunks 0 and 1 of the first pass
       bool v;
-      const float4* x = row_of(0, v);
+      const float4* x = row_of(min(live(0), n_my - 1), v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) xc[e] = __ldg(x + e);
     }
-    for (int k = 0; k < n_my; ++k) {
+    for (int kt = live(0), k = 0; kt < n_my; ++k) {
       bool valid, next_valid = false;
-      const float4* xrow = row_of(k, valid);
-      const float4* xnext = k + 1 < n_my ? row_of(k + 1, next_valid) : xrow;
+      const float4* xrow = row_of(kt, valid);
+      const int kt_next = live(kt + 1);
+      const float4* xnext = kt_next < n_my ? row_of(kt_next, next_valid) : xrow;
       const uint32_t tb = k % p.t_bufs, tph = (k / p.t_bufs) & 1u;
       if constexpr (kCacheX0) {
 #pragma unroll
         for (int e = 0; e < kXc; ++e) xc[e] = xn[e];
-        if (k + 1 < n_my) {
+        if (kt_next < n_my) {
 #pragma unroll
           for (int e = 0; e < kXc; ++e) xn[e] = __ldg(xnext + e);
         }
@@ -489,6 +504,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) mbar_arrive(t2_empty + 8 * tb);
         V2W_TR(k * 100 + 52);
       }
+      kt = kt_next;
     }
     if (warp == 4) V2W_TR_DUMP("epi");
   }

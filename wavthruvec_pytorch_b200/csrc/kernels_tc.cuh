@@ -53,6 +53,11 @@ constexpr int kStageWarpBytes = 2 * kStageYBytes + 2 * kStageHBytes;
 constexpr int kStageBytes = 8 * kStageWarpBytes;   // 48 KB
 
 struct Params {
+  // Variable-length batches (v2w_forward_ragged): utterance b only needs rows below
+  // row_limit[b] * rows_per_frame; tiles that start at or past it are skipped by every role.
+  // nullptr = uniform batch.
+  const int* row_limit;
+  int rows_per_frame;
   int batch, rows, cin, n_total, cmod, n_tile, n_tiles;
   int msub;             // 128-row sub-tiles per super-tile
   int s_tiles;          // super-tiles per utterance
@@ -275,6 +280,10 @@ struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tile_skipped(const int* row_limit, int rows_per_frame, int b, int row0) {
+  return row_limit != nullptr && row0 >= __ldg(row_limit + b) * rows_per_frame;
+}
+
 template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -336,6 +345,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nt = rem - st * p.n_tiles;
       const int ntaps = p.num_taps[nt];
       const int q0 = st * p.msub * kMTile;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const int nbox = (nsub * kMTile + p.halo[nt] + p.box_rows - 1) / p.box_rows;
       const int row0 = q0 + p.off_min[nt];
@@ -370,7 +380,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t tile_iter = 0;
     const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile, p.fp16);
     const uint32_t dhi = smem_desc_hi<KC>();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
@@ -378,8 +388,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ntaps = p.num_taps[nt];
       const int off_min = p.off_min[nt];
       const int q0 = st * p.msub * kMTile;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
+      ++tile_iter;   // counts processed tiles only
       mbar_wait(acc_empty + 8 * as, aph ^ 1u);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + as * stage_cols;
@@ -420,15 +432,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t hbuf = ybuf + 2 * kStageYBytes;
     uint32_t sbuf = 0;
     uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-      if ((tile_iter & 1u) != static_cast<uint32_t>(group)) continue;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
       const int q0 = st * p.msub * kMTile;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
+      const uint32_t it = tile_iter++;   // processed tiles only, like the MMA warp's count
+      if ((it & 1u) != static_cast<uint32_t>(group)) continue;
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
-      const uint32_t aph = (tile_iter >> 1) & 1u;
+      const uint32_t aph = (it >> 1) & 1u;
       mbar_wait(acc_full + 8 * group, aph);
       tcgen05_fence_after();
       const uint32_t t_lane = tmem_base + group * stage_cols +

@@ -476,6 +476,33 @@ int32_t v2w_model_get_cond(const v2w_model* m, int32_t i, v2w_cond_desc* out) {
   return V2W_OK;
 }
 
+int32_t v2w_model_halo_frames(const v2w_model* m) {
+  if (!m) return 0;
+  const v2w_config& c = m->cfg;
+  // walk back from the waveform: R = rows past the utterance's end (at the current resolution)
+  // that the last valid row depends on
+  int64_t R = 3;                                    // conv_post k = 7 (models.py:100)
+  for (int i = c.num_upsamples - 1; i >= 0; --i) {
+    int reach = 0;                                  // one MRF stage: the widest branch
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const int half = (c.resblock_kernel_sizes[j] - 1) / 2;
+      int r = 0;
+      if (c.resblock_type == 2) {
+        r = (c.resblock_dilation_sizes[j][0] + c.resblock_dilation_sizes[j][1]) * half;   // models.py:54-70
+      } else {
+        for (int d = 0; d < 3; ++d) r += (c.resblock_dilation_sizes[j][d] + 1) * half;    // models.py:14-44
+      }
+      reach = std::max(reach, r);
+    }
+    R += reach;
+    // ConvTranspose1d(k, stride u, padding p): output row t reads input rows <= floor((t + p) / u)
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i], pad = (k - u) / 2;
+    R = (R + pad + u - 1) / u;
+  }
+  R += 3;                                           // conv_pre k = 7 (models.py:83)
+  return (int32_t)R;
+}
+
 int32_t v2w_model_get_fused(const v2w_model* m, int32_t i, v2w_fused_desc* out) {
   if (!m || !out || i < 0 || i >= (int32_t)m->fused.size()) {
     set_error("v2w_model_get_fused: bad stage %d", i);

@@ -79,6 +79,7 @@ struct v2w_plan {
   int64_t cond_scale[V2W_MAX_STAGES], cond_shift[V2W_MAX_STAGES];
   int64_t xt = -1;        // transposed input
   int64_t post_in = -1;   // fp32 input of conv_post
+  int64_t row_limit = -1; // int32 [batch]: frames each utterance needs (variable-length batches)
   bool bound = false;
   const uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
@@ -323,7 +324,11 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   return V2W_OK;
 }
 
-static int launch_tc(const TcLaunch& L, cudaStream_t st) {
+static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
+                     int rows_per_frame = 0) {
+  TcLaunch L = L0;
+  L.prm.row_limit = row_limit;
+  L.prm.rows_per_frame = rows_per_frame;
   static bool attr_set = false;
   if (!attr_set) {
     V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64>,
@@ -351,13 +356,15 @@ static void launch_simt_bn(const simt::Params& p, int bn, dim3 grid, cudaStream_
   else simt::tapgemm_simt_kernel<TIn, 16><<<grid, simt::kThreads, 0, st>>>(p);
 }
 
-static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st) {
+static int launch_simt(const v2w_tapgemm_args& a, cudaStream_t st, const int* row_limit = nullptr,
+                       int rows_per_frame = 0) {
   if (!a.w32) {
     set_error("tapgemm(SIMT): w32 is null");
     return V2W_ERR_INVALID;
   }
   simt::Params p;
   std::memset(&p, 0, sizeof(p));
+  p.row_limit = row_limit; p.rows_per_frame = rows_per_frame;
   p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
   p.n_tile = a.n_tile;
   for (int t = 0; t < a.n_tiles; ++t) {
@@ -583,7 +590,11 @@ static int encode_fused_maps(const v2w_fused_desc& F, const v2w_op_desc& d, cons
   return V2W_OK;
 }
 
-static int launch_fused(const FusedLaunch& L, cudaStream_t st) {
+static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
+                        int rows_per_frame = 0) {
+  FusedLaunch L = L0;
+  L.prm.row_limit = row_limit; L.prm.rows_per_frame = rows_per_frame;
+  L.sprm.row_limit = row_limit; L.sprm.rows_per_frame = rows_per_frame;
   static bool attr_set = false;
   if (!attr_set) {
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128>,
@@ -751,6 +762,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   for (int i = 0; i < U; ++i)
     max_e = std::max(max_e, (int64_t)B * T * m->stage_up[i] * m->stage_channels[i]);
   const int64_t esz = bf ? 2 : 4;
+  P->row_limit = ws.take((int64_t)B * 4);
   P->xt = ws.take((int64_t)B * T * c.num_wv_feat * esz);
   Act pre;   // conv_pre output, leaky-relu'd for ups[0] (models.py:128)
   pre.slope = kLreluSlope;
@@ -1034,8 +1046,15 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   return V2W_OK;
 }
 
-int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
-                    float* out_dev, void* stream, int32_t* gpu_launches) {
+// One pass over the plan's op list.  `ragged`: x_dev is packed time-major rows and the waveform is
+// written un-padded (v2w_forward_ragged); the row offsets are already in the workspace.
+static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
+                       void* out_dev, const simt::RaggedOffsets* ro, int32_t out_format, void* stream,
+                       int32_t* gpu_launches) {
+  const bool ragged = ro != nullptr;
+  static const simt::RaggedOffsets no_offsets = {};
+  // variable-length batches: every row-tiled kernel skips the tiles no utterance needs
+  const int* lim = ragged ? reinterpret_cast<const int*>(p->ws + p->row_limit) : nullptr;
   if (!p || !x_dev || !spk_dev || !out_dev) {
     set_error("v2w_forward: null argument");
     return V2W_ERR_INVALID;
@@ -1059,6 +1078,24 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
     ++op_index;
     switch (o.d.kind) {
       case V2W_OP_TRANSPOSE_IN: {
+        if (ragged) {
+          dim3 grid((p->frames + 7) / 8, p->batch);
+          if (p->precision == V2W_PREC_FP16)
+            simt::gather_rows_kernel<__half><<<grid, 256, 0, st>>>(
+                x_dev, *ro, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames,
+                reinterpret_cast<int*>(p->ws + p->row_limit), v2w_model_halo_frames(m));
+          else if (bf)
+            simt::gather_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+                x_dev, *ro, reinterpret_cast<__nv_bfloat16*>(p->ws + p->xt), c.num_wv_feat, p->frames,
+                reinterpret_cast<int*>(p->ws + p->row_limit), v2w_model_halo_frames(m));
+          else
+            simt::gather_rows_kernel<float><<<grid, 256, 0, st>>>(
+                x_dev, *ro, reinterpret_cast<float*>(p->ws + p->xt), c.num_wv_feat, p->frames,
+                reinterpret_cast<int*>(p->ws + p->row_limit), v2w_model_halo_frames(m));
+          V2W_CUDA(cudaGetLastError());
+          ++launches;
+          break;
+        }
         dim3 grid((p->frames + 31) / 32, (c.num_wv_feat + 31) / 32, p->batch);
         if (p->precision == V2W_PREC_FP16)
           simt::transpose_in_kernel<__half><<<grid, 256, 0, st>>>(
@@ -1101,13 +1138,14 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
         break;
       }
       case V2W_OP_TAPGEMM: {
-        int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st) : launch_simt(o.g, st);
+        const int rpf = o.d.rows / p->frames;   // rows of this op per input frame
+        int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st, lim, rpf) : launch_simt(o.g, st, lim, rpf);
         if (rc) return rc;
         ++launches;
         break;
       }
       case V2W_OP_MRF_FUSED: {
-        int rc = launch_fused(o.fl, st);
+        int rc = launch_fused(o.fl, st, lim, o.d.rows / p->frames);
         if (rc) return rc;
         ++launches;
         break;
@@ -1116,17 +1154,23 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
         const v2w_layer_desc& L = m->layers[o.d.layer];
         const float* in = reinterpret_cast<const float*>(p->ws + o.d.in_act);
         dim3 grid((o.d.rows + simt::kPostOut - 1) / simt::kPostOut, p->batch);
+        simt::PostOut po;
+        po.y = static_cast<float*>(out_dev);
+        po.ragged = ragged ? 1 : 0;
+        const simt::RaggedOffsets& offs = ragged ? *ro : no_offsets;
+        po.up = m->total_up;
+        po.pcm16 = out_format == V2W_OUT_PCM16;
         if (L.cin == 16) {
           simt::PostWeights<16> pw;
           std::memcpy(pw.w, p->post_w.data(), sizeof(pw.w));
           pw.bias = p->post_bias;
-          simt::conv_post_kernel<16><<<grid, simt::kPostThreads, 0, st>>>(in, pw, out_dev, o.d.rows,
+          simt::conv_post_kernel<16><<<grid, simt::kPostThreads, 0, st>>>(in, pw, po, offs, o.d.rows,
                                                                          o.d.in_slope);
         } else if (L.cin == 32) {
           simt::PostWeights<32> pw;
           std::memcpy(pw.w, p->post_w.data(), sizeof(pw.w));
           pw.bias = p->post_bias;
-          simt::conv_post_kernel<32><<<grid, simt::kPostThreads, 0, st>>>(in, pw, out_dev, o.d.rows,
+          simt::conv_post_kernel<32><<<grid, simt::kPostThreads, 0, st>>>(in, pw, po, offs, o.d.rows,
                                                                          o.d.in_slope);
         } else {
           set_error("conv_post with %d input channels unsupported", L.cin);
@@ -1144,6 +1188,50 @@ int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const
   if (p->profiling) V2W_CUDA(cudaEventRecord(p->events[op_index], st));
   if (gpu_launches) *gpu_launches = launches;
   return V2W_OK;
+}
+
+int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
+                    float* out_dev, void* stream, int32_t* gpu_launches) {
+  return run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, stream, gpu_launches);
+}
+
+int32_t v2w_forward_ragged(v2w_plan* p, const float* x_rows_dev, const int32_t* row_offsets_host,
+                           const float* spk_dev, const float* noise_dev, void* out_packed_dev,
+                           int32_t out_format, void* stream, int32_t* gpu_launches) {
+  if (!p || !row_offsets_host) {
+    set_error("v2w_forward_ragged: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if (!p->bound) {
+    set_error("v2w_forward_ragged: plan is not bound to device buffers");
+    return V2W_ERR_STATE;
+  }
+  if (out_format != V2W_OUT_F32 && out_format != V2W_OUT_PCM16) {
+    set_error("v2w_forward_ragged: unknown output format %d", out_format);
+    return V2W_ERR_INVALID;
+  }
+  if (p->batch > simt::kMaxRaggedBatch) {
+    set_error("v2w_forward_ragged: at most %d utterances per call (plan has %d)", simt::kMaxRaggedBatch, p->batch);
+    return V2W_ERR_INVALID;
+  }
+  if (row_offsets_host[0] != 0) {
+    set_error("v2w_forward_ragged: row_offsets[0] must be 0");
+    return V2W_ERR_INVALID;
+  }
+  for (int b = 0; b < p->batch; ++b) {
+    const int64_t len = (int64_t)row_offsets_host[b + 1] - row_offsets_host[b];
+    if (len < 1 || len > p->frames) {
+      set_error("v2w_forward_ragged: utterance %d has %lld frames, the plan holds 1..%d", b,
+                (long long)len, p->frames);
+      return V2W_ERR_INVALID;
+    }
+  }
+  // the offsets travel as a by-value kernel parameter: nothing to upload, nothing to wait for
+  simt::RaggedOffsets ro;
+  std::memset(&ro, 0, sizeof(ro));
+  for (int b = 0; b <= p->batch; ++b) ro.off[b] = row_offsets_host[b];
+  return run_ops(p, x_rows_dev, spk_dev, noise_dev, out_packed_dev, &ro, out_format, stream,
+                 gpu_launches);
 }
 
 int32_t v2w_plan_set_profiling(v2w_plan* p, int32_t enabled) {

@@ -209,6 +209,44 @@ class NativeEngine:
         self.last_launches = n.value
         return out
 
+    def halo_frames(self) -> int:
+        """Input frames past an utterance's end that can reach its last valid output sample."""
+        return int(self._lib.v2w_model_halo_frames(self._model))
+
+    def forward_ragged(self, x_rows: torch.Tensor, lengths, spk: torch.Tensor, noise: torch.Tensor,
+                       plan_frames: int, pcm16: bool = False) -> torch.Tensor:
+        """Variable-length batch through v2w_forward_ragged.  `x_rows` = the utterances' [T_b, C]
+        feature rows concatenated (device, fp32), `lengths` = T_b per utterance (host ints).
+        Returns ONE packed waveform buffer (fp32, or int16 PCM): utterance b owns samples
+        [off_b * up, (off_b + T_b) * up) with off = exclusive prefix sum of `lengths`."""
+        lengths = [int(v) for v in lengths]
+        B = len(lengths)
+        if not x_rows.is_cuda:
+            raise RuntimeError("the native Vec2Wav generation path runs on sm_100 GPUs only and has "
+                               "no CPU fallback")
+        if x_rows.dim() != 2 or x_rows.shape[1] != self._module.h.num_wv_feat or x_rows.shape[0] != sum(lengths):
+            raise RuntimeError(f"x_rows must be [sum(lengths), {self._module.h.num_wv_feat}]")
+        if tuple(spk.shape) != (B, self._module.h.spk_dim) or tuple(noise.shape) != (B, self._module.h.noise_dim):
+            raise RuntimeError("spk_emb / noise must be [len(lengths), dim]")
+        dev = x_rows.device
+        x_rows = x_rows.detach().to(torch.float32).contiguous()
+        spk = spk.detach().to(device=dev, dtype=torch.float32).contiguous()
+        noise = noise.detach().to(device=dev, dtype=torch.float32).contiguous()
+        handle, _ws = self.plan(B, int(plan_frames), self._module.precision, dev)
+        offs = (C.c_int32 * (B + 1))()
+        for b, n_b in enumerate(lengths):
+            offs[b + 1] = offs[b] + n_b
+        out = torch.empty(offs[B] * self.total_upsample(),
+                          dtype=torch.int16 if pcm16 else torch.float32, device=dev)
+        n = C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            native.check(self._lib.v2w_forward_ragged(
+                handle, x_rows.data_ptr(), offs, spk.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                native.OUT_PCM16 if pcm16 else native.OUT_F32, C.c_void_p(stream), C.byref(n)))
+        self.last_launches = n.value
+        return out
+
     def forward_host(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor,
                      out: torch.Tensor, device) -> torch.Tensor:
         """Host (ideally pinned) tensors in and out through v2w_forward_host: H2D, forward, D2H,

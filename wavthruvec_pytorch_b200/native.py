@@ -26,6 +26,7 @@ TC_FLAG_FP16 = 0x100
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
+OUT_F32, OUT_PCM16 = 0, 1
 OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED = 0, 1, 2, 3, 4
 FUSED_MAX_SEG, FUSED_MAX_TAPS = 16, 96
 SEG_CONV1, SEG_SUM, SEG_CONV2 = 0, 1, 2
@@ -181,6 +182,9 @@ _SIGNATURES = [
     ("v2w_forward_host", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
+    ("v2w_forward_ragged", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    ("v2w_model_halo_frames", C.c_int32, [C.c_void_p]),
     ("v2w_pipeline_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("v2w_pipeline_submit", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("v2w_pipeline_wait", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
