@@ -120,6 +120,39 @@ def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2):
     return audio / mean, mean * 1e3, sample, threads, len(times)
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def torch_eager_context(gen, x, s, n, audio_per_step, steps=5):
+    import torch
+    out = {"note": "library context, not this repo's path: Generator._forward_autograd under no_grad "
+                   "(same ATen calls as vec2wav/models.py:116-147)"}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)),
+                      ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        try:
+            with torch.no_grad(), ctx:
+                for _ in range(2):
+                    gen._forward_autograd(x, s, n)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps):
+                    gen._forward_autograd(x, s, n)
+                b.record()
+                torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            out[name] = {"ms_per_step": ms, "value": audio_per_step / ms * 1e3}
+        except Exception as e:  # context only: never fail the bench line over it
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -340,7 +373,7 @@ def run_native_arm(args):
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "tapgemm_simt_kernel" if args.precision == "fp32" else "tapgemm_tc_kernel + mrf_stage_kernel",
+                         "kernel": "tapgemm_simt_kernel" if args.precision == "fp32" else "tapgemm_tc_kernel + mrf_stacked_kernel + mrf_stage_kernel",
                          "launches": len(gemm), "gemm_ms_per_step": gemm_ms,
                          "all_ops_ms_per_step": all_ms,
                          "algorithmic_gflop_per_step": gemm_flops / 1e9},
@@ -351,7 +384,12 @@ def run_native_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample, threads, _ = cpu_forward_timer(args, batch, frames, feat, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": sample, "host_cpu_count": os.cpu_count()}
+                                    "sample": sample, "host_cpu_count": os.cpu_count(),
+                                    "cpu_model": cpu_model()}
+            # Context only: the reference's own op sequence -- stock PyTorch/cuDNN ops,
+            # weight-norm hooks re-run every call -- on this same GPU, same inputs.  It is the
+            # drop-in's train()/autograd delegate, bit-identical to the reference on CPU.
+            line["torch_eager_gpu"] = torch_eager_context(gen, xd, sd_, nd, audio_per_step)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
