@@ -175,6 +175,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   tcgen05_fence_before();
   __syncthreads();
+  // everything above touched only kernel parameters and the (constant) packed weights: from here
+  // on the previous kernel's outputs are read and its inputs overwritten
+  pdl_launch_dependents();
+  pdl_wait();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 
 #include "common.h"
 #include "kernels_simt.cuh"
@@ -324,6 +325,35 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   return V2W_OK;
 }
 
+// Programmatic dependent launch: the tcgen05 kernels run their prologue (barrier init, TMEM
+// allocation, descriptor prefetch, bias staging) while the previous kernel's last CTAs are still
+// draining, and block in griddepcontrol.wait before they touch anything that kernel wrote.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("V2W_NO_PDL");
+    v = (e && std::atoi(e)) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
                      int rows_per_frame = 0) {
   TcLaunch L = L0;
@@ -340,11 +370,11 @@ static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit =
     attr_set = true;
   }
   if (L.kc == 64)
-    tc::tapgemm_tc_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
+    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
   else if (L.kc == 32)
-    tc::tapgemm_tc_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
+    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
   else
-    tc::tapgemm_tc_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm);
+    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<16>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
   V2W_CUDA(cudaGetLastError());
   return V2W_OK;
 }
@@ -615,22 +645,22 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
   }
   if (L.stacked) {
     if (L.channels == 64)
-      stacked::mrf_stacked_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
     else if (L.channels == 32)
-      stacked::mrf_stacked_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
     else
-      stacked::mrf_stacked_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.sprm);
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<16>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
     V2W_CUDA(cudaGetLastError());
     return V2W_OK;
   }
   if (L.channels == 128)
-    fused::mrf_stage_kernel<128><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   else if (L.channels == 64)
-    fused::mrf_stage_kernel<64><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   else if (L.channels == 32)
-    fused::mrf_stage_kernel<32><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   else
-    fused::mrf_stage_kernel<16><<<L.grid, tc::kThreads, L.smem, st>>>(L.tm_a, L.tm_w, L.prm);
+    V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<16>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   V2W_CUDA(cudaGetLastError());
   return V2W_OK;
 }
