@@ -98,8 +98,6 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
-using fused::ld_shared_f4;
-
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,

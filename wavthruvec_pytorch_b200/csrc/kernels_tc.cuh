@@ -51,6 +51,10 @@ constexpr int kMaxSub = 4;
 constexpr int kStageYBytes = 2048, kStageHBytes = 1024;
 constexpr int kStageWarpBytes = 2 * kStageYBytes + 2 * kStageHBytes;
 constexpr int kStageBytes = 8 * kStageWarpBytes;   // 48 KB
+// per epilogue warp: this tile's bias | scale | shift column vectors (n_tile <= 256 floats each),
+// staged once per tile so that the chunk loop reads them with LDS broadcasts instead of L1 round trips
+constexpr int kColVecWarpBytes = 3 * 256 * 4;
+constexpr int kColVecBytes = 8 * kColVecWarpBytes;   // 24 KB
 
 struct Params {
   // Variable-length batches (v2w_forward_ragged): utterance b only needs rows below
@@ -141,6 +145,13 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -440,6 +451,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const bool pow2 = (p.cmod & (p.cmod - 1)) == 0;
     const uint32_t ybuf = stage_base + (warp - 4) * kStageWarpBytes;
+    const uint32_t cvec = stage_base + (p.tma_out ? kStageBytes : 0) + (warp - 4) * kColVecWarpBytes;
     const uint32_t hbuf = ybuf + 2 * kStageYBytes;
     uint32_t sbuf = 0;
     uint32_t tile_iter = 0;
@@ -454,6 +466,20 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if ((it & 1u) != static_cast<uint32_t>(group)) continue;
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const uint32_t aph = (it >> 1) & 1u;
+      // column vectors of this tile (overlaps the wait for the accumulator)
+      for (int c = lane; c < p.n_tile; c += 32) {
+        const int col = nt * p.n_tile + c;
+        const int cb = pow2 ? (col & (p.cmod - 1)) : (col % p.cmod);
+        const float bv = p.bias ? __ldg(p.bias + cb) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 4 * c), "f"(bv) : "memory");
+        if (p.scale) {
+          const float sv = __ldg(p.scale + static_cast<size_t>(b) * p.cmod + cb);
+          const float hv = __ldg(p.shift + static_cast<size_t>(b) * p.cmod + cb);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 1024 + 4 * c), "f"(sv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 2048 + 4 * c), "f"(hv) : "memory");
+        }
+      }
+      __syncwarp();
       mbar_wait(acc_full + 8 * group, aph);
       tcgen05_fence_after();
       const uint32_t t_lane = tmem_base + group * stage_cols +
@@ -481,24 +507,21 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_ld16(t_lane + m * p.acc_cols + cc, r);
           tmem_ld_wait();
           if (valid) {
-            const int cb = pow2 ? (col & (p.cmod - 1)) : (col % p.cmod);
             float v[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
             if (p.bias) {
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cb + e));
+                const float4 t = ld_shared_f4(cvec + (cc + e) * 4);
                 v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
               }
             }
             if (p.scale) {
-              const float* sc = p.scale + static_cast<size_t>(b) * p.cmod + cb;
-              const float* sh = p.shift + static_cast<size_t>(b) * p.cmod + cb;
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + e));
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + e));
+                const float4 s4 = ld_shared_f4(cvec + 1024 + (cc + e) * 4);
+                const float4 h4 = ld_shared_f4(cvec + 2048 + (cc + e) * 4);
                 v[e] = fmaf(v[e], s4.x, h4.x);
                 v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
                 v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);

@@ -220,7 +220,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
-  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0);   // barriers (+ output staging)
+  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0) + tc::kColVecBytes;   // barriers (+ output staging) + column vectors
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
   int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
