@@ -368,6 +368,8 @@ def run_native_arm(args):
                     "h2d_bytes_per_step": int(xh.numel() + sh.numel() + nh.numel()) * 4,
                     "d2h_bytes_per_step": int(out_h.numel()) * 4, "steps": e2e_steps,
                     "api": "Generator.engine().host_pipeline -> v2w_pipeline_submit/wait (2 steps in flight)",
+                    "note": "every step copies its inputs H2D and its waveform D2H inside the timed region; no L2 flush "
+                            "between these steps (the inputs arrive through the copy), which is why it can edge past `value`",
                     "blocking_call_value": world * audio_per_step / (e2e_sync_s / e2e_steps)},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
