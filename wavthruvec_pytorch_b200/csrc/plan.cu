@@ -88,8 +88,15 @@ struct v2w_plan {
   float post_bias = 0.f;
   bool profiling = false;
   std::vector<cudaEvent_t> events;   // ops.size() + 1 when profiling
+  // The conditioning kernel only feeds the epilogue of ups[0]: it runs on a side stream, forked at
+  // the start of a forward and joined right before the first op that reads its scale/shift.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   ~v2w_plan() {
     for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -1103,9 +1110,21 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
   const bool bf = p->precision != V2W_PREC_FP32;
   int launches = 0;
   size_t op_index = 0;
+  static const bool no_fork = [] { const char* e = std::getenv("V2W_NO_FORK"); return e && std::atoi(e); }();
+  const bool fork = !p->profiling && !no_fork;
+  bool joined = true;
+  if (fork && !p->side) {
+    V2W_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    V2W_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    V2W_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  }
   for (Op& o : p->ops) {
     if (p->profiling) V2W_CUDA(cudaEventRecord(p->events[op_index], st));
     ++op_index;
+    if (!joined && o.d.kind == V2W_OP_TAPGEMM && o.d.cond_stage >= 0) {
+      V2W_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+      joined = true;
+    }
     switch (o.d.kind) {
       case V2W_OP_TRANSPOSE_IN: {
         if (ragged) {
@@ -1162,8 +1181,19 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
         const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * cmax) * 4;
         dim3 grid((unsigned)m->cond.size(), p->batch);
-        simt::cond_affine_kernel<<<grid, simt::kCondThreads, smem, st>>>(cp);
+        cudaStream_t cs = st;
+        if (fork) {
+          // everything this stream did before (the previous forward read scale/shift) is ordered first
+          V2W_CUDA(cudaEventRecord(p->ev_fork, st));
+          V2W_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+          cs = p->side;
+        }
+        simt::cond_affine_kernel<<<grid, simt::kCondThreads, smem, cs>>>(cp);
         V2W_CUDA(cudaGetLastError());
+        if (fork) {
+          V2W_CUDA(cudaEventRecord(p->ev_join, p->side));
+          joined = false;
+        }
         ++launches;
         break;
       }
@@ -1215,6 +1245,7 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         return V2W_ERR_STATE;
     }
   }
+  if (!joined) V2W_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));   // no op consumed it (not reached in practice)
   if (p->profiling) V2W_CUDA(cudaEventRecord(p->events[op_index], st));
   if (gpu_launches) *gpu_launches = launches;
   return V2W_OK;
