@@ -98,8 +98,10 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
+// C = 16 is latency-bound (four serial epilogue passes per tile, 64 small MMAs) and needs only 73 KB
+// of shared memory and 256 TMEM columns: two CTAs share an SM and hide each other's waits.
 template <int C>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ Params p) {
   constexpr int kRowBytes = C * 2;              // one K-chunk: the whole channel dimension

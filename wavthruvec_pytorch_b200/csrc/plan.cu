@@ -520,7 +520,11 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   p.fp16 = fp16 ? 1 : 0;
   // + barriers (512) + bias table + 1 KB alignment slack
   L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + (nb + 1) * C * 4 + 1024;
-  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
+  // C = 16: two CTAs per SM (kernels_stacked.cuh); they need 2 x smem and 2 x tmem_cols <= 512
+  int ctas_per_sm = 1;
+  if (C == 16 && 2 * L->smem <= 227 * 1024 && 2 * p.tmem_cols <= 512) ctas_per_sm = 2;
+  if (const char* e = std::getenv("V2W_FUSED_CTAS_PER_SM")) ctas_per_sm = std::min(ctas_per_sm, std::max(1, std::atoi(e)));
+  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, (int64_t)sms * ctas_per_sm);
   return encode_fused_maps(F, d, packed, ws, fp16, C, L);
 }
 
