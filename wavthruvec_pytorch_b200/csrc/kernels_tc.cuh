@@ -53,8 +53,7 @@ constexpr int kStageWarpBytes = 2 * kStageYBytes + 2 * kStageHBytes;
 constexpr int kStageBytes = 8 * kStageWarpBytes;   // 48 KB
 // per epilogue warp: this tile's bias | scale | shift column vectors (n_tile <= 256 floats each),
 // staged once per tile so that the chunk loop reads them with LDS broadcasts instead of L1 round trips
-constexpr int kColVecWarpBytes = 3 * 256 * 4;
-constexpr int kColVecBytes = 8 * kColVecWarpBytes;   // 24 KB
+// (3 * n_tile * 4 bytes per warp: Params::cvec_warp_bytes)
 
 struct Params {
   // Variable-length batches (v2w_forward_ragged): utterance b only needs rows below
@@ -62,6 +61,7 @@ struct Params {
   // nullptr = uniform batch.
   const int* row_limit;
   int rows_per_frame;
+  int cvec_warp_bytes;          // per epilogue warp: bias | scale | shift of the tile's columns
   int batch, rows, cin, n_total, cmod, n_tile, n_tiles;
   int msub;             // 128-row sub-tiles per super-tile
   int s_tiles;          // super-tiles per utterance
@@ -451,7 +451,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const bool pow2 = (p.cmod & (p.cmod - 1)) == 0;
     const uint32_t ybuf = stage_base + (warp - 4) * kStageWarpBytes;
-    const uint32_t cvec = stage_base + (p.tma_out ? kStageBytes : 0) + (warp - 4) * kColVecWarpBytes;
+    const uint32_t cvec = stage_base + (p.tma_out ? kStageBytes : 0) + (warp - 4) * p.cvec_warp_bytes;
     const uint32_t hbuf = ybuf + 2 * kStageYBytes;
     uint32_t sbuf = 0;
     uint32_t tile_iter = 0;
@@ -475,8 +475,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.scale) {
           const float sv = __ldg(p.scale + static_cast<size_t>(b) * p.cmod + cb);
           const float hv = __ldg(p.shift + static_cast<size_t>(b) * p.cmod + cb);
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 1024 + 4 * c), "f"(sv) : "memory");
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 2048 + 4 * c), "f"(hv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 4 * (p.n_tile + c)), "f"(sv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(cvec + 4 * (2 * p.n_tile + c)), "f"(hv) : "memory");
         }
       }
       __syncwarp();
@@ -520,8 +520,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.scale) {
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
-                const float4 s4 = ld_shared_f4(cvec + 1024 + (cc + e) * 4);
-                const float4 h4 = ld_shared_f4(cvec + 2048 + (cc + e) * 4);
+                const float4 s4 = ld_shared_f4(cvec + (p.n_tile + cc + e) * 4);
+                const float4 h4 = ld_shared_f4(cvec + (2 * p.n_tile + cc + e) * 4);
                 v[e] = fmaf(v[e], s4.x, h4.x);
                 v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
                 v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);

@@ -227,7 +227,9 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
-  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0) + tc::kColVecBytes;   // barriers (+ output staging) + column vectors
+  p.cvec_warp_bytes = 3 * a.n_tile * 4;
+  // barriers (+ output staging) + per-warp column vectors
+  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
   int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
