@@ -207,6 +207,65 @@ __device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_
                "r"(d)
                : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster execute one M = 256 MMA; each holds its own
+// 128 rows of A and HALF of the B tile, so shared-memory operand traffic per CTA drops from
+// 4 KB + N * 32 B to 4 KB + N * 16 B per MMA.  Shared-memory addresses from cvta are already
+// cluster-window addresses of the executing CTA; clearing bit 24 names the same offset in the
+// even (leader) CTA of the pair.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)),
+      "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* tm, int c0, int c1, int c2,
+                                                 uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)),
+      "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // same barrier offset in both CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
                "r"(cols)
@@ -302,7 +361,7 @@ __device__ __forceinline__ bool tile_skipped(const int* row_limit, int rows_per_
   return row_limit != nullptr && row0 >= __ldg(row_limit + b) * rows_per_frame;
 }
 
-template <int KC>
+template <int KC, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmH,
@@ -321,6 +380,12 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // kPair: a tile is 2 x msub x 128 rows, the CTA of rank r owns the r-th half; both CTAs walk the
+  // same tile sequence (tile_first, tile_step in units of pairs)
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int tile_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile_rows = (kPair ? 2 : 1) * p.msub * kMTile;
   const int tiles_per_b = p.s_tiles * p.n_tiles;
   const int total_tiles = p.batch * tiles_per_b;
   const uint32_t stage_cols = p.msub * p.acc_cols;   // TMEM columns per accumulator stage
@@ -339,14 +404,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, 4);
+      mbar_init(acc_empty + 8 * i, kPair ? 8 : 4);   // epilogue warps of both CTAs arrive on the leader's
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, tmem_cols);
+    else tmem_alloc(tmem_slot, tmem_cols);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
+  else __syncthreads();
   // everything above touched only kernel parameters and the (constant) packed weights: from here
   // on the previous kernel's outputs are read and its inputs overwritten
   pdl_launch_dependents();
@@ -359,27 +428,38 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================== TMA producer =====================================
     Ring ra, rw;
     const uint32_t box_bytes = p.box_rows * kRowBytes;
-    const uint32_t w_bytes = p.n_tile * kRowBytes;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int w_rows = kPair ? p.n_tile / 2 : p.n_tile;     // rows of the B tile this CTA holds
+    const uint32_t w_bytes = w_rows * kRowBytes;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
       const int ntaps = p.num_taps[nt];
-      const int q0 = st * p.msub * kMTile;
-      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
-      const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
+      const int q0t = st * tile_rows;                       // first row of the (pair's) tile
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0t)) continue;
+      const int q0 = q0t + (int)rank * p.msub * kMTile;     // first row of this CTA's half
+      // sub-tiles the MMA warp issues: set by the leader's half (the peer's rows may all lie past
+      // the end -- its loads are then zero-filled, its stores clipped)
+      const int nsub = min(p.msub, (p.rows - q0t + kMTile - 1) / kMTile);
       const int nbox = (nsub * kMTile + p.halo[nt] + p.box_rows - 1) / p.box_rows;
       const int row0 = q0 + p.off_min[nt];
-      const int wcol = nt * p.n_tile;
+      const int wcol = nt * p.n_tile + (int)rank * w_rows;
       for (int c = 0; c < p.num_chunks; ++c) {
         mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1u);
         if (elect_one()) {
           const uint32_t bar = full_a + 8 * ra.s;
-          mbar_expect_tx(bar, nbox * box_bytes);
           const uint32_t dst = smem_a + ra.s * p.stage_a_bytes;
-          for (int bx = 0; bx < nbox; ++bx)
-            tma_load_3d(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+          if constexpr (kPair) {
+            // both CTAs' bytes land on the LEADER's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(bar, 2 * nbox * box_bytes);
+            for (int bx = 0; bx < nbox; ++bx)
+              tma_load_3d_pair(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+          } else {
+            mbar_expect_tx(bar, nbox * box_bytes);
+            for (int bx = 0; bx < nbox; ++bx)
+              tma_load_3d(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+          }
         }
         __syncwarp();
         ra.advance(p.stages_a);
@@ -387,29 +467,36 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(empty_w + 8 * rw.s, rw.ph ^ 1u);
           if (elect_one()) {
             const uint32_t bar = full_w + 8 * rw.s;
-            mbar_expect_tx(bar, w_bytes);
-            tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
-                        p.tap_row[nt][j] * p.n_total + wcol, bar);
+            if constexpr (kPair) {
+              if (rank == 0) mbar_expect_tx(bar, 2 * w_bytes);
+              tma_load_2d_pair(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
+                               p.tap_row[nt][j] * p.n_total + wcol, bar);
+            } else {
+              mbar_expect_tx(bar, w_bytes);
+              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
+                          p.tap_row[nt][j] * p.n_total + wcol, bar);
+            }
           }
           __syncwarp();
           rw.advance(p.stages_w);
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ====================================== MMA issuer ======================================
+    // (pair mode: the leader CTA issues M = 256 MMAs for both; commits are multicast)
     Ring ra, rw;
     uint32_t tile_iter = 0;
-    const uint32_t idesc = make_idesc_bf16(kMTile, p.n_tile, p.fp16);
+    const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kMTile : kMTile, p.n_tile, p.fp16);
     const uint32_t dhi = smem_desc_hi<KC>();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
       const int ntaps = p.num_taps[nt];
       const int off_min = p.off_min[nt];
-      const int q0 = st * p.msub * kMTile;
+      const int q0 = st * tile_rows;
       if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
@@ -431,13 +518,24 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
               const uint64_t bd = smem_desc(dhi, w_addr);
 #pragma unroll
-              for (int kk = 0; kk < kKSteps; ++kk)
-                umma_bf16(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
-                          acc0 | (kk != 0));
+              for (int kk = 0; kk < kKSteps; ++kk) {
+                if constexpr (kPair)
+                  umma_bf16_pair(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
+                                 acc0 | (kk != 0));
+                else
+                  umma_bf16(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
+                            acc0 | (kk != 0));
+              }
             }
-            umma_commit(empty_w + 8 * rw.s);
-            if (j == ntaps - 1) umma_commit(empty_a + 8 * ra.s);
-            if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit(acc_full + 8 * as);
+            if constexpr (kPair) {
+              umma_commit_pair(empty_w + 8 * rw.s);
+              if (j == ntaps - 1) umma_commit_pair(empty_a + 8 * ra.s);
+              if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit_pair(acc_full + 8 * as);
+            } else {
+              umma_commit(empty_w + 8 * rw.s);
+              if (j == ntaps - 1) umma_commit(empty_a + 8 * ra.s);
+              if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit(acc_full + 8 * as);
+            }
           }
           __syncwarp();
           rw.advance(p.stages_w);
@@ -455,16 +553,17 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t hbuf = ybuf + 2 * kStageYBytes;
     uint32_t sbuf = 0;
     uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
-      const int q0 = st * p.msub * kMTile;
-      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
+      const int q0t = st * tile_rows;
+      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0t)) continue;
+      const int q0 = q0t + (int)rank * p.msub * kMTile;     // this CTA's rows
       const uint32_t it = tile_iter++;   // processed tiles only, like the MMA warp's count
       if ((it & 1u) != static_cast<uint32_t>(group)) continue;
-      const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
+      const int nsub = max(0, min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile));
       const uint32_t aph = (it >> 1) & 1u;
       // column vectors of this tile (overlaps the wait for the accumulator)
       for (int c = lane; c < p.n_tile; c += 32) {
@@ -608,14 +707,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * group);   // one arrival per warp
+      if (lane == 0) {                                      // one arrival per warp
+        if constexpr (kPair) mbar_arrive_leader(acc_empty + 8 * group);
+        else mbar_arrive(acc_empty + 8 * group);
+      }
     }
     if (p.tma_out && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if constexpr (kPair) {
+    cluster_sync_all();   // nobody frees TMEM or exits while the peer can still signal or read it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 }  // namespace tc

@@ -48,6 +48,7 @@ struct TcLaunch {
   int grid = 0;
   int smem = 0;
   int kc = 64;
+  bool pair = false;   // CTA pairs (cta_group::2): cluster of 2, each CTA holds half of the B tile
 };
 
 struct FusedLaunch {
@@ -223,7 +224,12 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   }
   p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
   p.fp16 = (a.tc_flags & 0x100) ? 1 : 0;   // V2W_TC_FLAG_FP16
-  p.stage_w_bytes = (int)align_up((int64_t)a.n_tile * kc * 2, 1024);
+  // CTA pairs for wide tiles: the layers with n_tile >= 128 are bound by shared-memory operand
+  // delivery (64 + N/2 clk per MMA); a pair shares B, which takes N/4 clk off every MMA.
+  static const bool no_pair = [] { const char* e = std::getenv("V2W_TC_NO_PAIR"); return e && std::atoi(e); }();
+  L->pair = !no_pair && a.n_tile >= 128 && sms >= 2;
+  const int w_rows = L->pair ? a.n_tile / 2 : a.n_tile;
+  p.stage_w_bytes = (int)align_up((int64_t)w_rows * kc * 2, 1024);
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
@@ -239,10 +245,11 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     p.box_rows = msub == 1 ? 32 : 64;
     const int boxes = (msub * tc::kMTile + halo_max + p.box_rows - 1) / p.box_rows;
     p.stage_a_bytes = boxes * p.box_rows * kc * 2;
-    p.s_tiles = (a.rows + msub * tc::kMTile - 1) / (msub * tc::kMTile);
+    const int tile_rows = (L->pair ? 2 : 1) * msub * tc::kMTile;
+    p.s_tiles = (a.rows + tile_rows - 1) / tile_rows;
     const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
     const bool fits = 2 * p.stage_a_bytes + 3 * p.stage_w_bytes <= budget;
-    if (msub == 1 || (fits && (tiles >= 2 * sms || forced))) {
+    if (msub == 1 || (fits && (tiles >= (L->pair ? sms : 2 * sms) || forced))) {
       if (!fits) {
         set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)",
                   p.stage_a_bytes, p.stage_w_bytes);
@@ -263,7 +270,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   L->kc = kc;
   L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + tail_bytes + 1024;
   const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
-  L->grid = (int)std::min<int64_t>(tiles, sms);
+  L->grid = L->pair ? 2 * (int)std::min<int64_t>(tiles, sms / 2) : (int)std::min<int64_t>(tiles, sms);
 
   EncodeTiledFn enc = nullptr;
   rc = get_encode_fn(&enc);
@@ -291,7 +298,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
       for (int j = 0; j < a.num_taps[t]; ++j) max_row = std::max(max_row, a.tap_row[t][j]);
     cuuint64_t dims[2] = {(cuuint64_t)a.cin, (cuuint64_t)(max_row + 1) * a.n_total};
     cuuint64_t strides[1] = {(cuuint64_t)a.cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)w_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L->tm_w, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      const_cast<void*>(a.w16), dims,
@@ -346,21 +353,38 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st,
-                              Args&&... args) {
+template <int kCluster, typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (kCluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = kCluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st,
+                              Args&&... args) {
+  return launch_ex<1>(kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
@@ -376,7 +400,23 @@ static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit =
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<32, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  if (L.pair) {
+    if (L.kc == 64)
+      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<64, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
+    else if (L.kc == 32)
+      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<32, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
+    else
+      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<16, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
+    V2W_CUDA(cudaGetLastError());
+    return V2W_OK;
   }
   if (L.kc == 64)
     V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
