@@ -191,6 +191,8 @@ typedef struct v2w_fused_desc {
   int32_t a0_boxes;            /* 64-row TMA boxes per input tile */
   int32_t num_segments, num_taps;      /* num_taps = MMA entries */
   int32_t stacked;
+  int32_t pair;                /* 1: one ResBlock1 conv pair c2(lrelu(c1(a) + b1)) + b2 + x (models.py:37-44): no `sum`
+                                  convolution, the middle activation does NOT see the residual, bsum = b2 */
   int32_t order[V2W_MAX_KERNELS];      /* stacked: model branch that runs as slot j */
   int32_t t_bufs, a0_bufs;             /* stacked: accumulator sets / input tiles in flight */
   int32_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];   /* branch: slot of a CONV2 */
@@ -213,6 +215,7 @@ typedef struct v2w_fused_desc {
 #define V2W_OP_TAPGEMM 2
 #define V2W_OP_CONV_POST 3     /* lrelu(0.01) -> Conv1d(16->1,k7) -> tanh */
 #define V2W_OP_MRF_FUSED 4     /* one whole multi-receptive-field stage (ResBlock2, C <= 128) */
+#define V2W_OP_PAIR_FUSED 5    /* one ResBlock1 conv pair (C <= 64): conv, leaky-relu, conv, + residual (+ MRF sum) */
 
 #define V2W_ENGINE_SIMT 0      /* FFMA tap-GEMM */
 #define V2W_ENGINE_TC 1        /* tcgen05 / TMEM / TMA tap-GEMM */
@@ -237,7 +240,8 @@ typedef struct v2w_op_desc {
   int64_t out_bf16;            /* bf16 leaky_relu(result, out_slope): the next conv's operand */
   float out_slope;
   int64_t flops;               /* 2 * real MACs of this op (0 for non-GEMM ops) */
-  int32_t stage;               /* upsample stage of an MRF_FUSED op, else -1 */
+  int32_t stage;               /* upsample stage of an MRF_FUSED / PAIR_FUSED op, else -1 */
+  int32_t pair;                /* PAIR_FUSED: index for v2w_model_get_pair, else -1 */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -253,6 +257,8 @@ int32_t v2w_model_num_layers(const struct v2w_model* m);
 int32_t v2w_model_get_layer(const struct v2w_model* m, int32_t index, v2w_layer_desc* out);
 int32_t v2w_model_get_cond(const struct v2w_model* m, int32_t stage, v2w_cond_desc* out);
 int32_t v2w_model_get_fused(const struct v2w_model* m, int32_t stage, v2w_fused_desc* out);
+int32_t v2w_model_num_pairs(const struct v2w_model* m);   /* fusable ResBlock1 conv pairs (0 for ResBlock2) */
+int32_t v2w_model_get_pair(const struct v2w_model* m, int32_t index, v2w_fused_desc* out);
 int32_t v2w_model_num_convs(const struct v2w_model* m);   /* expected v2w_params.num_convs */
 int64_t v2w_model_packed_bytes(const struct v2w_model* m);
 /* Fold weight norm (w = g*v/||v||, norm over all dims but 0 -- i.e. per INPUT channel for

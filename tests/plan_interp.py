@@ -156,6 +156,43 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                 ws[op.out_bf16] = half(lrelu(v, op.out_slope))
             if collect is not None:
                 collect[idx] = v
+        elif op.kind == native.OP_PAIR_FUSED:
+            # ResBlock1 conv pair in one kernel: t = conv1(A0) + b1; A1 = half(lrelu(t));
+            # out = (conv2(A1) + b2 + X0 [+ running MRF sum]) * scale      (models.py:37-44)
+            F = native.FusedDesc()
+            native.check(plan.lib.v2w_model_get_pair(plan.model, op.pair, C.byref(F)))
+            assert F.ok and F.pair and F.num_segments == 2
+            Cn = F.channels
+            A0 = ws[op.in_act].reshape(op.batch, op.rows, Cn)
+            X0 = ws[op.residual].reshape(op.batch, op.rows, Cn)
+            Wf = half_to_f32(u16(F.w_off, F.w_rows * Cn)).reshape(F.w_rows, Cn)
+            b1 = f32(plan.layers[F.first_layer].bias_off, Cn)
+            b2 = f32(F.bsum_off, Cn)
+            assert np.array_equal(b2, f32(plan.layers[F.first_layer + 1].bias_off, Cn))
+
+            def conv(A, seg):
+                acc = np.zeros((op.batch, op.rows, Cn), np.float32)
+                for t in range(F.seg_first[seg], F.seg_first[seg] + F.seg_ntaps[seg]):
+                    off = F.offset[t]
+                    W = Wf[F.w_row[t]: F.w_row[t] + Cn]
+                    sh = np.zeros_like(A)
+                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                    if hi > lo:
+                        sh[:, lo:hi] = A[:, lo + off: hi + off]
+                    acc += sh @ W.T
+                return acc
+
+            A1 = half(lrelu(conv(A0, 0) + b1, 0.1))
+            v = conv(A1, 1) + b2 + X0
+            if op.accum_in >= 0:
+                v = v + ws[op.accum_in].reshape(op.batch, op.rows, Cn)
+            v = (v * np.float32(op.out_scale)).astype(np.float32)
+            if op.out_f32 >= 0:
+                ws[op.out_f32] = v
+            if op.out_bf16 >= 0:
+                ws[op.out_bf16] = half(lrelu(v, op.out_slope))
+            if collect is not None:
+                collect[idx] = v
         elif op.kind == native.OP_MRF_FUSED:
             F = native.FusedDesc()
             native.check(plan.lib.v2w_model_get_fused(plan.model, op.stage, C.byref(F)))

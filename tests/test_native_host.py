@@ -148,6 +148,39 @@ def test_fused_and_unfused_plans_agree(monkeypatch):
     assert snr > 60.0
 
 
+def test_resblock1_pair_fusion(monkeypatch):
+    """ResBlock1: every (dilated conv, conv) pair of the C <= 64 stages is one PAIR_FUSED op.  It is
+    the same arithmetic with the same rounding points as the two tap-GEMMs it replaces (the
+    intermediate is rounded to 16 bits once either way), so the emulated outputs agree to fp32
+    summation-order noise; the plan has 27 launches fewer and the same FLOP total."""
+    g = load_golden("rb1_768_stress")
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    packed = eng.pack_host(native.HALF_FP16).numpy()
+    B, T = g.x.shape[0], g.x.shape[2]
+    fplan = plan_interp.HostPlan(eng, B, T, "fp16")
+    pairs = [op for op in fplan.ops if op.kind == native.OP_PAIR_FUSED]
+    assert len(pairs) == 27 and sorted({op.stage for op in pairs}) == [2, 3, 4]
+    assert len(fplan.ops) == 99 - 27
+    assert eng._lib.v2w_model_num_pairs(eng._model) == 27
+    F = native.FusedDesc()
+    native.check(eng._lib.v2w_model_get_pair(eng._model, pairs[-1].pair, C.byref(F)))
+    # last pair of the model: stage 4 (C = 16), k = 11, dilation 5 then 1
+    assert (F.ok, F.pair, F.stacked, F.channels, F.num_branches, F.num_taps, F.num_segments) == (1, 1, 1, 16, 1, 22, 2)
+    assert (F.hc, F.h1, F.rc, F.a0_boxes, F.t_bufs, F.w_rows) == (5, 25, 246, 5, 2, 22 * 16)
+    assert [F.offset[t] for t in range(11)] == [5 * (t - 5) for t in range(11)]
+    assert [F.shift[t] for t in range(11, 22)] == list(range(-5, 6)) and list(F.seg_acc[:2]) == [0, 0]
+    fused = plan_interp.run(fplan, packed, g.x, g.spk, g.noise)
+    monkeypatch.setenv("V2W_NO_FUSE", "1")
+    uplan = plan_interp.HostPlan(eng, B, T, "fp16")
+    assert len(uplan.ops) == 99 and sum(op.flops for op in uplan.ops) == sum(op.flops for op in fplan.ops)
+    plain = plan_interp.run(uplan, packed, g.x, g.spk, g.noise)
+    snr = fixtures.snr_db(plain, fused)
+    print(f"ResBlock1 pair-fused vs unfused (emulated): {snr:.1f} dB; vs reference {fixtures.snr_db(g.y, fused):.1f} dB")
+    assert snr > 100.0
+    assert fixtures.snr_db(g.y, fused) >= 45.0
+
+
 @pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 45.0), ("rb2_1024_warm", 45.0)])
 def test_bf16_plan_predicted_snr(name, min_snr):
     """Same op list with the device's bf16 rounding points (bf16 operands, fp32 accumulate,

@@ -69,7 +69,7 @@ def main():
                              tflops=op.flops / ms / 1e9, gbs=by / ms / 1e6, mb=by / 1e6,
                              resid=op.residual >= 0, accum=op.accum_in >= 0,
                              f32=op.out_f32 >= 0, b16=op.out_bf16 >= 0))
-        elif op.kind == native.OP_MRF_FUSED:
+        elif op.kind in (native.OP_MRF_FUSED, native.OP_PAIR_FUSED):
             C = op.n_tile
             by = op.batch * op.rows * C * (2 + 4 + (4 if op.out_f32 >= 0 else 0) + (2 if op.out_bf16 >= 0 else 0))
             rows.append(dict(i=i, kind="fused", stage=op.stage, cin=C, rows=op.rows, ms=ms,

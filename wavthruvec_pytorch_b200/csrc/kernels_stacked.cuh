@@ -93,6 +93,8 @@ struct Params {
   const float* x0;              // fp32 [B, L, C]
   const float* bias1[V2W_MAX_KERNELS];   // by slot
   const float* bsum;
+  const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
+  int e1_add_x0;                // 1: the middle activation sees the residual (ResBlock2); 0: ResBlock1 pair
   float mid_slope, res_scale, out_scale, out_slope;
   float* out_f32;
   __nv_bfloat16* out_bf16;
@@ -417,10 +419,11 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
-                v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
-                v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
-                v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;
-                v[4 * e + 3] = __uint_as_float(r[4 * e + 3]) + bb.w + xr[e].w;
+                const float ax = p.e1_add_x0 ? 1.f : 0.f;
+                v[4 * e] = fmaf(ax, xr[e].x, __uint_as_float(r[4 * e]) + bb.x);
+                v[4 * e + 1] = fmaf(ax, xr[e].y, __uint_as_float(r[4 * e + 1]) + bb.y);
+                v[4 * e + 2] = fmaf(ax, xr[e].z, __uint_as_float(r[4 * e + 2]) + bb.z);
+                v[4 * e + 3] = fmaf(ax, xr[e].w, __uint_as_float(r[4 * e + 3]) + bb.w);
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e)
@@ -477,13 +480,22 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             if (out_valid) {
               float v[16];
+              float4 acc4[4];
+              if (p.accum_in) {
+                const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(smem_bias + (p.nbranch * C + cc + 4 * e) * 4);
-                v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x) * p.out_scale;
-                v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y) * p.out_scale;
-                v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z) * p.out_scale;
-                v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w) * p.out_scale;
+                v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x + acc4[e].x) * p.out_scale;
+                v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y + acc4[e].y) * p.out_scale;
+                v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z + acc4[e].z) * p.out_scale;
+                v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
               }
               if (p.out_f32) {
                 float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);

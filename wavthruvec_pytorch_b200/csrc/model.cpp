@@ -191,6 +191,49 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
   return true;
 }
 
+// ResBlock1 conv pair  x' = c2(lrelu(c1(lrelu(x)) + b1)) + b2 + x  (models.py:37-44) as a two-segment
+// program of the stacked kernel: conv1 (dilation d) of the whole 256-row window into T1, the
+// epilogue turns it into A1 in shared memory, conv2 (dilation 1) into T2.  Halo = conv2's reach only
+// ((k - 1) / 2 rows: 246 of 256 window rows are central for k = 11).
+static v2w_fused_desc plan_pair(const v2w_model* m, int stage, int first_layer, int k, int d) {
+  v2w_fused_desc F;
+  std::memset(&F, 0, sizeof(F));
+  const int C = m->stage_channels[stage];
+  F.channels = C;
+  F.num_branches = 1;
+  F.first_layer = first_layer;
+  F.pair = 1;
+  F.stacked = 1;
+  if (m->cfg.resblock_type != 1 || (C != 16 && C != 32 && C != 64)) return F;
+  const int r = (k - 1) / 2;
+  const int hc = r, h1 = d * r;
+  const int rc = 256 - 2 * hc, a0_rows = 256 + 2 * h1;
+  if (rc < 64 || a0_rows > 64 * 7 || 2 * k > V2W_FUSED_MAX_TAPS) return F;
+  F.hc = hc; F.h1 = h1; F.rc = rc;
+  F.a0_boxes = (a0_rows + 63) / 64;
+  F.t_bufs = 2; F.a0_bufs = 2;
+  // TMEM columns of a sub-tile: [T2 | T1_0]
+  F.seg_type[0] = V2W_FUSED_SEG_CONV1; F.seg_branch[0] = -1;
+  F.seg_dcol[0] = C; F.seg_n[0] = C; F.seg_acc[0] = 0;
+  F.seg_wait[0] = V2W_FUSED_BIT_A0 | V2W_FUSED_BIT_T1(0);
+  F.seg_commit[0] = V2W_FUSED_BIT_T1(0) | V2W_FUSED_BIT_A0;
+  F.seg_first[0] = 0; F.seg_ntaps[0] = k;
+  F.seg_type[1] = V2W_FUSED_SEG_CONV2; F.seg_branch[1] = 0;
+  F.seg_dcol[1] = 0; F.seg_n[1] = C; F.seg_acc[1] = 0;          // the first conv2 MMA overwrites T2
+  F.seg_wait[1] = V2W_FUSED_BIT_A1(0) | V2W_FUSED_BIT_T2;
+  F.seg_commit[1] = V2W_FUSED_BIT_T2;
+  F.seg_first[1] = k; F.seg_ntaps[1] = k;
+  for (int t = 0; t < k; ++t) {
+    F.offset[t] = (t - r) * d;     F.shift[t] = h1 + (t - r) * d;  F.w_row[t] = t * C;
+    F.offset[k + t] = t - r;       F.shift[k + t] = t - r;         F.w_row[k + t] = (k + t) * C;
+  }
+  F.num_segments = 2;
+  F.num_taps = 2 * k;
+  F.w_rows = 2 * k * C;
+  F.ok = 1;
+  return F;
+}
+
 // Decide whether stage `i` can run as one fused kernel and lay out its program.
 // `first_layer` = index of branch 0's first conv in m->layers.
 static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_layer) {
@@ -394,9 +437,16 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
       } else {
         // ResBlock1.forward (models.py:37-44): (convs1[s] dil d[s], convs2[s] dil 1) x 3
         for (int s = 0; s < 3; ++s) {
+          const int first = (int)m->layers.size();
           add_conv1d(m, V2W_ROLE_RESBLOCK, i, base + 2 * s, ch, ch, k,
                      c->resblock_dilation_sizes[j][s]);
           add_conv1d(m, V2W_ROLE_RESBLOCK, i, base + 2 * s + 1, ch, ch, k, 1);
+          const v2w_fused_desc P = plan_pair(m, i, first, k, c->resblock_dilation_sizes[j][s]);
+          m->pair_of_layer.resize(m->layers.size(), -1);
+          if (P.ok) {
+            m->pair_of_layer[first] = (int)m->pairs.size();
+            m->pairs.push_back(P);
+          }
         }
       }
     }
@@ -438,13 +488,16 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
     cl.mean = off; off = align_up(off + (int64_t)cl.C * 4, 256);
     m->cond.push_back(cl);
   }
-  for (auto& F : m->fused) {
-    if (!F.ok) continue;
-    F.w_off = off;
-    off = align_up(off + (int64_t)F.w_rows * F.channels * 2, 1024);
-    F.bsum_off = off;
-    off = align_up(off + (int64_t)F.channels * 4, 1024);
+  for (auto* vec : {&m->fused, &m->pairs}) {
+    for (auto& F : *vec) {
+      if (!F.ok) continue;
+      F.w_off = off;
+      off = align_up(off + (int64_t)F.w_rows * F.channels * 2, 1024);
+      F.bsum_off = off;
+      off = align_up(off + (int64_t)F.channels * 4, 1024);
+    }
   }
+  m->pair_of_layer.resize(m->layers.size(), -1);
   m->packed_bytes = align_up(off, 1024);
   m->flops_per_frame = flops;
   *out = m;
@@ -501,6 +554,17 @@ int32_t v2w_model_halo_frames(const v2w_model* m) {
   }
   R += 3;                                           // conv_pre k = 7 (models.py:83)
   return (int32_t)R;
+}
+
+int32_t v2w_model_num_pairs(const v2w_model* m) { return m ? (int32_t)m->pairs.size() : 0; }
+
+int32_t v2w_model_get_pair(const v2w_model* m, int32_t i, v2w_fused_desc* out) {
+  if (!m || !out || i < 0 || i >= (int32_t)m->pairs.size()) {
+    set_error("v2w_model_get_pair: bad index %d", i);
+    return V2W_ERR_INVALID;
+  }
+  *out = m->pairs[i];
+  return V2W_OK;
 }
 
 int32_t v2w_model_get_fused(const v2w_model* m, int32_t i, v2w_fused_desc* out) {
@@ -616,13 +680,18 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
     }
   }
   // fused stages: tap matrices in issue order, from the folded fp32 weights packed above
-  for (const auto& F : m->fused) {
+  std::vector<const v2w_fused_desc*> all_fused;
+  for (const auto& F : m->fused) all_fused.push_back(&F);
+  for (const auto& F : m->pairs) all_fused.push_back(&F);
+  for (const v2w_fused_desc* Fp : all_fused) {
+    const v2w_fused_desc& F = *Fp;
     if (!F.ok) continue;
     const int C = F.channels;
     uint16_t* wf = reinterpret_cast<uint16_t*>(base + F.w_off);
     float* bsum = reinterpret_cast<float*>(base + F.bsum_off);
     for (int ch = 0; ch < C; ++ch) bsum[ch] = 0.f;
-    for (int j = 0; j < 2 * F.num_branches; ++j) {
+    // a ResBlock1 pair adds only conv2's bias at the end (b1 went into the middle activation)
+    for (int j = F.pair ? 1 : 0; j < 2 * F.num_branches; ++j) {
       const float* bl = reinterpret_cast<const float*>(base + m->layers[F.first_layer + j].bias_off);
       for (int ch = 0; ch < C; ++ch) bsum[ch] += bl[ch];
     }

@@ -554,7 +554,9 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * F.order[j]].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
   p.mid_slope = kLreluSlope;
-  p.res_scale = (float)nb;
+  p.res_scale = F.pair ? 1.0f : (float)nb;
+  p.e1_add_x0 = F.pair ? 0 : 1;
+  p.accum_in = d.accum_in >= 0 ? reinterpret_cast<const float*>(ws + d.accum_in) : nullptr;
   p.out_scale = d.out_scale;
   p.out_slope = d.out_slope;
   p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
@@ -860,9 +862,15 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     x0.bf16 = ws.take(max_e * 2);
     y1.bf16 = ws.take(max_e * 2);
   }
+  Act y2;    // ResBlock1, fused conv pairs: a pair reads its input WITH halo rows, so it cannot run in place
+  y2.slope = kLreluSlope;
   if (c.resblock_type == 1) {
     if (bf) t1.bf16 = ws.take(max_e * 2);
     else t1.f32 = ws.take(max_e * 4);
+    if (bf) {
+      y2.f32 = ws.take(max_e * 4);
+      y2.bf16 = ws.take(max_e * 2);
+    }
   }
   const int64_t next_bf16 = bf ? ws.take(max_e * 2) : -1;
   P->workspace_bytes = ws.off;
@@ -877,6 +885,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     o.d.in_act = o.d.residual = o.d.accum_in = o.d.out_f32 = o.d.out_bf16 = -1;
     o.d.cond_stage = -1;
     o.d.stage = -1;
+    o.d.pair = -1;
     o.d.in_slope = 1.f;
     o.d.out_scale = 1.f;
     o.d.out_slope = 1.f;
@@ -972,6 +981,32 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
         // ResBlock1 (models.py:37-44): x = c2(lrelu(c1(lrelu(x)))) + x, three times
         Act cur = x0;
         for (int s = 0; s < 3; ++s) {
+          const int pi = (bf && !force_simt && !no_fuse && ((fuse_mask >> i) & 1)) ? m->pair_of_layer[li] : -1;
+          if (pi >= 0) {
+            // conv pair in one kernel (kernels_stacked.cuh, pair program): the intermediate t1 never
+            // leaves the SM
+            const bool tail = s == 2;
+            const Act& dst = tail ? tail_out : (s == 0 ? y1 : y2);
+            Op o = blank(V2W_OP_PAIR_FUSED);
+            o.d.engine = V2W_ENGINE_TC;
+            o.d.layer = li;
+            o.d.stage = i;
+            o.d.pair = pi;
+            o.d.batch = B;
+            o.d.rows = rows;
+            o.d.n_tile = m->stage_channels[i];
+            o.d.n_tiles = 1;
+            o.d.in_act = cur.bf16; o.d.in_is_bf16 = 1;
+            o.d.residual = cur.f32;
+            o.d.accum_in = tail ? accum : -1;
+            o.d.out_scale = tail ? scale : 1.f;
+            o.d.out_f32 = dst.f32; o.d.out_bf16 = dst.bf16; o.d.out_slope = dst.slope;
+            o.d.flops = 2 * (m->layers[li].macs_per_row + m->layers[li + 1].macs_per_row) * (int64_t)rows * B;
+            P->ops.push_back(o);
+            li += 2;
+            if (!tail) cur = dst;
+            continue;
+          }
           emit(li++, rows, cur, -1, -1, -1, 1.f, t1);
           if (s < 2) {
             emit(li++, rows, t1, -1, cur.f32, -1, 1.f, y1);
@@ -1070,9 +1105,9 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   }
   const int tc_flags = p->precision == V2W_PREC_FP16 ? 0x100 : 0;
   for (Op& o : p->ops) {
-    if (o.d.kind == V2W_OP_MRF_FUSED) {
-      rc = prepare_fused(m, m->fused[o.d.stage], o.d, p->packed, p->ws,
-                         p->precision == V2W_PREC_FP16, &o.fl);
+    if (o.d.kind == V2W_OP_MRF_FUSED || o.d.kind == V2W_OP_PAIR_FUSED) {
+      const v2w_fused_desc& F = o.d.kind == V2W_OP_MRF_FUSED ? m->fused[o.d.stage] : m->pairs[o.d.pair];
+      rc = prepare_fused(m, F, o.d, p->packed, p->ws, p->precision == V2W_PREC_FP16, &o.fl);
       if (rc) return rc;
       continue;
     }
@@ -1250,6 +1285,7 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         ++launches;
         break;
       }
+      case V2W_OP_PAIR_FUSED:
       case V2W_OP_MRF_FUSED: {
         int rc = launch_fused(o.fl, st, lim, o.d.rows / p->frames);
         if (rc) return rc;

@@ -27,7 +27,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
 OUT_F32, OUT_PCM16 = 0, 1
-OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED = 0, 1, 2, 3, 4
+OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED, OP_PAIR_FUSED = 0, 1, 2, 3, 4, 5
 FUSED_MAX_SEG, FUSED_MAX_TAPS = 16, 96
 SEG_CONV1, SEG_SUM, SEG_CONV2 = 0, 1, 2
 ROLE_CONV_PRE, ROLE_UPSAMPLE, ROLE_RESBLOCK, ROLE_CONV_POST = 0, 1, 2, 3
@@ -114,6 +114,7 @@ class OpDesc(C.Structure):
         ("out_f32", C.c_int64), ("out_bf16", C.c_int64), ("out_slope", C.c_float),
         ("flops", C.c_int64),
         ("stage", C.c_int32),
+        ("pair", C.c_int32),
     ]
 
 
@@ -122,7 +123,7 @@ class FusedDesc(C.Structure):
         ("ok", C.c_int32), ("channels", C.c_int32), ("num_branches", C.c_int32),
         ("first_layer", C.c_int32), ("hc", C.c_int32), ("h1", C.c_int32), ("rc", C.c_int32),
         ("a0_boxes", C.c_int32), ("num_segments", C.c_int32), ("num_taps", C.c_int32),
-        ("stacked", C.c_int32), ("order", C.c_int32 * 4), ("t_bufs", C.c_int32), ("a0_bufs", C.c_int32),
+        ("stacked", C.c_int32), ("pair", C.c_int32), ("order", C.c_int32 * 4), ("t_bufs", C.c_int32), ("a0_bufs", C.c_int32),
         ("seg_type", C.c_int32 * FUSED_MAX_SEG), ("seg_branch", C.c_int32 * FUSED_MAX_SEG),
         ("seg_ntaps", C.c_int32 * FUSED_MAX_SEG), ("seg_first", C.c_int32 * FUSED_MAX_SEG),
         ("seg_flags", C.c_int32 * FUSED_MAX_SEG),
@@ -163,6 +164,8 @@ _SIGNATURES = [
     ("v2w_model_get_layer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(LayerDesc)]),
     ("v2w_model_get_cond", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(CondDesc)]),
     ("v2w_model_get_fused", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FusedDesc)]),
+    ("v2w_model_num_pairs", C.c_int32, [C.c_void_p]),
+    ("v2w_model_get_pair", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FusedDesc)]),
     ("v2w_model_num_convs", C.c_int32, [C.c_void_p]),
     ("v2w_model_packed_bytes", C.c_int64, [C.c_void_p]),
     ("v2w_model_pack", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
