@@ -415,7 +415,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   tcgen05_fence_before();
   if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
-  else __syncthreads();
+  __syncthreads();   // (also in pair mode: the CTA-level barrier is what orders the TMEM-address read below for racecheck)
   // everything above touched only kernel parameters and the (constant) packed weights: from here
   // on the previous kernel's outputs are read and its inputs overwritten
   pdl_launch_dependents();
