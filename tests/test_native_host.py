@@ -149,10 +149,10 @@ def test_fused_and_unfused_plans_agree(monkeypatch):
 
 
 def test_resblock1_pair_fusion(monkeypatch):
-    """ResBlock1: every (dilated conv, conv) pair of the C <= 64 stages is one PAIR_FUSED op.  It is
+    """ResBlock1: every (dilated conv, conv) pair of the C <= 128 stages is one PAIR_FUSED op.  It is
     the same arithmetic with the same rounding points as the two tap-GEMMs it replaces (the
     intermediate is rounded to 16 bits once either way), so the emulated outputs agree to fp32
-    summation-order noise; the plan has 27 launches fewer and the same FLOP total."""
+    summation-order noise; the plan has 36 launches fewer and the same FLOP total."""
     g = load_golden("rb1_768_stress")
     gen = dropin_in_state(g)
     eng = gen.engine()
@@ -160,9 +160,13 @@ def test_resblock1_pair_fusion(monkeypatch):
     B, T = g.x.shape[0], g.x.shape[2]
     fplan = plan_interp.HostPlan(eng, B, T, "fp16")
     pairs = [op for op in fplan.ops if op.kind == native.OP_PAIR_FUSED]
-    assert len(pairs) == 27 and sorted({op.stage for op in pairs}) == [2, 3, 4]
-    assert len(fplan.ops) == 99 - 27
-    assert eng._lib.v2w_model_num_pairs(eng._model) == 27
+    assert len(pairs) == 36 and sorted({op.stage for op in pairs}) == [1, 2, 3, 4]
+    assert len(fplan.ops) == 99 - 36
+    assert eng._lib.v2w_model_num_pairs(eng._model) == 36
+    native.check(eng._lib.v2w_model_get_pair(eng._model, pairs[0].pair, C.byref(F := native.FusedDesc())))
+    # first pair: stage 1 (C = 128) runs the plain program of kernels_fused.cuh, k = 3, dilation 1
+    assert (F.ok, F.pair, F.stacked, F.channels, F.num_taps, F.hc, F.h1, F.rc) == (1, 1, 0, 128, 6, 1, 1, 254)
+    assert [F.shift[t] for t in range(6)] == [0, 1, 2, 0, 1, 2] and list(F.seg_flags[:2]) == [1, 2]
     F = native.FusedDesc()
     native.check(eng._lib.v2w_model_get_pair(eng._model, pairs[-1].pair, C.byref(F)))
     # last pair of the model: stage 4 (C = 16), k = 11, dilation 5 then 1

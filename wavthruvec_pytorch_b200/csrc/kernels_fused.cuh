@@ -74,7 +74,10 @@ struct Params {
   int shift[kMaxTaps];          // operand row (sub-tile 0) of each tap inside its A tile
   const float* x0;              // fp32 [B, L, C]
   const float* bias1[V2W_MAX_KERNELS];
-  const float* bsum;            // sum_j (b1_j + b2_j)
+  const float* bsum;            // sum_j (b1_j + b2_j)   (ResBlock1 pair: b2)
+  const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
+  int pair;                     // 1: ResBlock1 conv pair -- no `sum` segment (the first conv2 MMA overwrites T2)
+                                //    and the middle activation does not see the residual
   float mid_slope;              // leaky-relu between the convs of a block (0.1)
   float res_scale;              // nk: multiplier of X0 in the final sum
   float out_scale;              // 1/nk
@@ -253,6 +256,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           a_chunk_bytes = a0_chunk_bytes;
         } else {
           slot = n2 % kSlots;
+          if (p.pair) mbar_wait(t2_empty + 8 * buf, tph ^ 1u);   // no `sum` segment: conv2 is T2's first writer
           mbar_wait(a1_full + 8 * slot, (n2 / kSlots) & 1u);
           d_tmem = tmem_t2 + buf * K::kT1Cols;
           a_tile = smem_a1 + slot * K::kA1Bytes;
@@ -277,7 +281,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 w_addr = smem_w + r.s * p.stage_w_bytes;
               }
               const uint64_t bd = smem_desc(dhi, w_addr);
-              const uint32_t acc0 = (sg.type == kSegConv2) || (t != 0) || (c != 0);
+              const uint32_t acc0 = (sg.type == kSegConv2 && !p.pair) || (t != 0) || (c != 0);
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
                 const uint64_t ad = (static_cast<uint64_t>(dhi) << 32) |
@@ -370,10 +374,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
-                v[4 * e] = __uint_as_float(r[4 * e]) + bb.x + xr[e].x;
-                v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + bb.y + xr[e].y;
-                v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + bb.z + xr[e].z;
-                v[4 * e + 3] = __uint_as_float(r[4 * e + 3]) + bb.w + xr[e].w;
+                const float ax = p.pair ? 0.f : 1.f;
+                v[4 * e] = fmaf(ax, xr[e].x, __uint_as_float(r[4 * e]) + bb.x);
+                v[4 * e + 1] = fmaf(ax, xr[e].y, __uint_as_float(r[4 * e + 1]) + bb.y);
+                v[4 * e + 2] = fmaf(ax, xr[e].z, __uint_as_float(r[4 * e + 2]) + bb.z);
+                v[4 * e + 3] = fmaf(ax, xr[e].w, __uint_as_float(r[4 * e + 3]) + bb.w);
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e)
@@ -432,13 +437,22 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld_wait();
           if (valid) {
             float v[16];
+            float4 acc4[4];
+            if (p.accum_in) {
+              const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bsum + cc + 4 * e));
-              v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x) * p.out_scale;
-              v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y) * p.out_scale;
-              v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z) * p.out_scale;
-              v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w) * p.out_scale;
+              v[4 * e] = (__uint_as_float(r[4 * e]) + bb.x + p.res_scale * xr[e].x + acc4[e].x) * p.out_scale;
+              v[4 * e + 1] = (__uint_as_float(r[4 * e + 1]) + bb.y + p.res_scale * xr[e].y + acc4[e].y) * p.out_scale;
+              v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z + acc4[e].z) * p.out_scale;
+              v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
             }
             if (p.out_f32) {
               float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);

@@ -204,9 +204,35 @@ static v2w_fused_desc plan_pair(const v2w_model* m, int stage, int first_layer, 
   F.first_layer = first_layer;
   F.pair = 1;
   F.stacked = 1;
-  if (m->cfg.resblock_type != 1 || (C != 16 && C != 32 && C != 64)) return F;
+  if (m->cfg.resblock_type != 1 || (C != 16 && C != 32 && C != 64 && C != 128)) return F;
   const int r = (k - 1) / 2;
   const int hc = r, h1 = d * r;
+  if (C == 128) {
+    // plain program of kernels_fused.cuh (two K-chunks; T2 rows start hc rows into the window)
+    F.stacked = 0;
+    const int rc = 256 - 2 * hc, a0_rows = 256 + hc + 2 * h1;
+    if (rc < 64 || a0_rows > 64 * 5 || 2 * k > V2W_FUSED_MAX_TAPS) return F;   // A0 80 KB + A1 64 KB + ring
+    F.hc = hc; F.h1 = h1; F.rc = rc;
+    F.a0_boxes = (a0_rows + 63) / 64;
+    for (int sgi = 0; sgi < 2; ++sgi) {
+      F.seg_type[sgi] = sgi == 0 ? V2W_FUSED_SEG_CONV1 : V2W_FUSED_SEG_CONV2;
+      F.seg_branch[sgi] = 0;
+      F.seg_ntaps[sgi] = k;
+      F.seg_first[sgi] = sgi * k;
+      F.seg_n[sgi] = C;
+    }
+    F.seg_flags[0] = 1;   // conv1 is the last reader of the input tile
+    F.seg_flags[1] = 2;   // conv2 is the last segment
+    for (int t = 0; t < k; ++t) {
+      F.offset[t] = (t - r) * d;  F.shift[t] = h1 + (t - r) * d;      F.w_row[t] = t * C;
+      F.offset[k + t] = t - r;    F.shift[k + t] = hc + (t - r);      F.w_row[k + t] = (k + t) * C;
+    }
+    F.num_segments = 2;
+    F.num_taps = 2 * k;
+    F.w_rows = 2 * k * C;
+    F.ok = 1;
+    return F;
+  }
   const int rc = 256 - 2 * hc, a0_rows = 256 + 2 * h1;
   if (rc < 64 || a0_rows > 64 * 7 || 2 * k > V2W_FUSED_MAX_TAPS) return F;
   F.hc = hc; F.h1 = h1; F.rc = rc;

@@ -621,7 +621,9 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * j].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
   p.mid_slope = kLreluSlope;
-  p.res_scale = (float)F.num_branches;
+  p.res_scale = F.pair ? 1.0f : (float)F.num_branches;
+  p.pair = F.pair;
+  p.accum_in = d.accum_in >= 0 ? reinterpret_cast<const float*>(ws + d.accum_in) : nullptr;
   p.out_scale = d.out_scale;
   p.out_slope = d.out_slope;
   p.out_f32 = d.out_f32 >= 0 ? reinterpret_cast<float*>(ws + d.out_f32) : nullptr;
