@@ -326,6 +326,12 @@ int32_t v2w_forward_ragged(struct v2w_plan* p, const float* x_rows_dev, const in
  * receptive field of conv_pre .. conv_post, in frames, rounded up). */
 int32_t v2w_model_halo_frames(const struct v2w_model* m);
 
+/* Feature-file reader: NumPy .npy, little-endian float32, C order, shape [T, C]
+ * or [1, T, C] as prepare_data.py:87 writes wav2vec features.  v2w_npy_read_f32 copies the rows into
+ * `dst` (room for max_rows x cols floats; ideally pinned) and returns the frame count.  Host only. */
+int32_t v2w_npy_shape(const char* path, int64_t* rows, int64_t* cols);
+int32_t v2w_npy_read_f32(const char* path, float* dst, int64_t max_rows, int64_t cols, int64_t* rows);
+
 /* Pipelined generation from HOST buffers (throughput API): up to two steps in flight on three
  * library-owned streams -- H2D of step i+1 and D2H of step i-1 overlap the kernels of step i.
  * Staging buffers are owned by the pipeline (cudaMalloc).  Every submitted step still copies its

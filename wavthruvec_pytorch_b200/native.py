@@ -188,6 +188,8 @@ _SIGNATURES = [
     ("v2w_forward_ragged", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     ("v2w_model_halo_frames", C.c_int32, [C.c_void_p]),
+    ("v2w_npy_shape", C.c_int32, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("v2w_npy_read_f32", C.c_int32, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     ("v2w_pipeline_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("v2w_pipeline_submit", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("v2w_pipeline_wait", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
