@@ -22,7 +22,7 @@ batches: measured on B200, 64 utterances of 1-10 s, one skipping launch sequence
 zero-padded batch and four bucketed launches (profiles/r01_varlen.json).
 
 Every returned sample equals what the reference computes for the zero-padded batch and then
-truncates (`tests/test_varlen.py` pins the halo against the oracle).  Host logic only; the
+truncates (pinned in `tests/test_varlen.py`).  Host logic only; the
 arithmetic is libv2w's.
 """
 from __future__ import annotations
