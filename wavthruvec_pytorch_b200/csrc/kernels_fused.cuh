@@ -1,11 +1,15 @@
-// Fused multi-receptive-field stage for C <= 128 (ResBlock2):  one kernel computes
+// Fused multi-receptive-field stage (ResBlock2), plain program:  one kernel computes
 //
 //     x_out = (1/nk) * sum_j  ResBlock2_j(x)            (vec2wav/models.py:65-70,135-141)
 //
 // for a 226-row tile without the intermediates ever leaving the SM.  Unfused, one stage moves
 // ~74 B per output element through HBM (six convs x [16-bit operand + fp32 residual in, fp32 +
-// 16-bit out]); fused it is ~10 B (A0 + fp32 X0 in, 16-bit or fp32 out), which turns these stages
-// from HBM-/L1-bound into MMA-bound.
+// 16-bit out]); fused it is ~10 B (A0 + fp32 X0 in, 16-bit or fp32 out).
+//
+// In the shipped plans this kernel runs the C = 128 stage (two K-chunks of 64 channels; TMEM and
+// shared memory are full there, everything is single buffered) and the C = 128 conv pairs of
+// ResBlock1 (Params::pair).  C <= 64 runs kernels_stacked.cuh; the C <= 64 instantiations below are
+// kept as the A/B baseline of that kernel (V2W_FUSED_NO_STACK=1).
 //
 // Algebra (per branch j: conv1_j dilation d0, conv2_j dilation d1_j; A0 = half(lrelu(X0))):
 //     Y1_j  = conv1_j(A0) + b1_j + X0                       (fp32)
@@ -20,21 +24,15 @@
 // of halo per side (hc = max_j d1_j (k_j - 1)/2 = 15, rc = 226).  conv1_j is evaluated on the whole
 // window (its output feeds conv2's halo), conv_sum and conv2_j on the 256 rows starting at q0c (the
 // last 2*hc of them are discarded).  A0 tile = window + h1 rows per side (h1 = d0 (kmax - 1)/2).
-// Channels are processed in K-chunks of 64 (one 128-byte swizzle span); C = 128 has two.
 //
 // Roles: warp 0 TMA producer (A0 tile, weight taps), warp 1 MMA issuer (one elected lane issues a
-// whole segment), warps 4-11 epilogue (thread = window row).
+// whole segment), warps 4-11 epilogue (thread = window row).  The segment program comes from the
+// host (model.cpp plan_fused_stage / plan_pair): for C = 128  c1_0, SUM, then c2_j, c1_{j+1}, so that
+// conv_sum covers the first epilogue; for a ResBlock1 pair  c1, c2  (no SUM: conv2 is T2's first
+// writer and waits for the previous tile's final pass).
 //
-// Buffering (kSlots): for C <= 64 T1/A1 are double buffered across branches (conv1_{j+1} overlaps the
-// epilogue of branch j, conv2_j overlaps the epilogue of branch j+1) and A0/T2 across tiles.  C = 128
-// fills TMEM (T1 256 + T2 256 columns) and shared memory (A0 80 KB + A1 64 KB + weight ring 64 KB),
-// so everything is single buffered there and the segment order puts conv_sum behind conv1_0 to cover
-// the first epilogue.  The segment program comes from the host (model.cpp plan_fused_stage).
-//
-// Weights: for C <= 32 all taps of the stage (53 x C x C x 2 B = 27 / 106 KB) are loaded ONCE per
-// CTA and stay resident; the MMA loop then has no per-tap barrier at all.  (The first version
-// streamed every tap through an 8-deep ring and measured ~430 clk per tap at C = 16 against ~16 clk
-// of MMA work.)  C >= 64 streams (tap, K-chunk) blocks through a ring.
+// Weights stream per (tap, K-chunk) through a ring for C >= 64; the C <= 32 instantiations keep all
+// taps resident.  The conv1 biases are staged in shared memory; barrier arrivals are one per warp.
 #pragma once
 
 #include "kernels_tc.cuh"
