@@ -109,7 +109,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                : "memory");
 }
 
-template <int C>
+// kPair (C = 128): two CTAs of a cluster walk the tile list in lockstep, each with its OWN window,
+// input tile, A1 buffers and accumulators; what they share is the weight operand -- every MMA is one
+// cta_group::2 instruction over both windows with half of the tap matrix in each CTA's shared memory
+// (6 KB instead of 8 KB of operand reads per CTA and MMA at N = 128).  Barrier plumbing as in
+// tapgemm_tc_kernel: loads land on the leader's full barriers, commits are multicast, the epilogue
+// warps of both CTAs arrive on the leader's barriers.
+template <int C, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ Params p) {
@@ -135,6 +141,21 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.tiles_per_b;
+  static_assert(!kPair || !Cfg<C>::kResident, "CTA pairs are wired for the streamed-weight configuration");
+  // Tile slots: without pairs a slot is a tile; with pairs slot ts holds tiles 2 ts (leader) and
+  // 2 ts + 1 (peer; possibly past the end -- that CTA then runs on zero-filled loads and stores nothing)
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int slot_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int slot_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_slots = kPair ? (total_tiles + 1) / 2 : total_tiles;
+  auto tile_dead = [&](int tile) {   // past the end, or past its utterance's row limit
+    if (tile >= total_tiles) return true;
+    const int b = tile / p.tiles_per_b;
+    return tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc);
+  };
+  auto slot_skipped = [&](int ts) {  // every role evaluates the same predicate: the pair stays in lockstep
+    return kPair ? (tile_dead(2 * ts) && tile_dead(2 * ts + 1)) : tile_dead(ts);
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -143,11 +164,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(a0_full + 8 * i, 1);
       mbar_init(a0_empty + 8 * i, 1);
       mbar_init(t1_full + 8 * i, 1);
-      mbar_init(t1_empty + 8 * i, 8);
-      mbar_init(a1_full + 8 * i, 8);
+      mbar_init(t1_empty + 8 * i, kPair ? 16 : 8);   // epilogue warps (of both CTAs)
+      mbar_init(a1_full + 8 * i, kPair ? 16 : 8);
       mbar_init(a1_empty + 8 * i, 1);
       mbar_init(t2_full + 8 * i, 1);
-      mbar_init(t2_empty + 8 * i, 8);
+      mbar_init(t2_empty + 8 * i, kPair ? 16 : 8);
     }
     for (int i = 0; i < kMaxStagesW; ++i) {
       mbar_init(w_full + 8 * i, 1);
@@ -157,7 +178,10 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, K::kTmemCols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, K::kTmemCols);
+    else tmem_alloc(tmem_slot, K::kTmemCols);
+  }
   // conv1 biases in shared memory ([branch][C]): an LDS broadcast in the per-branch epilogue
   // instead of an L1 round trip on its critical path (bsum stays in global memory: C = 128 needs
   // every remaining byte for the fifth weight stage)
@@ -168,6 +192,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_bias + 4 * t), "f"(v) : "memory");
   }
   tcgen05_fence_before();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
   __syncthreads();
   // everything above touched only kernel parameters and the (constant) packed weights: from here
   // on the previous kernel's outputs are read and its inputs overwritten
@@ -190,21 +215,29 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_b;
+    for (int ts = slot_first; ts < num_slots; ts += slot_step) {
+      if (slot_skipped(ts)) continue;
+      const int tile = kPair ? 2 * ts + (int)rank : ts;
+      const int b = tile / p.tiles_per_b;            // == batch for a peer tile past the end: zero fill
       const int ti = tile - b * p.tiles_per_b;
-      if (tile_skipped(p.row_limit, p.rows_per_frame, b, ti * p.rc)) continue;
       const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the A0 tile
       const uint32_t buf = tile_iter % kSlots, ph = (tile_iter / kSlots) & 1u;
-      ++tile_iter;   // processed tiles only (every role counts the same way)
+      ++tile_iter;   // processed slots only (every role counts the same way)
       mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
       if (elect_one()) {
         const uint32_t bar = a0_full + 8 * buf;
-        mbar_expect_tx(bar, K::kChunks * p.a0_boxes * K::kBoxBytes);
+        const uint32_t bytes = K::kChunks * p.a0_boxes * K::kBoxBytes;
+        if constexpr (kPair) {
+          if (rank == 0) mbar_expect_tx(bar, 2 * bytes);   // both CTAs' tiles land on the leader's barrier
+        } else {
+          mbar_expect_tx(bar, bytes);
+        }
         for (int c = 0; c < K::kChunks; ++c)
-          for (int bx = 0; bx < p.a0_boxes; ++bx)
-            tma_load_3d(smem_a0 + buf * a0_bytes + c * a0_chunk_bytes + bx * K::kBoxBytes, &tmA,
-                        c * K::kKC, row0 + bx * kBoxRows, b, bar);
+          for (int bx = 0; bx < p.a0_boxes; ++bx) {
+            const uint32_t dst = smem_a0 + buf * a0_bytes + c * a0_chunk_bytes + bx * K::kBoxBytes;
+            if constexpr (kPair) tma_load_3d_pair(dst, &tmA, c * K::kKC, row0 + bx * kBoxRows, b, bar);
+            else tma_load_3d(dst, &tmA, c * K::kKC, row0 + bx * kBoxRows, b, bar);
+          }
       }
       __syncwarp();
       if (!K::kResident) {
@@ -213,8 +246,15 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(w_empty + 8 * rw.s, rw.ph ^ 1u);
             if (elect_one()) {
               const uint32_t bar = w_full + 8 * rw.s;
-              mbar_expect_tx(bar, K::kWBytes);
-              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * K::kKC, t * C, bar);
+              if constexpr (kPair) {
+                // this CTA's half of the tap matrix (C / 2 rows of n)
+                if (rank == 0) mbar_expect_tx(bar, K::kWBytes);
+                tma_load_2d_pair(smem_w + rw.s * p.stage_w_bytes, &tmW, c * K::kKC,
+                                 t * C + (int)rank * (C / 2), bar);
+              } else {
+                mbar_expect_tx(bar, K::kWBytes);
+                tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * K::kKC, t * C, bar);
+              }
             }
             __syncwarp();
             rw.advance(p.stages_w);
@@ -222,18 +262,15 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ====================================== MMA issuer ======================================
     Ring rw;
     uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
-    const uint32_t idesc = make_idesc_bf16(kMTile, C, p.fp16);
+    const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kMTile : kMTile, C, p.fp16);
     const uint32_t dhi = smem_desc_hi<K::kKC>();
     if (K::kResident) mbar_wait(w_all, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      {
-        const int b = tile / p.tiles_per_b;
-        if (tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc)) continue;
-      }
+    for (int ts = slot_first; ts < num_slots; ts += slot_step) {
+      if (slot_skipped(ts)) continue;
       const uint32_t buf = tile_iter % kSlots, tph = (tile_iter / kSlots) & 1u;
       ++tile_iter;
       mbar_wait(a0_full + 8 * buf, tph);
@@ -286,19 +323,31 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     (a_t + ((c * a_chunk_bytes + m * (kMTile * kRowBytes)) >> 4));
 #pragma unroll
                 for (int kk = 0; kk < K::kKSteps; ++kk)
-                  umma_bf16(d_tmem + m * K::kAccCols, ad + 2 * kk, bd + 2 * kk, idesc,
-                            acc0 | (kk != 0));
+                  if constexpr (kPair)
+                    umma_bf16_pair(d_tmem + m * K::kAccCols, ad + 2 * kk, bd + 2 * kk, idesc,
+                                   acc0 | (kk != 0));
+                  else
+                    umma_bf16(d_tmem + m * K::kAccCols, ad + 2 * kk, bd + 2 * kk, idesc,
+                              acc0 | (kk != 0));
               }
               if (!K::kResident) {
-                umma_commit(w_empty + 8 * r.s);
+                if constexpr (kPair) umma_commit_pair(w_empty + 8 * r.s);
+                else umma_commit(w_empty + 8 * r.s);
                 r.advance(p.stages_w);
               }
             }
           }
-          if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
-          if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
-          if (sg.flags & kSegFlagReleaseA0) umma_commit(a0_empty + 8 * buf);
-          if (sg.flags & kSegFlagLast) umma_commit(t2_full + 8 * buf);
+          if constexpr (kPair) {
+            if (sg.type == kSegConv1) umma_commit_pair(t1_full + 8 * slot);
+            if (sg.type == kSegConv2) umma_commit_pair(a1_empty + 8 * slot);
+            if (sg.flags & kSegFlagReleaseA0) umma_commit_pair(a0_empty + 8 * buf);
+            if (sg.flags & kSegFlagLast) umma_commit_pair(t2_full + 8 * buf);
+          } else {
+            if (sg.type == kSegConv1) umma_commit(t1_full + 8 * slot);
+            if (sg.type == kSegConv2) umma_commit(a1_empty + 8 * slot);
+            if (sg.flags & kSegFlagReleaseA0) umma_commit(a0_empty + 8 * buf);
+            if (sg.flags & kSegFlagLast) umma_commit(t2_full + 8 * buf);
+          }
         }
         __syncwarp();
         if (!K::kResident) {
@@ -318,16 +367,18 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kNC = C / 16;                   // 16-column chunks per row
     constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_b;
-      const int ti = tile - b * p.tiles_per_b;
+    for (int ts = slot_first; ts < num_slots; ts += slot_step) {
+      if (slot_skipped(ts)) continue;
+      const int tile = kPair ? 2 * ts + (int)rank : ts;
+      const bool live = tile < total_tiles;          // a peer tile past the end computes on zeros, stores nothing
+      const int b = live ? tile / p.tiles_per_b : 0;
+      const int ti = live ? tile - b * p.tiles_per_b : 0;
       const int q0c = ti * p.rc;
-      if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0c)) continue;
       const uint32_t tile_it = tile_iter++;
       // ---- per branch: T1 -> A1 = half(lrelu(conv1 + b1 + X0)) in shared memory ----
       {
         const int gr = q0c - p.hc + i;
-        const bool valid = gr >= 0 && gr < p.rows;
+        const bool valid = live && gr >= 0 && gr < p.rows;
         const float4* xrow = reinterpret_cast<const float4*>(
             p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
         float4 xc[kXc];
@@ -396,8 +447,13 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {              // one arrival per warp
-            mbar_arrive(a1_full + 8 * slot);
-            mbar_arrive(t1_empty + 8 * slot);
+            if constexpr (kPair) {
+              mbar_arrive_leader(a1_full + 8 * slot);
+              mbar_arrive_leader(t1_empty + 8 * slot);
+            } else {
+              mbar_arrive(a1_full + 8 * slot);
+              mbar_arrive(t1_empty + 8 * slot);
+            }
           }
         }
       }
@@ -405,7 +461,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       {
         const uint32_t t2s = tile_it % kSlots, t2ph = (tile_it / kSlots) & 1u;
         const int gr = q0c + i;
-        const bool valid = i < p.rc && gr < p.rows;
+        const bool valid = live && i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
         const float4* xrow = reinterpret_cast<const float4*>(p.x0 + row_base);
         float4 xc[kXc];
@@ -472,14 +528,22 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t2_empty + 8 * t2s);
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_leader(t2_empty + 8 * t2s);
+          else mbar_arrive(t2_empty + 8 * t2s);
+        }
       }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
+  if constexpr (kPair) {
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, K::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, K::kTmemCols);
+  }
 }
 
 }  // namespace fused

@@ -56,6 +56,7 @@ struct FusedLaunch {
   fused::Params prm;       // plain program (kernels_fused.cuh)
   stacked::Params sprm;    // stacked program (kernels_stacked.cuh)
   bool stacked = false;
+  bool pair = false;       // plain program as CTA pairs (cta_group::2), C = 128
   int grid = 0;
   int smem = 0;
   int channels = 0;
@@ -632,7 +633,11 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   p.w_region_bytes = w_bytes_total;
   p.fp16 = fp16 ? 1 : 0;
   L->smem = slots * (a0_bytes + a1_bytes) + w_bytes_total + 512 + bias_bytes + 1024;
-  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, sms);
+  // C = 128: CTA pairs share the weight operand (kernels_fused.cuh); each CTA holds C / 2 rows of a tap matrix
+  static const bool no_pair = [] { const char* e = std::getenv("V2W_FUSED_NO_PAIR"); return e && std::atoi(e); }();
+  L->pair = C == 128 && !no_pair && sms >= 2;
+  const int64_t tiles = (int64_t)d.batch * p.tiles_per_b;
+  L->grid = L->pair ? 2 * (int)std::min<int64_t>((tiles + 1) / 2, sms / 2) : (int)std::min<int64_t>(tiles, sms);
 
   return encode_fused_maps(F, d, packed, ws, fp16, kc, L);
 }
@@ -663,7 +668,7 @@ static int encode_fused_maps(const v2w_fused_desc& F, const v2w_op_desc& d, cons
   {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)F.w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(L->pair ? C / 2 : C)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L->tm_w, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      const_cast<uint8_t*>(packed + F.w_off), dims, strides, box, estr,
@@ -685,6 +690,8 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
   static bool attr_set = false;
   if (!attr_set) {
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<64>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -710,7 +717,9 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
     V2W_CUDA(cudaGetLastError());
     return V2W_OK;
   }
-  if (L.channels == 128)
+  if (L.channels == 128 && L.pair)
+    V2W_CUDA(launch_ex<2>(fused::mrf_stage_kernel<128, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+  else if (L.channels == 128)
     V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   else if (L.channels == 64)
     V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
