@@ -102,8 +102,10 @@ struct Params {
 
 // C = 16 is latency-bound (four serial epilogue passes per tile, 64 small MMAs) and needs only 73 KB
 // of shared memory and 256 TMEM columns: two CTAs share an SM and hide each other's waits.
-template <int C>
-__global__ void __launch_bounds__(kThreads, C == 16 ? 2 : 1)
+// kPair (C = 64): CTA pairs in lockstep, each with its own window and buffers, sharing the weight
+// operand through cta_group::2 MMAs -- the same construction as mrf_stage_kernel<128, true>.
+template <int C, bool kPair = false>
+__global__ void __launch_bounds__(kThreads, (C == 16 && !kPair) ? 2 : 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ Params p) {
   constexpr int kRowBytes = C * 2;              // one K-chunk: the whole channel dimension
@@ -130,15 +132,31 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.tiles_per_b;
-  const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  static_assert(!kPair || C == 64, "CTA pairs are wired for the streamed-weight configuration");
+  // Tile slots: a slot is one tile, or with CTA pairs the two tiles 2 s (leader) and 2 s + 1 (peer;
+  // possibly past the end: that CTA then computes on zero-filled loads and stores nothing)
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int cta = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nctas = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_slots = kPair ? (total_tiles + 1) / 2 : total_tiles;
+  const int n_my = (num_slots - cta + nctas - 1) / nctas;
+  auto tile_of = [&](int kt) {                  // this CTA's tile of its kt-th slot
+    const int slot = cta + kt * nctas;
+    return kPair ? 2 * slot + (int)rank : slot;
+  };
+  auto tile_dead = [&](int tile) {
+    if (tile >= total_tiles) return true;
+    const int b = tile / p.tiles_per_b;
+    return tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc);
+  };
   // Variable-length batches: first local tile index >= kt whose rows some utterance still needs.
   // Every role walks the same sequence  kt = live(0), live(kt + 1), ...  and numbers the tiles it
   // meets k = 0, 1, ... (buffer indices and barrier phases follow k, addresses follow kt).
   auto live = [&](int kt) {
     for (; kt < n_my; ++kt) {
-      const int tile = blockIdx.x + kt * gridDim.x;
-      const int b = tile / p.tiles_per_b;
-      if (!tile_skipped(p.row_limit, p.rows_per_frame, b, (tile - b * p.tiles_per_b) * p.rc)) break;
+      const int slot = cta + kt * nctas;
+      const bool dead = kPair ? (tile_dead(2 * slot) && tile_dead(2 * slot + 1)) : tile_dead(slot);
+      if (!dead) break;   // a pair skips a slot only when neither CTA needs it: lockstep
     }
     return kt;
   };
@@ -150,23 +168,26 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(a0_full + 8 * i, 1);
       mbar_init(a0_empty + 8 * i, 1);
       mbar_init(t2_full + 8 * i, 1);
-      mbar_init(t2_empty + 8 * i, 8);
+      mbar_init(t2_empty + 8 * i, kPair ? 16 : 8);   // epilogue warps (of both CTAs)
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(w_full + 8 * i, 1);
       mbar_init(w_empty + 8 * i, 1);
       mbar_init(t1_full + 8 * i, 1);
-      mbar_init(t1_empty + 8 * i, 8);
+      mbar_init(t1_empty + 8 * i, kPair ? 16 : 8);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(a1_full + 8 * i, 8);
-      mbar_init(a1_full + 8 * (4 + i), 8);
+      mbar_init(a1_full + 8 * i, kPair ? 16 : 8);
+      mbar_init(a1_full + 8 * (4 + i), kPair ? 16 : 8);
     }
     mbar_init(w_all, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    else tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   // biases of every pass in shared memory ([slot][C], then bsum[C]): an LDS broadcast in the
   // epilogue instead of an L1 round trip on its critical path
   const uint32_t smem_bias = bars + 512;
@@ -176,6 +197,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_bias + 4 * t), "f"(v) : "memory");
   }
   tcgen05_fence_before();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
   __syncthreads();
   // everything above touched only kernel parameters and the (constant) packed weights: from here
   // on the previous kernel's outputs are read and its inputs overwritten
@@ -205,9 +227,17 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const uint32_t bar = w_full + 8 * rw.s;
               const uint32_t dst = smem_w + rw.s * p.stage_w_bytes;
               const int row = p.w_row[sg.first + t];
-              mbar_expect_tx(bar, sg.n * kRowBytes);
-              for (int q = 0; q < sg.n / C; ++q)
-                tma_load_2d(dst + q * kWBlockBytes, &tmW, 0, row + q * C, bar);
+              if constexpr (kPair) {
+                // this CTA's half of the stacked block: rows [rank * n/2, (rank + 1) * n/2), C/2-row boxes
+                if (rank == 0) mbar_expect_tx(bar, sg.n * kRowBytes);
+                const int half = sg.n / 2;
+                for (int q = 0; q < half / (C / 2); ++q)
+                  tma_load_2d_pair(dst + q * (kWBlockBytes / 2), &tmW, 0, row + (int)rank * half + q * (C / 2), bar);
+              } else {
+                mbar_expect_tx(bar, sg.n * kRowBytes);
+                for (int q = 0; q < sg.n / C; ++q)
+                  tma_load_2d(dst + q * kWBlockBytes, &tmW, 0, row + q * C, bar);
+              }
             }
             __syncwarp();
             rw.advance(p.stages_w);
@@ -218,21 +248,27 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 2) {
     // ================================= input tile producer ==================================
     for (int kt = live(0), k = 0; kt < n_my; kt = live(kt + 1), ++k) {
-      const int tile = blockIdx.x + kt * gridDim.x;
-      const int b = tile / p.tiles_per_b;
+      const int tile = tile_of(kt);
+      const int b = tile / p.tiles_per_b;            // == batch for a peer tile past the end: zero fill
       const int ti = tile - b * p.tiles_per_b;
       const int row0 = ti * p.rc - p.hc - p.h1;      // first row of the input tile
       const uint32_t buf = k % p.a0_bufs, ph = (k / p.a0_bufs) & 1u;
       mbar_wait(a0_empty + 8 * buf, ph ^ 1u);
       if (elect_one()) {
         const uint32_t bar = a0_full + 8 * buf;
-        mbar_expect_tx(bar, p.a0_boxes * kBoxBytes);
-        for (int bx = 0; bx < p.a0_boxes; ++bx)
-          tma_load_3d(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b, bar);
+        if constexpr (kPair) {
+          if (rank == 0) mbar_expect_tx(bar, 2 * p.a0_boxes * kBoxBytes);
+          for (int bx = 0; bx < p.a0_boxes; ++bx)
+            tma_load_3d_pair(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b, bar);
+        } else {
+          mbar_expect_tx(bar, p.a0_boxes * kBoxBytes);
+          for (int bx = 0; bx < p.a0_boxes; ++bx)
+            tma_load_3d(smem_a0 + buf * a0_bytes + bx * kBoxBytes, &tmA, 0, row0 + bx * kBoxRows, b, bar);
+        }
       }
       __syncwarp();
     }
-  } else if (warp == 1 || (warp == 3 && p.mma_warps == 2)) {
+  } else if ((warp == 1 || (warp == 3 && p.mma_warps == 2)) && rank == 0) {
     // ====================================== MMA issuer ======================================
     // With two accumulator sets (C <= 32) warps 1 and 3 take alternate tiles: each thread's
     // tcgen05.commit covers exactly its own tile's MMAs, the sets and input buffers are indexed by
@@ -295,20 +331,23 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t acc0 = sg.acc | (t != 0);
 #pragma unroll
             for (int kk = 0; kk < kKSteps; ++kk)
-              umma_bf16(d_tmem, (hi | ad_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+              if constexpr (kPair) umma_bf16_pair(d_tmem, (hi | ad_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+              else umma_bf16(d_tmem, (hi | ad_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
 #pragma unroll
             for (int kk = 0; kk < kKSteps; ++kk)
-              umma_bf16(d_tmem1, (hi | ad1_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+              if constexpr (kPair) umma_bf16_pair(d_tmem1, (hi | ad1_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
+              else umma_bf16(d_tmem1, (hi | ad1_lo) + 2 * kk, (hi | bd_lo) + 2 * kk, idesc, acc0 | (kk != 0));
             if (!kResident) {
-              umma_commit(w_empty + 8 * r.s);
+              if constexpr (kPair) umma_commit_pair(w_empty + 8 * r.s);
+              else umma_commit(w_empty + 8 * r.s);
               r.advance(p.stages_w);
             }
           }
           for (uint32_t w = sg.commit; w; w &= w - 1) {
             const int bit = __ffs(w) - 1;
-            if (bit < 4) umma_commit(t1_full + 8 * (tb * 4 + bit));
-            else if (bit == 4) umma_commit(t2_full + 8 * tb);
-            else umma_commit(a0_empty + 8 * ab);
+            const uint32_t bar = bit < 4 ? t1_full + 8 * (tb * 4 + bit) : (bit == 4 ? t2_full + 8 * tb : a0_empty + 8 * ab);
+            if constexpr (kPair) umma_commit_pair(bar);
+            else umma_commit(bar);
           }
         }
         __syncwarp();
@@ -339,11 +378,12 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const bool central = i >= p.hc && i < p.hc + p.rc;
     // fp32 X0 row of tile `k` for this thread (clamped to a valid row; `valid` says whether it counts)
     auto row_of = [&](int kt, bool& valid) -> const float4* {
-      const int tile = blockIdx.x + kt * gridDim.x;
-      const int b = tile / p.tiles_per_b;
-      const int ti = tile - b * p.tiles_per_b;
+      const int tile = tile_of(kt);
+      const bool live_tile = tile < total_tiles;       // a peer tile past the end stores nothing
+      const int b = live_tile ? tile / p.tiles_per_b : 0;
+      const int ti = live_tile ? tile - b * p.tiles_per_b : 0;
       const int gr = ti * p.rc - p.hc + i;
-      valid = gr >= 0 && gr < p.rows;
+      valid = live_tile && gr >= 0 && gr < p.rows;
       return reinterpret_cast<const float4*>(
           p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
     };
@@ -441,8 +481,13 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {              // one arrival per warp: 256 arrivals serialise on the barrier
-          mbar_arrive(a1_full + 8 * (tb * 4 + j));
-          mbar_arrive(t1_empty + 8 * (tb * 4 + j));
+          if constexpr (kPair) {
+            mbar_arrive_leader(a1_full + 8 * (tb * 4 + j));
+            mbar_arrive_leader(t1_empty + 8 * (tb * 4 + j));
+          } else {
+            mbar_arrive(a1_full + 8 * (tb * 4 + j));
+            mbar_arrive(t1_empty + 8 * (tb * 4 + j));
+          }
         }
         V2W_TR(k * 100 + j * 10 + 3);
       }
@@ -517,7 +562,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t2_empty + 8 * tb);
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_leader(t2_empty + 8 * tb);
+          else mbar_arrive(t2_empty + 8 * tb);
+        }
         V2W_TR(k * 100 + 52);
       }
       kt = kt_next;
@@ -526,8 +574,13 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (kPair) {
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 }  // namespace stacked

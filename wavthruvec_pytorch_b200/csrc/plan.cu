@@ -510,6 +510,9 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
     return V2W_ERR_INVALID;
   }
   p.tmem_cols = cols;
+  // C = 64 (streamed weights, one accumulator set): CTA pairs share the weight operand
+  static const bool no_cpair = [] { const char* e = std::getenv("V2W_FUSED_NO_PAIR"); return e && std::atoi(e); }();
+  L->pair = C == 64 && !no_cpair && sms >= 2;
   int max_n = 0;
   for (int s = 0; s < F.num_segments; ++s) {
     stacked::Segment& g = p.seg[s];
@@ -520,7 +523,7 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
     g.acc = F.seg_acc[s]; g.wait = F.seg_wait[s]; g.commit = F.seg_commit[s];
     // tcgen05 instruction descriptor, kind::f16: D fp32, A/B bf16 (1) or fp16 (0), K-major, M = 128
     const uint32_t fmt = fp16 ? 0u : 1u;
-    g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.n >> 3) << 17) | ((128u >> 4) << 24);
+    g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.n >> 3) << 17) | (((L->pair ? 256u : 128u) >> 4) << 24);
     max_n = std::max(max_n, g.n);
   }
   const int row_bytes = C * 2;
@@ -569,7 +572,11 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   int ctas_per_sm = 1;
   if (C == 16 && 2 * L->smem <= 227 * 1024 && 2 * p.tmem_cols <= 512) ctas_per_sm = 2;
   if (const char* e = std::getenv("V2W_FUSED_CTAS_PER_SM")) ctas_per_sm = std::min(ctas_per_sm, std::max(1, std::atoi(e)));
-  L->grid = (int)std::min<int64_t>((int64_t)d.batch * p.tiles_per_b, (int64_t)sms * ctas_per_sm);
+  {
+    const int64_t tiles = (int64_t)d.batch * p.tiles_per_b;
+    L->grid = L->pair ? 2 * (int)std::min<int64_t>((tiles + 1) / 2, sms / 2)
+                      : (int)std::min<int64_t>(tiles, (int64_t)sms * ctas_per_sm);
+  }
   return encode_fused_maps(F, d, packed, ws, fp16, C, L);
 }
 
@@ -699,6 +706,8 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<32>,
@@ -708,7 +717,9 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
     attr_set = true;
   }
   if (L.stacked) {
-    if (L.channels == 64)
+    if (L.channels == 64 && L.pair)
+      V2W_CUDA(launch_ex<2>(stacked::mrf_stacked_kernel<64, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.channels == 64)
       V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
     else if (L.channels == 32)
       V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
