@@ -193,6 +193,8 @@ typedef struct v2w_fused_desc {
   int32_t stacked;
   int32_t pair;                /* 1: one ResBlock1 conv pair c2(lrelu(c1(a) + b1)) + b2 + x (models.py:37-44): no `sum`
                                   convolution, the middle activation does NOT see the residual, bsum = b2 */
+  int32_t post;                /* 1: last stage with conv_post folded into its final pass (hc is 3 rows wider:
+                                  every central row finds its 7 neighbours inside the window) */
   int32_t order[V2W_MAX_KERNELS];      /* stacked: model branch that runs as slot j */
   int32_t t_bufs, a0_bufs;             /* stacked: accumulator sets / input tiles in flight */
   int32_t seg_type[V2W_FUSED_MAX_SEG], seg_branch[V2W_FUSED_MAX_SEG];   /* branch: slot of a CONV2 */
@@ -242,6 +244,7 @@ typedef struct v2w_op_desc {
   int64_t flops;               /* 2 * real MACs of this op (0 for non-GEMM ops) */
   int32_t stage;               /* upsample stage of an MRF_FUSED / PAIR_FUSED op, else -1 */
   int32_t pair;                /* PAIR_FUSED: index for v2w_model_get_pair, else -1 */
+  int32_t post;                /* MRF_FUSED: 1 when conv_post + tanh run inside this op (no CONV_POST op follows) */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */

@@ -244,6 +244,20 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                 for t in range(F.seg_first[sgi], F.seg_first[sgi] + F.seg_ntaps[sgi]):
                     T2 += tap(A1[F.seg_branch[sgi]], t, 0)
             v = ((T2 + bsum + np.float32(nb) * X0) * np.float32(op.out_scale)).astype(np.float32)
+            if op.post:
+                # conv_post + tanh inside the stage's final pass (models.py:143-145)
+                assert F.post and op.out_f32 < 0 and op.out_bf16 < 0
+                Lp = plan.layers[F.first_layer + 2 * nb]
+                A = lrelu(v, op.out_slope)
+                Wp = f32(Lp.w32_off, 7 * Lp.cin).reshape(7, Lp.cin)
+                Ap = np.pad(A, ((0, 0), (3, 3), (0, 0)))
+                y = np.full((op.batch, op.rows), f32(Lp.bias_off, 1)[0], np.float32)
+                for j in range(7):
+                    y += Ap[:, j: j + op.rows] @ Wp[j]
+                out = np.tanh(y).astype(np.float32)[:, None, :]
+                if collect is not None:
+                    collect[idx] = v
+                continue
             if op.out_f32 >= 0:
                 ws[op.out_f32] = v
             if op.out_bf16 >= 0:

@@ -265,6 +265,12 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     assert [op.n_tile for op in fused] == [128, 64, 32, 16]
     assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 12
     assert sum(op.flops for op in fplan.ops) == total
+    # conv_post + tanh run inside the last stage's final pass: 18 launches, no CONV_POST op
+    assert len(fplan.ops) == 18 and fplan.ops[-1].kind == native.OP_MRF_FUSED
+    assert [op.post for op in fused] == [0, 0, 0, 1] and fused[-1].out_f32 < 0 and fused[-1].out_bf16 < 0
+    F4 = native.FusedDesc()
+    native.check(eng._lib.v2w_model_get_fused(eng._model, 4, C.byref(F4)))
+    assert (F4.post, F4.hc, F4.rc, F4.channels) == (1, 18, 220, 16)      # 3 more halo rows for the 7-tap conv_post
     F = native.FusedDesc()
     native.check(eng._lib.v2w_model_get_fused(eng._model, 2, C.byref(F)))
     # C = 64: stacked program, one accumulator set, `sum` of the first offset group split off

@@ -33,6 +33,7 @@
 #pragma once
 
 #include "kernels_fused.cuh"
+#include "kernels_simt.cuh"
 
 // Developer timeline (build with V2W_NVCC_EXTRA=-DV2W_TRACE): CTA 0 prints SM-clock stamps of its MMA
 // warp and of epilogue warp 4 for the first tiles.  Compiled out otherwise.
@@ -94,6 +95,14 @@ struct Params {
   const float* bias1[V2W_MAX_KERNELS];   // by slot
   const float* bsum;
   const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
+  // conv_post folded into the final pass of the LAST stage (C <= 32): leaky_relu(0.01) -> Conv1d(C -> 1,
+  // k = 7) -> tanh (models.py:143-145).  The stage's halo is 3 rows wider so that every central row
+  // finds its 7 neighbours in the same window; the waveform is the kernel's only output.
+  int post;
+  float post_w[7 * 32];         // [tap][channel], stride C
+  float post_bias;
+  simt::PostOut post_out;
+  simt::RaggedOffsets post_ro;
   int e1_add_x0;                // 1: the middle activation sees the residual (ResBlock2); 0: ResBlock1 pair
   float mid_slope, res_scale, out_scale, out_slope;
   float* out_f32;
@@ -191,6 +200,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // biases of every pass in shared memory ([slot][C], then bsum[C]): an LDS broadcast in the
   // epilogue instead of an L1 round trip on its critical path
   const uint32_t smem_bias = bars + 512;
+  const uint32_t smem_part = smem_bias + (((p.nbranch + 1) * C * 4 + 15) & ~15);   // conv_post partials, 2 x [7][256] (post only)
   for (int t = threadIdx.x; t < (p.nbranch + 1) * C; t += kThreads) {
     const int j = t / C, ch = t - j * C;
     const float v = j < p.nbranch ? p.bias1[j][ch] : p.bsum[ch];
@@ -490,6 +500,86 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
         V2W_TR(k * 100 + j * 10 + 3);
+      }
+      // ---- final pass with conv_post folded in (last stage, C <= 32) ----
+      if constexpr (C <= 32) {
+        if (p.post) {
+          // rows conv_post needs from this window: the central rows and 3 on either side (all of them
+          // have complete conv2 sums: the true halo is hc - 3)
+          const bool need = valid && i >= p.hc - 3 && i < p.hc + p.rc + 3;
+          mbar_wait(t2_full + 8 * tb, tph);
+          tcgen05_fence_after();
+          const uint32_t t2 = t_row + tb * p.tile_cols;
+          float part[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) part[j] = 0.f;
+#pragma unroll
+          for (int cp = 0; cp < kNC; cp += kPair) {
+            uint32_t rr[kPair][16];
+#pragma unroll
+            for (int u = 0; u < kPair; ++u) tmem_ld16(t2 + (cp + u) * 16, rr[u]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < kPair; ++u) {
+              const int ci = cp + u;
+              const int cc = ci * 16;
+              if (need) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 bb = ld_shared_f4(smem_bias + (p.nbranch * C + cc + 4 * e) * 4);
+                  const float4 xr = xc[ci * 4 + e];
+                  float a[4];
+                  a[0] = lrelu((__uint_as_float(rr[u][4 * e]) + bb.x + p.res_scale * xr.x) * p.out_scale, p.out_slope);
+                  a[1] = lrelu((__uint_as_float(rr[u][4 * e + 1]) + bb.y + p.res_scale * xr.y) * p.out_scale, p.out_slope);
+                  a[2] = lrelu((__uint_as_float(rr[u][4 * e + 2]) + bb.z + p.res_scale * xr.z) * p.out_scale, p.out_slope);
+                  a[3] = lrelu((__uint_as_float(rr[u][4 * e + 3]) + bb.w + p.res_scale * xr.w) * p.out_scale, p.out_slope);
+#pragma unroll
+                  for (int j = 0; j < 7; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) part[j] = fmaf(a[q], p.post_w[j * C + cc + 4 * e + q], part[j]);
+                }
+              }
+            }
+          }
+          // T2 is drained: hand it back before the exchange through shared memory
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t2_empty + 8 * tb);
+          const uint32_t pb = smem_part + (k & 1) * (7 * kWin * 4);
+#pragma unroll
+          for (int j = 0; j < 7; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(pb + (j * kWin + i) * 4), "f"(part[j]) : "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
+          if (valid && central) {
+            // y[t] = bias + sum_j w[j] . x[t + j - 3]; row t + j - 3 is window row i + j - 3
+            float sum = p.post_bias;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(pb + (j * kWin + i + j - 3) * 4));
+              sum += v;
+            }
+            const float y = tanhf(sum);
+            const size_t row_idx = (reinterpret_cast<const float*>(xrow) - p.x0) / C;   // b * rows + t
+            const int b = static_cast<int>(row_idx / p.rows);
+            const int t = static_cast<int>(row_idx - static_cast<size_t>(b) * p.rows);
+            if (!p.post_out.ragged) {
+              p.post_out.y[row_idx] = y;
+            } else {
+              const int first = p.post_ro.off[b];
+              if (t < (p.post_ro.off[b + 1] - first) * p.post_out.up) {
+                const size_t o = static_cast<size_t>(first) * p.post_out.up + t;
+                if (p.post_out.pcm16)
+                  reinterpret_cast<short*>(p.post_out.y)[o] =
+                      static_cast<short>(__float2int_rn(fminf(fmaxf(y * 32768.f, -32768.f), 32767.f)));
+                else
+                  p.post_out.y[o] = y;
+              }
+            }
+          }
+          kt = kt_next;
+          continue;
+        }
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk on the central rows of the window ----
       {

@@ -125,6 +125,13 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
     hc = std::max(hc, c.resblock_dilation_sizes[order[j]][1] * r[j]);
     entries += k;
   }
+  // Last stage with few channels: conv_post (C -> 1, k = 7) runs inside the final pass; 3 more halo
+  // rows so that every central row finds its 7 neighbours in the window (kernels_stacked.cuh)
+  static const bool no_post = [] { const char* e = std::getenv("V2W_NO_POST_FUSE"); return e && std::atoi(e); }();
+  if (i == c.num_upsamples - 1 && C <= 32 && !no_post) {
+    F.post = 1;
+    hc += 3;
+  }
   const int h1 = d0 * r[nb - 1];
   entries += 2 * r[nb - 1] + 1 + (split_sum ? 2 * r[0] + 1 : 0);
   const int rc = 256 - 2 * hc;
@@ -187,7 +194,6 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
   F.num_taps = nent;
   F.w_rows = wrow;
   F.ok = 1;
-  (void)i;
   return true;
 }
 

@@ -534,7 +534,7 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   }
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * row_bytes;
   const int a1_bytes = fused::kWin * row_bytes;
-  const int budget = 227 * 1024 - 1024 - 512 - (nb + 1) * C * 4;
+  const int budget = 227 * 1024 - 1024 - 512 - (nb + 1) * C * 4 - (F.post ? 2 * 7 * fused::kWin * 4 + 16 : 0);
   const int left = budget - p.a0_bufs * a0_bytes - nb * a1_bytes;
   if (C <= 32) {
     p.stages_w = 1;
@@ -567,7 +567,8 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   p.out_bf16 = d.out_bf16 >= 0 ? reinterpret_cast<__nv_bfloat16*>(ws + d.out_bf16) : nullptr;
   p.fp16 = fp16 ? 1 : 0;
   // + barriers (512) + bias table + 1 KB alignment slack
-  L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + (nb + 1) * C * 4 + 1024;
+  const int post_bytes = F.post ? 2 * 7 * fused::kWin * 4 + 16 : 0;   // conv_post partials (kernels_stacked.cuh)
+  L->smem = p.a0_bufs * a0_bytes + nb * a1_bytes + p.w_region_bytes + 512 + (nb + 1) * C * 4 + post_bytes + 1024;
   // C = 16: two CTAs per SM (kernels_stacked.cuh); they need 2 x smem and 2 x tmem_cols <= 512
   int ctas_per_sm = 1;
   if (C == 16 && 2 * L->smem <= 227 * 1024 && 2 * p.tmem_cols <= 512) ctas_per_sm = 2;
@@ -689,11 +690,29 @@ static int encode_fused_maps(const v2w_fused_desc& F, const v2w_op_desc& d, cons
   return V2W_OK;
 }
 
+struct PostFold {            // conv_post folded into a fused stage (v2w_op_desc::post)
+  const float* w = nullptr;  // host [7][C]
+  float bias = 0.f;
+  simt::PostOut out;
+  const simt::RaggedOffsets* ro = nullptr;
+};
+
 static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
-                        int rows_per_frame = 0) {
+                        int rows_per_frame = 0, const PostFold* post = nullptr) {
   FusedLaunch L = L0;
   L.prm.row_limit = row_limit; L.prm.rows_per_frame = rows_per_frame;
   L.sprm.row_limit = row_limit; L.sprm.rows_per_frame = rows_per_frame;
+  if (post) {
+    if (!L.stacked || L.channels > 32) {
+      set_error("conv_post folding needs the stacked kernel with C <= 32");
+      return V2W_ERR_STATE;
+    }
+    L.sprm.post = 1;
+    std::memcpy(L.sprm.post_w, post->w, sizeof(float) * 7 * L.channels);
+    L.sprm.post_bias = post->bias;
+    L.sprm.post_out = post->out;
+    if (post->ro) L.sprm.post_ro = *post->ro;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128>,
@@ -854,6 +873,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   const int B = batch, T = frames;
   const bool force_simt = std::getenv("V2W_FORCE_SIMT") != nullptr;
   const bool no_fuse = std::getenv("V2W_NO_FUSE") != nullptr;
+  bool post_folded = false;   // conv_post runs inside the last fused stage
   const int fuse_mask = std::getenv("V2W_FUSE_MASK") ? std::atoi(std::getenv("V2W_FUSE_MASK")) : -1;
 
   Bump ws;
@@ -908,6 +928,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     o.d.cond_stage = -1;
     o.d.stage = -1;
     o.d.pair = -1;
+    o.d.post = 0;
     o.d.in_slope = 1.f;
     o.d.out_scale = 1.f;
     o.d.out_slope = 1.f;
@@ -985,6 +1006,13 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
       o.d.out_f32 = stage_out.f32; o.d.out_bf16 = stage_out.bf16; o.d.out_slope = stage_out.slope;
       for (int q = 0; q < 2 * nk; ++q)
         o.d.flops += 2 * m->layers[li + q].macs_per_row * (int64_t)rows * B;
+      if (last_stage && m->fused[i].post) {
+        // conv_post + tanh inside the stage's final pass: the waveform is this op's output
+        o.d.post = 1;
+        o.d.out_f32 = o.d.out_bf16 = -1;
+        o.d.flops += 2 * m->layers[li + 2 * nk].macs_per_row * (int64_t)rows * B;
+        post_folded = true;
+      }
       P->ops.push_back(o);
       li += 2 * nk;
       cur_in = stage_out;
@@ -1041,7 +1069,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     }
     cur_in = stage_out;
   }
-  {
+  if (!post_folded) {
     Op o = blank(V2W_OP_CONV_POST);
     o.d.layer = li;
     o.d.batch = B; o.d.rows = rows;
@@ -1309,7 +1337,17 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
       }
       case V2W_OP_PAIR_FUSED:
       case V2W_OP_MRF_FUSED: {
-        int rc = launch_fused(o.fl, st, lim, o.d.rows / p->frames);
+        PostFold pf;
+        if (o.d.post) {
+          pf.w = p->post_w.data();
+          pf.bias = p->post_bias;
+          pf.out.y = static_cast<float*>(out_dev);
+          pf.out.ragged = ragged ? 1 : 0;
+          pf.out.up = m->total_up;
+          pf.out.pcm16 = out_format == V2W_OUT_PCM16;
+          pf.ro = ro;
+        }
+        int rc = launch_fused(o.fl, st, lim, o.d.rows / p->frames, o.d.post ? &pf : nullptr);
         if (rc) return rc;
         ++launches;
         break;
