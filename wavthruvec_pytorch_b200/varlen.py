@@ -35,6 +35,7 @@ import torch
 # a few microseconds each against ~1.2 us per frame-utterance at cfg2 rates).  Only the bucket
 # count depends on it.
 LAUNCH_COST_FRAMES = 64
+MAX_UTTERANCES_PER_CALL = 512   # simt::kMaxRaggedBatch: row offsets travel as a kernel parameter
 
 
 def plan_buckets(lengths: Sequence[int], halo: int, max_buckets: int = 4,
@@ -106,6 +107,13 @@ def generate_varlen(gen, feats: Sequence[torch.Tensor], spk_emb: torch.Tensor, n
         raise RuntimeError("feats, spk_emb and noise disagree on the batch size")
     up = eng.total_upsample()
     result: List[torch.Tensor] = [None] * len(lengths)
+    if len(lengths) > MAX_UTTERANCES_PER_CALL:
+        # v2w_forward_ragged takes at most 512 utterances per call: consecutive chunks, each padded
+        # (and tile-skipped) like a batch of its own
+        for a in range(0, len(lengths), MAX_UTTERANCES_PER_CALL):
+            b = min(a + MAX_UTTERANCES_PER_CALL, len(lengths))
+            result[a:b] = generate_varlen(gen, feats[a:b], spk_emb[a:b], noise[a:b], pcm16, max_buckets)
+        return result
     for idx, plan_t in plan_buckets(lengths, eng.halo_frames(), max_buckets):
         rows = torch.cat([feats[i] for i in idx], dim=0)
         sel = torch.as_tensor(idx, device=spk_emb.device)
