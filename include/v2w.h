@@ -193,6 +193,7 @@ typedef struct v2w_fused_desc {
   int32_t stacked;
   int32_t pair;                /* 1: one ResBlock1 conv pair c2(lrelu(c1(a) + b1)) + b2 + x (models.py:37-44): no `sum`
                                   convolution, the middle activation does NOT see the residual, bsum = b2 */
+  int32_t preload;             /* 1: T1 pre-loaded with x + b1 by the epilogue; conv1 accumulates on top (C = 64) */
   int32_t post;                /* 1: last stage with conv_post folded into its final pass (hc is 3 rows wider:
                                   every central row finds its 7 neighbours inside the window) */
   int32_t order[V2W_MAX_KERNELS];      /* stacked: model branch that runs as slot j */

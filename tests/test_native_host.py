@@ -279,8 +279,10 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     assert (F.t_bufs, F.a0_bufs, list(F.order[:3]), F.w_rows) == (1, 1, [0, 1, 2], 53 * 64)
     assert list(F.seg_type[:7]) == [0, 1, 0, 0, 2, 2, 2] and list(F.seg_ntaps[:7]) == [3, 3, 4, 4, 3, 7, 11]
     assert list(F.seg_dcol[:7]) == [64, 0, 0, 0, 0, 0, 0] and list(F.seg_n[:7]) == [192, 64, 192, 128, 64, 64, 64]
-    assert list(F.seg_acc[:7]) == [0, 0, 1, 1, 1, 1, 1]
-    assert list(F.seg_wait[:7]) == [T1(2) | A0, T2, 0, 0, A1(0), A1(1), A1(2)]
+    # T1 is pre-loaded with x + b1 by the epilogue: conv1 accumulates from its first MMA and waits for
+    # "T1 pre-loaded" (bit T1(0)); the split-off `sum` taps still overwrite T2
+    assert F.preload == 1 and list(F.seg_acc[:7]) == [1, 0, 1, 1, 1, 1, 1]
+    assert list(F.seg_wait[:7]) == [T1(0) | A0, T2, 0, 0, A1(0), A1(1), A1(2)]
     assert list(F.seg_commit[:7]) == [T1(0), 0, T1(1), T1(2) | A0, 0, 0, T2]
     assert [F.offset[t] for t in range(14)] == [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]
     assert [F.shift[t] for t in range(14)] == [5 + o for o in [-1, 0, 1, -1, 0, 1, -3, -2, 2, 3, -5, -4, 4, 5]]

@@ -104,6 +104,10 @@ struct Params {
   simt::PostOut post_out;
   simt::RaggedOffsets post_ro;
   int e1_add_x0;                // 1: the middle activation sees the residual (ResBlock2); 0: ResBlock1 pair
+  // C = 64: the epilogue PRE-LOADS T1_j with X0 + b1_j (tcgen05.st) while conv2 of the previous tile
+  // runs, conv1 accumulates on top, and the per-slot pass is load-activate-store only.  The
+  // "T1 of slot 0 free" barrier then means "T1 of this tile pre-loaded" (waited with the full parity).
+  int preload;
   float mid_slope, res_scale, out_scale, out_slope;
   float* out_f32;
   __nv_bfloat16* out_bf16;
@@ -310,7 +314,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const Segment sg = p.seg[s];
         for (uint32_t w = sg.wait; w; w &= w - 1) {
           const int bit = __ffs(w) - 1;
-          if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), tph ^ 1u);
+          if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), p.preload ? tph : (tph ^ 1u));
           else if (bit == 4) mbar_wait(t2_empty + 8 * tb, tph ^ 1u);
           else if (bit == 5) mbar_wait(a0_full + 8 * ab, aph);
           else mbar_wait(a1_full + 8 * (tb * 4 + bit - 8), tph);
@@ -412,6 +416,38 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
       for (int e = 0; e < 8; ++e) xc[e] = __ldg(x + e);
     }
+    // P(kt): T1_j := X0 + b1_j for every slot of the tile at local index kt (its accumulator set)
+    auto preload_t1 = [&](int kt, uint32_t tb_p) {
+      bool v;
+      const float4* x = row_of(kt, v);
+      const uint32_t t1s = t_row + tb_p * p.tile_cols;
+#pragma unroll
+      for (int ci = 0; ci < kNC; ++ci) {
+        float4 xr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xr[e] = __ldg(x + ci * 4 + e);
+        for (int j = 0; j < p.nbranch; ++j) {
+          uint32_t r[16];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 bb = ld_shared_f4(smem_bias + (j * C + ci * 16 + 4 * e) * 4);
+            r[4 * e] = __float_as_uint(xr[e].x + bb.x);
+            r[4 * e + 1] = __float_as_uint(xr[e].y + bb.y);
+            r[4 * e + 2] = __float_as_uint(xr[e].z + bb.z);
+            r[4 * e + 3] = __float_as_uint(xr[e].w + bb.w);
+          }
+          tmem_st16(t1s + (p.nbranch - j) * C + ci * 16, r);
+        }
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_leader(t1_empty + 8 * (tb_p * 4));
+        else mbar_arrive(t1_empty + 8 * (tb_p * 4));
+      }
+    };
+    if (p.preload && live(0) < n_my) preload_t1(live(0), 0);
     for (int kt = live(0), k = 0; kt < n_my; ++k) {
       bool valid, next_valid = false;
       const float4* xrow = row_of(kt, valid);
@@ -460,8 +496,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               // C = 64: a two-chunk window that runs ahead of the consumer -- past the end of
               // this pass it wraps to chunks 0, 1 of the next pass (same row, L1/L2 hits)
               const int nc = ci + 2 < kNC ? ci + 2 : ci + 2 - kNC;
+              if (!p.preload) {   // (pre-loaded accumulators: this pass does not read X0 at all)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + nc * 4 + e);
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + nc * 4 + e);
+              }
             }
             uint32_t h[8];
             if (valid) {
@@ -469,11 +507,12 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
-                const float ax = p.e1_add_x0 ? 1.f : 0.f;
-                v[4 * e] = fmaf(ax, xr[e].x, __uint_as_float(r[4 * e]) + bb.x);
-                v[4 * e + 1] = fmaf(ax, xr[e].y, __uint_as_float(r[4 * e + 1]) + bb.y);
-                v[4 * e + 2] = fmaf(ax, xr[e].z, __uint_as_float(r[4 * e + 2]) + bb.z);
-                v[4 * e + 3] = fmaf(ax, xr[e].w, __uint_as_float(r[4 * e + 3]) + bb.w);
+                const float ax = (p.e1_add_x0 && !p.preload) ? 1.f : 0.f;   // pre-loaded: already in T1
+                const float ab = p.preload ? 0.f : 1.f;
+                v[4 * e] = fmaf(ax, xr[e].x, fmaf(ab, bb.x, __uint_as_float(r[4 * e])));
+                v[4 * e + 1] = fmaf(ax, xr[e].y, fmaf(ab, bb.y, __uint_as_float(r[4 * e + 1])));
+                v[4 * e + 2] = fmaf(ax, xr[e].z, fmaf(ab, bb.z, __uint_as_float(r[4 * e + 2])));
+                v[4 * e + 3] = fmaf(ax, xr[e].w, fmaf(ab, bb.w, __uint_as_float(r[4 * e + 3])));
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e)
@@ -493,14 +532,17 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {              // one arrival per warp: 256 arrivals serialise on the barrier
           if constexpr (kPair) {
             mbar_arrive_leader(a1_full + 8 * (tb * 4 + j));
-            mbar_arrive_leader(t1_empty + 8 * (tb * 4 + j));
+            if (!p.preload) mbar_arrive_leader(t1_empty + 8 * (tb * 4 + j));
           } else {
             mbar_arrive(a1_full + 8 * (tb * 4 + j));
-            mbar_arrive(t1_empty + 8 * (tb * 4 + j));
+            if (!p.preload) mbar_arrive(t1_empty + 8 * (tb * 4 + j));
           }
         }
         V2W_TR(k * 100 + j * 10 + 3);
       }
+      // every T1 of this tile has been consumed: pre-load the next tile's (single accumulator set),
+      // in the time the tensor pipe spends on this tile's conv2 segments
+      if (p.preload && kt_next < n_my) preload_t1(kt_next, 0);
       // ---- final pass with conv_post folded in (last stage, C <= 32) ----
       if constexpr (C <= 32) {
         if (p.post) {
@@ -585,6 +627,12 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       {
         const bool out_valid = valid && central;
         const size_t row_base = reinterpret_cast<const float*>(xrow) - p.x0;
+        if constexpr (!kCacheX0) {
+          if (p.preload) {   // the X0 window was not kept running by the per-slot passes: prime it here
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e);
+          }
+        }
         V2W_TR(k * 100 + 50);
         mbar_wait(t2_full + 8 * tb, tph);
         tcgen05_fence_after();
@@ -610,8 +658,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
               // past the end of the tile's last pass the window moves on to the next tile's row
               const float4* src = ci + 2 < kNC ? xrow + (ci + 2) * 4 : xnext + (ci + 2 - kNC) * 4;
+              if (!p.preload || ci + 2 < kNC) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e);
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e);
+              }
             }
             if (out_valid) {
               float v[16];

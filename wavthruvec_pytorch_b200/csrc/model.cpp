@@ -139,6 +139,11 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
   if (rc < 64 || a0_rows > 64 * 7 || entries > V2W_FUSED_MAX_TAPS || 2 * nb + 2 > V2W_FUSED_MAX_SEG)
     return false;
   F.stacked = 1;
+  {
+    // single accumulator set with `sum` split off (C = 64): T1 can be pre-loaded by the epilogue
+    static const bool no_preload = [] { const char* e = std::getenv("V2W_FUSED_NO_PRELOAD"); return e && std::atoi(e); }();
+    F.preload = (C == 64 && split_sum && !no_preload) ? 1 : 0;
+  }
   for (int j = 0; j < nb; ++j) F.order[j] = order[j];
   F.hc = hc; F.h1 = h1; F.rc = rc;
   F.a0_boxes = (a0_rows + 63) / 64;
@@ -168,8 +173,11 @@ static bool plan_stacked(const v2w_model* m, int i, v2w_fused_desc& F) {
     const int nblk = nb - j + ((first && split_sum) ? 0 : 1);
     // The epilogue drains T1_0 .. T1_{nb-1}, then T2, in that order: "the last one is free" implies
     // the earlier ones are, so the first segment of a tile names ONE accumulator barrier.
-    begin(V2W_FUSED_SEG_CONV1, -1, (first && split_sum) ? C : 0, nblk * C, first ? 0 : 1,
-          first ? (V2W_FUSED_BIT_A0 | (split_sum ? V2W_FUSED_BIT_T1(nb - 1) : V2W_FUSED_BIT_T2)) : 0,
+    // preload: the accumulators hold x + b1 when conv1 starts, so its first MMA accumulates too, and
+    // the barrier it waits for is "T1 pre-loaded" (bit T1(0), full-parity wait in the kernel)
+    begin(V2W_FUSED_SEG_CONV1, -1, (first && split_sum) ? C : 0, nblk * C, (first && !F.preload) ? 0 : 1,
+          first ? (V2W_FUSED_BIT_A0 | (F.preload ? V2W_FUSED_BIT_T1(0)
+                                                 : (split_sum ? V2W_FUSED_BIT_T1(nb - 1) : V2W_FUSED_BIT_T2))) : 0,
           V2W_FUSED_BIT_T1(j));
     for (int t = -r[j]; t <= r[j]; ++t)
       if (std::abs(t) > lo) entry(t * d0, h1 + t * d0);

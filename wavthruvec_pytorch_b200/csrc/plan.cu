@@ -560,6 +560,7 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   p.mid_slope = kLreluSlope;
   p.res_scale = F.pair ? 1.0f : (float)nb;
   p.e1_add_x0 = F.pair ? 0 : 1;
+  p.preload = F.preload;
   p.accum_in = d.accum_in >= 0 ? reinterpret_cast<const float*>(ws + d.accum_in) : nullptr;
   p.out_scale = d.out_scale;
   p.out_slope = d.out_slope;

@@ -124,7 +124,7 @@ class FusedDesc(C.Structure):
         ("ok", C.c_int32), ("channels", C.c_int32), ("num_branches", C.c_int32),
         ("first_layer", C.c_int32), ("hc", C.c_int32), ("h1", C.c_int32), ("rc", C.c_int32),
         ("a0_boxes", C.c_int32), ("num_segments", C.c_int32), ("num_taps", C.c_int32),
-        ("stacked", C.c_int32), ("pair", C.c_int32), ("post", C.c_int32), ("order", C.c_int32 * 4), ("t_bufs", C.c_int32), ("a0_bufs", C.c_int32),
+        ("stacked", C.c_int32), ("pair", C.c_int32), ("preload", C.c_int32), ("post", C.c_int32), ("order", C.c_int32 * 4), ("t_bufs", C.c_int32), ("a0_bufs", C.c_int32),
         ("seg_type", C.c_int32 * FUSED_MAX_SEG), ("seg_branch", C.c_int32 * FUSED_MAX_SEG),
         ("seg_ntaps", C.c_int32 * FUSED_MAX_SEG), ("seg_first", C.c_int32 * FUSED_MAX_SEG),
         ("seg_flags", C.c_int32 * FUSED_MAX_SEG),
