@@ -507,12 +507,12 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
-                const float ax = (p.e1_add_x0 && !p.preload) ? 1.f : 0.f;   // pre-loaded: already in T1
-                const float ab = p.preload ? 0.f : 1.f;
-                v[4 * e] = fmaf(ax, xr[e].x, fmaf(ab, bb.x, __uint_as_float(r[4 * e])));
-                v[4 * e + 1] = fmaf(ax, xr[e].y, fmaf(ab, bb.y, __uint_as_float(r[4 * e + 1])));
-                v[4 * e + 2] = fmaf(ax, xr[e].z, fmaf(ab, bb.z, __uint_as_float(r[4 * e + 2])));
-                v[4 * e + 3] = fmaf(ax, xr[e].w, fmaf(ab, bb.w, __uint_as_float(r[4 * e + 3])));
+                // selects, not multiplies by 0: in pre-load mode this pass does not load xr
+                const bool ax = p.e1_add_x0 && !p.preload, ab = !p.preload;
+                v[4 * e] = __uint_as_float(r[4 * e]) + (ab ? bb.x : 0.f) + (ax ? xr[e].x : 0.f);
+                v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + (ab ? bb.y : 0.f) + (ax ? xr[e].y : 0.f);
+                v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + (ab ? bb.z : 0.f) + (ax ? xr[e].z : 0.f);
+                v[4 * e + 3] = __uint_as_float(r[4 * e + 3]) + (ab ? bb.w : 0.f) + (ax ? xr[e].w : 0.f);
               }
 #pragma unroll
               for (int e = 0; e < 8; ++e)
