@@ -330,6 +330,41 @@ int32_t v2w_forward_ragged(struct v2w_plan* p, const float* x_rows_dev, const in
  * receptive field of conv_pre .. conv_post, in frames, rounded up). */
 int32_t v2w_model_halo_frames(const struct v2w_model* m);
 
+/* train()-mode forward under no_grad: what ConditionalBatchNorm1d does when
+ * module.training is set (vec2wav/modules.py:14,16,20-30; callers vec2wav/train.py:138,167 and the
+ * warm-up loops that converge sigma / fill the running statistics):
+ *   - BatchNorm1d normalises with the statistics of THIS batch (biased variance over batch x time,
+ *     eps 1e-5) and updates running_mean / running_var in place
+ *     (r <- (1 - momentum) r + momentum s, unbiased variance for running_var);
+ *   - the spectral-norm Linear runs ONE power iteration first (v <- normalize(W^T u),
+ *     u <- normalize(W v), eps 1e-12), stores u and v in place and divides by sigma = u.(W v).
+ * Everything else (the convolutions) is mode-independent and comes from the packed buffer.  Per stage
+ * the transposed conv runs twice: once raw (bias only) into a scratch tensor for the batch statistics
+ * (bn_stats_kernel), then -- after sn_train_kernel + cond_affine_kernel produced this batch's
+ * scale/shift -- the plan's normal op with the affine in its epilogue.  All pointers are DEVICE fp32
+ * tensors of the module itself (the caller bumps num_batches_tracked, an int64 the library never reads).
+ * The conditioning section of the packed buffer is not read by this call, so the packed buffer stays
+ * usable across train-mode forwards; an eval-mode forward afterwards needs a re-pack (u, v and the
+ * running statistics changed).  Padded batches only. */
+typedef struct v2w_train_stage {
+  const float* fc_weight;      /* fcs.i.weight [128, spk_dim+noise_dim] */
+  const float* fc_bias;        /* fcs.i.bias [128] */
+  const float* sn_weight_orig; /* cbns.i.layer.weight_orig [2C,128] */
+  const float* sn_bias;        /* cbns.i.layer.bias [2C] */
+  float* sn_u;                 /* cbns.i.layer.weight_u [2C]   in/out */
+  float* sn_v;                 /* cbns.i.layer.weight_v [128]  in/out */
+  float* bn_running_mean;      /* cbns.i.batch_nrom.running_mean [C]  in/out */
+  float* bn_running_var;       /* cbns.i.batch_nrom.running_var  [C]  in/out */
+} v2w_train_stage;
+typedef struct v2w_train_state {
+  int32_t num_stages;
+  float momentum;              /* nn.BatchNorm1d default 0.1 */
+  v2w_train_stage stage[V2W_MAX_STAGES];
+} v2w_train_state;
+int32_t v2w_forward_train(struct v2w_plan* p, const float* x_dev, const float* spk_dev,
+                          const float* noise_dev, float* out_dev, const v2w_train_state* state,
+                          void* stream, int32_t* gpu_launches);
+
 /* Feature-file reader: NumPy .npy, little-endian float32, C order, shape [T, C]
  * or [1, T, C] as prepare_data.py:87 writes wav2vec features.  v2w_npy_read_f32 copies the rows into
  * `dst` (room for max_rows x cols floats; ideally pinned) and returns the frame count.  Host only. */

@@ -68,10 +68,51 @@ def run_case(name: str) -> Path:
     return path
 
 
+TRAIN_STEPS = 2
+
+
+def run_train_case(name: str) -> Path:
+    """train()-mode forwards under no_grad: from the fixture state of `name`,
+    TRAIN_STEPS forwards of the golden inputs with module.training set; stores every output and the
+    buffers the forwards mutate (BN running stats + counter, spectral-norm u / v) after each step."""
+    overrides, state, batch, frames, seed = fixtures.GOLDEN_CASES[name]
+    models, _ = ref_import.load_reference()
+    h = ref_import.RefHParams(**overrides)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gen = fixtures.construct(models.Generator, h)
+        fixtures.apply_state(gen, state)
+    x, s, n = fixtures.make_inputs(h, batch, frames, seed)
+    arrays = {"steps": np.array(TRAIN_STEPS)}
+    for k, v in fixtures.small_state(gen).items():
+        arrays["small/" + k] = v
+    gen.train()
+    for step in range(TRAIN_STEPS):
+        with torch.no_grad():
+            y = gen(x * (1.0 + 0.25 * step), s, n)
+        arrays[f"y{step}"] = y.numpy()
+        for k, v in fixtures.small_state(gen).items():
+            arrays[f"after{step}/" + k] = v
+    path = OUT_DIR / f"{name}_train.npz"
+    np.savez_compressed(path, **arrays)
+    print(f"{name}_train: {TRAIN_STEPS} train() forwards, |y|max={np.abs(y.numpy()).max():.4f} "
+          f"-> {path.name} ({path.stat().st_size/1024:.0f} KiB)")
+    return path
+
+
+TRAIN_CASES = ("rb2_768_stress", "rb1_1024_stress")
+
+
 def main(argv):
     names = argv or list(fixtures.GOLDEN_CASES)
     for n in names:
-        run_case(n)
+        if n.endswith("_train"):
+            run_train_case(n[:-len("_train")])
+        else:
+            run_case(n)
+    if not argv:
+        for n in TRAIN_CASES:
+            run_train_case(n)
 
 
 if __name__ == "__main__":

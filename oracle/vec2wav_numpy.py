@@ -1,4 +1,4 @@
-"""numpy restatement of Generator.forward in eval() mode (TEST INFRASTRUCTURE ONLY).
+"""numpy restatement of Generator.forward, eval() and train()-under-no_grad modes (TEST INFRASTRUCTURE ONLY).
 
 Plain array arithmetic from the formulas -- no torch convolution is involved, so it checks the
 *semantics* (padding, transposed-conv indexing, weight-norm axis, gamma/beta order, the two
@@ -80,6 +80,36 @@ def cbn_eval(x, z, sd, prefix: str, dtype):
     return gamma[:, :, None] * xh + beta[:, :, None]
 
 
+def cbn_train(x, z, sd, prefix: str, dtype, momentum: float = 0.1, sn_eps: float = 1e-12):
+    """ConditionalBatchNorm1d.forward with module.training set (vec2wav/modules.py:14,16,20-30).
+    nn.BatchNorm1d normalises with THIS batch's statistics (biased variance over batch x time) and
+    moves the running statistics by `momentum` (unbiased variance); torch.nn.utils.spectral_norm
+    runs one power iteration first -- v <- normalize(W^T u), u <- normalize(W v), both stored --
+    and divides by sigma = u . (W v).  MUTATES `sd` like the module mutates its buffers."""
+    n = x.shape[0] * x.shape[2]
+    mean = x.mean(axis=(0, 2))
+    var = x.var(axis=(0, 2))                     # biased
+    xh = (x - mean.reshape(1, -1, 1)) / np.sqrt(var.reshape(1, -1, 1) + BN_EPS)
+    rm, rv = sd[prefix + ".batch_nrom.running_mean"], sd[prefix + ".batch_nrom.running_var"]
+    sd[prefix + ".batch_nrom.running_mean"] = ((1 - momentum) * rm.astype(dtype) + momentum * mean).astype(rm.dtype)
+    sd[prefix + ".batch_nrom.running_var"] = ((1 - momentum) * rv.astype(dtype)
+                                              + momentum * var * n / (n - 1)).astype(rv.dtype)
+    sd[prefix + ".batch_nrom.num_batches_tracked"] = sd[prefix + ".batch_nrom.num_batches_tracked"] + 1
+    W = sd[prefix + ".layer.weight_orig"].astype(dtype)
+    u = sd[prefix + ".layer.weight_u"].astype(dtype)
+    v = W.T @ u
+    v = v / max(np.sqrt((v * v).sum()), sn_eps)
+    u = W @ v
+    u = u / max(np.sqrt((u * u).sum()), sn_eps)
+    sd[prefix + ".layer.weight_u"] = u.astype(sd[prefix + ".layer.weight_u"].dtype)
+    sd[prefix + ".layer.weight_v"] = v.astype(sd[prefix + ".layer.weight_v"].dtype)
+    sigma = u @ (W @ v)
+    gb = z @ (W / sigma).T + sd[prefix + ".layer.bias"].astype(dtype)
+    C = x.shape[1]
+    gamma, beta = gb[:, :C], gb[:, C:]
+    return gamma[:, :, None] * xh + beta[:, :, None]
+
+
 def resblock2(x, sd, prefix, k, dil, dtype):
     """ResBlock2.forward (vec2wav/models.py:65-70): dilations dil[0], dil[1] only."""
     for s in range(2):
@@ -103,8 +133,9 @@ def resblock1(x, sd, prefix, k, dil, dtype):
 
 
 def generator_forward(sd: Dict[str, np.ndarray], h, x, spk, noise, dtype=np.float64,
-                      return_pre_tanh: bool = False, taps: Optional[List] = None):
-    """Generator.forward (vec2wav/models.py:116-147), eval() semantics.
+                      return_pre_tanh: bool = False, taps: Optional[List] = None, train: bool = False):
+    """Generator.forward (vec2wav/models.py:116-147), eval() semantics; `train=True`: train()
+    semantics under no_grad (batch-statistic BN, power iteration), `sd` is updated in place.
 
     x [B, num_wv_feat, T], spk [B, spk_dim], noise [B, noise_dim] -> [B, 1, 320 T].
     `taps`, if a list, receives (name, ndarray) of intermediate activations."""
@@ -120,7 +151,7 @@ def generator_forward(sd: Dict[str, np.ndarray], h, x, spk, noise, dtype=np.floa
         x = conv_transpose1d(x, effective_weight(sd, f"ups.{i}", dtype),
                              sd[f"ups.{i}.bias"].astype(dtype), u, (k - u) // 2)        # :129
         z = cond @ sd[f"fcs.{i}.weight"].astype(dtype).T + sd[f"fcs.{i}.bias"].astype(dtype)
-        x = cbn_eval(x, z, sd, f"cbns.{i}", dtype)                                      # :134
+        x = (cbn_train if train else cbn_eval)(x, z, sd, f"cbns.{i}", dtype)            # :134
         if taps is not None:
             taps.append((f"cbn.{i}", x))
         xs = None

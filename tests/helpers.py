@@ -34,6 +34,17 @@ def load_golden(name: str):
                            y64=z["y64"], small=small, checksums=sums)
 
 
+def load_train_golden(name: str):
+    """tests/golden/<name>_train.npz (oracle/make_golden.py:run_train_case): train()-mode forwards of
+    the reference from the fixture state of golden `name`; step k feeds x * (1 + 0.25 k)."""
+    z = np.load(GOLDEN_DIR / f"{name}_train.npz")
+    steps = int(z["steps"])
+    return SimpleNamespace(
+        steps=steps, y=[z[f"y{k}"] for k in range(steps)],
+        after=[{key[len(f"after{k}/"):]: z[key] for key in z.files if key.startswith(f"after{k}/")}
+               for k in range(steps)])
+
+
 _MODULE_CACHE = {}
 
 

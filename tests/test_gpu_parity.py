@@ -12,7 +12,7 @@ from wavthruvec_pytorch_b200 import native
 
 import gemm_ref
 import plan_interp
-from helpers import dropin_in_state, hparams, load_golden, t
+from helpers import dropin_in_state, hparams, load_golden, load_train_golden, t
 
 pytestmark = pytest.mark.gpu
 
@@ -284,3 +284,103 @@ def test_state_change_triggers_refold():
     gen.remove_weight_norm()
     c = _native(gen, g, "fp32")
     assert np.abs(c - b).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# train()-mode forward under no_grad on the device (v2w_forward_train)
+# ----------------------------------------------------------------------------------------------
+def _check_buffers(sd, want, rtol_stats, rtol_uv):
+    for key, w in want.items():
+        got = sd[key].detach().cpu().numpy()
+        if key.endswith("num_batches_tracked"):
+            assert int(got) == int(w), key
+        elif key.endswith("weight_u") or key.endswith("weight_v"):
+            np.testing.assert_allclose(got, w, rtol=rtol_uv, atol=rtol_uv * 1e-2, err_msg=key)
+        else:
+            np.testing.assert_allclose(got, w, rtol=rtol_stats, atol=rtol_stats * 1e-2, err_msg=key)
+
+
+TRAIN_BF16_MIN_SNR_DB = 40.0   # bf16 operands under batch-statistic BN: 42.0 dB predicted by CPU emulation
+                               # with identical rounding points; 'auto' runs fp16 operands
+
+
+@pytest.mark.parametrize("name,precision", [("rb2_768_stress", "fp32"), ("rb2_768_stress", "auto"),
+                                            ("rb2_768_stress", "bf16"),
+                                            ("rb1_1024_stress", "fp32"), ("rb1_1024_stress", "auto")])
+def test_train_mode_forward_matches_reference(name, precision):
+    """Outputs and mutated buffers of consecutive train()-mode forwards against the unmodified
+    reference (tests/golden/*_train.npz)."""
+    g = load_golden(name)
+    tg = load_train_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0").train()
+    gen.precision = precision
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    for k in range(tg.steps):
+        with torch.no_grad():
+            y = gen(x * (1.0 + 0.25 * k), s, n)
+        torch.cuda.synchronize()
+        assert gen.engine().last_launches > 18       # the native path ran (stats + power iteration kernels too)
+        y = y.cpu().numpy()
+        if precision == "fp32":
+            err = np.abs(y - tg.y[k]).max()
+            print(f"{name} train step {k}: fp32 max-abs {err:.2e}")
+            assert err <= FP32_MAX_ABS
+            _check_buffers(gen.state_dict(), tg.after[k], 1e-4, 1e-5)
+        else:
+            snr = fixtures.snr_db(tg.y[k], y)
+            print(f"{name} train step {k}: {precision} ({gen.train_precision}) SNR {snr:.1f} dB")
+            assert snr >= (TRAIN_BF16_MIN_SNR_DB if precision == "bf16" else BF16_MIN_SNR_DB)
+            _check_buffers(gen.state_dict(), tg.after[k], 2e-2, 1e-5)
+
+
+def test_train_mode_then_eval_refolds():
+    """After native train()-mode forwards the eval() fold must see the new u / v / running statistics."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    gen.precision = "fp32"
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    with torch.no_grad():
+        gen.eval()
+        before = gen(x, s, n).clone()
+        gen.train()
+        for _ in range(3):
+            gen(x * 1.5, s, n)
+        gen.eval()
+        after = gen(x, s, n)
+        ref = gen._forward_autograd(x, s, n)
+    assert np.abs((after - ref).cpu().numpy()).max() <= FP32_MAX_ABS
+    assert np.abs((after - before).cpu().numpy()).max() > 1e-3   # the statistics did move
+
+
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_train_mode_full_size_against_delegate(precision):
+    """B=4, T=200 (256k rows in the last stage: multi-CTA statistics with double atomics): native
+    train()-mode forwards against the PyTorch delegate on a twin module, outputs and buffers."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from wavthruvec_pytorch_b200 import Generator
+    h = hparams(resblock=1, num_wv_feat=768)
+    twins = []
+    for _ in range(2):
+        gen = fixtures.construct(Generator, h)
+        fixtures.redraw_variance_preserving(gen)
+        twins.append(gen.to("cuda:0").train())
+    mine, ref = twins
+    mine.precision = precision
+    for step, (B, T) in enumerate(((4, 200), (3, 77))):
+        x, s, n = (a.cuda() for a in fixtures.make_inputs(h, B, T, 21 + step))
+        with torch.no_grad():
+            y = mine(x, s, n)
+            want = ref._forward_autograd(x, s, n)
+        y, want = y.cpu().numpy(), want.cpu().numpy()
+        small = {k: v.detach().cpu().numpy() for k, v in ref.state_dict().items() if fixtures.is_small_key(k)}
+        if precision == "fp32":
+            err = np.abs(y - want).max()
+            print(f"train B={B} T={T}: fp32 max-abs {err:.2e}")
+            assert err <= FP32_MAX_ABS
+            _check_buffers(mine.state_dict(), small, 1e-4, 1e-5)
+        else:
+            snr = fixtures.snr_db(want, y)
+            print(f"train B={B} T={T}: {mine.train_precision} SNR {snr:.1f} dB")
+            assert snr >= BF16_MIN_SNR_DB
+            _check_buffers(mine.state_dict(), small, 2e-2, 1e-5)

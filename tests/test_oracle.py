@@ -6,7 +6,7 @@ import torch
 
 from oracle import fixtures, ref_import, vec2wav_numpy, vec2wav_torch_cpu
 
-from helpers import assert_checksums, dropin_in_state, hparams, load_golden, t
+from helpers import assert_checksums, dropin_in_state, hparams, load_golden, load_train_golden, t
 
 CASES = list(fixtures.GOLDEN_CASES)
 
@@ -102,3 +102,22 @@ def test_against_live_reference():
             a = ref(x, s, n)
         c = vec2wav_torch_cpu.generator_forward(ref.state_dict(), h, x, s, n)
         assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_1024_stress"])
+def test_numpy_restatement_train_mode(name):
+    """train()-mode semantics (batch-statistic BN, one power iteration, buffer updates; SURVEY 8(f)
+    row 2) restated in numpy fp64 sit on what the unmodified reference produced, outputs AND the
+    mutated buffers, step after step."""
+    g = load_golden(name)
+    tg = load_train_golden(name)
+    gen = dropin_in_state(g, cache=False)
+    sd = vec2wav_numpy.state_dict_to_numpy(gen)
+    for k in range(tg.steps):
+        y = vec2wav_numpy.generator_forward(sd, gen.h, g.x * (1.0 + 0.25 * k), g.spk, g.noise, train=True)
+        assert np.abs(y - tg.y[k]).max() < 2e-5
+        for key, want in tg.after[k].items():
+            if key.endswith("num_batches_tracked"):
+                assert int(sd[key]) == int(want), key
+            else:
+                np.testing.assert_allclose(sd[key], want, rtol=2e-5, atol=1e-7, err_msg=key)

@@ -252,6 +252,7 @@ struct CondStage {
   const float* rstd; const float* mean;
   float* scale; float* shift;   // [B][C]
   int C;
+  const float* inv_sigma;       // train() mode: snw is the raw weight_orig, *inv_sigma = 1/sigma of this forward; else null
 };
 struct CondParams {
   CondStage st[V2W_MAX_STAGES];
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondPar
   }
   __syncthreads();
   const float4 z4 = *reinterpret_cast<const float4*>(z + 4 * lane);
+  const float isg = S.inv_sigma ? __ldg(S.inv_sigma) : 1.f;
   for (int r0 = warp * kRows; r0 < 2 * S.C; r0 += kWarps * kRows) {
     float4 w4[kRows];
 #pragma unroll
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondPar
     for (int r = 0; r < kRows; ++r) {
       float v = w4[r].x * z4.x + w4[r].y * z4.y + w4[r].z * z4.z + w4[r].w * z4.w;
       v = warp_sum(v);
-      if (lane == 0) gb[r0 + r] = v + S.snb[r0 + r];
+      if (lane == 0) gb[r0 + r] = v * isg + S.snb[r0 + r];
     }
   }
   __syncthreads();
@@ -322,6 +324,149 @@ __global__ void __launch_bounds__(kCondThreads) cond_affine_kernel(const CondPar
     const float sc = gb[c] * S.rstd[c];
     S.scale[static_cast<size_t>(b) * S.C + c] = sc;
     S.shift[static_cast<size_t>(b) * S.C + c] = gb[S.C + c] - sc * S.mean[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// train()-mode conditional batch norm (vec2wav/modules.py:14,16,20-30)
+// ---------------------------------------------------------------------------------------------
+// Per-channel sum and sum of squares of a channels-last fp32 tensor y[R][C] (R = batch x time rows,
+// C a power of two, 4 <= C <= 1024) -> sums[0][c] += sum, sums[1][c] += sum of squares (double; the
+// caller zeroes them).  HBM-bound: every thread reads float4s of consecutive channels, a CTA walks
+// whole rows so a warp's loads are contiguous; fp32 partial sums are flushed into double accumulators
+// every kStatRun rows, so the variance E[y^2] - E[y]^2 is formed from double sums.
+constexpr int kStatThreads = 256;
+constexpr int kStatRun = 16;
+
+__global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const float* __restrict__ y, long long R,
+                                                               int C, double* __restrict__ sums) {
+  __shared__ double red[kStatThreads][8];
+  const int c4n = C >> 2;                       // float4s per row
+  const int groups = kStatThreads / c4n > 0 ? kStatThreads / c4n : 1;
+  const int c4 = threadIdx.x % c4n, g = threadIdx.x / c4n;
+  const bool active = g < groups && c4n <= kStatThreads;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    // c4n <= 256 here: one float4 column per thread, `groups` rows in flight per CTA
+    for (long long r0 = (long long)blockIdx.x * groups * kStatRun; r0 < R;
+         r0 += (long long)gridDim.x * groups * kStatRun) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int i = 0; i < kStatRun; ++i) {
+        const long long r = r0 + (long long)i * groups + g;
+        if (r < R) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * C) + c4);
+          s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+          q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]);
+          q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[k] += s[k]; acc[4 + k] += q[k]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (g == 0 && active) {
+    for (int gg = 1; gg < groups; ++gg)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += red[gg * c4n + c4][k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(sums + 4 * c4 + k, acc[k]);
+      atomicAdd(sums + C + 4 * c4 + k, acc[4 + k]);
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch /* >= 33 floats */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();                 // scratch free (previous use read)
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// One CTA per stage call.  (1) one spectral-norm power iteration exactly as
+// torch.nn.utils.spectral_norm does in training mode: v <- normalize(W^T u), u <- normalize(W v)
+// (eps 1e-12), sigma = u . (W v); u, v stored in place, 1/sigma to the workspace.  (2) batch
+// statistics from the double sums: mean, rstd = 1/sqrt(biased var + eps) to the workspace, running
+// statistics updated in place with `momentum` (unbiased variance), as nn.BatchNorm1d in training mode.
+struct SnTrainParams {
+  const float* W;        // [2C][128]
+  float* u; float* v;    // [2C], [128]
+  const double* sums;    // [2][C]
+  float* run_mean; float* run_var;
+  float* mean; float* rstd; float* inv_sigma;   // workspace outputs
+  int C;
+  long long count;       // values per channel (batch x time)
+  float momentum, eps;
+};
+constexpr int kSnThreads = 512;
+
+__global__ void __launch_bounds__(kSnThreads) sn_train_kernel(const SnTrainParams p) {
+  __shared__ float us[2 * 1024 / 2];   // [2C], C <= 512
+  __shared__ float vs[128];
+  __shared__ float part[4][128];
+  __shared__ float ts[2 * 1024 / 2];   // W v
+  __shared__ float scratch[33];
+  const int R = 2 * p.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = threadIdx.x; r < R; r += kSnThreads) us[r] = p.u[r];
+  __syncthreads();
+  {  // v = W^T u : thread (slice, k), coalesced over k
+    const int k = threadIdx.x & 127, sl = threadIdx.x >> 7;
+    float a = 0.f;
+    for (int r = sl; r < R; r += 4) a = fmaf(__ldg(p.W + (size_t)r * 128 + k), us[r], a);
+    part[sl][k] = a;
+  }
+  __syncthreads();
+  float vk = 0.f;
+  if (threadIdx.x < 128) vk = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+  const float vn = sqrtf(block_sum(vk * vk, scratch));
+  if (threadIdx.x < 128) {
+    vk = vk / fmaxf(vn, 1e-12f);
+    vs[threadIdx.x] = vk;
+    p.v[threadIdx.x] = vk;
+  }
+  __syncthreads();
+  const float4 v4 = *reinterpret_cast<const float4*>(vs + 4 * lane);
+  for (int r = warp; r < R; r += kSnThreads / 32) {   // t = W v : one warp per row
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.W + (size_t)r * 128) + lane);
+    float a = w4.x * v4.x + w4.y * v4.y + w4.z * v4.z + w4.w * v4.w;
+    a = warp_sum(a);
+    if (lane == 0) ts[r] = a;
+  }
+  __syncthreads();
+  float tt = 0.f;
+  for (int r = threadIdx.x; r < R; r += kSnThreads) tt = fmaf(ts[r], ts[r], tt);
+  const float tn = fmaxf(sqrtf(block_sum(tt, scratch)), 1e-12f);
+  float su = 0.f;
+  for (int r = threadIdx.x; r < R; r += kSnThreads) {
+    const float un = ts[r] / tn;
+    p.u[r] = un;
+    su = fmaf(un, ts[r], su);
+  }
+  const float sigma = block_sum(su, scratch);
+  if (threadIdx.x == 0) *p.inv_sigma = 1.f / sigma;
+  const double n = (double)p.count;
+  for (int c = threadIdx.x; c < p.C; c += kSnThreads) {
+    const double m = p.sums[c] / n;
+    double var = p.sums[p.C + c] / n - m * m;
+    if (var < 0) var = 0;
+    p.mean[c] = (float)m;
+    p.rstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+    const double unb = p.count > 1 ? var * n / (n - 1.0) : var;
+    p.run_mean[c] = (1.f - p.momentum) * p.run_mean[c] + p.momentum * (float)m;
+    p.run_var[c] = (1.f - p.momentum) * p.run_var[c] + p.momentum * (float)unb;
   }
 }
 

@@ -68,6 +68,11 @@ struct Op {
   TcLaunch tcl;         // TC engine only
   FusedLaunch fl;       // MRF_FUSED ops
   bool tc_ready = false;
+  // train() mode (v2w_forward_train): the same transposed conv with bias only, fp32 result into the
+  // statistics scratch -- no affine, no 16-bit copy
+  v2w_tapgemm_args g_raw;
+  TcLaunch tcl_raw;
+  bool has_raw = false;
 };
 
 }  // namespace v2w
@@ -83,6 +88,10 @@ struct v2w_plan {
   int64_t xt = -1;        // transposed input
   int64_t post_in = -1;   // fp32 input of conv_post
   int64_t row_limit = -1; // int32 [batch]: frames each utterance needs (variable-length batches)
+  // train() mode scratch: raw ups output (fp32, aliases the first-conv buffer of the resblocks, dead at
+  // that point), per-stage double sums [2][C], batch mean / rstd [C], 1/sigma
+  int64_t tr_y = -1;
+  int64_t tr_sums[V2W_MAX_STAGES], tr_mean[V2W_MAX_STAGES], tr_rstd[V2W_MAX_STAGES], tr_isg[V2W_MAX_STAGES];
   bool bound = false;
   const uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
@@ -916,6 +925,13 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     }
   }
   const int64_t next_bf16 = bf ? ws.take(max_e * 2) : -1;
+  P->tr_y = y1.f32;
+  for (int i = 0; i < U; ++i) {
+    P->tr_sums[i] = ws.take((int64_t)2 * m->stage_channels[i] * 8);
+    P->tr_mean[i] = ws.take((int64_t)m->stage_channels[i] * 4);
+    P->tr_rstd[i] = ws.take((int64_t)m->stage_channels[i] * 4);
+    P->tr_isg[i] = ws.take(4);
+  }
   P->workspace_bytes = ws.off;
   P->post_in = sum_f32;
 
@@ -1202,6 +1218,21 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       if (rc) return rc;
       o.tc_ready = true;
     }
+    o.has_raw = false;
+    if (o.d.cond_stage >= 0) {
+      o.g_raw = g;
+      o.g_raw.scale = o.g_raw.shift = nullptr;
+      o.g_raw.out_f32 = reinterpret_cast<float*>(at(p->tr_y));
+      o.g_raw.out_bf16 = nullptr;
+      o.g_raw.out_slope = 1.f;
+      rc = validate_gemm(o.g_raw);
+      if (rc) return rc;
+      if (g.engine == V2W_ENGINE_TC) {
+        rc = prepare_tc(o.g_raw, &o.tcl_raw);
+        if (rc) return rc;
+      }
+      o.has_raw = true;
+    }
   }
   {
     // conv_post's 7 x C weights travel as a by-value kernel parameter (constant bank operands)
@@ -1215,11 +1246,71 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   return V2W_OK;
 }
 
+// train() mode, one upsample stage (vec2wav/modules.py:20-30 with module.training set): raw transposed
+// conv -> per-channel batch statistics -> power iteration + running-stat update -> this batch's
+// scale/shift.  The plan's own op (same GEMM, affine epilogue) follows.
+static int32_t train_stage_affine(v2w_plan* p, Op& o, const v2w_train_state& tr, const float* spk_dev,
+                                  const float* noise_dev, cudaStream_t st, int* launches) {
+  const v2w_model* m = p->model;
+  const v2w_config& c = m->cfg;
+  const int i = o.d.cond_stage;
+  const v2w_train_stage& T = tr.stage[i];
+  const int C = m->stage_channels[i];
+  if (!o.has_raw) {
+    set_error("v2w_forward_train: stage %d has no raw launch", i);
+    return V2W_ERR_STATE;
+  }
+  if (C < 4 || C > 512 || (C & (C - 1))) {
+    set_error("v2w_forward_train: %d channels unsupported by the statistics kernels", C);
+    return V2W_ERR_INVALID;
+  }
+  int rc = o.g_raw.engine == V2W_ENGINE_TC ? launch_tc(o.tcl_raw, st) : launch_simt(o.g_raw, st);
+  if (rc) return rc;
+  double* sums = reinterpret_cast<double*>(p->ws + p->tr_sums[i]);
+  V2W_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * C * 8, st));
+  const long long R = (long long)p->batch * o.d.rows * m->layers[o.d.layer].up;   // rows of [R][C]
+  const int groups = simt::kStatThreads / (C / 4);
+  const long long per_cta = (long long)groups * simt::kStatRun;
+  int sms = 148;
+  sm_count(&sms);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((R + per_cta - 1) / per_cta, (long long)sms * 8));
+  simt::bn_stats_kernel<<<grid, simt::kStatThreads, 0, st>>>(reinterpret_cast<const float*>(p->ws + p->tr_y), R, C, sums);
+  V2W_CUDA(cudaGetLastError());
+  simt::SnTrainParams sp;
+  sp.W = T.sn_weight_orig; sp.u = T.sn_u; sp.v = T.sn_v;
+  sp.sums = sums;
+  sp.run_mean = T.bn_running_mean; sp.run_var = T.bn_running_var;
+  sp.mean = reinterpret_cast<float*>(p->ws + p->tr_mean[i]);
+  sp.rstd = reinterpret_cast<float*>(p->ws + p->tr_rstd[i]);
+  sp.inv_sigma = reinterpret_cast<float*>(p->ws + p->tr_isg[i]);
+  sp.C = C;
+  sp.count = R;
+  sp.momentum = tr.momentum;
+  sp.eps = kBnEps;
+  simt::sn_train_kernel<<<1, simt::kSnThreads, 0, st>>>(sp);
+  V2W_CUDA(cudaGetLastError());
+  simt::CondParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  simt::CondStage& S = cp.st[0];
+  S.fcw = T.fc_weight; S.fcb = T.fc_bias; S.snw = T.sn_weight_orig; S.snb = T.sn_bias;
+  S.rstd = sp.rstd; S.mean = sp.mean; S.inv_sigma = sp.inv_sigma;
+  S.scale = reinterpret_cast<float*>(p->ws + p->cond_scale[i]);
+  S.shift = reinterpret_cast<float*>(p->ws + p->cond_shift[i]);
+  S.C = C;
+  cp.spk = spk_dev; cp.noise = noise_dev;
+  cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
+  const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * C) * 4;
+  simt::cond_affine_kernel<<<dim3(1, p->batch), simt::kCondThreads, smem, st>>>(cp);
+  V2W_CUDA(cudaGetLastError());
+  *launches += 4;
+  return V2W_OK;
+}
+
 // One pass over the plan's op list.  `ragged`: x_dev is packed time-major rows and the waveform is
 // written un-padded (v2w_forward_ragged); the row offsets are already in the workspace.
 static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
                        void* out_dev, const simt::RaggedOffsets* ro, int32_t out_format, void* stream,
-                       int32_t* gpu_launches) {
+                       int32_t* gpu_launches, const v2w_train_state* tr = nullptr) {
   const bool ragged = ro != nullptr;
   static const simt::RaggedOffsets no_offsets = {};
   // variable-length batches: every row-tiled kernel skips the tiles no utterance needs
@@ -1243,7 +1334,7 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
   int launches = 0;
   size_t op_index = 0;
   static const bool no_fork = [] { const char* e = std::getenv("V2W_NO_FORK"); return e && std::atoi(e); }();
-  const bool fork = !p->profiling && !no_fork;
+  const bool fork = !p->profiling && !no_fork && !tr;
   bool joined = true;
   if (fork && !p->side) {
     V2W_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
@@ -1292,6 +1383,7 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         break;
       }
       case V2W_OP_COND_AFFINE: {
+        if (tr) break;   // train(): scale/shift come from this batch's statistics, stage by stage
         simt::CondParams cp;
         std::memset(&cp, 0, sizeof(cp));
         int cmax = 0;
@@ -1331,6 +1423,10 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
       }
       case V2W_OP_TAPGEMM: {
         const int rpf = o.d.rows / p->frames;   // rows of this op per input frame
+        if (tr && o.d.cond_stage >= 0) {
+          int rc = train_stage_affine(p, o, *tr, spk_dev, noise_dev, st, &launches);
+          if (rc) return rc;
+        }
         int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st, lim, rpf) : launch_simt(o.g, st, lim, rpf);
         if (rc) return rc;
         ++launches;
@@ -1397,6 +1493,33 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
 int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
                     float* out_dev, void* stream, int32_t* gpu_launches) {
   return run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, stream, gpu_launches);
+}
+
+int32_t v2w_forward_train(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
+                          float* out_dev, const v2w_train_state* state, void* stream,
+                          int32_t* gpu_launches) {
+  if (!p || !state) {
+    set_error("v2w_forward_train: null argument");
+    return V2W_ERR_INVALID;
+  }
+  if (state->num_stages != p->model->cfg.num_upsamples) {
+    set_error("v2w_forward_train: state has %d stages, the model %d", state->num_stages,
+              p->model->cfg.num_upsamples);
+    return V2W_ERR_INVALID;
+  }
+  if (!(state->momentum >= 0.f && state->momentum <= 1.f)) {
+    set_error("v2w_forward_train: momentum %g out of [0, 1]", (double)state->momentum);
+    return V2W_ERR_INVALID;
+  }
+  for (int i = 0; i < state->num_stages; ++i) {
+    const v2w_train_stage& T = state->stage[i];
+    if (!T.fc_weight || !T.fc_bias || !T.sn_weight_orig || !T.sn_bias || !T.sn_u || !T.sn_v ||
+        !T.bn_running_mean || !T.bn_running_var) {
+      set_error("v2w_forward_train: null pointer in stage %d", i);
+      return V2W_ERR_INVALID;
+    }
+  }
+  return run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, stream, gpu_launches, state);
 }
 
 int32_t v2w_forward_ragged(v2w_plan* p, const float* x_rows_dev, const int32_t* row_offsets_host,

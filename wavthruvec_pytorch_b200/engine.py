@@ -115,12 +115,14 @@ class NativeEngine:
         del host
         return packed
 
-    def _refresh(self) -> None:
+    def _refresh(self, train: bool = False) -> None:
         """Drop the folded weights (and the plans bound to them) when any parameter or buffer
         changed: storage pointer or in-place version counter (optimizer step, load_state_dict,
         manual edits), or the weight-norm structure (remove_weight_norm on any sub-block).
         Module._apply (.to()/.cuda()/.float()) replaces buffer objects and calls invalidate().
-        The tensor list is cached because walking the module tree costs ~4x the check itself."""
+        The tensor list is cached because walking the module tree costs ~4x the check itself.
+        `train`: the caller is the train()-mode forward, which reads the convolutions from the packed
+        buffer but none of its conditioning section -- only a change of a convolution invalidates."""
         if self._convs is None:
             self._convs = self._module.conv_modules()
         structure = tuple("weight_v" in c._parameters for c in self._convs)
@@ -128,10 +130,13 @@ class NativeEngine:
             self._tensors = self._state_tensors()
             self._structure = structure
         sig = self._signature(self._tensors)
-        if sig != self._packed_sig:
+        n = 3 * len(self._convs)
+        conv_sig, cond_sig = sig[:n], sig[n:]
+        old = self._packed_sig
+        if old is None or old[0] != conv_sig or (not train and old[1] != cond_sig):
             self._packed.clear()
             self._drop_plans()   # plans hold pointers into the packed buffer
-            self._packed_sig = sig
+            self._packed_sig = (conv_sig, cond_sig)
 
     def _packed_on(self, device: torch.device, half_format: int) -> torch.Tensor:
         buf = self._packed.get((device, half_format))
@@ -141,9 +146,9 @@ class NativeEngine:
         return buf
 
     # ------------------------------------------------------------------------------------------
-    def plan(self, batch: int, frames: int, precision: str, device: torch.device):
+    def plan(self, batch: int, frames: int, precision: str, device: torch.device, train: bool = False):
         """(plan handle, workspace) for this problem size; created and bound on first use."""
-        self._refresh()
+        self._refresh(train)
         key = (batch, frames, precision, device)
         hit = self._plans.get(key)
         if hit is not None:
@@ -206,6 +211,54 @@ class NativeEngine:
             native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(),
                                                noise.data_ptr(), out.data_ptr(),
                                                C.c_void_p(stream), C.byref(n)))
+        self.last_launches = n.value
+        return out
+
+    def forward_train(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        """train()-mode forward under no_grad through v2w_forward_train:
+        batch-statistic BN and one spectral-norm power iteration per stage on the device, with the
+        reference's side effects -- `running_mean` / `running_var`, `weight_u` / `weight_v` updated in
+        place, `num_batches_tracked` incremented (vec2wav/modules.py:14,16 with module.training set)."""
+        self._check_inputs(x, spk, noise)
+        if not x.is_cuda or spk.device != x.device or noise.device != x.device:
+            raise RuntimeError("forward_train takes CUDA tensors on one device (no CPU fallback)")
+        m = self._module
+        dev = x.device
+        x = x.detach().to(torch.float32).contiguous()
+        spk = spk.detach().to(torch.float32).contiguous()
+        noise = noise.detach().to(torch.float32).contiguous()
+        B, _, T = x.shape
+        st = native.TrainState()
+        st.num_stages = len(m.cbns)
+        momentum = m.cbns[0].batch_nrom.momentum
+        if momentum is None:
+            raise RuntimeError("BatchNorm1d(momentum=None) (cumulative average) is not supported natively")
+        st.momentum = float(momentum)
+        counters = []
+        for i, (fc, cbn) in enumerate(zip(m.fcs, m.cbns)):
+            bn, lin = cbn.batch_nrom, cbn.layer
+            if bn.momentum != momentum:
+                raise RuntimeError("all stages must share one BatchNorm momentum")
+            ts = (fc.weight, fc.bias, lin.weight_orig, lin.bias, lin.weight_u, lin.weight_v,
+                  bn.running_mean, bn.running_var)
+            for (name, _), t in zip(native.TrainStage._fields_, ts):
+                if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError(f"stage {i} {name}: expected a contiguous fp32 tensor on {dev}")
+                setattr(st.stage[i], name, t.data_ptr())
+            counters.append(bn.num_batches_tracked)
+        handle, _ws = self.plan(B, T, m.train_precision, dev, train=True)
+        out = torch.empty((B, 1, T * self.total_upsample()), dtype=torch.float32, device=dev)
+        n = C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            native.check(self._lib.v2w_forward_train(handle, x.data_ptr(), spk.data_ptr(),
+                                                     noise.data_ptr(), out.data_ptr(), C.byref(st),
+                                                     C.c_void_p(stream), C.byref(n)))
+        with torch.no_grad():
+            torch._foreach_add_(counters, 1)
+        # u, v and the running statistics changed behind autograd's version counters: the folded
+        # conditioning section is stale for eval(); the convolutions are not
+        self._packed_sig = (self._packed_sig[0], None)
         self.last_launches = n.value
         return out
 

@@ -10,12 +10,16 @@ arithmetic runs:
   spectral norm and BN running statistics are folded once per parameter version instead of on
   every call.  There is no CPU or eager fallback for this path: without the library or without
   an sm_100 GPU it raises.
-* ``train()`` (or grad enabled) needs autograd, batch-statistic BN and the spectral-norm power
-  iteration; it runs through stock PyTorch ops with the reference's exact op order
-  (``_forward_autograd``).  That is a mode delegation, not a fallback of the native path.
+* ``train()`` under ``torch.no_grad()`` on a CUDA device (validation and warm-up loops) also runs
+  in libv2w (``v2w_forward_train``): batch-statistic BN, one spectral-norm power iteration per
+  stage and the in-place buffer updates of the reference.
+* With grad enabled the forward needs autograd; it runs through stock PyTorch ops with the
+  reference's exact op order (``_forward_autograd``; also ``train()`` on CPU tensors).  That is a
+  mode delegation, not a fallback of the native path.
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Optional
 
@@ -143,6 +147,15 @@ class Generator(nn.Module):
             value = "fp16" if self.h.resblock == '1' else "bf16"
         return value
 
+    @property
+    def train_precision(self) -> str:
+        """Arithmetic of the native train()-mode forward.  'auto' means fp16 operands for both block
+        types: batch-statistic BN renormalises every stage to unit scale, so operand rounding noise is
+        carried at full scale through all five stages -- bf16 operands give 42 dB on the stress fixture
+        (predicted by CPU emulation with the same rounding points, measured 42.4), fp16 60 dB."""
+        value = (self._precision or os.environ.get("V2W_PRECISION", "auto")).lower()
+        return "fp16" if value == "auto" else value
+
     @precision.setter
     def precision(self, value: str) -> None:
         if value not in ("auto", "bf16", "fp16", "fp32"):
@@ -192,6 +205,10 @@ class Generator(nn.Module):
             raise TypeError("spk_emb is required (vec2wav/models.py:120 concatenates it)")
         if noise is None:
             noise = torch.randn(x.shape[0], self.h.noise_dim, device=x.device, dtype=x.dtype)
+        if self.training and not torch.is_grad_enabled() and x.is_cuda and not os.environ.get("V2W_NO_NATIVE_TRAIN"):
+            # train() under no_grad (validation / warm-up loops): batch-statistic BN and the power
+            # iteration run on the device too
+            return self.engine().forward_train(x, spk_emb, noise)
         if self.training or torch.is_grad_enabled():
             if not self.training and not self._warned_grad:
                 self._warned_grad = True

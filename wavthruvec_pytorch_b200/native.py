@@ -137,6 +137,16 @@ class FusedDesc(C.Structure):
     ]
 
 
+class TrainStage(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "fc_weight", "fc_bias", "sn_weight_orig", "sn_bias", "sn_u", "sn_v",
+        "bn_running_mean", "bn_running_var")]
+
+
+class TrainState(C.Structure):
+    _fields_ = [("num_stages", C.c_int32), ("momentum", C.c_float), ("stage", TrainStage * MAX_STAGES)]
+
+
 class TapGemmArgs(C.Structure):
     _fields_ = [
         ("engine", C.c_int32),
@@ -185,6 +195,9 @@ _SIGNATURES = [
       C.POINTER(C.c_int32)]),
     ("v2w_forward_host", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+      C.POINTER(C.c_int32)]),
+    ("v2w_forward_train", C.c_int32,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(TrainState), C.c_void_p,
       C.POINTER(C.c_int32)]),
     ("v2w_forward_ragged", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
