@@ -365,6 +365,35 @@ int32_t v2w_forward_train(struct v2w_plan* p, const float* x_dev, const float* s
                           const float* noise_dev, float* out_dev, const v2w_train_state* state,
                           void* stream, int32_t* gpu_launches);
 
+/* Log-mel spectrogram of a generated waveform: the consumer the reference runs
+ * on every generator output in validation and for the mel loss -- mel_spectrogram(y, n_fft, num_mels,
+ * sampling_rate, hop_size, win_size, fmin, fmax, center=False) of vec2wav/dataset.py:53-77, called at
+ * vec2wav/train.py:172-173,266-268,282-284 with the values of vec2wav/hparams.py:50-61:
+ *   reflect-pad by (n_fft - hop)/2 -> STFT (periodic Hann window, one-sided, no centring)
+ *   -> sqrt(re^2 + im^2 + 1e-9) -> Slaney mel filterbank (librosa.filters.mel defaults: slaney scale,
+ *   area normalisation) -> log(max(., 1e-5)).
+ * The STFT is ONE tap-GEMM on the tcgen05 engine: frames are hop-sample rows, the n_fft/hop taps are
+ * row shifts of the same TMA tile, the windowed DFT basis is the weight; fp16 operands split in
+ * high + low parts along K (x_hi W_hi + x_lo W_hi + x_hi W_lo, fp32 accumulation in TMEM) keep ~22
+ * mantissa bits.  Requires hop % 16 == 0, n_fft % hop == 0, n_fft / hop <= 16, win <= n_fft,
+ * samples > (n_fft - hop) / 2. */
+typedef struct v2w_mel_config {
+  int32_t n_fft, hop_size, win_size, num_mels, sampling_rate;
+  float fmin, fmax;            /* fmax <= 0: sampling_rate / 2 (the reference passes fmax_for_loss = None) */
+} v2w_mel_config;
+struct v2w_mel;
+int32_t v2w_mel_create(const v2w_mel_config* cfg, int32_t batch, int32_t samples, struct v2w_mel** out);
+void v2w_mel_destroy(struct v2w_mel* m);
+int32_t v2w_mel_num_frames(const struct v2w_mel* m);          /* samples / hop_size */
+int64_t v2w_mel_workspace_bytes(const struct v2w_mel* m);
+/* Host copy of the filterbank [num_mels][n_fft/2 + 1] (tests pin it against librosa's formula). */
+int32_t v2w_mel_get_filterbank(const struct v2w_mel* m, float* out_host);
+/* Attach 256-byte aligned device memory and upload the DFT basis and the filterbank (synchronous). */
+int32_t v2w_mel_bind(struct v2w_mel* m, void* workspace_dev);
+/* wav_dev fp32 [batch][samples] -> out_dev fp32 [batch][num_mels][frames].  Asynchronous on `stream`. */
+int32_t v2w_mel_forward(struct v2w_mel* m, const float* wav_dev, float* out_dev, void* stream,
+                        int32_t* gpu_launches);
+
 /* Feature-file reader: NumPy .npy, little-endian float32, C order, shape [T, C]
  * or [1, T, C] as prepare_data.py:87 writes wav2vec features.  v2w_npy_read_f32 copies the rows into
  * `dst` (room for max_rows x cols floats; ideally pinned) and returns the frame count.  Host only. */

@@ -100,19 +100,75 @@ def run_train_case(name: str) -> Path:
     return path
 
 
+MEL_PARAMS = dict(n_fft=1024, num_mels=80, sampling_rate=16000, hop_size=256, win_size=1024, fmin=0, fmax=None)
+#                 vec2wav/hparams.py:50-61 (fmax_for_loss = None is what train.py:172-173,266-268 pass)
+
+
+def mel_test_waves(batch: int, samples: int, seed: int) -> np.ndarray:
+    """Seeded speech-like test signals in (-1, 1): a few drifting harmonics, noise bursts, a silent gap."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(samples) / 16000.0
+    out = np.zeros((batch, samples), dtype=np.float64)
+    for b in range(batch):
+        f0 = rng.uniform(90, 260)
+        for hnum in range(1, 12):
+            out[b] += rng.uniform(0.02, 0.2) / hnum * np.sin(2 * np.pi * f0 * hnum * t * (1 + 0.05 * np.sin(2 * np.pi * 3 * t))
+                                                             + rng.uniform(0, 6.28))
+        out[b] += 0.02 * rng.standard_normal(samples) * (np.sin(2 * np.pi * 2.5 * t + b) > 0.3)
+        gap = rng.integers(0, max(1, samples - samples // 8))
+        out[b, gap: gap + samples // 8] *= 1e-4
+    return np.clip(out, -0.99, 0.99).astype(np.float32)
+
+
+def run_mel_case() -> Path:
+    """Log-mel of seeded waveforms by the reference's own mel_spectrogram (vec2wav/dataset.py:53-77), run
+    unmodified; librosa is absent from this image, so its import is shimmed: librosa.filters.mel ->
+    oracle.mel_numpy.slaney_mel_filterbank (restated from librosa's published algorithm; the file also
+    stores torchaudio's independent slaney filterbank for the cross-check)."""
+    import importlib
+    import types
+    import torchaudio
+    from . import mel_numpy
+    ref_import.load_reference()
+    lib, util, filt = (types.ModuleType(n) for n in ("librosa", "librosa.util", "librosa.filters"))
+    util.normalize = lambda x, *a, **k: x
+    filt.mel = mel_numpy.slaney_mel_filterbank
+    lib.util, lib.filters = util, filt
+    sys.modules.update({"librosa": lib, "librosa.util": util, "librosa.filters": filt})
+    ds = importlib.import_module("dataset")
+    arrays = {}
+    for tag, (batch, samples, seed) in {"a": (2, 16000, 31), "b": (3, 5000, 32)}.items():
+        y = mel_test_waves(batch, samples, seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ds.mel_basis.clear(); ds.hann_window.clear()
+            m = ds.mel_spectrogram(torch.from_numpy(y), **MEL_PARAMS)
+        arrays[f"y_{tag}"] = y
+        arrays[f"mel_{tag}"] = m.numpy()
+    arrays["fb_torchaudio"] = torchaudio.functional.melscale_fbanks(
+        513, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="slaney").T.contiguous().numpy()
+    path = OUT_DIR / "mel_reference.npz"
+    np.savez_compressed(path, **arrays)
+    print(f"mel_reference: {[(k, v.shape) for k, v in arrays.items()]} -> {path.name} ({path.stat().st_size/1024:.0f} KiB)")
+    return path
+
+
 TRAIN_CASES = ("rb2_768_stress", "rb1_1024_stress")
 
 
 def main(argv):
     names = argv or list(fixtures.GOLDEN_CASES)
     for n in names:
-        if n.endswith("_train"):
+        if n == "mel":
+            run_mel_case()
+        elif n.endswith("_train"):
             run_train_case(n[:-len("_train")])
         else:
             run_case(n)
     if not argv:
         for n in TRAIN_CASES:
             run_train_case(n)
+        run_mel_case()
 
 
 if __name__ == "__main__":

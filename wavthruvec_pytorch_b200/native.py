@@ -147,6 +147,12 @@ class TrainState(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("momentum", C.c_float), ("stage", TrainStage * MAX_STAGES)]
 
 
+class MelConfig(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("hop_size", C.c_int32), ("win_size", C.c_int32),
+                ("num_mels", C.c_int32), ("sampling_rate", C.c_int32),
+                ("fmin", C.c_float), ("fmax", C.c_float)]
+
+
 class TapGemmArgs(C.Structure):
     _fields_ = [
         ("engine", C.c_int32),
@@ -202,6 +208,13 @@ _SIGNATURES = [
     ("v2w_forward_ragged", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     ("v2w_model_halo_frames", C.c_int32, [C.c_void_p]),
+    ("v2w_mel_create", C.c_int32, [C.POINTER(MelConfig), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    ("v2w_mel_destroy", None, [C.c_void_p]),
+    ("v2w_mel_num_frames", C.c_int32, [C.c_void_p]),
+    ("v2w_mel_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("v2w_mel_get_filterbank", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("v2w_mel_bind", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("v2w_mel_forward", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("v2w_npy_shape", C.c_int32, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("v2w_npy_read_f32", C.c_int32, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     ("v2w_pipeline_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
