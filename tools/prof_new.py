@@ -1,0 +1,26 @@
+"""One train()-mode forward (cfg2) and one log-mel call between cudaProfilerStart/Stop, for
+`ncu --profile-from-start off` (tools/gpu_final2.sh)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from oracle import fixtures  # noqa: E402
+from wavthruvec_pytorch_b200 import Generator, HParams, mel_spectrogram  # noqa: E402
+
+P = dict(n_fft=1024, num_mels=80, sampling_rate=16000, hop_size=256, win_size=1024, fmin=0, fmax=None)
+h = HParams()
+gen = fixtures.construct(Generator, h).to("cuda:0").train()
+x, s, n = (a.cuda() for a in fixtures.make_inputs(h, 16, 200, 1))
+with torch.no_grad():
+    for _ in range(2):
+        y = gen(x, s, n)
+        m = mel_spectrogram(y.squeeze(1), **P)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    y = gen(x, s, n)
+    m = mel_spectrogram(y.squeeze(1), **P)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+print("ok", tuple(y.shape), tuple(m.shape))

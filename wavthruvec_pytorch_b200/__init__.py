@@ -3,6 +3,7 @@ vec2wav.models.Generator).  See DESIGN.md / INTEGRATION.md at the repository roo
 from .hparams import FRAMES_PER_SECOND, SAMPLES_PER_FRAME, HParams
 from .models import Generator, ResBlock1, ResBlock2
 from .modules import ConditionalBatchNorm1d
+from .mel import mel_spectrogram
 
 __all__ = ["Generator", "ResBlock1", "ResBlock2", "ConditionalBatchNorm1d", "HParams",
-           "FRAMES_PER_SECOND", "SAMPLES_PER_FRAME"]
+           "FRAMES_PER_SECOND", "SAMPLES_PER_FRAME", "mel_spectrogram"]
