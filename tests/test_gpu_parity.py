@@ -384,3 +384,41 @@ def test_train_mode_full_size_against_delegate(precision):
             print(f"train B={B} T={T}: {mine.train_precision} SNR {snr:.1f} dB")
             assert snr >= BF16_MIN_SNR_DB
             _check_buffers(mine.state_dict(), small, 2e-2, 1e-5)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 2), (1, 7), (5, 1)])
+def test_shortest_inputs_against_delegate(B, T):
+    """Edge sizes: one or two frames per utterance (every tile is mostly zero padding, the TMA boxes
+    are larger than the tensors), eval and train() modes, against the PyTorch delegate on the same GPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, B, T, 40 + T))
+    with torch.no_grad():
+        ref = gen._forward_autograd(x, s, n).cpu().numpy()
+        for precision, check in (("fp32", None), ("bf16", BF16_MIN_SNR_DB), ("fp16", BF16_MIN_SNR_DB)):
+            gen.precision = precision
+            y = gen(x, s, n).cpu().numpy()
+            assert y.shape == (B, 1, 320 * T)
+            if check is None:
+                assert np.abs(y - ref).max() <= FP32_MAX_ABS
+            else:
+                snr = fixtures.snr_db(ref, y)
+                print(f"B={B} T={T} {precision}: SNR {snr:.1f} dB")
+                assert snr >= check
+    twin = dropin_in_state(g, cache=False).to("cuda:0").train()
+    gen.train()
+    gen.precision = "fp32"
+    with torch.no_grad():
+        y = gen(x, s, n).cpu().numpy()
+        want = twin._forward_autograd(x, s, n).cpu().numpy()
+    assert np.abs(y - want).max() <= FP32_MAX_ABS
+
+
+def test_empty_batch_returns_empty_waveform():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    with torch.no_grad():
+        y = gen(torch.zeros(0, 768, 10, device="cuda"), torch.zeros(0, 192, device="cuda"), torch.zeros(0, 192, device="cuda"))
+    assert tuple(y.shape) == (0, 1, 3200) and y.dtype == torch.float32

@@ -8,7 +8,6 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from oracle import fixtures  # noqa: E402  (seeded construction helpers only)
 from wavthruvec_pytorch_b200 import Generator, HParams  # noqa: E402
 
 
@@ -28,8 +27,10 @@ def timed(fn, reps):
 def main():
     B, T = 16, 200
     h = HParams()
-    gen = fixtures.construct(Generator, h).to("cuda:0").train()
-    x, s, n = (a.cuda() for a in fixtures.make_inputs(h, B, T, 1))
+    torch.manual_seed(1234)
+    gen = Generator(h).to("cuda:0").train()
+    x, s, n = (torch.randn(B, h.num_wv_feat, T, device="cuda"), torch.randn(B, h.spk_dim, device="cuda"),
+               torch.randn(B, h.noise_dim, device="cuda"))
     out = {"config": f"cfg2 B={B} T={T} ResBlock2 train() under no_grad"}
     with torch.no_grad():
         for prec in ("auto", "bf16", "fp32"):

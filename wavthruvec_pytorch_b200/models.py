@@ -205,6 +205,9 @@ class Generator(nn.Module):
             raise TypeError("spk_emb is required (vec2wav/models.py:120 concatenates it)")
         if noise is None:
             noise = torch.randn(x.shape[0], self.h.noise_dim, device=x.device, dtype=x.dtype)
+        if x.dim() == 3 and x.shape[0] == 0 and not torch.is_grad_enabled():
+            # empty batch: nothing to launch (the reference's convolutions return an empty tensor too)
+            return x.new_zeros((0, 1, x.shape[2] * self.engine().total_upsample()), dtype=torch.float32)
         if self.training and not torch.is_grad_enabled() and x.is_cuda and not os.environ.get("V2W_NO_NATIVE_TRAIN"):
             # train() under no_grad (validation / warm-up loops): batch-statistic BN and the power
             # iteration run on the device too
