@@ -276,6 +276,14 @@ int32_t v2w_model_pack(const struct v2w_model* m, const v2w_params* params, void
  * an FP32 plan accepts either). */
 int32_t v2w_model_pack_half(const struct v2w_model* m, const v2w_params* params, void* packed_host,
                             int32_t half_format);
+/* Re-fold ONLY the conditioning section (fcs, spectral-norm sigma, BN running statistics) -- what changes
+ * when train()-mode forwards moved u, v and the running statistics but no convolution.  The section is
+ * the byte range [offset, offset + bytes) of the packed format (v2w_model_cond_region); `region_host`
+ * receives exactly those bytes, to be copied over the same range of every device copy of the packed
+ * buffer (plans bound to it stay valid). */
+int32_t v2w_model_cond_region(const struct v2w_model* m, int64_t* offset, int64_t* bytes);
+int32_t v2w_model_pack_cond(const struct v2w_model* m, const v2w_cond_params* cond, int32_t num_stages,
+                            void* region_host);
 /* Algorithmic FLOPs (2*MAC, zero polyphase blocks excluded) per input frame. */
 int64_t v2w_model_flops_per_frame(const struct v2w_model* m);
 

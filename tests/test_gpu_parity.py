@@ -422,3 +422,21 @@ def test_empty_batch_returns_empty_waveform():
     with torch.no_grad():
         y = gen(torch.zeros(0, 768, 10, device="cuda"), torch.zeros(0, 192, device="cuda"), torch.zeros(0, 192, device="cuda"))
     assert tuple(y.shape) == (0, 1, 3200) and y.dtype == torch.float32
+
+
+def test_conditioning_edit_refolds_in_place():
+    """A change of the conditioning buffers alone (no convolution touched) goes through the in-place
+    conditioning re-pack: plans survive, the output follows the new statistics."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    gen.precision = "fp32"
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    with torch.no_grad():
+        gen(x, s, n)
+        plans_before = dict(gen.engine()._plans)
+        gen.cbns[1].batch_nrom.running_mean.add_(0.05)
+        gen.cbns[3].layer.weight_u.mul_(0.8)
+        y = gen(x, s, n)
+        ref = gen._forward_autograd(x, s, n)
+    assert gen.engine()._plans == plans_before and plans_before      # same plan objects: no full re-fold
+    assert np.abs((y - ref).cpu().numpy()).max() <= FP32_MAX_ABS

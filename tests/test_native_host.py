@@ -333,3 +333,34 @@ def test_autograd_delegate_matches_reference_output():
         y = gen(t(g.x), t(g.spk), t(g.noise))
     assert y.requires_grad
     np.testing.assert_allclose(y.detach().numpy(), g.y, rtol=0, atol=2e-6)
+
+
+def test_cond_only_repack_equals_full_pack():
+    """v2w_model_pack_cond writes exactly the conditioning byte range of v2w_model_pack (what the engine
+    refreshes in place after train()-mode forwards moved u / v / the running statistics)."""
+    import ctypes as C
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False)
+    eng = gen.engine()
+    full = eng.pack_host().numpy().copy()
+    with torch.no_grad():      # move every conditioning tensor a little
+        for cbn in gen.cbns:
+            cbn.batch_nrom.running_mean.add_(0.05)
+            cbn.batch_nrom.running_var.mul_(1.3)
+            cbn.layer.weight_u.mul_(0.9)
+    full2 = eng.pack_host().numpy()
+    nstage = len(gen.cbns)
+    ts = eng._state_tensors()[3 * len(gen.conv_modules()):]
+    host = [t.detach().float().contiguous() for t in ts]
+    cond = (native.CondParams * nstage)()
+    for i in range(nstage):
+        for (name, _), tt in zip(native.CondParams._fields_, host[8 * i: 8 * i + 8]):
+            setattr(cond[i], name, tt.data_ptr())
+    off, nb = C.c_int64(0), C.c_int64(0)
+    native.check(eng._lib.v2w_model_cond_region(eng._model, C.byref(off), C.byref(nb)))
+    region = torch.empty(nb.value, dtype=torch.uint8)
+    native.check(eng._lib.v2w_model_pack_cond(eng._model, cond, nstage, region.data_ptr()))
+    lo, hi = off.value, off.value + nb.value
+    assert np.array_equal(full2[lo:hi], region.numpy())
+    assert not np.array_equal(full[lo:hi], full2[lo:hi])
+    assert np.array_equal(full[:lo], full2[:lo]) and np.array_equal(full[hi:], full2[hi:])   # nothing else depends on them

@@ -617,6 +617,75 @@ int32_t v2w_model_get_fused(const v2w_model* m, int32_t i, v2w_fused_desc* out) 
 }
 
 int32_t v2w_model_num_convs(const v2w_model* m) { return m ? m->num_convs : 0; }
+}  // extern "C"
+
+// Conditioning section of one stage: fcs copied, spectral norm folded with the STORED u, v (eval()
+// semantics of modules.py:16: sigma = u . (W v), no power iteration), BN running statistics as
+// mean / rstd.  `base` + the layout's offsets is where the section goes.
+static int pack_cond_stage(uint8_t* base, const v2w::CondLayout& cl, const v2w_cond_params& q, int stage) {
+  using namespace v2w;
+  if (!q.fc_weight || !q.fc_bias || !q.sn_weight_orig || !q.sn_u || !q.sn_v || !q.sn_bias ||
+      !q.bn_mean || !q.bn_var) {
+    set_error("v2w_model_pack: cond stage %d has a null pointer", stage);
+    return V2W_ERR_INVALID;
+  }
+  std::memcpy(base + cl.fcw, q.fc_weight, (size_t)kZ * cl.D * 4);
+  std::memcpy(base + cl.fcb, q.fc_bias, (size_t)kZ * 4);
+  double sigma = 0.0;
+  for (int r = 0; r < 2 * cl.C; ++r) {
+    double wv = 0.0;
+    for (int c2 = 0; c2 < kZ; ++c2) wv += (double)q.sn_weight_orig[(size_t)r * kZ + c2] * q.sn_v[c2];
+    sigma += (double)q.sn_u[r] * wv;
+  }
+  const float fsigma = (float)sigma;
+  float* snw = reinterpret_cast<float*>(base + cl.snw);
+  for (int e = 0; e < 2 * cl.C * kZ; ++e) snw[e] = q.sn_weight_orig[e] / fsigma;
+  std::memcpy(base + cl.snb, q.sn_bias, (size_t)2 * cl.C * 4);
+  float* rstd = reinterpret_cast<float*>(base + cl.rstd);
+  float* mean = reinterpret_cast<float*>(base + cl.mean);
+  for (int ch = 0; ch < cl.C; ++ch) {
+    rstd[ch] = 1.0f / std::sqrt(q.bn_var[ch] + kBnEps);
+    mean[ch] = q.bn_mean[ch];
+  }
+  return V2W_OK;
+}
+
+extern "C" {
+
+int32_t v2w_model_cond_region(const v2w_model* m, int64_t* offset, int64_t* bytes) {
+  if (!m || !offset || !bytes || m->cond.empty()) {
+    v2w::set_error("v2w_model_cond_region: null argument");
+    return V2W_ERR_INVALID;
+  }
+  const v2w::CondLayout& last = m->cond.back();
+  *offset = m->cond.front().fcw;
+  *bytes = v2w::align_up(last.mean + (int64_t)last.C * 4, 256) - *offset;
+  return V2W_OK;
+}
+
+int32_t v2w_model_pack_cond(const v2w_model* m, const v2w_cond_params* cond, int32_t num_stages,
+                            void* region_host) {
+  if (!m || !cond || !region_host || num_stages != (int32_t)m->cond.size()) {
+    v2w::set_error("v2w_model_pack_cond: bad argument (stages %d, model %d)", num_stages,
+                   m ? (int)m->cond.size() : -1);
+    return V2W_ERR_INVALID;
+  }
+  int64_t off = 0, bytes = 0;
+  int rc = v2w_model_cond_region(m, &off, &bytes);
+  if (rc) return rc;
+  std::memset(region_host, 0, (size_t)bytes);
+  uint8_t* base = static_cast<uint8_t*>(region_host) - off;   // the layouts hold whole-buffer offsets
+  for (size_t i = 0; i < m->cond.size(); ++i) {
+    rc = pack_cond_stage(base, m->cond[i], cond[i], (int)i);
+    if (rc) return rc;
+  }
+  return V2W_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 int64_t v2w_model_packed_bytes(const v2w_model* m) { return m ? m->packed_bytes : 0; }
 int64_t v2w_model_flops_per_frame(const v2w_model* m) { return m ? m->flops_per_frame : 0; }
 
@@ -692,32 +761,8 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
     }
   }
   for (size_t i = 0; i < m->cond.size(); ++i) {
-    const CondLayout& cl = m->cond[i];
-    const v2w_cond_params& q = P->cond[i];
-    if (!q.fc_weight || !q.fc_bias || !q.sn_weight_orig || !q.sn_u || !q.sn_v || !q.sn_bias ||
-        !q.bn_mean || !q.bn_var) {
-      set_error("v2w_model_pack: cond stage %d has a null pointer", (int)i);
-      return V2W_ERR_INVALID;
-    }
-    std::memcpy(base + cl.fcw, q.fc_weight, (size_t)kZ * cl.D * 4);
-    std::memcpy(base + cl.fcb, q.fc_bias, (size_t)kZ * 4);
-    // spectral_norm in eval(): sigma = u . (W v) with the stored u, v (no power iteration)
-    double sigma = 0.0;
-    for (int r = 0; r < 2 * cl.C; ++r) {
-      double wv = 0.0;
-      for (int c2 = 0; c2 < kZ; ++c2) wv += (double)q.sn_weight_orig[(size_t)r * kZ + c2] * q.sn_v[c2];
-      sigma += (double)q.sn_u[r] * wv;
-    }
-    const float fsigma = (float)sigma;
-    float* snw = reinterpret_cast<float*>(base + cl.snw);
-    for (int e = 0; e < 2 * cl.C * kZ; ++e) snw[e] = q.sn_weight_orig[e] / fsigma;
-    std::memcpy(base + cl.snb, q.sn_bias, (size_t)2 * cl.C * 4);
-    float* rstd = reinterpret_cast<float*>(base + cl.rstd);
-    float* mean = reinterpret_cast<float*>(base + cl.mean);
-    for (int ch = 0; ch < cl.C; ++ch) {
-      rstd[ch] = 1.0f / std::sqrt(q.bn_var[ch] + kBnEps);
-      mean[ch] = q.bn_mean[ch];
-    }
+    int rc = pack_cond_stage(base, m->cond[i], P->cond[i], (int)i);
+    if (rc) return rc;
   }
   // fused stages: tap matrices in issue order, from the folded fp32 weights packed above
   std::vector<const v2w_fused_desc*> all_fused;

@@ -133,10 +133,32 @@ class NativeEngine:
         n = 3 * len(self._convs)
         conv_sig, cond_sig = sig[:n], sig[n:]
         old = self._packed_sig
-        if old is None or old[0] != conv_sig or (not train and old[1] != cond_sig):
+        if old is None or old[0] != conv_sig or not self._packed:
             self._packed.clear()
             self._drop_plans()   # plans hold pointers into the packed buffer
             self._packed_sig = (conv_sig, cond_sig)
+        elif not train and old[1] != cond_sig:
+            # only u / v / running statistics / fcs moved (train()-mode forwards, or a caller editing the
+            # buffers): re-fold the conditioning section in place, plans and convolutions stay
+            self._repack_cond()
+            self._packed_sig = (conv_sig, cond_sig)
+
+    def _repack_cond(self) -> None:
+        nstage = self._cfg.num_upsamples
+        ts = self._tensors[3 * len(self._convs):]
+        host = [t.detach().to("cpu", torch.float32).contiguous() for t in ts]
+        cond = (native.CondParams * nstage)()
+        for i in range(nstage):
+            for (name, _), t in zip(native.CondParams._fields_, host[8 * i: 8 * i + 8]):
+                setattr(cond[i], name, _ptr(t))
+        off, nbytes = C.c_int64(0), C.c_int64(0)
+        native.check(self._lib.v2w_model_cond_region(self._model, C.byref(off), C.byref(nbytes)))
+        region = torch.empty(nbytes.value, dtype=torch.uint8)
+        native.check(self._lib.v2w_model_pack_cond(self._model, cond, nstage, region.data_ptr()))
+        for (device, _fmt), buf in self._packed.items():
+            with torch.cuda.device(device):
+                # stream-ordered behind every forward already enqueued on the current stream
+                buf[off.value: off.value + nbytes.value].copy_(region)
 
     def _packed_on(self, device: torch.device, half_format: int) -> torch.Tensor:
         buf = self._packed.get((device, half_format))

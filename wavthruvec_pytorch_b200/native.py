@@ -187,6 +187,8 @@ _SIGNATURES = [
     ("v2w_model_packed_bytes", C.c_int64, [C.c_void_p]),
     ("v2w_model_pack", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
     ("v2w_model_pack_half", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32]),
+    ("v2w_model_cond_region", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("v2w_model_pack_cond", C.c_int32, [C.c_void_p, C.POINTER(CondParams), C.c_int32, C.c_void_p]),
     ("v2w_model_flops_per_frame", C.c_int64, [C.c_void_p]),
     ("v2w_plan_create", C.c_int32,
      [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
