@@ -408,6 +408,19 @@ int32_t v2w_mel_forward(struct v2w_mel* m, const float* wav_dev, float* out_dev,
 int32_t v2w_npy_shape(const char* path, int64_t* rows, int64_t* cols);
 int32_t v2w_npy_read_f32(const char* path, float* dst, int64_t max_rows, int64_t cols, int64_t* rows);
 
+/* Batch forms for the file pipeline: one call per batch of utterances, `threads` workers inside the library,
+ * no per-file work on the host language's side.  v2w_npy_shapes reads n headers; v2w_npy_read_batch reads
+ * n payloads into ONE row buffer, file i at dst + row_off[i] * cols (the caller's prefix sums of the
+ * shapes: the packed x_rows layout of v2w_forward_ragged), failing if a file no longer has
+ * rows_expected[i] frames; v2w_wav_write_batch writes n 16-bit mono RIFF/WAVE files from one packed PCM
+ * buffer (utterance i = pcm[sample_off[i] .. + samples[i])).  On failure the first failing file's
+ * message is the error text.  Host only. */
+int32_t v2w_npy_shapes(const char* const* paths, int32_t n, int64_t* rows, int64_t* cols, int32_t threads);
+int32_t v2w_npy_read_batch(const char* const* paths, int32_t n, float* dst, const int64_t* row_off,
+                           const int64_t* rows_expected, int64_t cols, int32_t threads);
+int32_t v2w_wav_write_batch(const char* const* paths, int32_t n, const int16_t* pcm, const int64_t* sample_off,
+                            const int64_t* samples, int32_t sampling_rate, int32_t threads);
+
 /* Pipelined generation from HOST buffers (throughput API): up to two steps in flight on three
  * library-owned streams -- H2D of step i+1 and D2H of step i-1 overlap the kernels of step i.
  * Staging buffers are owned by the pipeline (cudaMalloc).  Every submitted step still copies its

@@ -106,3 +106,49 @@ def test_files_to_wav_matches_generate_varlen(tmp_path):
     assert stats2.batches > 1 and stats2.utterances == 7
     for it, n in zip(items, lengths):
         assert _read_wav(out2 / f"{it.name}.wav").size == n * 320
+
+
+def test_batch_io(tmp_path):
+    """The per-batch library calls of the file pipeline: headers, payloads into one packed row buffer,
+    WAV files out of one packed PCM buffer -- against numpy / scipy readers."""
+    import ctypes as C
+    from scipy.io import wavfile
+    from wavthruvec_pytorch_b200 import native
+    rng = np.random.default_rng(3)
+    lengths = [5, 9, 1, 33, 2]
+    paths, arrs = [], []
+    for i, n in enumerate(lengths):
+        a = rng.standard_normal((1, n, 768)).astype(np.float32)
+        np.save(tmp_path / f"u{i}.npy", a)
+        paths.append(str(tmp_path / f"u{i}.npy"))
+        arrs.append(a[0])
+    rows, cols = files.feature_shapes(paths, threads=3)
+    assert rows.tolist() == lengths and set(cols.tolist()) == {768}
+    lib = native.load()
+    i64p = C.POINTER(C.c_int64)
+    dst = np.full((sum(lengths) + 2, 768), 7.0, dtype=np.float32)
+    off = np.zeros(len(lengths), dtype=np.int64)
+    np.cumsum(rows[:-1], out=off[1:])
+    native.check(lib.v2w_npy_read_batch(files._c_paths(paths), len(paths), dst.ctypes.data, off.ctypes.data_as(i64p),
+                                        rows.ctypes.data_as(i64p), 768, 4))
+    assert np.array_equal(dst[:-2], np.concatenate(arrs)) and float(dst[-1, 0]) == 7.0
+    wrong = rows.copy()
+    wrong[1] += 1                                             # layout computed from a stale header
+    with pytest.raises(native.V2WError, match="expected"):
+        native.check(lib.v2w_npy_read_batch(files._c_paths(paths), len(paths), dst.ctypes.data, off.ctypes.data_as(i64p),
+                                            wrong.ctypes.data_as(i64p), 768, 2))
+    with pytest.raises(ValueError, match="cannot open"):
+        files.feature_shapes(paths + [str(tmp_path / "missing.npy")], threads=2)
+    assert files.feature_shapes([], threads=2)[0].size == 0
+    pcm = rng.integers(-32768, 32767, size=1000).astype(np.int16)
+    wavs = [str(tmp_path / f"w{i}.wav") for i in range(3)]
+    so, sn = np.array([0, 100, 400], dtype=np.int64), np.array([100, 300, 600], dtype=np.int64)
+    native.check(lib.v2w_wav_write_batch(files._c_paths(wavs), 3, pcm.ctypes.data, so.ctypes.data_as(i64p),
+                                         sn.ctypes.data_as(i64p), 16000, 2))
+    for p, o, n in zip(wavs, so, sn):
+        sr, w = wavfile.read(p)
+        assert sr == 16000 and w.dtype == np.int16 and np.array_equal(w, pcm[o:o + n])
+        assert np.array_equal(_read_wav(p), pcm[o:o + n])
+    with pytest.raises(native.V2WError, match="cannot create"):
+        native.check(lib.v2w_wav_write_batch(files._c_paths([str(tmp_path / "no_dir" / "x.wav")]), 1, pcm.ctypes.data,
+                                             so.ctypes.data_as(i64p), sn.ctypes.data_as(i64p), 16000, 1))

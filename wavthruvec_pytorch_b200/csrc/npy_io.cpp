@@ -2,11 +2,16 @@
 // float32, C order, shape [T, C] or [1, T, C] (prepare_data.py:87 saves last_hidden_state).  Used by
 // wavthruvec_pytorch_b200/files.py from reader threads: a ctypes call releases the GIL, so the file
 // reads of a batch really run in parallel and land directly in the caller's (pinned) buffer.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "common.h"
 
@@ -145,6 +150,109 @@ int32_t v2w_npy_read_f32(const char* path, float* dst, int64_t max_rows, int64_t
   if (rc) return rc;
   *rows = info.rows;
   return V2W_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Batch forms: one call per BATCH of utterances instead of one per file, worker threads inside the
+// library.  The Python side of files.py makes three ctypes calls per batch (no per-file Python work,
+// no intermediate copy: every payload lands at its final offset of the pinned row arena).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// Runs fn(i) for i in [0, n) on `threads` workers; returns the first failing item's code, with its
+// error text re-raised on the calling thread (set_error is thread-local).
+template <typename Fn>
+int for_each_parallel(int32_t n, int32_t threads, Fn fn) {
+  std::atomic<int32_t> next(0);
+  std::atomic<int> first_rc(0);
+  std::mutex mu;
+  std::string first_msg;
+  auto work = [&]() {
+    for (;;) {
+      const int32_t i = next.fetch_add(1);
+      if (i >= n || first_rc.load() != 0) return;
+      const int rc = fn(i);
+      if (rc) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (first_rc.load() == 0) {
+          first_rc.store(rc);
+          first_msg = v2w_last_error();
+        }
+      }
+    }
+  };
+  const int32_t nt = std::max(1, std::min(threads, n));
+  std::vector<std::thread> pool;
+  for (int32_t t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  if (first_rc.load()) set_error("%s", first_msg.c_str());
+  return first_rc.load();
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t v2w_npy_shapes(const char* const* paths, int32_t n, int64_t* rows, int64_t* cols, int32_t threads) {
+  if (!paths || !rows || !cols || n < 0) {
+    set_error("v2w_npy_shapes: bad argument");
+    return V2W_ERR_INVALID;
+  }
+  return for_each_parallel(n, threads, [&](int32_t i) { return (int)v2w_npy_shape(paths[i], rows + i, cols + i); });
+}
+
+int32_t v2w_npy_read_batch(const char* const* paths, int32_t n, float* dst, const int64_t* row_off,
+                           const int64_t* rows_expected, int64_t cols, int32_t threads) {
+  if (!paths || !dst || !row_off || !rows_expected || n < 0 || cols < 1) {
+    set_error("v2w_npy_read_batch: bad argument");
+    return V2W_ERR_INVALID;
+  }
+  return for_each_parallel(n, threads, [&](int32_t i) {
+    int64_t got = 0;
+    int rc = v2w_npy_read_f32(paths[i], dst + row_off[i] * cols, rows_expected[i], cols, &got);
+    if (!rc && got != rows_expected[i]) {
+      set_error("%s: %lld frames, the batch layout expected %lld (file changed since its header was read)",
+                paths[i], (long long)got, (long long)rows_expected[i]);
+      rc = V2W_ERR_INVALID;
+    }
+    return rc;
+  });
+}
+
+int32_t v2w_wav_write_batch(const char* const* paths, int32_t n, const int16_t* pcm, const int64_t* sample_off,
+                            const int64_t* samples, int32_t sampling_rate, int32_t threads) {
+  if (!paths || !pcm || !sample_off || !samples || n < 0 || sampling_rate < 1) {
+    set_error("v2w_wav_write_batch: bad argument");
+    return V2W_ERR_INVALID;
+  }
+  return for_each_parallel(n, threads, [&](int32_t i) {
+    const uint64_t bytes = (uint64_t)samples[i] * 2;
+    if (samples[i] < 0 || bytes > 0xffffffffull - 36) {
+      set_error("%s: %lld samples do not fit a RIFF file", paths[i], (long long)samples[i]);
+      return (int)V2W_ERR_INVALID;
+    }
+    FILE* f = fopen(paths[i], "wb");
+    if (!f) {
+      set_error("%s: cannot create", paths[i]);
+      return (int)V2W_ERR_INVALID;
+    }
+    // 44-byte canonical header: PCM, mono, 16 bit (what scipy.io.wavfile.write emits for int16)
+    unsigned char h[44];
+    auto u32 = [&](int at, uint32_t v) { h[at] = v & 255; h[at + 1] = (v >> 8) & 255; h[at + 2] = (v >> 16) & 255; h[at + 3] = (v >> 24) & 255; };
+    auto u16 = [&](int at, uint32_t v) { h[at] = v & 255; h[at + 1] = (v >> 8) & 255; };
+    memcpy(h, "RIFF", 4); u32(4, (uint32_t)(36 + bytes)); memcpy(h + 8, "WAVEfmt ", 8);
+    u32(16, 16); u16(20, 1); u16(22, 1); u32(24, (uint32_t)sampling_rate); u32(28, (uint32_t)sampling_rate * 2);
+    u16(32, 2); u16(34, 16); memcpy(h + 36, "data", 4); u32(40, (uint32_t)bytes);
+    const bool ok = fwrite(h, 1, 44, f) == 44 && fwrite(pcm + sample_off[i], 2, (size_t)samples[i], f) == (size_t)samples[i];
+    if (fclose(f) != 0 || !ok) {
+      set_error("%s: short write", paths[i]);
+      return (int)V2W_ERR_INVALID;
+    }
+    return (int)V2W_OK;
+  });
 }
 
 }  // extern "C"

@@ -8,15 +8,17 @@ side of the generator, in the reference's own on-disk formats).
 The reference consumes these through VocoderDataset / collate_fn_tensor (vec2wav/dataset.py:181-228)
 and draws one noise vector per utterance for every batch (vec2wav/train.py:165-166, 259-260; here with a
 seeded generator on the device).  `synthesize_files` does the same for
-generation, as a three-stage host pipeline around the native variable-length path:
+generation, as a three-stage host pipeline around the native variable-length path, with three library
+calls per BATCH and no per-file work in Python:
 
-    reader threads:  np.load, speaker embeddings cached per speaker
-    main thread:     packs a batch (frame budget) into a pinned arena = the x_rows layout of
-                     v2w_forward_ragged, ONE H2D copy, device noise, forward_ragged(pcm16), D2H
-    writer thread:   16-bit mono RIFF/WAVE files
+    prefetch thread: v2w_npy_read_batch -- worker threads inside libv2w read every payload of batch k+1
+                     straight to its final offset of a pinned arena (= the x_rows layout of
+                     v2w_forward_ragged); speaker embeddings cached per speaker
+    main thread:     ONE H2D copy, device noise, forward_ragged(pcm16), ONE D2H copy
+    writer thread:   v2w_wav_write_batch -- 16-bit mono RIFF/WAVE files of batch k-1
 
-Threads overlap because np.load / file writes / CUDA calls release the GIL.  Host plumbing only; the
-arithmetic is libv2w's.
+The ctypes calls release the GIL, so the three stages overlap.  Host plumbing only; the arithmetic is
+libv2w's.
 """
 from __future__ import annotations
 
@@ -124,46 +126,124 @@ class Stats:
         return self.audio_s / self.wall_s if self.wall_s > 0 else 0.0
 
 
+def _c_paths(paths: Sequence[str]):
+    import ctypes as C
+    return (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+
+
+def feature_shapes(paths: Sequence[str], threads: int = 4) -> Tuple[np.ndarray, np.ndarray]:
+    """(frames, channels) of every feature file, read by libv2w worker threads in ONE call
+    (v2w_npy_shapes)."""
+    import ctypes as C
+    from . import native
+    n = len(paths)
+    rows, cols = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+    if n:
+        try:
+            native.check(native.load().v2w_npy_shapes(
+                _c_paths(paths), n, rows.ctypes.data_as(C.POINTER(C.c_int64)),
+                cols.ctypes.data_as(C.POINTER(C.c_int64)), int(threads)))
+        except RuntimeError as e:
+            raise ValueError(str(e)) from None
+    return rows, cols
+
+
 def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str, out_dir: str,
-                     max_batch_frames: int = 16000, max_batch_utts: int = 128, readers: int = 2,
+                     max_batch_frames: int = 16000, max_batch_utts: int = 128, readers: int = 4,
                      seed: int = 1234, sampling_rate: int = 16000, max_utt_frames: int = 2000) -> Stats:
     """Generate <out_dir>/<speaker>/<utt>.wav for every item.  `gen`: drop-in Generator in eval()
     mode on a CUDA device.  A batch closes at `max_batch_frames` feature frames or
-    `max_batch_utts` utterances, whichever comes first (items keep their order)."""
+    `max_batch_utts` utterances, whichever comes first (items keep their order).
+
+    Per BATCH the host does three library calls and no per-file work: v2w_npy_read_batch (`readers`
+    worker threads, every payload lands at its final offset of a pinned row arena = the x_rows layout
+    of v2w_forward_ragged), the ragged forward with PCM16 output, v2w_wav_write_batch.  A prefetch
+    thread fills the arena of batch k+1 and a writer thread emits batch k-1 while batch k is on the GPU."""
+    import ctypes as C
+    from . import native
     if gen.training:
         raise RuntimeError("synthesize_files is the eval()-mode generation path")
     dev = next(gen.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("the native Vec2Wav generation path runs on sm_100 GPUs only and has no CPU fallback")
+    lib = native.load()
     h = gen.h
+    stats = Stats()
+    t0 = time.perf_counter()
+    n_items = len(items)
+    if n_items == 0:
+        return stats
+    readers = max(1, int(readers))
+    feat_paths = [os.path.join(feat_dir, it.name + ".npy") for it in items]
+    wav_paths = [os.path.join(out_dir, it.name + ".wav") for it in items]
+    rows, cols = feature_shapes(feat_paths, readers)
+    max_utt_frames = min(max_utt_frames, max_batch_frames)
+    for i in range(n_items):
+        if cols[i] != h.num_wv_feat:
+            raise ValueError(f"{feat_paths[i]}: {cols[i]} feature channels, expected {h.num_wv_feat}")
+        if rows[i] > max_utt_frames:
+            raise ValueError(f"{feat_paths[i]}: {rows[i]} frames do not fit the {max_utt_frames}-frame limit")
+    # batches [lo, hi) in item order
+    batches: List[Tuple[int, int]] = []
+    lo, frames = 0, 0
+    for i in range(n_items):
+        if i > lo and (frames + rows[i] > max_batch_frames or i - lo >= max_batch_utts):
+            batches.append((lo, i))
+            lo, frames = i, 0
+        frames += int(rows[i])
+    batches.append((lo, n_items))
+    for d in sorted({os.path.dirname(p) for p in wav_paths}):
+        os.makedirs(d, exist_ok=True)
+
     spk_cache = SpeakerCache(spk_emb_dir, h.spk_dim)
     rng = torch.Generator(device=dev)
     rng.manual_seed(seed)
-    to_write: "queue.Queue" = queue.Queue(maxsize=8)
+    eng = gen.engine()
+    up = eng.total_upsample()
     errors: List[BaseException] = []
-    made_dirs = set()
-    # reader threads take item indices in order; results are re-ordered by index in the main thread
-    next_index = [0]
-    lock = threading.Lock()
+    # Two pinned arenas [frames, C] that alternate between batches.  Plan shapes are quantised
+    # (utterance count to a multiple of 8 by appending 1-frame dummies whose output is dropped, frames
+    # to a multiple of 32) so that successive batches reuse plans; a longer plan only means the longest
+    # utterance is padded like the shorter ones, which is what the reference does to it in any batch
+    # that holds a longer one.
+    arena_rows = max_batch_frames + max_batch_utts + 8
+    arenas = [torch.empty(arena_rows, h.num_wv_feat, dtype=torch.float32).pin_memory() for _ in range(2)]
+    arena_tokens = [queue.Queue(), queue.Queue()]     # event of the H2D copy that last read the arena
+    for q in arena_tokens:
+        q.put(None)
+    ready: "queue.Queue" = queue.Queue(maxsize=1)
+    to_write: "queue.Queue" = queue.Queue(maxsize=4)
+    pcm_pool: "queue.Queue" = queue.Queue()           # pinned PCM buffers cycle main -> writer -> main
+    for _ in range(3):
+        pcm_pool.put(torch.empty(arena_rows * up, dtype=torch.int16).pin_memory())
+    i64p = C.POINTER(C.c_int64)
 
-    def reader():
+    def prefetch():
         try:
-            while not errors:
-                # buffer first, index second: the thread that owns the next index in line always
-                # already owns a buffer, so out-of-order arrivals cannot starve it
-                buf = scratch.get()                                  # pre-faulted pinned buffer, recycled
-                with lock:
-                    i = next_index[0]
-                    next_index[0] += 1
-                if i >= len(items):
-                    scratch.put(buf)
+            for k, (lo, hi) in enumerate(batches):
+                a = k & 1
+                ev = arena_tokens[a].get()
+                if ev is not None:
+                    ev.synchronize()                  # the H2D copy of batch k-2 has left this arena
+                if errors:
                     return
-                it = items[i]
-                feats = load_features(os.path.join(feat_dir, it.name + ".npy"), h.num_wv_feat, out=buf)
-                loaded.put((i, feats, spk_cache.get(it.speaker), buf))   # file -> host buffer without the GIL
+                r = np.ascontiguousarray(rows[lo:hi])
+                off = np.zeros(hi - lo, dtype=np.int64)
+                np.cumsum(r[:-1], out=off[1:])
+                try:
+                    native.check(lib.v2w_npy_read_batch(
+                        _c_paths(feat_paths[lo:hi]), hi - lo, arenas[a].data_ptr(), off.ctypes.data_as(i64p),
+                        r.ctypes.data_as(i64p), h.num_wv_feat, readers))
+                except RuntimeError as e:
+                    raise ValueError(str(e)) from None
+                real = hi - lo
+                spk = torch.zeros(real + (-real) % 8, h.spk_dim)
+                for j in range(real):
+                    spk[j] = spk_cache.get(items[lo + j].speaker)
+                ready.put((k, spk))
         except BaseException as e:   # surfaced in the main thread
             errors.append(e)
-            loaded.put((-1, None, None, None))
+            ready.put(None)
 
     def writer():
         try:
@@ -171,121 +251,61 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
                 job = to_write.get()
                 if job is None:
                     return
-                done_event, pcm_host, names, lengths, pcm_buf = job
+                done_event, pcm_buf, lo, hi = job
                 done_event.synchronize()
-                off = 0
-                for name, n in zip(names, lengths):
-                    path = os.path.join(out_dir, name + ".wav")
-                    d = os.path.dirname(path)
-                    if d not in made_dirs:
-                        os.makedirs(d, exist_ok=True)
-                        made_dirs.add(d)
-                    varlen.write_wav(path, pcm_host[off:off + n], sampling_rate)
-                    off += n
-                pcm_pool.put(pcm_buf)
+                samples = np.ascontiguousarray(rows[lo:hi]) * up
+                off = np.zeros(hi - lo, dtype=np.int64)
+                np.cumsum(samples[:-1], out=off[1:])
+                try:
+                    native.check(lib.v2w_wav_write_batch(
+                        _c_paths(wav_paths[lo:hi]), hi - lo, pcm_buf.data_ptr(), off.ctypes.data_as(i64p),
+                        samples.ctypes.data_as(i64p), int(sampling_rate), max(2, readers // 2)))
+                finally:
+                    pcm_pool.put(pcm_buf)
         except BaseException as e:
             errors.append(e)
 
-    # Reader scratch: pinned [max_utt_frames, C] buffers handed reader -> main thread -> reader.  No
-    # per-file allocation (a fresh 1 MB tensor per file page-faults and serialises the readers).
-    max_utt_frames = min(max_utt_frames, max_batch_frames)
-    n_scratch = 4 * max(1, readers) + 2
-    scratch: "queue.Queue" = queue.Queue()
-    for _ in range(n_scratch):
-        scratch.put(torch.empty(max_utt_frames, h.num_wv_feat, dtype=torch.float32).pin_memory())
-    loaded = queue.Queue(maxsize=n_scratch)
-    threads = [threading.Thread(target=reader, daemon=True) for _ in range(max(1, readers))]
+    pt = threading.Thread(target=prefetch, daemon=True)
     wt = threading.Thread(target=writer, daemon=True)
-    for t in threads + [wt]:
-        t.start()
-
-    stats = Stats()
-    t0 = time.perf_counter()
-    pending: Dict[int, tuple] = {}
-    want = 0
-    batch: List[tuple] = []
-    frames = 0
-    eng = gen.engine()
-    up = eng.total_upsample()
-    # Two pinned arenas [frames, C] that alternate between batches: a batch's rows are packed here --
-    # exactly the x_rows layout of v2w_forward_ragged -- and go to the device in ONE copy.
-    # Plan shapes are quantised (utterance count to a multiple of 8 by appending 1-frame dummies whose
-    # output is dropped, frames to a multiple of 32) so that successive batches reuse plans; a longer
-    # plan only means the longest utterance is padded like the shorter ones, which is what the
-    # reference does to it in any batch that holds a longer one.
-    arena_rows = max_batch_frames + max_batch_utts + 8
-    arenas = [torch.empty(arena_rows, h.num_wv_feat, dtype=torch.float32).pin_memory() for _ in range(2)]
-    arena_free = [torch.cuda.Event(), torch.cuda.Event()]
-    n_flush = [0]
-    # pinned PCM buffers cycle main thread -> writer -> main thread
-    pcm_pool: "queue.Queue" = queue.Queue()
-    for _ in range(3):
-        pcm_pool.put(torch.empty(arena_rows * up, dtype=torch.int16).pin_memory())
-
-    # batch under construction: (item index, frames, speaker embedding); its rows are already in the arena
-    def add(i, f, s_emb, buf):
-        nonlocal frames
-        if not batch:
-            arena_free[n_flush[0] & 1].synchronize()   # the H2D copy that last read this arena is done
-        n = f.shape[0]
-        arenas[n_flush[0] & 1][frames:frames + n].copy_(f)
-        scratch.put(buf)                               # the reader's buffer goes straight back
-        batch.append((i, n, s_emb))
-        frames += n
-
-    def flush():
-        nonlocal batch, frames
-        if not batch:
-            return
-        a = n_flush[0] & 1
-        n_flush[0] += 1
-        arena = arenas[a]
-        lengths = [n for _, n, _ in batch]
-        off = frames
-        real = len(batch)
-        dummies = (-real) % 8
-        arena[off:off + dummies].zero_()
-        lengths += [1] * dummies
-        rows_dev = arena[:off + dummies].to(dev, non_blocking=True)
-        arena_free[a].record()
-        spk = torch.zeros(real + dummies, h.spk_dim)
-        for j, (_, _, s_emb) in enumerate(batch):
-            spk[j] = s_emb
-        spk = spk.to(dev)
-        noise = torch.randn(real + dummies, h.noise_dim, device=dev, generator=rng)
-        plan_frames = -(-max(lengths) // 32) * 32
-        packed = eng.forward_ragged(rows_dev, lengths, spk, noise, plan_frames, pcm16=True)
-        n_valid = off * up
-        pcm_buf = pcm_pool.get()
-        pcm_host = pcm_buf[:n_valid]
-        pcm_host.copy_(packed[:n_valid], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        to_write.put((ev, pcm_host, [items[i].name for i, _, _ in batch],
-                      [n * up for n in lengths[:real]], pcm_buf))
-        stats.utterances += real
-        stats.audio_s += n_valid / sampling_rate
-        stats.batches += 1
-        batch, frames = [], 0
-
+    pt.start()
+    wt.start()
     with torch.no_grad():
-        while want < len(items):
-            while want not in pending:
-                try:
-                    i, f, s, buf = loaded.get(timeout=120)
-                except queue.Empty:
-                    raise RuntimeError(f"feature readers made no progress for 120 s (waiting for item {want})") from None
-                if errors:
-                    raise errors[0]
-                pending[i] = (f, s, buf)
-            f, s, buf = pending.pop(want)
-            if batch and (frames + f.shape[0] > max_batch_frames or len(batch) >= max_batch_utts):
-                flush()
-            add(want, f, s, buf)
-            want += 1
-        flush()
+        for k, (lo, hi) in enumerate(batches):
+            try:
+                got = ready.get(timeout=120)
+            except queue.Empty:
+                raise RuntimeError(f"the feature reader made no progress for 120 s (batch {k})") from None
+            if got is None or errors:
+                raise errors[0]
+            _, spk = got
+            a = k & 1
+            real = hi - lo
+            dummies = (-real) % 8
+            lengths = [int(v) for v in rows[lo:hi]]
+            off = sum(lengths)
+            arenas[a][off:off + dummies].zero_()
+            lengths += [1] * dummies
+            rows_dev = arenas[a][:off + dummies].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            arena_tokens[a].put(ev)
+            noise = torch.randn(real + dummies, h.noise_dim, device=dev, generator=rng)
+            plan_frames = -(-max(lengths) // 32) * 32
+            packed = eng.forward_ragged(rows_dev, lengths, spk.to(dev), noise, plan_frames, pcm16=True)
+            n_valid = off * up
+            pcm_buf = pcm_pool.get()
+            pcm_buf[:n_valid].copy_(packed[:n_valid], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            to_write.put((done, pcm_buf, lo, hi))
+            stats.utterances += real
+            stats.audio_s += n_valid / sampling_rate
+            stats.batches += 1
+            if errors:
+                raise errors[0]
     to_write.put(None)
     wt.join()
+    pt.join()
     if errors:
         raise errors[0]
     torch.cuda.synchronize(dev)

@@ -219,6 +219,11 @@ _SIGNATURES = [
     ("v2w_mel_forward", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     ("v2w_npy_shape", C.c_int32, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("v2w_npy_read_f32", C.c_int32, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    ("v2w_npy_shapes", C.c_int32, [C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
+    ("v2w_npy_read_batch", C.c_int32, [C.POINTER(C.c_char_p), C.c_int32, C.c_void_p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.c_int64, C.c_int32]),
+    ("v2w_wav_write_batch", C.c_int32, [C.POINTER(C.c_char_p), C.c_int32, C.c_void_p, C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     ("v2w_pipeline_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ("v2w_pipeline_submit", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("v2w_pipeline_wait", C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
