@@ -152,3 +152,18 @@ def test_batch_io(tmp_path):
     with pytest.raises(native.V2WError, match="cannot create"):
         native.check(lib.v2w_wav_write_batch(files._c_paths([str(tmp_path / "no_dir" / "x.wav")]), 1, pcm.ctypes.data,
                                              so.ctypes.data_as(i64p), sn.ctypes.data_as(i64p), 16000, 1))
+
+
+def test_plan_batches():
+    assert files.plan_batches([], 100, 4) == []
+    assert files.plan_batches([10, 20, 30], 100, 8) == [(0, 3)]
+    assert files.plan_batches([60, 50, 40, 10, 200, 5], 100, 8) == [(0, 1), (1, 4), (4, 5), (5, 6)]
+    assert files.plan_batches([1] * 10, 100, 4) == [(0, 4), (4, 8), (8, 10)]
+    rng = np.random.default_rng(0)
+    rows = rng.integers(1, 500, size=300).tolist()
+    b = files.plan_batches(rows, 4000, 32)
+    assert b[0][0] == 0 and b[-1][1] == 300 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    for lo, hi in b:
+        assert hi - lo <= 32 and (sum(rows[lo:hi]) <= 4000 or hi - lo == 1)
+        if hi < 300:   # greedy: the next utterance did not fit
+            assert sum(rows[lo:hi]) + rows[hi] > 4000 or hi - lo == 32

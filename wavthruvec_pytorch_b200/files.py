@@ -148,6 +148,21 @@ def feature_shapes(paths: Sequence[str], threads: int = 4) -> Tuple[np.ndarray, 
     return rows, cols
 
 
+def plan_batches(rows: Sequence[int], max_batch_frames: int, max_batch_utts: int) -> List[Tuple[int, int]]:
+    """Item ranges [lo, hi) in order: a batch closes when the next utterance would exceed the frame
+    budget or the utterance cap (a single over-long utterance still gets a batch of its own)."""
+    batches: List[Tuple[int, int]] = []
+    lo, frames = 0, 0
+    for i, n in enumerate(rows):
+        if i > lo and (frames + int(n) > max_batch_frames or i - lo >= max_batch_utts):
+            batches.append((lo, i))
+            lo, frames = i, 0
+        frames += int(n)
+    if len(rows):
+        batches.append((lo, len(rows)))
+    return batches
+
+
 def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str, out_dir: str,
                      max_batch_frames: int = 16000, max_batch_utts: int = 128, readers: int = 4,
                      seed: int = 1234, sampling_rate: int = 16000, max_utt_frames: int = 2000) -> Stats:
@@ -183,15 +198,7 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
             raise ValueError(f"{feat_paths[i]}: {cols[i]} feature channels, expected {h.num_wv_feat}")
         if rows[i] > max_utt_frames:
             raise ValueError(f"{feat_paths[i]}: {rows[i]} frames do not fit the {max_utt_frames}-frame limit")
-    # batches [lo, hi) in item order
-    batches: List[Tuple[int, int]] = []
-    lo, frames = 0, 0
-    for i in range(n_items):
-        if i > lo and (frames + rows[i] > max_batch_frames or i - lo >= max_batch_utts):
-            batches.append((lo, i))
-            lo, frames = i, 0
-        frames += int(rows[i])
-    batches.append((lo, n_items))
+    batches = plan_batches(rows, max_batch_frames, max_batch_utts)
     for d in sorted({os.path.dirname(p) for p in wav_paths}):
         os.makedirs(d, exist_ok=True)
 
