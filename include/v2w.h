@@ -346,10 +346,11 @@ int32_t v2w_model_halo_frames(const struct v2w_model* m);
  *     (r <- (1 - momentum) r + momentum s, unbiased variance for running_var);
  *   - the spectral-norm Linear runs ONE power iteration first (v <- normalize(W^T u),
  *     u <- normalize(W v), eps 1e-12), stores u and v in place and divides by sigma = u.(W v).
- * Everything else (the convolutions) is mode-independent and comes from the packed buffer.  Per stage
+ * Everything else (the convolutions) is mode-independent and comes from the packed buffer.  The power
+ * iterations and gamma / beta of all stages run up front (sn_train_kernel, cond_affine_kernel); per stage
  * the transposed conv runs twice: once raw (bias only) into a scratch tensor for the batch statistics
- * (bn_stats_kernel), then -- after sn_train_kernel + cond_affine_kernel produced this batch's
- * scale/shift -- the plan's normal op with the affine in its epilogue.  All pointers are DEVICE fp32
+ * (bn_stats_kernel, folded into scale/shift by bn_finalize_kernel), then the plan's normal op with the
+ * affine in its epilogue.  All pointers are DEVICE fp32
  * tensors of the module itself (the caller bumps num_batches_tracked, an int64 the library never reads).
  * The conditioning section of the packed buffer is not read by this call, so the packed buffer stays
  * usable across train-mode forwards; an eval-mode forward afterwards needs a re-pack (u, v and the

@@ -399,29 +399,29 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /* >= 33 floa
   return scratch[32];
 }
 
-// One CTA per stage call.  (1) one spectral-norm power iteration exactly as
+// One CTA per stage (grid = stages): one spectral-norm power iteration exactly as
 // torch.nn.utils.spectral_norm does in training mode: v <- normalize(W^T u), u <- normalize(W v)
-// (eps 1e-12), sigma = u . (W v); u, v stored in place, 1/sigma to the workspace.  (2) batch
-// statistics from the double sums: mean, rstd = 1/sqrt(biased var + eps) to the workspace, running
-// statistics updated in place with `momentum` (unbiased variance), as nn.BatchNorm1d in training mode.
-struct SnTrainParams {
+// (eps 1e-12), sigma = u . (W v); u, v stored in place, 1/sigma to the workspace.  Independent of the
+// activations, so all stages run up front on the side stream, followed by cond_affine_kernel with
+// rstd = 1, mean = 0 (its scale / shift outputs are then gamma / beta).
+struct SnStage {
   const float* W;        // [2C][128]
   float* u; float* v;    // [2C], [128]
-  const double* sums;    // [2][C]
-  float* run_mean; float* run_var;
-  float* mean; float* rstd; float* inv_sigma;   // workspace outputs
+  float* inv_sigma;      // workspace output
   int C;
-  long long count;       // values per channel (batch x time)
-  float momentum, eps;
+};
+struct SnTrainParams {
+  SnStage st[V2W_MAX_STAGES];
 };
 constexpr int kSnThreads = 512;
 
-__global__ void __launch_bounds__(kSnThreads) sn_train_kernel(const SnTrainParams p) {
+__global__ void __launch_bounds__(kSnThreads) sn_train_kernel(const SnTrainParams prm) {
   __shared__ float us[2 * 1024 / 2];   // [2C], C <= 512
   __shared__ float vs[128];
   __shared__ float part[4][128];
   __shared__ float ts[2 * 1024 / 2];   // W v
   __shared__ float scratch[33];
+  const SnStage& p = prm.st[blockIdx.x];
   const int R = 2 * p.C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = threadIdx.x; r < R; r += kSnThreads) us[r] = p.u[r];
@@ -461,13 +461,34 @@ __global__ void __launch_bounds__(kSnThreads) sn_train_kernel(const SnTrainParam
   }
   const float sigma = block_sum(su, scratch);
   if (threadIdx.x == 0) *p.inv_sigma = 1.f / sigma;
+}
+
+// Batch statistics into the affine, one thread per (utterance, channel): mean and biased variance from
+// the double sums, scale = gamma * rsqrt(var + eps), shift = beta - mean * scale written over gamma /
+// beta; the threads of utterance 0 also move the running statistics by `momentum` (unbiased variance),
+// as nn.BatchNorm1d does in training mode.
+struct BnFinalizeParams {
+  const double* sums;    // [2][C]
+  float* scale; float* shift;          // [B][C]: gamma / beta in, scale / shift out
+  float* run_mean; float* run_var;     // [C] in/out
+  int C, batch;
+  long long count;       // values per channel (batch x time)
+  float momentum, eps;
+};
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinalizeParams p) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.batch * p.C) return;
+  const int c = idx % p.C;
   const double n = (double)p.count;
-  for (int c = threadIdx.x; c < p.C; c += kSnThreads) {
-    const double m = p.sums[c] / n;
-    double var = p.sums[p.C + c] / n - m * m;
-    if (var < 0) var = 0;
-    p.mean[c] = (float)m;
-    p.rstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+  const double m = p.sums[c] / n;
+  double var = p.sums[p.C + c] / n - m * m;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+  const float sc = p.scale[idx] * rstd;
+  p.scale[idx] = sc;
+  p.shift[idx] = p.shift[idx] - sc * (float)m;
+  if (idx < p.C) {
     const double unb = p.count > 1 ? var * n / (n - 1.0) : var;
     p.run_mean[c] = (1.f - p.momentum) * p.run_mean[c] + p.momentum * (float)m;
     p.run_var[c] = (1.f - p.momentum) * p.run_var[c] + p.momentum * (float)unb;

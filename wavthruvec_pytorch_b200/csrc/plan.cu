@@ -91,7 +91,8 @@ struct v2w_plan {
   // train() mode scratch: raw ups output (fp32, aliases the first-conv buffer of the resblocks, dead at
   // that point), per-stage double sums [2][C], batch mean / rstd [C], 1/sigma
   int64_t tr_y = -1;
-  int64_t tr_sums[V2W_MAX_STAGES], tr_mean[V2W_MAX_STAGES], tr_rstd[V2W_MAX_STAGES], tr_isg[V2W_MAX_STAGES];
+  int64_t tr_sums[V2W_MAX_STAGES], tr_isg[V2W_MAX_STAGES];
+  int64_t tr_ones = -1, tr_zeros = -1;   // fp32 [max C]: rstd = 1, mean = 0 for the gamma / beta pass
   bool bound = false;
   const uint8_t* packed = nullptr;
   uint8_t* ws = nullptr;
@@ -928,9 +929,13 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   P->tr_y = y1.f32;
   for (int i = 0; i < U; ++i) {
     P->tr_sums[i] = ws.take((int64_t)2 * m->stage_channels[i] * 8);
-    P->tr_mean[i] = ws.take((int64_t)m->stage_channels[i] * 4);
-    P->tr_rstd[i] = ws.take((int64_t)m->stage_channels[i] * 4);
     P->tr_isg[i] = ws.take(4);
+  }
+  {
+    int cmax = 0;
+    for (int i = 0; i < U; ++i) cmax = std::max(cmax, m->stage_channels[i]);
+    P->tr_ones = ws.take((int64_t)cmax * 4);
+    P->tr_zeros = ws.take((int64_t)cmax * 4);
   }
   P->workspace_bytes = ws.off;
   P->post_in = sum_f32;
@@ -1242,27 +1247,72 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
                         cudaMemcpyDeviceToHost));
     V2W_CUDA(cudaMemcpy(&p->post_bias, p->packed + L.bias_off, 4, cudaMemcpyDeviceToHost));
   }
+  {
+    int cmax = 0;
+    for (int c : m->stage_channels) cmax = std::max(cmax, c);
+    std::vector<float> ones((size_t)cmax, 1.f);
+    V2W_CUDA(cudaMemcpy(p->ws + p->tr_ones, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+    V2W_CUDA(cudaMemset(p->ws + p->tr_zeros, 0, (size_t)cmax * 4));
+  }
   p->bound = true;
   return V2W_OK;
 }
 
-// train() mode, one upsample stage (vec2wav/modules.py:20-30 with module.training set): raw transposed
-// conv -> per-channel batch statistics -> power iteration + running-stat update -> this batch's
-// scale/shift.  The plan's own op (same GEMM, affine epilogue) follows.
-static int32_t train_stage_affine(v2w_plan* p, Op& o, const v2w_train_state& tr, const float* spk_dev,
-                                  const float* noise_dev, cudaStream_t st, int* launches) {
+// train() mode, conditioning that does not depend on the activations (vec2wav/modules.py:16,24 with
+// module.training set): the power iteration of every stage and gamma / beta = SN-Linear(fcs(spk|noise)),
+// on the side stream while conv_pre runs.  cond_affine_kernel runs with rstd = 1, mean = 0, so its
+// scale / shift outputs hold gamma / beta until bn_finalize_kernel folds the batch statistics in.
+static int32_t train_conditioning(v2w_plan* p, const v2w_train_state& tr, const float* spk_dev,
+                                  const float* noise_dev, cudaStream_t cs, int* launches) {
   const v2w_model* m = p->model;
   const v2w_config& c = m->cfg;
+  simt::SnTrainParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  simt::CondParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  int cmax = 0;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const v2w_train_stage& T = tr.stage[i];
+    const int C = m->stage_channels[i];
+    if (C < 4 || C > 512 || (C & (C - 1))) {
+      set_error("v2w_forward_train: %d channels unsupported by the statistics kernels", C);
+      return V2W_ERR_INVALID;
+    }
+    cmax = std::max(cmax, C);
+    sp.st[i].W = T.sn_weight_orig; sp.st[i].u = T.sn_u; sp.st[i].v = T.sn_v;
+    sp.st[i].inv_sigma = reinterpret_cast<float*>(p->ws + p->tr_isg[i]);
+    sp.st[i].C = C;
+    simt::CondStage& S = cp.st[i];
+    S.fcw = T.fc_weight; S.fcb = T.fc_bias; S.snw = T.sn_weight_orig; S.snb = T.sn_bias;
+    S.rstd = reinterpret_cast<const float*>(p->ws + p->tr_ones);
+    S.mean = reinterpret_cast<const float*>(p->ws + p->tr_zeros);
+    S.inv_sigma = sp.st[i].inv_sigma;
+    S.scale = reinterpret_cast<float*>(p->ws + p->cond_scale[i]);
+    S.shift = reinterpret_cast<float*>(p->ws + p->cond_shift[i]);
+    S.C = C;
+  }
+  simt::sn_train_kernel<<<c.num_upsamples, simt::kSnThreads, 0, cs>>>(sp);
+  V2W_CUDA(cudaGetLastError());
+  cp.spk = spk_dev; cp.noise = noise_dev;
+  cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
+  const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * cmax) * 4;
+  simt::cond_affine_kernel<<<dim3((unsigned)c.num_upsamples, p->batch), simt::kCondThreads, smem, cs>>>(cp);
+  V2W_CUDA(cudaGetLastError());
+  *launches += 2;
+  return V2W_OK;
+}
+
+// train() mode, one upsample stage (vec2wav/modules.py:20-30 with module.training set): raw transposed
+// conv -> per-channel batch statistics -> scale/shift of this batch (+ running-stat update).  The
+// plan's own op (same GEMM, affine epilogue) follows.
+static int32_t train_stage_affine(v2w_plan* p, Op& o, const v2w_train_state& tr, cudaStream_t st, int* launches) {
+  const v2w_model* m = p->model;
   const int i = o.d.cond_stage;
   const v2w_train_stage& T = tr.stage[i];
   const int C = m->stage_channels[i];
   if (!o.has_raw) {
     set_error("v2w_forward_train: stage %d has no raw launch", i);
     return V2W_ERR_STATE;
-  }
-  if (C < 4 || C > 512 || (C & (C - 1))) {
-    set_error("v2w_forward_train: %d channels unsupported by the statistics kernels", C);
-    return V2W_ERR_INVALID;
   }
   int rc = o.g_raw.engine == V2W_ENGINE_TC ? launch_tc(o.tcl_raw, st) : launch_simt(o.g_raw, st);
   if (rc) return rc;
@@ -1276,33 +1326,18 @@ static int32_t train_stage_affine(v2w_plan* p, Op& o, const v2w_train_state& tr,
   const int grid = (int)std::max<long long>(1, std::min<long long>((R + per_cta - 1) / per_cta, (long long)sms * 8));
   simt::bn_stats_kernel<<<grid, simt::kStatThreads, 0, st>>>(reinterpret_cast<const float*>(p->ws + p->tr_y), R, C, sums);
   V2W_CUDA(cudaGetLastError());
-  simt::SnTrainParams sp;
-  sp.W = T.sn_weight_orig; sp.u = T.sn_u; sp.v = T.sn_v;
-  sp.sums = sums;
-  sp.run_mean = T.bn_running_mean; sp.run_var = T.bn_running_var;
-  sp.mean = reinterpret_cast<float*>(p->ws + p->tr_mean[i]);
-  sp.rstd = reinterpret_cast<float*>(p->ws + p->tr_rstd[i]);
-  sp.inv_sigma = reinterpret_cast<float*>(p->ws + p->tr_isg[i]);
-  sp.C = C;
-  sp.count = R;
-  sp.momentum = tr.momentum;
-  sp.eps = kBnEps;
-  simt::sn_train_kernel<<<1, simt::kSnThreads, 0, st>>>(sp);
+  simt::BnFinalizeParams fp;
+  fp.sums = sums;
+  fp.scale = reinterpret_cast<float*>(p->ws + p->cond_scale[i]);
+  fp.shift = reinterpret_cast<float*>(p->ws + p->cond_shift[i]);
+  fp.run_mean = T.bn_running_mean; fp.run_var = T.bn_running_var;
+  fp.C = C; fp.batch = p->batch;
+  fp.count = R;
+  fp.momentum = tr.momentum;
+  fp.eps = kBnEps;
+  simt::bn_finalize_kernel<<<(p->batch * C + 255) / 256, 256, 0, st>>>(fp);
   V2W_CUDA(cudaGetLastError());
-  simt::CondParams cp;
-  std::memset(&cp, 0, sizeof(cp));
-  simt::CondStage& S = cp.st[0];
-  S.fcw = T.fc_weight; S.fcb = T.fc_bias; S.snw = T.sn_weight_orig; S.snb = T.sn_bias;
-  S.rstd = sp.rstd; S.mean = sp.mean; S.inv_sigma = sp.inv_sigma;
-  S.scale = reinterpret_cast<float*>(p->ws + p->cond_scale[i]);
-  S.shift = reinterpret_cast<float*>(p->ws + p->cond_shift[i]);
-  S.C = C;
-  cp.spk = spk_dev; cp.noise = noise_dev;
-  cp.spk_dim = c.spk_dim; cp.noise_dim = c.noise_dim;
-  const int smem = (c.spk_dim + c.noise_dim + 128 + 2 * C) * 4;
-  simt::cond_affine_kernel<<<dim3(1, p->batch), simt::kCondThreads, smem, st>>>(cp);
-  V2W_CUDA(cudaGetLastError());
-  *launches += 4;
+  *launches += 3;
   return V2W_OK;
 }
 
@@ -1383,7 +1418,22 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         break;
       }
       case V2W_OP_COND_AFFINE: {
-        if (tr) break;   // train(): scale/shift come from this batch's statistics, stage by stage
+        if (tr) {
+          // train(): power iterations and gamma / beta of every stage on the side stream; the batch
+          // statistics are folded in stage by stage (bn_finalize_kernel)
+          if (!p->side) {
+            V2W_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+            V2W_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            V2W_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+          }
+          V2W_CUDA(cudaEventRecord(p->ev_fork, st));
+          V2W_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+          int rc = train_conditioning(p, *tr, spk_dev, noise_dev, p->side, &launches);
+          if (rc) return rc;
+          V2W_CUDA(cudaEventRecord(p->ev_join, p->side));
+          joined = false;
+          break;
+        }
         simt::CondParams cp;
         std::memset(&cp, 0, sizeof(cp));
         int cmax = 0;
@@ -1424,7 +1474,7 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
       case V2W_OP_TAPGEMM: {
         const int rpf = o.d.rows / p->frames;   // rows of this op per input frame
         if (tr && o.d.cond_stage >= 0) {
-          int rc = train_stage_affine(p, o, *tr, spk_dev, noise_dev, st, &launches);
+          int rc = train_stage_affine(p, o, *tr, st, &launches);
           if (rc) return rc;
         }
         int rc = o.g.engine == V2W_ENGINE_TC ? launch_tc(o.tcl, st, lim, rpf) : launch_simt(o.g, st, lim, rpf);
