@@ -301,12 +301,9 @@ int32_t v2w_mel_forward(v2w_mel* m, const float* wav_dev, float* out_dev, void* 
   int rc = v2w_tapgemm(&g, stream);
   if (rc) return rc;
   {
-    static bool attr = false;
     const int smem = m->nbins * (mel::kMelFrames + 1) * 4;
-    if (!attr) {
+    if (smem > 48 * 1024)   // per device, and only n_fft > 2048 needs it: not worth caching
       V2W_CUDA_M(cudaFuncSetAttribute(mel::mel_log_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
     if (smem > 200 * 1024) {
       set_error("v2w_mel_forward: n_fft=%d too large for the filterbank kernel", c.n_fft);
       return V2W_ERR_INVALID;

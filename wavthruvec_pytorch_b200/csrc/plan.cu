@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -154,6 +155,14 @@ static int sm_count(int* out) {
   }
   *out = n;
   return V2W_OK;
+}
+
+// cudaFuncSetAttribute is per DEVICE: a process that drives more than one GPU must raise the dynamic
+// shared-memory limit of every kernel once per device, not once per process.
+static uint64_t device_bit() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;   // 0: never cached
+  return 1ull << dev;
 }
 
 static int pow2_ceil(int v) {
@@ -403,8 +412,9 @@ static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit =
   TcLaunch L = L0;
   L.prm.row_limit = row_limit;
   L.prm.rows_per_frame = rows_per_frame;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_devs.load() & dev_bit) || !dev_bit) {
     V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<32>,
@@ -417,7 +427,7 @@ static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit =
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_devs.fetch_or(dev_bit);
   }
   if (L.pair) {
     if (L.kc == 64)
@@ -724,8 +734,9 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
     L.sprm.post_out = post->out;
     if (post->ro) L.sprm.post_ro = *post->ro;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devs{0};
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_devs.load() & dev_bit) || !dev_bit) {
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true>,
@@ -744,7 +755,7 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_devs.fetch_or(dev_bit);
   }
   if (L.stacked) {
     if (L.channels == 64 && L.pair)
