@@ -364,3 +364,54 @@ def test_cond_only_repack_equals_full_pack():
     assert np.array_equal(full2[lo:hi], region.numpy())
     assert not np.array_equal(full[lo:hi], full2[lo:hi])
     assert np.array_equal(full[:lo], full2[:lo]) and np.array_equal(full[hi:], full2[hi:])   # nothing else depends on them
+
+
+def test_train_and_mel_entry_points_validate_before_touching_the_gpu():
+    """Error behaviour of the widened C-ABI (v2w_forward_train, v2w_mel_*) that needs no device:
+    argument validation first, call-order violations (not bound) second, never a crash."""
+    import ctypes as C
+    lib = native.load()
+    gen = Generator(hparams())
+    eng = gen.engine()
+    plan = C.c_void_p()
+    native.check(lib.v2w_plan_create(eng._model, 2, 8, native.PREC_FP32, C.byref(plan)))
+    try:
+        st = native.TrainState()
+        st.num_stages = 4                      # the model has 5
+        st.momentum = 0.1
+        one = C.c_void_p(256)                  # any non-null value: never dereferenced on these paths
+        rc = lib.v2w_forward_train(plan, one, one, one, one, C.byref(st), None, None)
+        assert rc == -1 and "stages" in native.last_error()
+        st.num_stages = 5
+        rc = lib.v2w_forward_train(plan, one, one, one, one, C.byref(st), None, None)
+        assert rc == -1 and "null pointer in stage 0" in native.last_error()
+        for i in range(5):
+            for name, _ in native.TrainStage._fields_:
+                setattr(st.stage[i], name, 256)
+        st.momentum = 1.5
+        rc = lib.v2w_forward_train(plan, one, one, one, one, C.byref(st), None, None)
+        assert rc == -1 and "momentum" in native.last_error()
+        st.momentum = 0.1
+        rc = lib.v2w_forward_train(plan, one, one, one, one, C.byref(st), None, None)
+        assert rc == -3 and "not bound" in native.last_error()
+        assert lib.v2w_forward_train(plan, one, one, one, one, None, None, None) == -1
+    finally:
+        lib.v2w_plan_destroy(plan)
+    cfg = native.MelConfig(1024, 256, 1024, 80, 16000, 0.0, 0.0)
+    mel = C.c_void_p()
+    native.check(lib.v2w_mel_create(C.byref(cfg), 2, 8000, C.byref(mel)))
+    try:
+        assert lib.v2w_mel_num_frames(mel) == 31 and lib.v2w_mel_workspace_bytes(mel) > 0
+        rc = lib.v2w_mel_forward(mel, C.c_void_p(256), C.c_void_p(256), None, None)
+        assert rc == -3 and "not bound" in native.last_error()
+        assert lib.v2w_mel_bind(mel, C.c_void_p(100)) == -1          # unaligned workspace
+    finally:
+        lib.v2w_mel_destroy(mel)
+    for bad in (native.MelConfig(1024, 250, 1024, 80, 16000, 0.0, 0.0),     # hop % 16
+                native.MelConfig(1024, 256, 2048, 80, 16000, 0.0, 0.0),     # win > n_fft
+                native.MelConfig(1024, 256, 1024, 80, 16000, 9000.0, 8000.0),   # fmin >= fmax
+                native.MelConfig(8192, 16, 8192, 80, 16000, 0.0, 0.0)):     # n_fft / hop > 16 taps
+        h = C.c_void_p()
+        assert lib.v2w_mel_create(C.byref(bad), 1, 20000, C.byref(h)) == -1 and not h.value
+    h = C.c_void_p()
+    assert lib.v2w_mel_create(C.byref(cfg), 1, 300, C.byref(h)) == -1       # shorter than the reflect padding
