@@ -415,3 +415,19 @@ def test_train_and_mel_entry_points_validate_before_touching_the_gpu():
         assert lib.v2w_mel_create(C.byref(bad), 1, 20000, C.byref(h)) == -1 and not h.value
     h = C.c_void_p()
     assert lib.v2w_mel_create(C.byref(cfg), 1, 300, C.byref(h)) == -1       # shorter than the reflect padding
+
+
+def test_pack_is_independent_of_the_thread_count(monkeypatch):
+    """The weight fold runs as parallel (layer, tap) tasks writing disjoint regions: same bytes with 1, 3
+    and the default number of host threads, both 16-bit formats."""
+    gen = Generator(hparams(resblock='1'))
+    eng = gen.engine()
+    monkeypatch.setenv("V2W_PACK_THREADS", "1")
+    one = [eng.pack_host(f).numpy().copy() for f in (native.HALF_BF16, native.HALF_FP16)]
+    monkeypatch.setenv("V2W_PACK_THREADS", "3")
+    three = [eng.pack_host(f).numpy().copy() for f in (native.HALF_BF16, native.HALF_FP16)]
+    monkeypatch.delenv("V2W_PACK_THREADS")
+    dflt = [eng.pack_host(f).numpy() for f in (native.HALF_BF16, native.HALF_FP16)]
+    for a, b, c in zip(one, three, dflt):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert not np.array_equal(one[0], one[1])

@@ -5,7 +5,10 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "v2w.h"
@@ -47,6 +50,31 @@ static inline uint16_t fp16_bits(float f) {
   const uint32_t rem = u & 0x1fffu;
   if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
   return (uint16_t)(sign | h);
+}
+
+// fn(i) for i in [0, n) on up to `threads` host threads (dynamic scheduling; the caller's thread works
+// too).  For independent, infallible tasks -- the per-layer weight folds of v2w_model_pack.
+template <typename Fn>
+static inline void parallel_for(int n, int threads, Fn fn) {
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+  };
+  const int nt = threads < 1 ? 1 : (threads > n ? n : threads);
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+}
+
+// Host threads of the weight fold: $V2W_PACK_THREADS, else min(8, hardware threads).
+static inline int pack_threads() {
+  if (const char* e = std::getenv("V2W_PACK_THREADS")) {
+    const int v = std::atoi(e);
+    if (v >= 1) return v > 64 ? 64 : v;
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  return hw == 0 ? 1 : (hw > 8 ? 8 : (int)hw);
 }
 
 constexpr uint32_t kPackedMagic = 0x50573256u;  // "V2WP"
