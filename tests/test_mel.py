@@ -103,3 +103,27 @@ def test_native_mel_full_size_against_torch_stft():
     k = 5
     shifted = mel.mel_spectrogram(y[:, k * 256:].contiguous(), **p)
     assert (shifted[:, :, 2:-2] - got[:, :, k + 2:-2]).abs().max().item() < 1e-4
+
+
+@pytest.mark.gpu
+def test_native_mel_other_parameters():
+    """A configuration away from the reference's defaults: window shorter than n_fft (torch.stft centres
+    it), 40 mels between 50 Hz and 7 kHz at 22.05 kHz, hop 128, a length that is no multiple of the hop."""
+    p = dict(n_fft=512, num_mels=40, sampling_rate=22050, hop_size=128, win_size=400, fmin=50.0, fmax=7000.0)
+    y = torch.from_numpy(mel_test_waves(3, 9001, 5)).cuda()
+    got = mel.mel_spectrogram(y, **p).cpu().numpy()
+    ref64 = mel_numpy.mel_spectrogram(y.cpu().numpy(), **p)
+    assert got.shape == ref64.shape == (3, 40, 9001 // 128)
+    pad = (p["n_fft"] - p["hop_size"]) // 2
+    yp = torch.nn.functional.pad(y.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    spec = torch.stft(yp, p["n_fft"], hop_length=p["hop_size"], win_length=p["win_size"],
+                      window=torch.hann_window(p["win_size"], device=y.device), center=False,
+                      normalized=False, onesided=True, return_complex=True)
+    mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2 + 1e-9)
+    fb = torch.from_numpy(mel_numpy.slaney_mel_filterbank(22050, 512, 40, 50.0, 7000.0)).cuda()
+    lib = torch.log(torch.clamp(torch.matmul(fb, mag), min=1e-5)).cpu().numpy()
+    assert np.abs(lib - ref64).max() < 5e-3                   # the restatement agrees with torch.stft here too
+    d = np.abs(got - ref64)
+    loud = ref64 > -8.0
+    print(f"mel (512/128/400, 40 mels): max {d.max():.2e}, loud bins {d[loud].max():.2e}, mean {d.mean():.2e}")
+    assert d[loud].max() < 1e-3 and d.mean() < 2e-5 and d.max() < 1e-2
