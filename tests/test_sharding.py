@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from wavthruvec_pytorch_b200.sharding import generate_sharded, shard_bounds, shard_sizes
+from wavthruvec_pytorch_b200.sharding import generate_sharded, shard_bounds, shard_by_frames, shard_sizes
 
 
 def test_shard_bounds_cover_and_order():
@@ -63,3 +63,22 @@ def test_generate_sharded_world2_gloo(tmp_path, total):
     got = np.load(out)
     assert got.shape == (total, 1, 6 * 320)
     np.testing.assert_array_equal(got, want)
+
+
+def test_shard_by_frames_balances_variable_length_items():
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 5, 64, 513):
+            frames = rng.integers(50, 501, size=n).tolist()
+            spans = shard_by_frames(frames, world)
+            assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == n
+            assert all(b == c for (_, b), (c, _) in zip(spans, spans[1:]))
+            loads = [sum(frames[lo:hi]) for lo, hi in spans]
+            if n >= 8 * world:      # no rank is off the ideal share by more than one longest utterance
+                ideal = sum(frames) / world
+                assert max(abs(v - ideal) for v in loads) <= max(frames)
+    assert shard_by_frames([100, 100, 100, 100], 2) == [(0, 2), (2, 4)]
+    assert shard_by_frames([400, 10, 10, 10], 2) == [(0, 1), (1, 4)]
+    assert shard_by_frames([7], 3) in ([(0, 0), (0, 0), (0, 1)], [(0, 1), (1, 1), (1, 1)], [(0, 0), (0, 1), (1, 1)])
+    with pytest.raises(ValueError):
+        shard_by_frames([1, 2], 0)

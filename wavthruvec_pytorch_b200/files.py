@@ -318,3 +318,17 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
     torch.cuda.synchronize(dev)
     stats.wall_s = time.perf_counter() - t0
     return stats
+
+
+def synthesize_files_sharded(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str, out_dir: str,
+                             rank: int, world: int, readers: int = 4, **kwargs) -> Stats:
+    """One process per GPU over a corpus: every rank reads the headers (cheap, one library call), all
+    derive the same frame-balanced contiguous partition (`sharding.shard_by_frames`) and each
+    synthesises its own range -- independent utterances, no collective.  Per-rank noise streams are
+    decorrelated through the seed."""
+    from .sharding import shard_by_frames
+    rows, _ = feature_shapes([os.path.join(feat_dir, it.name + ".npy") for it in items], readers)
+    lo, hi = shard_by_frames(rows, world)[rank]
+    kwargs.setdefault("seed", 1234)
+    kwargs["seed"] = int(kwargs["seed"]) + rank
+    return synthesize_files(gen, items[lo:hi], feat_dir, spk_emb_dir, out_dir, readers=readers, **kwargs)

@@ -27,6 +27,28 @@ def shard_sizes(total: int, world: int) -> List[int]:
     return [hi - lo for lo, hi in (shard_bounds(total, world, r) for r in range(world))]
 
 
+def shard_by_frames(frames, world: int) -> List[Tuple[int, int]]:
+    """Contiguous item ranges [lo, hi), one per rank, balanced by total FRAMES instead of item count --
+    for variable-length corpora (the file pipeline): rank r's range ends where the running frame count
+    first reaches (r + 1) / world of the total.  Every rank computes the same partition from the same
+    frame counts; ranges may be empty when there are fewer items than ranks."""
+    if world < 1:
+        raise ValueError(f"bad world size {world}")
+    frames = [int(f) for f in frames]
+    if any(f < 0 for f in frames):
+        raise ValueError("negative frame count")
+    total = sum(frames)
+    bounds, lo, acc, i = [], 0, 0, 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        while i < len(frames) and (acc + frames[i] / 2.0 <= target or r == world - 1):
+            acc += frames[i]
+            i += 1
+        bounds.append((lo, i))
+        lo = i
+    return bounds
+
+
 def generate_sharded(forward: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], torch.Tensor],
                      x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor,
                      group: Optional[dist.ProcessGroup] = None, dst: int = 0,
