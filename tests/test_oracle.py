@@ -121,3 +121,31 @@ def test_numpy_restatement_train_mode(name):
                 assert int(sd[key]) == int(want), key
             else:
                 np.testing.assert_allclose(sd[key], want, rtol=2e-5, atol=1e-7, err_msg=key)
+
+
+def test_train_mode_operand_precision_prediction(monkeypatch):
+    """Why train()-mode forwards default to fp16 operands: the fp64 restatement with every
+    convolution's operands rounded to a 16-bit format (the tensor-core plans' rounding points) predicts
+    42 dB for bf16 under batch-statistic BN -- below the 45 dB bar; measured on B200: 42.4 dB -- and
+    60 dB for fp16 (measured 60.3 dB); in eval() mode the same bf16 emulation stays above the bar."""
+    import plan_interp
+    g = load_golden("rb2_768_stress")
+    tg = load_train_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False)
+    c1, ct = vec2wav_numpy.conv1d, vec2wav_numpy.conv_transpose1d
+
+    def run(rnd, train):
+        monkeypatch.setattr(vec2wav_numpy, "conv1d", lambda x, w, b, d, p: c1(rnd(x), rnd(w), b, d, p))
+        monkeypatch.setattr(vec2wav_numpy, "conv_transpose1d", lambda x, w, b, s, p: ct(rnd(x), rnd(w), b, s, p))
+        sd = vec2wav_numpy.state_dict_to_numpy(gen)
+        y = vec2wav_numpy.generator_forward(sd, gen.h, g.x, g.spk, g.noise, train=train)
+        return fixtures.snr_db(tg.y[0] if train else g.y, y)
+
+    bf16 = lambda a: plan_interp.bf16_round(a.astype(np.float32)).astype(np.float64)
+    fp16 = lambda a: a.astype(np.float16).astype(np.float64)
+    snr_bf16_train, snr_fp16_train, snr_bf16_eval = run(bf16, True), run(fp16, True), run(bf16, False)
+    print(f"predicted SNR: train bf16 {snr_bf16_train:.1f} dB, train fp16 {snr_fp16_train:.1f} dB, "
+          f"eval bf16 {snr_bf16_eval:.1f} dB")
+    assert 38.0 < snr_bf16_train < 45.0
+    assert snr_fp16_train >= 55.0
+    assert snr_bf16_eval >= 50.0
