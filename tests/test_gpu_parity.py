@@ -335,6 +335,8 @@ def test_train_mode_forward_matches_reference(name, precision):
 
 def test_train_mode_then_eval_refolds():
     """After native train()-mode forwards the eval() fold must see the new u / v / running statistics."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = load_golden("rb2_768_stress")
     gen = dropin_in_state(g, cache=False).to("cuda:0")
     gen.precision = "fp32"
@@ -427,6 +429,8 @@ def test_empty_batch_returns_empty_waveform():
 def test_conditioning_edit_refolds_in_place():
     """A change of the conditioning buffers alone (no convolution touched) goes through the in-place
     conditioning re-pack: plans survive, the output follows the new statistics."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = load_golden("rb2_768_stress")
     gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
     gen.precision = "fp32"
