@@ -36,6 +36,7 @@ GOLDEN_CASES = {
     "rb2_768_fresh": (dict(resblock=1, num_wv_feat=768), "fresh", 1, 16, 14),
     "rb1_1024_stress": (dict(resblock='1', num_wv_feat=1024), "stress", 1, 20, 15),
     "rb2_768_stress_tiny": (dict(resblock=1, num_wv_feat=768), "stress", 3, 3, 16),
+    "rb2_1024_stress": (dict(resblock=1, num_wv_feat=1024), "stress", 2, 24, 17),
 }
 
 

@@ -74,3 +74,54 @@ def assert_checksums(gen, g, rtol=0.0):
 
 def t(a):
     return torch.from_numpy(np.ascontiguousarray(a))
+
+
+# ----------------------------------------------------------------------------------------------
+# config-size pins (oracle/make_config_pins.py): compact pins of reference outputs at BASELINE sizes
+# ----------------------------------------------------------------------------------------------
+def load_config_pin(name: str):
+    z = np.load(GOLDEN_DIR / f"{name}.npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    overrides = {k: (v[4:] if isinstance(v, str) and v.startswith("str:") else v)
+                 for k, v in meta["overrides"].items()}
+    small = {k[len("small/"):]: z[k] for k in z.files if k.startswith("small/")}
+    return SimpleNamespace(name=name, meta=meta, overrides=overrides, state=meta["state"],
+                           batch=meta["batch"], frames=meta["frames"], seed=meta["seed"], small=small,
+                           idx=z["idx"], y_s=z["y_s"], sum=z["sum"], sumsq=z["sumsq"],
+                           full_b=z["full_b"], y_full=z["y_full"])
+
+
+def pin_inputs(pin):
+    """The seeded inputs of a config-size pin (regenerated, never stored)."""
+    h = hparams(**pin.overrides)
+    return fixtures.make_inputs(h, pin.batch, pin.frames, pin.seed)
+
+
+def compare_with_pin(pin, y) -> dict:
+    """y: [B, 1, L] fp32 waveform (numpy) produced from pin_inputs(pin).  Compares the strided samples,
+    the whole stored utterances and the per-utterance float64 sums with what the reference produced."""
+    flat = np.ascontiguousarray(y, dtype=np.float32).reshape(pin.batch, -1)
+    got_s = flat.reshape(-1)[pin.idx]
+    got_f = flat[pin.full_b]
+    ref = np.concatenate([pin.y_s.reshape(-1), pin.y_full.reshape(-1)]).astype(np.float64)
+    got = np.concatenate([got_s.reshape(-1), got_f.reshape(-1)]).astype(np.float64)
+    d = flat.astype(np.float64)
+    energy = np.sqrt(np.maximum(pin.sumsq, 1e-30))
+    return {
+        "max_abs": float(np.abs(ref - got).max()),
+        "snr_db": fixtures.snr_db(ref, got),
+        # per-utterance sums cover every sample of every utterance: |sum(y) - sum(ref)| / sqrt(L sumsq)
+        "sum_err": float((np.abs(d.sum(axis=1) - pin.sum) / (energy * np.sqrt(flat.shape[1]))).max()),
+        "sumsq_rel": float((np.abs((d * d).sum(axis=1) - pin.sumsq) / np.maximum(pin.sumsq, 1e-30)).max()),
+        "nan": bool(np.isnan(flat).any()),
+    }
+
+
+def dropin_for_pin(pin):
+    from wavthruvec_pytorch_b200 import Generator
+    h = hparams(**pin.overrides)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gen = fixtures.construct(Generator, h)
+    fixtures.apply_state_from_golden(gen, pin.state, pin.small)
+    return gen

@@ -91,7 +91,7 @@ def test_tapgemm_tc_super_tile_heights(monkeypatch, msub, cin, n, rows):
 # whole forward against the goldens written by the reference
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
-                                  "rb1_1024_stress", "rb2_768_stress_tiny"])
+                                  "rb1_1024_stress", "rb2_768_stress_tiny", "rb2_1024_stress"])
 def test_fp32_plan_max_abs(name):
     g = load_golden(name)
     gen = dropin_in_state(g, cache=False).to("cuda:0")
@@ -109,7 +109,7 @@ def test_fp32_plan_fresh_state():
     assert (np.abs(y) > 0.99).mean() > 0.95 and np.abs(y - g.y).max() < 1e-3
 
 
-@pytest.mark.parametrize("name", ["rb2_768_stress", "rb2_1024_warm", "rb2_768_stress_tiny"])
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb2_1024_warm", "rb2_768_stress_tiny", "rb2_1024_stress"])
 def test_bf16_plan_snr(name):
     g = load_golden(name)
     gen = dropin_in_state(g, cache=False).to("cuda:0")

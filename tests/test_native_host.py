@@ -109,7 +109,7 @@ def test_pack_matches_numpy_fold():
 
 
 @pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
-                                  "rb2_768_stress_tiny", "rb1_1024_stress"])
+                                  "rb2_768_stress_tiny", "rb1_1024_stress", "rb2_1024_stress"])
 def test_fp32_plan_reproduces_reference(name):
     """Layer table + folding + packing + op wiring, executed in numpy fp32: max-abs <= 1e-5
     against the reference output (the device FP32 plan's bar is 1e-4)."""
@@ -185,7 +185,7 @@ def test_resblock1_pair_fusion(monkeypatch):
     assert fixtures.snr_db(g.y, fused) >= 45.0
 
 
-@pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 45.0), ("rb2_1024_warm", 45.0)])
+@pytest.mark.parametrize("name,min_snr", [("rb2_768_stress", 45.0), ("rb2_1024_warm", 45.0), ("rb2_1024_stress", 45.0)])
 def test_bf16_plan_predicted_snr(name, min_snr):
     """Same op list with the device's bf16 rounding points (bf16 operands, fp32 accumulate,
     fp32 residual stream): the waveform SNR bar of the bf16 path, predicted on the CPU."""

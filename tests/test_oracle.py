@@ -33,7 +33,7 @@ def test_torch_cpu_port_is_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
-                                  "rb2_768_stress_tiny", "rb1_1024_stress"])
+                                  "rb2_768_stress_tiny", "rb1_1024_stress", "rb2_1024_stress"])
 def test_numpy_restatement_fp64(name):
     """Independent arithmetic (no ATen conv): must sit on the reference's own fp64 run."""
     g = load_golden(name)
