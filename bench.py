@@ -3,23 +3,31 @@ per second).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
 
-One "step" = one forward of the workload batch.  At N=1 the workload is BASELINE.json
-configs[1] (cfg2: batch 16 x 4 s utterances, 768-ch features, bf16 path, shipped-default
-ResBlock2).  N>1 (torchrun, one rank per GPU): every rank generates its own cfg2 batch -- batches
-of independent utterances shard with no collective on the hot path ("weak" scaling); NCCL is
-used only for the barrier, the max-over-ranks timing and one output gather after the timed
-region.
+One "step" = one forward of the workload batch.
+
+  N = 1   BASELINE.json configs[1] (cfg2: batch 16 x 4 s utterances, 768-ch features, bf16 path,
+          shipped-default ResBlock2).  `--config` selects another configuration.
+  N > 1   (torchrun, one rank per GPU) BASELINE.json configs[4] (cfg5): batch 512 x 10 s utterances
+          split into contiguous shards (256 / 128 / 64 utterances per GPU at N = 2 / 4 / 8,
+          sharding.shard_bounds) -- total work is fixed, "scaling": "strong".  No collective on the
+          forward; NCCL carries the barrier, the max-over-ranks timing and the gather of every step's
+          waveforms to rank 0, which is warmed and TIMED: `value` excludes it (per-step CUDA events
+          around the forward), `value_incl_gather` is the steady-state rate of sharding.ShardedStream
+          (gather of step i overlapped with the forward of step i + 1).  `--scaling weak` restores the
+          round-1 behaviour (every rank runs its own copy of --config).
 
 Keys of the JSON line (see the task contract):
   value      whole-job audio-s/s, inputs resident in HBM, per-step CUDA-event times summed over K
              steps, max over ranks; L2 is flushed (256 MB write) before every timed step.
-  e2e        same metric through Generator.engine().forward_host -> v2w_forward_host: pinned host
+  e2e        same metric through Generator.engine().host_pipeline -> v2w_pipeline_*: pinned host
              inputs, H2D + forward + D2H inside the timed region.
-  roofline   tensor-bound: algorithmic FLOPs of the tcgen05 tap-GEMM launches / their summed
-             CUDA-event durations (events recorded by the library around each launch, extra steps
-             after the timed region), against MEASURED_PEAKS.json's sustained bf16 figure.
+  roofline   tensor-bound: algorithmic FLOPs of one step / ms_per_step of the TIMED region, against
+             MEASURED_PEAKS.json's sustained bf16 figure (`gemm_ms_per_step`: the per-op CUDA-event sum
+             of a separate profiling pass, PDL overlap off, kept for reference).
+  parity     after the timed loop: one forward of the SAME shape on the stress fixture against the pin
+             the unmodified reference wrote for that shape (tests/golden/cfg*_stress.npz).
   cpu_baseline  the oracle's torch-CPU port of the reference forward on this box's host cores,
-             bounded sample, rank 0 at N=1 only.
+             rank 0 at N=1 only.
 """
 from __future__ import annotations
 
@@ -44,7 +52,12 @@ CONFIGS = {
     "cfg3": (32, 300, 1024),
     "cfg4": (1, 1500, 768),
     "cfg5_per_gpu": (64, 500, 768),
+    "cfg5": (512, 500, 768),
 }
+#: config -> pin written by the reference (oracle/make_config_pins.py); cfg5 shards are checked in
+#: blocks of 64 utterances against the per-GPU pin (utterances are independent)
+PINS = {"cfg1": "cfg1_stress", "cfg2": "cfg2_stress", "cfg3": "cfg3_stress", "cfg4": "cfg4_stress",
+        "cfg5_per_gpu": "cfg5gpu_stress", "cfg5": "cfg5gpu_stress"}
 FRAMES_PER_SECOND = 50
 METRIC = "audio-sec/sec Vec2Wav gen"
 UNIT = "audio-s/s"
@@ -56,12 +69,25 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--config", default=None, choices=list(CONFIGS))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"])
     ap.add_argument("--resblock", default="2", choices=["1", "2"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the forward from a CUDA graph (latency path)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = max(args.gpus, world)
+    if args.scaling == "auto":
+        args.scaling = "strong" if (n > 1 and args.config in (None, "cfg5")) else "weak"
+    if args.config is None:
+        args.config = "cfg5" if (n > 1 and args.scaling == "strong") else "cfg2"
+    if args.precision is None:
+        args.precision = "fp16" if args.resblock == "1" else "bf16"
+    return args
 
 
 def make_hparams(args, feat):
@@ -81,8 +107,14 @@ def workload_name(args, batch, frames, feat):
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle's torch port of the reference forward on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2):
-    """Times oracle.vec2wav_torch_cpu.generator_forward on a bounded sample of the workload.
+def cpu_sample_batch(batch, frames):
+    """The whole batch when one CPU forward stays around a second (cfg1, cfg2, cfg4), else the largest
+    prefix of about 4000 frames (cfg3: 13 of 32 utterances, cfg5: 8 of 512)."""
+    return batch if batch * frames <= 4000 else max(1, 4000 // frames)
+
+
+def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2, cap_s=150.0):
+    """Times oracle.vec2wav_torch_cpu.generator_forward on the workload (or a bounded sample of it).
     Returns (audio_s_per_s, ms_per_step, sample description, threads, steps done)."""
     import torch
     from oracle import fixtures, vec2wav_torch_cpu
@@ -96,17 +128,22 @@ def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2):
     h = make_hparams(args, feat)
     gen = fixtures.construct(Generator, h).eval()
     sd = {k: v.detach() for k, v in gen.state_dict().items()}
-    sample_b = min(batch, 2)
+    sample_b = cpu_sample_batch(batch, frames)
     x, s, n = fixtures.make_inputs(h, sample_b, frames, 1234)
     threads = torch.get_num_threads()
+    t_cap = time.perf_counter() + cap_s
     for _ in range(warmup):
         vec2wav_torch_cpu.generator_forward(sd, h, x, s, n)
+        if time.perf_counter() > t_cap - cap_s / 2:
+            break
     times = []
     t_end = time.perf_counter() + seconds
     while True:
         t0 = time.perf_counter()
         vec2wav_torch_cpu.generator_forward(sd, h, x, s, n)
         times.append(time.perf_counter() - t0)
+        if time.perf_counter() > t_cap:
+            break
         if steps is not None:
             if len(times) >= steps:
                 break
@@ -114,9 +151,9 @@ def cpu_forward_timer(args, batch, frames, feat, seconds, steps=None, warmup=2):
             break
     audio = sample_b * frames / FRAMES_PER_SECOND
     mean = sum(times) / len(times)
-    sample = (f"{sample_b} of the {batch} utterances of the workload ({frames} frames each), "
-              f"{len(times)} forwards, fp32 torch-CPU port of the reference forward "
-              f"(oracle/vec2wav_torch_cpu.py), mean {mean * 1e3:.1f} ms, best {min(times) * 1e3:.1f} ms")
+    what = "the whole batch" if sample_b == batch else f"{sample_b} of the {batch} utterances of the workload"
+    sample = (f"{what} ({frames} frames each), {len(times)} forwards, fp32 torch-CPU port of the reference "
+              f"forward (oracle/vec2wav_torch_cpu.py), mean {mean * 1e3:.1f} ms, best {min(times) * 1e3:.1f} ms")
     return audio / mean, mean * 1e3, sample, threads, len(times)
 
 
@@ -130,16 +167,20 @@ def cpu_model():
     return "unknown"
 
 
-def torch_eager_context(gen, x, s, n, audio_per_step, steps=5):
+def torch_eager_context(gen, x, s, n, audio_per_step, steps=10, warm=6):
     import torch
     out = {"note": "library context, not this repo's path: Generator._forward_autograd under no_grad "
-                   "(same ATen calls as vec2wav/models.py:116-147)"}
+                   "(same ATen calls as vec2wav/models.py:116-147), cudnn.benchmark on as in train.py:24, "
+                   f"{warm} warm-up + {steps} timed forwards"}
+    bench_flag = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
     for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)),
                       ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
         try:
             with torch.no_grad(), ctx:
-                for _ in range(2):
+                for _ in range(warm):
                     gen._forward_autograd(x, s, n)
+                torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 for _ in range(steps):
@@ -150,6 +191,7 @@ def torch_eager_context(gen, x, s, n, audio_per_step, steps=5):
             out[name] = {"ms_per_step": ms, "value": audio_per_step / ms * 1e3}
         except Exception as e:  # context only: never fail the bench line over it
             out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    torch.backends.cudnn.benchmark = bench_flag
     return out
 
 
@@ -158,15 +200,14 @@ def run_reference_arm(args):
     if rank != 0:
         return
     batch, frames, feat = CONFIGS[args.config]
-    import torch
     v, ms, sample, threads, done = cpu_forward_timer(args, batch, frames, feat, seconds=1e9,
-                                                     steps=args.steps, warmup=max(1, args.warmup))
+                                                     steps=args.steps, warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": done, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": done, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, batch, frames, feat),
-                   "note": "host cores only; each step is a bounded sample of the workload"},
+                   "note": "host cores only (rank 0); a step is one CPU forward of the sample named in cpu_baseline.sample"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "host_cpu_count": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -231,12 +272,50 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------
+# parity self-check (checker only: the stress fixture + the reference-made pin of this shape)
+# --------------------------------------------------------------------------------------------
+def parity_check(args, dev, local_batch, frames, feat):
+    """One forward of the timed shape on the stress fixture, compared with what the unmodified
+    reference produced for it.  A shard bigger than the pin's batch is checked block by block (the
+    pin's inputs tiled: utterances are independent, so every block must reproduce the pin)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import compare_with_pin, dropin_for_pin, load_config_pin, pin_inputs
+    name = PINS[args.config] if args.resblock == "2" else ("cfg2_rb1_stress" if args.config == "cfg2" else None)
+    if name is None or not (ROOT / "tests" / "golden" / f"{name}.npz").exists():
+        return {"fixture": None, "note": "no reference pin for this configuration"}
+    pin = load_config_pin(name)
+    if pin.frames != frames or pin.overrides["num_wv_feat"] != feat or local_batch % pin.batch:
+        return {"fixture": name, "note": f"shape mismatch: pin {pin.batch}x{pin.frames}, timed {local_batch}x{frames}"}
+    gen = dropin_for_pin(pin).to(dev).eval()
+    gen.precision = args.precision
+    reps = local_batch // pin.batch
+    x, s, n = (a.repeat(reps, *([1] * (a.dim() - 1))).to(dev) for a in pin_inputs(pin))
+    with torch.no_grad():
+        y = gen(x, s, n).cpu().numpy()
+    worst = None
+    for r in range(reps):
+        c = compare_with_pin(pin, y[r * pin.batch:(r + 1) * pin.batch])
+        if worst is None or c["snr_db"] < worst["snr_db"]:
+            worst = c
+    bar_ok = (worst["max_abs"] <= 1e-4) if args.precision == "fp32" else (worst["snr_db"] >= 45.0)
+    del gen
+    torch.cuda.empty_cache()
+    return {"fixture": f"tests/golden/{name}.npz", "state": "stress", "shape": [local_batch, frames, feat],
+            "blocks": reps, "snr_db": worst["snr_db"], "max_abs": worst["max_abs"], "sum_err": worst["sum_err"],
+            "nan": worst["nan"], "bar": "max-abs <= 1e-4" if args.precision == "fp32" else "SNR >= 45 dB",
+            "pass": bool(bar_ok and not worst["nan"])}
+
+
+# --------------------------------------------------------------------------------------------
 # native arm
 # --------------------------------------------------------------------------------------------
 def run_native_arm(args):
     import torch
     import torch.distributed as dist
     from wavthruvec_pytorch_b200 import Generator, native
+    from wavthruvec_pytorch_b200.sharding import ShardedStream, shard_bounds, shard_sizes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,13 +329,23 @@ def run_native_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    batch, frames, feat = CONFIGS[args.config]
+    g_batch, frames, feat = CONFIGS[args.config]
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        lo, hi = shard_bounds(g_batch, world, rank)
+        batch = hi - lo                       # this rank's shard of the global batch
+        total_utts = g_batch
+    else:
+        batch = g_batch                       # every rank runs the whole configuration (weak scaling)
+        total_utts = g_batch * world
     h = make_hparams(args, feat)
     torch.manual_seed(1234)                      # hp.seed (vec2wav/hparams.py:37)
     gen = Generator(h).eval().to(dev)
     gen.precision = args.precision
     eng = gen.engine()
-    # distinct utterances per rank (seed offset); same shapes => weak scaling
+    if args.graph:
+        gen.use_cuda_graph = True
+    # distinct utterances per rank (seed offset)
     rng = torch.Generator().manual_seed(1234 + rank)
     x = torch.randn(batch, feat, frames, generator=rng)
     s = torch.randn(batch, h.spk_dim, generator=rng)
@@ -265,7 +354,8 @@ def run_native_arm(args):
     xh, sh, nh = x.pin_memory(), s.pin_memory(), n.pin_memory()
     out_h = torch.empty((batch, 1, frames * 320), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    audio_per_step = batch * frames / FRAMES_PER_SECOND
+    audio_per_step = total_utts * frames / FRAMES_PER_SECOND      # whole job, all ranks
+    steps = args.steps
 
     def barrier():
         if world > 1:
@@ -280,13 +370,13 @@ def run_native_arm(args):
         launches_per_step = eng.last_launches
 
         # ---- value: device-resident inputs, per-step events, L2 flushed before each step ----
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         sampler = ClockSampler(local)
         barrier()
         sampler.start()
         wall0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(steps):
             flush.zero_()
             starts[i].record()
             y = gen(xd, sd_, nd)
@@ -296,13 +386,44 @@ def run_native_arm(args):
         step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
         total_ms = sum(step_ms)
 
+        # ---- multi-GPU: the output gather to rank 0, warmed and timed ----
+        gather_ms = gather_loop_ms = 0.0
+        if world > 1:
+            fwd = lambda a, b, c: gen(a, b, c)
+            stream = ShardedStream(fwd, total_utts)
+            for _ in range(3):                      # warm: communicator init, NCCL buffers, allocator
+                stream.step(xd, sd_, nd)
+            stream.flush()
+            # (a) one blocking gather by itself
+            sizes = shard_sizes(total_utts, world)
+            from wavthruvec_pytorch_b200.sharding import _gather_padded
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                _gather_padded(y, sizes, rank, 0, None)
+            b.record()
+            torch.cuda.synchronize(dev)
+            gather_ms = a.elapsed_time(b) / 3
+            # (b) steady state: K steps, gather of step i under the forward of step i + 1
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                stream.step(xd, sd_, nd)
+            stream.flush()
+            b.record()
+            torch.cuda.synchronize(dev)
+            gather_loop_ms = a.elapsed_time(b)
+            barrier()
+
         # ---- e2e: pinned host buffers through the C-ABI.  Every step copies its inputs H2D and its
         # whole waveform D2H inside the timed region.  Two flavours: one blocking v2w_forward_host
         # call per step, and the streaming v2w_pipeline_* API (same copies, overlapped with the
         # kernels of the neighbouring steps) -- the latter is the throughput figure reported as e2e.
         for _ in range(3):
             eng.forward_host(xh, sh, nh, out_h, dev)
-        e2e_steps = max(5, min(args.steps, 50))
+        e2e_steps = max(5, min(steps, 50))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -323,32 +444,37 @@ def run_native_arm(args):
         pipe.close()
         clocks = sampler.stop()
 
-        # ---- roofline: per-op events on the tcgen05 tap-GEMM launches ----
+        # ---- per-op events on the tcgen05 launches (separate pass: PDL overlap is off under profiling) ----
         prof = eng.profile_ops(xd, sd_, nd, reps=5, before_each=lambda: flush.zero_())
 
-    t = torch.tensor([total_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
+        # ---- parity self-check on the timed shape ----
+        parity = None
+        if not args.no_parity:
+            try:
+                parity = parity_check(args, dev, batch, frames, feat)
+            except Exception as e:
+                parity = {"error": f"{type(e).__name__}: {e}"[:300], "pass": False}
+
+    t = torch.tensor([total_ms, e2e_s, e2e_sync_s, gather_ms, gather_loop_ms,
+                      0.0 if (parity is None or parity.get("pass", True)) else 1.0,
+                      -(parity or {}).get("snr_db", 1e9) if parity and parity.get("snr_db") is not None else -1e9],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # output gather (outside the timed region): the only data collective of the job
-        g0 = time.perf_counter()
-        gathered = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
-        dist.gather(y, gathered, dst=0)
-        torch.cuda.synchronize(dev)
-        gather_ms = (time.perf_counter() - g0) * 1e3
-    else:
-        gather_ms = 0.0
-    total_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_s, e2e_sync_s, gather_ms, gather_loop_ms = (float(v) for v in t[:5])
+    parity_fail_any, worst_snr = bool(t[5] > 0), -float(t[6])
 
     if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = world * audio_per_step / (ms_per_step * 1e-3)
-        e2e_value = world * audio_per_step / (e2e_s / e2e_steps)
+        ms_per_step = total_ms / steps
+        value = audio_per_step / (ms_per_step * 1e-3)
+        e2e_value = audio_per_step / (e2e_s / e2e_steps)
         peak_tf, peak_gbs, peak_src = measured_peaks()
         gemm = [(op, ms) for op, ms in prof if op.kind in (native.OP_TAPGEMM, native.OP_MRF_FUSED, native.OP_PAIR_FUSED)]
         gemm_flops = sum(op.flops for op, _ in gemm)
         gemm_ms = sum(ms for _, ms in gemm)
         all_ms = sum(ms for _, ms in prof)
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # one GPU's share of the timed step: its algorithmic FLOPs / its ms_per_step
+        achieved = gemm_flops / (ms_per_step * 1e-3) / 1e12
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
@@ -357,37 +483,55 @@ def run_native_arm(args):
             except Exception:
                 traffic = None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": workload_name(args, batch, frames, feat),
+            "config": {"workload": workload_name(args, g_batch, frames, feat),
                        "per_gpu_batch": batch, "l2": "flushed with a 256 MB write before every step",
-                       "precision": args.precision, "sharding": f"dp{world} (independent utterances)"},
+                       "precision": args.precision,
+                       "sharding": (f"{g_batch} utterances in contiguous shards of {batch} per GPU (sharding.shard_bounds), "
+                                    f"no collective on the forward, NCCL gather of every step's waveforms to rank 0")
+                       if strong else f"dp{world} (every rank runs the whole configuration)",
+                       "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(xh.numel() + sh.numel() + nh.numel()) * 4,
                     "d2h_bytes_per_step": int(out_h.numel()) * 4, "steps": e2e_steps,
                     "api": "Generator.engine().host_pipeline -> v2w_pipeline_submit/wait (2 steps in flight)",
-                    "note": "every step copies its inputs H2D and its waveform D2H inside the timed region; no L2 flush "
-                            "between these steps (the inputs arrive through the copy), which is why it can edge past `value`",
-                    "blocking_call_value": world * audio_per_step / (e2e_sync_s / e2e_steps)},
-            "gpu_launches": launches_per_step * args.steps,
+                    "note": "every step copies its inputs H2D and its waveform D2H inside the timed region (bytes are per GPU); "
+                            "no L2 flush between these steps (the inputs arrive through the copy), which is why it can edge past `value`",
+                    "blocking_call_value": audio_per_step / (e2e_sync_s / e2e_steps)},
+            "gpu_launches": launches_per_step * steps,
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "tapgemm_simt_kernel" if args.precision == "fp32" else "tapgemm_tc_kernel + mrf_stacked_kernel + mrf_stage_kernel",
-                         "launches": len(gemm), "gemm_ms_per_step": gemm_ms,
-                         "all_ops_ms_per_step": all_ms,
+                         "launches": len(gemm), "definition": "algorithmic FLOPs of one step (per GPU) / ms_per_step of the timed region",
+                         "gemm_ms_per_step": gemm_ms, "all_ops_ms_per_step": all_ms,
+                         "achieved_over_gemm_ms": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
                          "algorithmic_gflop_per_step": gemm_flops / 1e9},
+            "parity": parity,
             "clocks": clocks,
             "wall_s_timed_region": wall,
-            "gather_ms": gather_ms,
         }
+        if world > 1:
+            loop_ms = gather_loop_ms / steps
+            line["value_incl_gather"] = audio_per_step / (loop_ms * 1e-3)
+            line["gather"] = {"ms_blocking": gather_ms, "ms_per_step_incl_gather": loop_ms,
+                              "bytes_to_rank0": int(total_utts * frames * 320 * 4),
+                              "note": "warmed; ms_blocking = one gather alone (CUDA events, max over ranks); "
+                                      "ms_per_step_incl_gather = steady state of sharding.ShardedStream, the gather of "
+                                      "step i overlapped with the forward of step i+1 (no L2 flush inside this loop: "
+                                      "the shard's working set is far larger than L2)"}
+            if parity is not None:
+                line["parity"]["all_ranks_pass"] = not parity_fail_any
+                line["parity"]["worst_rank_snr_db"] = worst_snr
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, sample, threads, _ = cpu_forward_timer(args, batch, frames, feat, args.cpu_seconds)
+            v, ms, sample, threads, _ = cpu_forward_timer(args, g_batch, frames, feat, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": sample, "host_cpu_count": os.cpu_count(),
                                     "cpu_model": cpu_model()}
+        if world == 1 and not args.no_eager:
             # Context only: the reference's own op sequence -- stock PyTorch/cuDNN ops,
             # weight-norm hooks re-run every call -- on this same GPU, same inputs.  It is the
             # drop-in's train()/autograd delegate, bit-identical to the reference on CPU.

@@ -311,6 +311,18 @@ int32_t v2w_plan_bind(struct v2w_plan* p, const void* packed_dev, void* workspac
 int32_t v2w_forward(struct v2w_plan* p, const float* x_dev, const float* spk_dev,
                     const float* noise_dev, float* out_dev, void* stream,
                     int32_t* gpu_launches);
+
+/* The same forward replayed from a CUDA graph (the latency path: batch-1 / long-form requests, where
+ * the ~18 launches of a forward cost more host time than device time).  The first call with a given
+ * (x_dev, spk_dev, noise_dev, out_dev) pointer tuple on a plan that has already run once captures the
+ * forward (programmatic-dependent-launch edges and the conditioning fork / join included) into a graph
+ * and instantiates it; later calls with the same pointers are one cudaGraphLaunch.  Up to 8 pointer
+ * tuples are cached per plan (least recently used evicted); after 16 consecutive misses the plan stops
+ * capturing and the call is exactly v2w_forward.  `replayed`, if non-NULL, receives 1 when the call was
+ * a graph launch.  Results are bit-identical to v2w_forward (same kernels, same launch parameters). */
+int32_t v2w_forward_graph(struct v2w_plan* p, const float* x_dev, const float* spk_dev,
+                          const float* noise_dev, float* out_dev, void* stream, int32_t* gpu_launches,
+                          int32_t* replayed);
 /* Same call with HOST buffers (pinned recommended): H2D of the three inputs, the forward,
  * D2H of the waveform, all on `stream`; returns after the stream is synchronised.  Uses
  * staging areas inside the bound workspace. */

@@ -167,3 +167,19 @@ def test_plan_batches():
         assert hi - lo <= 32 and (sum(rows[lo:hi]) <= 4000 or hi - lo == 1)
         if hi < 300:   # greedy: the next utterance did not fit
             assert sum(rows[lo:hi]) + rows[hi] > 4000 or hi - lo == 32
+
+
+def test_plan_batches_bounds_the_padded_plan_rectangle():
+    """127 short utterances must not ride with one 2000-frame utterance in a 128 x 2016 plan."""
+    rows = [20] * 127 + [2000]
+    unbounded = files.plan_batches(rows, 16000, 128)
+    assert unbounded == [(0, 128)]
+    bounded = files.plan_batches(rows, 16000, 128, max_plan_frames=32000)
+    assert bounded[-1] == (127, 128) and bounded[0][0] == 0
+    for lo, hi in bounded:
+        utts = -(-(hi - lo) // 8) * 8
+        longest = -(-max(rows[lo:hi]) // 32) * 32
+        assert utts * longest <= 32000 or hi - lo == 1
+    # homogeneous corpora are unaffected
+    rows = [200] * 64
+    assert files.plan_batches(rows, 6400, 32, max_plan_frames=12800) == files.plan_batches(rows, 6400, 32)

@@ -444,3 +444,73 @@ def test_conditioning_edit_refolds_in_place():
         ref = gen._forward_autograd(x, s, n)
     assert gen.engine()._plans == plans_before and plans_before      # same plan objects: no full re-fold
     assert np.abs((y - ref).cpu().numpy()).max() <= FP32_MAX_ABS
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA-graph replay (latency path): same kernels, same launch parameters => bit-identical
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch,frames", [("rb2_768_stress", 1, 100), ("rb2_768_stress", 2, 61),
+                                               ("rb1_768_stress", 1, 40)])
+def test_cuda_graph_replay_is_bit_identical(name, batch, frames):
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, batch, frames, 5))
+    eng = gen.engine()
+    with torch.no_grad():
+        want = gen(x, s, n).clone()                       # stream path (also the plan's first run)
+        gen.use_cuda_graph = True
+        out = torch.empty_like(want)
+        side = torch.cuda.Stream()
+        for stream in (torch.cuda.current_stream(), side):      # the legacy default stream and a created one
+            with torch.cuda.stream(stream):
+                hits = []
+                for k in range(4):
+                    out.zero_()
+                    eng.forward_into(x, s, n, out)
+                    hits.append(eng.last_graph_replay)
+                    stream.synchronize()
+                    assert torch.equal(out, want), f"replay {k} differs from the stream path"
+                assert all(hits), hits                    # captured on the first call with these pointers
+                assert eng.last_launches > 0
+        # new inputs in the same buffers: the graph reads the buffers, not a snapshot
+        x2, s2, n2 = (a.cuda() for a in fixtures.make_inputs(gen.h, batch, frames, 6))
+        gen.use_cuda_graph = False
+        want2 = gen(x2, s2, n2).clone()
+        gen.use_cuda_graph = True
+        x.copy_(x2); s.copy_(s2); n.copy_(n2)
+        eng.forward_into(x, s, n, out)
+        torch.cuda.synchronize()
+        assert eng.last_graph_replay and torch.equal(out, want2)
+        # Generator.forward in graph mode (fresh output tensors from the caching allocator)
+        ys = [gen(x, s, n) for _ in range(6)]
+        torch.cuda.synchronize()
+        assert all(torch.equal(y, want2) for y in ys)
+        # a parameter edit re-folds, rebinds and drops the captured graphs
+        gen.conv_post.bias.add_(0.05)
+        y3 = gen(x, s, n)
+        gen.use_cuda_graph = False
+        assert torch.equal(y3, gen(x, s, n)) and not torch.equal(y3, want2)
+
+
+def test_plan_cache_is_bounded_and_stream_keyed():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    eng = gen.engine()
+    eng.max_plans = 3
+    with torch.no_grad():
+        outs = {}
+        for frames in (8, 9, 10, 11, 12, 8):
+            x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, 1, frames, frames))
+            y = gen(x, s, n)
+            if frames in outs:
+                assert torch.equal(outs[frames], y)       # re-created plan gives the same answer
+            outs[frames] = y
+            assert len(eng._plans) <= 3
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            y_side = gen(x, s, n)
+        side.synchronize()
+        assert torch.equal(y_side, outs[8])
+        keys = list(eng._plans)
+        assert len({k[4] for k in keys}) == 2             # one plan per stream

@@ -52,6 +52,19 @@ def test_rejects_bad_arguments():
         mel.filterbank(1000, 80, 16000, 0, None, hop_size=250)          # hop % 16 != 0
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_autograd_delegate_matches_reference_and_has_gradients(tag):
+    """With autograd enabled and an input that requires grad (the mel-L1 loss of train.py:172-174) the call
+    must be differentiable: it is delegated to the reference's op sequence, never to the grad-less kernels."""
+    z = _golden()
+    y = torch.from_numpy(z[f"y_{tag}"]).clone().requires_grad_(True)
+    got = mel.mel_spectrogram(y, **MEL_PARAMS)
+    assert got.requires_grad and got.grad_fn is not None
+    assert np.abs(got.detach().numpy() - z[f"mel_{tag}"]).max() < 1e-4
+    got.abs().mean().backward()
+    assert y.grad is not None and torch.isfinite(y.grad).all() and float(y.grad.abs().sum()) > 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_native_mel_matches_reference(tag):

@@ -105,7 +105,26 @@ struct v2w_plan {
   // the start of a forward and joined right before the first op that reads its scale/shift.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // CUDA-graph replay (v2w_forward_graph): one instantiated graph per pointer tuple, LRU
+  struct GraphEntry {
+    const void *x, *spk, *noise, *out;
+    cudaGraphExec_t exec;
+    int launches;
+    uint64_t stamp;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  int graph_miss_streak = 0;
+  bool ran_once = false;          // lazy per-device initialisation happened outside any capture
+  cudaStream_t cap = nullptr;     // capture stream
+  void drop_graphs() {
+    for (GraphEntry& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+    graph_miss_streak = 0;
+  }
   ~v2w_plan() {
+    drop_graphs();
+    if (cap) cudaStreamDestroy(cap);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -1161,6 +1180,8 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
     set_error("v2w_plan_bind: null argument");
     return V2W_ERR_INVALID;
   }
+  p->drop_graphs();   // captured launches hold the old buffers' addresses
+  p->ran_once = false;
   if ((reinterpret_cast<uintptr_t>(packed_dev) & 255) ||
       (reinterpret_cast<uintptr_t>(workspace_dev) & 255)) {
     set_error("v2w_plan_bind: buffers must be 256-byte aligned");
@@ -1553,7 +1574,72 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
 
 int32_t v2w_forward(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
                     float* out_dev, void* stream, int32_t* gpu_launches) {
-  return run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, stream, gpu_launches);
+  int32_t rc = run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, stream, gpu_launches);
+  if (rc == V2W_OK) p->ran_once = true;
+  return rc;
+}
+
+int32_t v2w_forward_graph(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,
+                          float* out_dev, void* stream, int32_t* gpu_launches, int32_t* replayed) {
+  constexpr size_t kMaxGraphs = 8;
+  constexpr int kMissLimit = 16;
+  if (replayed) *replayed = 0;
+  if (!p) {
+    set_error("v2w_forward_graph: null plan");
+    return V2W_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (v2w_plan::GraphEntry& g : p->graphs) {
+    if (g.x == x_dev && g.spk == spk_dev && g.noise == noise_dev && g.out == out_dev) {
+      V2W_CUDA(cudaGraphLaunch(g.exec, st));
+      g.stamp = ++p->graph_clock;
+      p->graph_miss_streak = 0;
+      if (gpu_launches) *gpu_launches = g.launches;
+      if (replayed) *replayed = 1;
+      return V2W_OK;
+    }
+  }
+  // First run of a plan, profiling, or pointer tuples that never repeat: plain stream launches.
+  if (!p->ran_once || p->profiling || p->graph_miss_streak >= kMissLimit)
+    return v2w_forward(p, x_dev, spk_dev, noise_dev, out_dev, stream, gpu_launches);
+  ++p->graph_miss_streak;
+  // Captured on a stream of the plan's own (the caller's may be the legacy default stream, which cannot
+  // be captured); the instantiated graph is then launched on the caller's stream.
+  if (!p->cap) V2W_CUDA(cudaStreamCreateWithFlags(&p->cap, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  V2W_CUDA(cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeThreadLocal));
+  int32_t launches = 0;
+  const int32_t rc = run_ops(p, x_dev, spk_dev, noise_dev, out_dev, nullptr, V2W_OUT_F32, p->cap, &launches);
+  const cudaError_t ce = cudaStreamEndCapture(p->cap, &graph);   // always leave capture mode
+  if (rc != V2W_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    set_error("v2w_forward_graph: stream capture failed: %s", cudaGetErrorString(ce));
+    return V2W_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    set_error("v2w_forward_graph: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    return V2W_ERR_CUDA;
+  }
+  if (p->graphs.size() >= kMaxGraphs) {
+    size_t victim = 0;
+    for (size_t i = 1; i < p->graphs.size(); ++i)
+      if (p->graphs[i].stamp < p->graphs[victim].stamp) victim = i;
+    cudaGraphExecDestroy(p->graphs[victim].exec);
+    p->graphs.erase(p->graphs.begin() + victim);
+  }
+  p->graphs.push_back({x_dev, spk_dev, noise_dev, out_dev, exec, launches, ++p->graph_clock});
+  V2W_CUDA(cudaGraphLaunch(exec, st));
+  if (gpu_launches) *gpu_launches = launches;
+  if (replayed) *replayed = 1;
+  return V2W_OK;
 }
 
 int32_t v2w_forward_train(v2w_plan* p, const float* x_dev, const float* spk_dev, const float* noise_dev,

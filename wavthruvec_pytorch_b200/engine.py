@@ -6,6 +6,9 @@ module's parameter storage; all arithmetic happens in libv2w (include/v2w.h).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
+from collections import OrderedDict
 from typing import Dict, List, Tuple
 
 import torch
@@ -29,11 +32,19 @@ class NativeEngine:
         self._model = handle
         self._packed: Dict[Tuple, torch.Tensor] = {}     # (device, 16-bit format) -> packed weights
         self._packed_sig = None
-        self._plans: Dict[Tuple, Tuple[C.c_void_p, torch.Tensor]] = {}
+        # (batch, frames, precision, device, stream) -> (plan handle, workspace), least recently used
+        # first.  Bounded by count and by workspace bytes: a validation loop that feeds every utterance
+        # at its own length would otherwise keep one ~96 KB-per-frame workspace per distinct length.
+        self._plans: "OrderedDict[Tuple, Tuple[C.c_void_p, torch.Tensor]]" = OrderedDict()
+        self.max_plans = int(os.environ.get("V2W_MAX_PLANS", "16"))
+        self.max_workspace_bytes = int(float(os.environ.get("V2W_MAX_WORKSPACE_GB", "48")) * (1 << 30))
+        self._lock = threading.RLock()     # plan cache + folding cache are shared by every caller thread
+        self._pinned: Dict[Tuple, int] = {}   # plans a HostPipeline holds on to: never evicted
         self._convs = None        # cached module list / tensor list for the per-call change check
         self._tensors = None
         self._structure = None
         self.last_launches = 0
+        self.last_graph_replay = False
 
     def __del__(self):
         try:
@@ -46,9 +57,27 @@ class NativeEngine:
 
     # ------------------------------------------------------------------------------------------
     def _drop_plans(self):
+        if getattr(self, "_pinned", None) and any(self._pinned.values()):
+            raise RuntimeError("parameters changed while a HostPipeline of this module is open; close() it first")
         for plan, _ws in self._plans.values():
             self._lib.v2w_plan_destroy(plan)
         self._plans.clear()
+
+    def _evict(self, incoming_bytes: int) -> None:
+        """Make room for one more plan: least recently used plans go first.  Their workspaces are
+        returned to PyTorch's caching allocator, which keeps the memory ordered behind the kernels
+        already enqueued on the stream that last used it."""
+        def total():
+            return sum(ws.numel() for _p, ws in self._plans.values())
+        while (len(self._plans) >= self.max_plans or total() + incoming_bytes > self.max_workspace_bytes):
+            victim = next((k for k in self._plans if not self._pinned.get(k)), None)
+            if victim is None:
+                break
+            plan, _ws = self._plans.pop(victim)
+            self._lib.v2w_plan_destroy(plan)
+
+    def workspace_bytes(self) -> int:
+        return sum(ws.numel() for _p, ws in self._plans.values())
 
     def invalidate(self):
         self._packed.clear()
@@ -169,11 +198,21 @@ class NativeEngine:
 
     # ------------------------------------------------------------------------------------------
     def plan(self, batch: int, frames: int, precision: str, device: torch.device, train: bool = False):
-        """(plan handle, workspace) for this problem size; created and bound on first use."""
+        """(plan handle, workspace) for this problem size ON THE CURRENT STREAM of `device`; created and
+        bound on first use.  A plan owns a workspace, a side stream and fork / join events, so it serves
+        one stream at a time: callers on different streams (or threads using different streams) get
+        separate plans; callers sharing a stream are serialised by that stream."""
+        with self._lock:
+            return self._plan_locked(batch, frames, precision, device, train)
+
+    def _plan_locked(self, batch, frames, precision, device, train):
         self._refresh(train)
-        key = (batch, frames, precision, device)
+        with torch.cuda.device(device):
+            stream_id = torch.cuda.current_stream(device).cuda_stream
+        key = (batch, frames, precision, device, stream_id)
         hit = self._plans.get(key)
         if hit is not None:
+            self._plans.move_to_end(key)
             return hit
         prec = native.PRECISIONS[precision]
         packed = self._packed_on(device, native.HALF_FP16 if precision == "fp16" else native.HALF_BF16)
@@ -181,6 +220,7 @@ class NativeEngine:
         native.check(self._lib.v2w_plan_create(self._model, batch, frames, prec, C.byref(handle)))
         try:
             ws_bytes = int(self._lib.v2w_plan_workspace_bytes(handle))
+            self._evict(ws_bytes)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
             with torch.cuda.device(device):
                 native.check(self._lib.v2w_plan_bind(handle, packed.data_ptr(), ws.data_ptr()))
@@ -230,9 +270,44 @@ class NativeEngine:
         n = C.c_int32(0)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(),
-                                               noise.data_ptr(), out.data_ptr(),
-                                               C.c_void_p(stream), C.byref(n)))
+            if getattr(self._module, "use_cuda_graph", False):
+                # latency path: replay from a CUDA graph keyed by the four device pointers (a serving
+                # loop with preallocated buffers, or PyTorch's allocator handing the same blocks back)
+                hit = C.c_int32(0)
+                native.check(self._lib.v2w_forward_graph(handle, x.data_ptr(), spk.data_ptr(),
+                                                         noise.data_ptr(), out.data_ptr(),
+                                                         C.c_void_p(stream), C.byref(n), C.byref(hit)))
+                self.last_graph_replay = bool(hit.value)
+            else:
+                native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(),
+                                                   noise.data_ptr(), out.data_ptr(),
+                                                   C.c_void_p(stream), C.byref(n)))
+        self.last_launches = n.value
+        return out
+
+    def forward_into(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """forward() into a caller-owned output tensor: with `use_cuda_graph` and preallocated
+        fp32 contiguous buffers every call after the second is a single graph launch."""
+        self._check_inputs(x, spk, noise)
+        dev = x.device
+        B, _, T = x.shape
+        for t in (x, spk, noise, out):
+            if not t.is_cuda or t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("forward_into takes contiguous fp32 CUDA tensors on one device")
+        if tuple(out.shape) != (B, 1, T * self.total_upsample()):
+            raise RuntimeError("out has the wrong shape")
+        handle, _ws = self.plan(B, T, self._module.precision, dev)
+        n, hit = C.c_int32(0), C.c_int32(0)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            fn = self._lib.v2w_forward_graph if getattr(self._module, "use_cuda_graph", False) else None
+            if fn is not None:
+                native.check(fn(handle, x.data_ptr(), spk.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                                C.c_void_p(stream), C.byref(n), C.byref(hit)))
+            else:
+                native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(), noise.data_ptr(),
+                                                   out.data_ptr(), C.c_void_p(stream), C.byref(n)))
+        self.last_graph_replay = bool(hit.value)
         self.last_launches = n.value
         return out
 
@@ -348,8 +423,11 @@ class NativeEngine:
         """Streaming generation from pinned host buffers (v2w_pipeline_*): copies of neighbouring
         steps overlap the kernels of the current one."""
         dev = torch.device(device)
-        handle, _ws = self.plan(batch, frames, self._module.precision, dev)
-        return HostPipeline(self, handle, batch, frames, dev)
+        with self._lock:
+            handle, _ws = self.plan(batch, frames, self._module.precision, dev)
+            key = next(k for k, v in self._plans.items() if v[0] is handle)
+            self._pinned[key] = self._pinned.get(key, 0) + 1
+        return HostPipeline(self, handle, batch, frames, dev, key)
 
     def profile_ops(self, x, spk, noise, reps: int = 3, before_each=None):
         """Per-op device times (ms, mean over `reps` forwards) from CUDA events recorded by the
@@ -387,8 +465,9 @@ class HostPipeline:
     kernels launched.  Host tensors must be contiguous fp32 CPU tensors (pinned for overlap) and
     stay alive until `wait` returns."""
 
-    def __init__(self, engine: NativeEngine, plan_handle, batch, frames, device):
+    def __init__(self, engine: NativeEngine, plan_handle, batch, frames, device, plan_key=None):
         self._engine = engine
+        self._plan_key = plan_key
         self._lib = engine._lib
         self._device = device
         self._shape = (batch, frames)
@@ -422,6 +501,9 @@ class HostPipeline:
         if self._handle:
             self._lib.v2w_pipeline_destroy(self._handle)
             self._handle = None
+            if self._plan_key is not None:
+                with self._engine._lock:
+                    self._engine._pinned[self._plan_key] = max(0, self._engine._pinned.get(self._plan_key, 1) - 1)
 
     def __del__(self):
         try:

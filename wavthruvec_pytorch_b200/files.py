@@ -148,16 +148,25 @@ def feature_shapes(paths: Sequence[str], threads: int = 4) -> Tuple[np.ndarray, 
     return rows, cols
 
 
-def plan_batches(rows: Sequence[int], max_batch_frames: int, max_batch_utts: int) -> List[Tuple[int, int]]:
+def plan_batches(rows: Sequence[int], max_batch_frames: int, max_batch_utts: int,
+                 max_plan_frames: Optional[int] = None) -> List[Tuple[int, int]]:
     """Item ranges [lo, hi) in order: a batch closes when the next utterance would exceed the frame
-    budget or the utterance cap (a single over-long utterance still gets a batch of its own)."""
+    budget or the utterance cap (a single over-long utterance still gets a batch of its own), or -- with
+    `max_plan_frames` -- when the padded rectangle of its plan (utterances rounded up to 8 x longest
+    utterance rounded up to 32: what the workspace is sized by) would."""
     batches: List[Tuple[int, int]] = []
-    lo, frames = 0, 0
+    lo, frames, longest = 0, 0, 0
     for i, n in enumerate(rows):
-        if i > lo and (frames + int(n) > max_batch_frames or i - lo >= max_batch_utts):
-            batches.append((lo, i))
-            lo, frames = i, 0
-        frames += int(n)
+        n = int(n)
+        if i > lo:
+            utts = -(-(i - lo + 1) // 8) * 8
+            rect = utts * (-(-max(longest, n) // 32) * 32)
+            if (frames + n > max_batch_frames or i - lo >= max_batch_utts
+                    or (max_plan_frames is not None and rect > max_plan_frames)):
+                batches.append((lo, i))
+                lo, frames, longest = i, 0, 0
+        frames += n
+        longest = max(longest, n)
     if len(rows):
         batches.append((lo, len(rows)))
     return batches
@@ -165,7 +174,8 @@ def plan_batches(rows: Sequence[int], max_batch_frames: int, max_batch_utts: int
 
 def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str, out_dir: str,
                      max_batch_frames: int = 16000, max_batch_utts: int = 128, readers: int = 4,
-                     seed: int = 1234, sampling_rate: int = 16000, max_utt_frames: int = 2000) -> Stats:
+                     seed: int = 1234, sampling_rate: int = 16000, max_utt_frames: int = 2000,
+                     reader_timeout_s: Optional[float] = None, max_plan_frames: Optional[int] = None) -> Stats:
     """Generate <out_dir>/<speaker>/<utt>.wav for every item.  `gen`: drop-in Generator in eval()
     mode on a CUDA device.  A batch closes at `max_batch_frames` feature frames or
     `max_batch_utts` utterances, whichever comes first (items keep their order).
@@ -173,7 +183,13 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
     Per BATCH the host does three library calls and no per-file work: v2w_npy_read_batch (`readers`
     worker threads, every payload lands at its final offset of a pinned row arena = the x_rows layout
     of v2w_forward_ragged), the ragged forward with PCM16 output, v2w_wav_write_batch.  A prefetch
-    thread fills the arena of batch k+1 and a writer thread emits batch k-1 while batch k is on the GPU."""
+    thread fills the arena of batch k+1 and a writer thread emits batch k-1 while batch k is on the GPU.
+
+    The workspace of a batch is sized utterances x longest utterance (the plan is a padded rectangle), so a
+    batch also closes when that product would exceed `max_plan_frames` (default 2 x max_batch_frames): 127
+    short utterances can no longer ride with one 2000-frame utterance in a 128 x 2016 plan.
+    `reader_timeout_s`: give up when the reader delivers nothing for this long (default: wait as long as
+    the reader thread is alive)."""
     import ctypes as C
     from . import native
     if gen.training:
@@ -198,7 +214,8 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
             raise ValueError(f"{feat_paths[i]}: {cols[i]} feature channels, expected {h.num_wv_feat}")
         if rows[i] > max_utt_frames:
             raise ValueError(f"{feat_paths[i]}: {rows[i]} frames do not fit the {max_utt_frames}-frame limit")
-    batches = plan_batches(rows, max_batch_frames, max_batch_utts)
+    batches = plan_batches(rows, max_batch_frames, max_batch_utts,
+                           max_plan_frames if max_plan_frames is not None else 2 * max_batch_frames)
     for d in sorted({os.path.dirname(p) for p in wav_paths}):
         os.makedirs(d, exist_ok=True)
 
@@ -276,43 +293,74 @@ def synthesize_files(gen, items: Sequence[Item], feat_dir: str, spk_emb_dir: str
     wt = threading.Thread(target=writer, daemon=True)
     pt.start()
     wt.start()
-    with torch.no_grad():
-        for k, (lo, hi) in enumerate(batches):
-            try:
-                got = ready.get(timeout=120)
-            except queue.Empty:
-                raise RuntimeError(f"the feature reader made no progress for 120 s (batch {k})") from None
-            if got is None or errors:
-                raise errors[0]
-            _, spk = got
-            a = k & 1
-            real = hi - lo
-            dummies = (-real) % 8
-            lengths = [int(v) for v in rows[lo:hi]]
-            off = sum(lengths)
-            arenas[a][off:off + dummies].zero_()
-            lengths += [1] * dummies
-            rows_dev = arenas[a][:off + dummies].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            arena_tokens[a].put(ev)
-            noise = torch.randn(real + dummies, h.noise_dim, device=dev, generator=rng)
-            plan_frames = -(-max(lengths) // 32) * 32
-            packed = eng.forward_ragged(rows_dev, lengths, spk.to(dev), noise, plan_frames, pcm16=True)
-            n_valid = off * up
-            pcm_buf = pcm_pool.get()
-            pcm_buf[:n_valid].copy_(packed[:n_valid], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-            to_write.put((done, pcm_buf, lo, hi))
-            stats.utterances += real
-            stats.audio_s += n_valid / sampling_rate
-            stats.batches += 1
-            if errors:
-                raise errors[0]
-    to_write.put(None)
-    wt.join()
-    pt.join()
+    failure: Optional[BaseException] = None
+    try:
+        # everything below runs on `dev` and on ITS current stream, whatever the caller's current device is
+        # (events recorded on another device's stream would not cover these copies)
+        with torch.cuda.device(dev), torch.no_grad():
+            stream = torch.cuda.current_stream(dev)
+            for k, (lo, hi) in enumerate(batches):
+                waited = 0.0
+                while True:
+                    try:
+                        got = ready.get(timeout=1.0)
+                        break
+                    except queue.Empty:
+                        waited += 1.0
+                        if errors:
+                            raise errors[0]
+                        if not pt.is_alive():
+                            raise RuntimeError(f"the feature reader stopped without delivering batch {k}") from None
+                        if reader_timeout_s is not None and waited >= reader_timeout_s:
+                            raise RuntimeError(f"the feature reader made no progress for {reader_timeout_s:g} s "
+                                               f"(batch {k})") from None
+                if got is None or errors:
+                    raise errors[0]
+                _, spk = got
+                a = k & 1
+                real = hi - lo
+                dummies = (-real) % 8
+                lengths = [int(v) for v in rows[lo:hi]]
+                off = sum(lengths)
+                arenas[a][off:off + dummies].zero_()
+                lengths += [1] * dummies
+                rows_dev = arenas[a][:off + dummies].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                arena_tokens[a].put(ev)
+                noise = torch.randn(real + dummies, h.noise_dim, device=dev, generator=rng)
+                plan_frames = -(-max(lengths) // 32) * 32
+                packed = eng.forward_ragged(rows_dev, lengths, spk.to(dev), noise, plan_frames, pcm16=True)
+                n_valid = off * up
+                pcm_buf = pcm_pool.get()
+                pcm_buf[:n_valid].copy_(packed[:n_valid], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(stream)
+                to_write.put((done, pcm_buf, lo, hi))
+                stats.utterances += real
+                stats.audio_s += n_valid / sampling_rate
+                stats.batches += 1
+                if errors:
+                    raise errors[0]
+    except BaseException as e:
+        failure = e
+    finally:
+        # Never leave the helper threads blocked (they hold ~130 MB of pinned arenas): flag the failure,
+        # unblock the prefetch thread's put / get, hand the writer its sentinel, join both.
+        if failure is not None:
+            errors.append(failure)
+            for q in arena_tokens:
+                q.put(None)
+            while pt.is_alive():
+                try:
+                    ready.get(timeout=0.05)
+                except queue.Empty:
+                    pass
+        to_write.put(None)
+        wt.join()
+        pt.join()
+    if failure is not None:
+        raise failure
     if errors:
         raise errors[0]
     torch.cuda.synchronize(dev)

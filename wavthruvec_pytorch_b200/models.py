@@ -131,6 +131,9 @@ class Generator(nn.Module):
         object.__setattr__(self, "_engine", None)
         self._precision = precision
         self._warned_grad = False
+        #: replay eval()-mode forwards from a CUDA graph (latency path for batch-1 / long-form requests;
+        #: see v2w_forward_graph in include/v2w.h).  Also via $V2W_CUDA_GRAPH=1.
+        self.use_cuda_graph = bool(int(os.environ.get("V2W_CUDA_GRAPH", "0") or 0))
 
     # ------------------------------------------------------------------------------------------
     # native engine plumbing
@@ -170,6 +173,13 @@ class Generator(nn.Module):
             eng = NativeEngine(self)
             object.__setattr__(self, "_engine", eng)
         return eng
+
+    def __getstate__(self):
+        # torch.save(module) / copy.deepcopy: the native engine holds ctypes handles and device
+        # workspaces; it is rebuilt on first use (only state_dict() is the portable format anyway)
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        return state
 
     def invalidate(self) -> None:
         """Force a re-fold of the weights on the next native forward (normally automatic:

@@ -201,6 +201,9 @@ _SIGNATURES = [
     ("v2w_forward", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
+    ("v2w_forward_graph", C.c_int32,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+      C.POINTER(C.c_int32)]),
     ("v2w_forward_host", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
