@@ -287,6 +287,25 @@ int32_t v2w_model_pack_cond(const struct v2w_model* m, const v2w_cond_params* co
 /* Algorithmic FLOPs (2*MAC, zero polyphase blocks excluded) per input frame. */
 int64_t v2w_model_flops_per_frame(const struct v2w_model* m);
 
+/* ---- device-side fold --------------------------------------------------------------- */
+/* The same fold as v2w_model_pack_half, on the device: what the reference recomputes in its
+ * weight_norm / spectral_norm forward-pre hooks on every call (vec2wav/models.py:5,83-100;
+ * vec2wav/modules.py:16) straight from the module's own DEVICE parameter storage into a device packed
+ * buffer -- no device-to-host copy of any parameter, stream-ordered, four kernel launches.
+ * v2w_packer_create uploads the fold tables of `m` to the CURRENT device (once per model and device).
+ * v2w_packer_run: every pointer of `params` is a DEVICE pointer (same layouts as v2w_conv_params /
+ * v2w_cond_params); `packed_dev` = v2w_model_packed_bytes() bytes.  The result is bit-identical to
+ * the host packer's.  Folding into a buffer that plans are bound to is allowed: the plans stay valid
+ * (the format's offsets do not move); call v2w_plan_refresh_weights on each of them afterwards.
+ * v2w_packer_run_cond re-folds only the conditioning section (cf. v2w_model_pack_cond). */
+struct v2w_packer;
+int32_t v2w_packer_create(const struct v2w_model* m, struct v2w_packer** out);
+int32_t v2w_packer_run(struct v2w_packer* pk, const v2w_params* params_dev, void* packed_dev,
+                       int32_t half_format, void* stream, int32_t* gpu_launches);
+int32_t v2w_packer_run_cond(struct v2w_packer* pk, const v2w_cond_params* cond_dev, int32_t num_stages,
+                            void* packed_dev, void* stream);
+void v2w_packer_destroy(struct v2w_packer* pk);
+
 /* ---- plan --------------------------------------------------------------------------- */
 int32_t v2w_plan_create(const struct v2w_model* m, int32_t batch, int32_t frames,
                         int32_t precision, struct v2w_plan** out);
@@ -300,6 +319,10 @@ int32_t v2w_plan_set_engine(struct v2w_plan* p, int32_t index, int32_t engine);
 /* Attach device memory: `packed_dev` = device copy of the packed weights, `workspace_dev` =
  * v2w_plan_workspace_bytes() bytes, both 256-byte aligned.  Builds the TMA tensor maps. */
 int32_t v2w_plan_bind(struct v2w_plan* p, const void* packed_dev, void* workspace_dev);
+/* The packed buffer a plan is bound to was re-folded in place (v2w_packer_run on `stream`): re-read the
+ * few weights the plan keeps as kernel parameters (conv_post's 7 x C taps and bias) once the fold has
+ * finished, and drop captured CUDA graphs (they hold the old values).  Blocks on `stream`. */
+int32_t v2w_plan_refresh_weights(struct v2w_plan* p, void* stream);
 
 /* Generator.forward(x, spk_emb, noise) (vec2wav/models.py:116-147), eval semantics.
  *   x_dev     fp32 [batch, num_wv_feat, frames]  channels-first, as collate_fn_tensor emits

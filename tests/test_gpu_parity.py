@@ -470,7 +470,9 @@ def test_cuda_graph_replay_is_bit_identical(name, batch, frames):
                     hits.append(eng.last_graph_replay)
                     stream.synchronize()
                     assert torch.equal(out, want), f"replay {k} differs from the stream path"
-                assert all(hits), hits                    # captured on the first call with these pointers
+                # a created stream has a plan of its own (plans are stream-keyed): its first call is that plan's
+                # first, plain run; every other call is a replay captured on first sight of these pointers
+                assert all(hits[1:]) and (hits[0] or stream is side), hits
                 assert eng.last_launches > 0
         # new inputs in the same buffers: the graph reads the buffers, not a snapshot
         x2, s2, n2 = (a.cuda() for a in fixtures.make_inputs(gen.h, batch, frames, 6))
@@ -514,3 +516,66 @@ def test_plan_cache_is_bounded_and_stream_keyed():
         assert torch.equal(y_side, outs[8])
         keys = list(eng._plans)
         assert len({k[4] for k in keys}) == 2             # one plan per stream
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side weight fold (v2w_packer_*): bit-identical to the host packer, plans survive a re-fold
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_stress"])
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_device_fold_matches_host_packer(name, fmt):
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    eng = gen.engine()
+    half = native.HALF_FP16 if fmt == "fp16" else native.HALF_BF16
+    eng._tensors = eng._state_tensors()
+    assert eng._device_foldable(torch.device("cuda:0"))
+    dev_buf = eng.pack_device(torch.device("cuda:0"), half)
+    torch.cuda.synchronize()
+    assert eng.last_fold_launches == 4
+    host_buf = eng.pack_host(half)
+    d, h = dev_buf.cpu().numpy(), host_buf.numpy()
+    assert d.shape == h.shape
+    diff = np.flatnonzero(d != h)
+    assert diff.size == 0, f"{diff.size} of {d.size} packed bytes differ, first at {diff[:8]}"
+    # after remove_weight_norm the fold reads plain `weight` tensors (g == NULL)
+    gen.remove_weight_norm()
+    eng._tensors = eng._state_tensors()
+    d2 = eng.pack_device(torch.device("cuda:0"), half).cpu().numpy()
+    h2 = eng.pack_host(half).numpy()
+    assert np.array_equal(d2, h2)
+    # weight norm removed = the same effective weights up to fp32 rounding of g * v / ||v||
+    assert np.mean(d2 != h) < 0.35
+
+
+def test_refold_in_place_keeps_plans(monkeypatch):
+    """An in-place parameter edit on a CUDA module re-folds on the device into the SAME packed buffer:
+    no plan is destroyed, the next forward sees the new weights (conv_post's kernel-parameter copy too)."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    eng = gen.engine()
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    with torch.no_grad():
+        gen.precision = "bf16"
+        y0 = gen(x, s, n).clone()
+        plans = dict(eng._plans)
+        bufs = {k: v.data_ptr() for k, v in eng._packed.items()}
+        gen.conv_post.bias.add_(0.25)
+        gen.resblocks[4].convs[1].weight_g.mul_(1.5)
+        gen.ups[2].weight_v.mul_(0.5)                     # weight norm: scaling v changes nothing
+        y1 = gen(x, s, n).clone()
+        assert dict(eng._plans) == plans and {k: v.data_ptr() for k, v in eng._packed.items()} == bufs
+        assert eng.last_fold_launches == 4
+        # the same state folded from scratch on the host
+        monkeypatch.setenv("V2W_HOST_FOLD", "1")
+        eng.invalidate()
+        y2 = gen(x, s, n)
+        monkeypatch.delenv("V2W_HOST_FOLD")
+    assert not torch.equal(y0, y1)
+    assert torch.equal(y1, y2)
+    # fp32 plan against the autograd delegate after the edit
+    with torch.no_grad():
+        gen.precision = "fp32"
+        y3 = gen(x, s, n)
+        want = gen._forward_autograd(x, s, n)
+    assert (y3 - want).abs().max().item() < 1e-4

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libv2w.so"
-SOURCES = [CSRC / "model.cpp", CSRC / "npy_io.cpp", CSRC / "plan.cu", CSRC / "mel.cu"]
+SOURCES = [CSRC / "model.cpp", CSRC / "npy_io.cpp", CSRC / "plan.cu", CSRC / "mel.cu", CSRC / "pack_dev.cu"]
 HEADERS = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "v2w.h"]
 
 NVCC_FLAGS = [

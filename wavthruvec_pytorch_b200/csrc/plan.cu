@@ -1290,6 +1290,22 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
   return V2W_OK;
 }
 
+int32_t v2w_plan_refresh_weights(v2w_plan* p, void* stream) {
+  if (!p || !p->bound) {
+    set_error("v2w_plan_refresh_weights: plan is not bound");
+    return V2W_ERR_STATE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const v2w_layer_desc& L = p->model->layers.back();
+  p->post_w.assign((size_t)L.num_taps * L.cin, 0.f);
+  V2W_CUDA(cudaMemcpyAsync(p->post_w.data(), p->packed + L.w32_off, p->post_w.size() * 4,
+                           cudaMemcpyDeviceToHost, st));
+  V2W_CUDA(cudaMemcpyAsync(&p->post_bias, p->packed + L.bias_off, 4, cudaMemcpyDeviceToHost, st));
+  V2W_CUDA(cudaStreamSynchronize(st));
+  p->drop_graphs();
+  return V2W_OK;
+}
+
 // train() mode, conditioning that does not depend on the activations (vec2wav/modules.py:16,24 with
 // module.training set): the power iteration of every stage and gamma / beta = SN-Linear(fcs(spk|noise)),
 // on the side stream while conv_pre runs.  cond_affine_kernel runs with rstd = 1, mean = 0, so its

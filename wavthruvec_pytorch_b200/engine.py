@@ -40,6 +40,8 @@ class NativeEngine:
         self.max_workspace_bytes = int(float(os.environ.get("V2W_MAX_WORKSPACE_GB", "48")) * (1 << 30))
         self._lock = threading.RLock()     # plan cache + folding cache are shared by every caller thread
         self._pinned: Dict[Tuple, int] = {}   # plans a HostPipeline holds on to: never evicted
+        self._packers: Dict[torch.device, C.c_void_p] = {}   # device-side fold tables, one per device
+        self.last_fold_launches = 0
         self._convs = None        # cached module list / tensor list for the per-call change check
         self._tensors = None
         self._structure = None
@@ -49,6 +51,8 @@ class NativeEngine:
     def __del__(self):
         try:
             self._drop_plans()
+            for pk in getattr(self, "_packers", {}).values():
+                self._lib.v2w_packer_destroy(pk)
             if getattr(self, "_model", None):
                 self._lib.v2w_model_destroy(self._model)
                 self._model = None
@@ -163,6 +167,11 @@ class NativeEngine:
         conv_sig, cond_sig = sig[:n], sig[n:]
         old = self._packed_sig
         if old is None or old[0] != conv_sig or not self._packed:
+            if old is not None and self._packed and self._refold_on_device():
+                # every packed buffer was re-folded IN PLACE on its device (v2w_packer_run, stream-ordered):
+                # plans, workspaces and TMA descriptors stay
+                self._packed_sig = (conv_sig, cond_sig)
+                return
             self._packed.clear()
             self._drop_plans()   # plans hold pointers into the packed buffer
             self._packed_sig = (conv_sig, cond_sig)
@@ -172,8 +181,82 @@ class NativeEngine:
             self._repack_cond()
             self._packed_sig = (conv_sig, cond_sig)
 
+    # -- device-side fold (v2w_packer_*): no parameter ever leaves the device ----------------------
+    def _device_foldable(self, device: torch.device) -> bool:
+        if os.environ.get("V2W_HOST_FOLD"):
+            return False
+        if self._tensors is None:
+            self._tensors = self._state_tensors()
+        return all(t is None or (t.is_cuda and t.device == device and t.dtype == torch.float32 and t.is_contiguous())
+                   for t in self._tensors)
+
+    def _packer(self, device: torch.device):
+        pk = self._packers.get(device)
+        if pk is None:
+            handle = C.c_void_p()
+            with torch.cuda.device(device):
+                native.check(self._lib.v2w_packer_create(self._model, C.byref(handle)))
+            pk = self._packers[device] = handle
+        return pk
+
+    def _device_params(self):
+        """v2w_params over the module's own device storage (kept alive by the returned tuple)."""
+        ts = self._tensors
+        nconv = self._lib.v2w_model_num_convs(self._model)
+        nstage = self._cfg.num_upsamples
+        if len(ts) != 3 * nconv + 8 * nstage:
+            raise RuntimeError("module structure does not match the native layer table")
+        convs = (native.ConvParams * nconv)()
+        for i in range(nconv):
+            v, g, b = ts[3 * i: 3 * i + 3]
+            convs[i].v = _ptr(v)
+            convs[i].g = _ptr(g) if g is not None else None
+            convs[i].bias = _ptr(b)
+        cond = (native.CondParams * nstage)()
+        base = 3 * nconv
+        for i in range(nstage):
+            for (name, _), t in zip(native.CondParams._fields_, ts[base + 8 * i: base + 8 * i + 8]):
+                setattr(cond[i], name, _ptr(t))
+        return native.Params(nconv, convs, nstage, cond), convs, cond
+
+    def pack_device(self, device: torch.device, half_format: int = native.HALF_BF16,
+                    out: torch.Tensor = None) -> torch.Tensor:
+        """Fold + pack on the device (v2w_packer_run) on the current stream of `device`: four launches,
+        bit-identical to pack_host.  `out`: an existing packed buffer to fold into (in place)."""
+        params, _convs, _cond = self._device_params()
+        nbytes = int(self._lib.v2w_model_packed_bytes(self._model))
+        if out is None:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        n = C.c_int32(0)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            native.check(self._lib.v2w_packer_run(self._packer(device), C.byref(params), out.data_ptr(),
+                                                  half_format, C.c_void_p(stream), C.byref(n)))
+        self.last_fold_launches = n.value
+        return out
+
+    def _refold_on_device(self) -> bool:
+        if not all(self._device_foldable(dev) for (dev, _fmt) in self._packed):
+            return False
+        for (dev, fmt), buf in self._packed.items():
+            self.pack_device(dev, fmt, out=buf)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                for key, (plan, _ws) in self._plans.items():
+                    if key[3] == dev and (native.HALF_FP16 if key[2] == "fp16" else native.HALF_BF16) == fmt:
+                        native.check(self._lib.v2w_plan_refresh_weights(plan, C.c_void_p(stream)))
+        return True
+
     def _repack_cond(self) -> None:
         nstage = self._cfg.num_upsamples
+        if all(self._device_foldable(dev) for (dev, _fmt) in self._packed):
+            _params, _convs, cond = self._device_params()
+            for (dev, _fmt), buf in self._packed.items():
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    native.check(self._lib.v2w_packer_run_cond(self._packer(dev), cond, nstage, buf.data_ptr(),
+                                                               C.c_void_p(stream)))
+            return
         ts = self._tensors[3 * len(self._convs):]
         host = [t.detach().to("cpu", torch.float32).contiguous() for t in ts]
         cond = (native.CondParams * nstage)()
@@ -192,7 +275,10 @@ class NativeEngine:
     def _packed_on(self, device: torch.device, half_format: int) -> torch.Tensor:
         buf = self._packed.get((device, half_format))
         if buf is None:
-            buf = self.pack_host(half_format).to(device)
+            if self._device_foldable(device):
+                buf = self.pack_device(device, half_format)
+            else:
+                buf = self.pack_host(half_format).to(device)
             self._packed[(device, half_format)] = buf
         return buf
 

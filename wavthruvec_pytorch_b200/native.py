@@ -198,6 +198,12 @@ _SIGNATURES = [
     ("v2w_plan_get_op", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(OpDesc)]),
     ("v2w_plan_set_engine", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     ("v2w_plan_bind", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("v2w_plan_refresh_weights", C.c_int32, [C.c_void_p, C.c_void_p]),
+    ("v2w_packer_create", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("v2w_packer_run", C.c_int32, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.POINTER(C.c_int32)]),
+    ("v2w_packer_run_cond", C.c_int32, [C.c_void_p, C.POINTER(CondParams), C.c_int32, C.c_void_p, C.c_void_p]),
+    ("v2w_packer_destroy", None, [C.c_void_p]),
     ("v2w_forward", C.c_int32,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.POINTER(C.c_int32)]),
