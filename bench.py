@@ -469,7 +469,7 @@ def run_native_arm(args):
         value = audio_per_step / (ms_per_step * 1e-3)
         e2e_value = audio_per_step / (e2e_s / e2e_steps)
         peak_tf, peak_gbs, peak_src = measured_peaks()
-        gemm = [(op, ms) for op, ms in prof if op.kind in (native.OP_TAPGEMM, native.OP_MRF_FUSED, native.OP_PAIR_FUSED)]
+        gemm = [(op, ms) for op, ms in prof if op.kind in native.GEMM_OPS]
         gemm_flops = sum(op.flops for op, _ in gemm)
         gemm_ms = sum(ms for _, ms in gemm)
         all_ms = sum(ms for _, ms in prof)

@@ -212,6 +212,35 @@ typedef struct v2w_fused_desc {
   int64_t bsum_off;            /* packed: fp32 [channels] = sum_j (b1_j + b2_j) */
 } v2w_fused_desc;
 
+/* Wide multi-receptive-field stage (ResBlock2, C >= 64): the stage as TWO tap-GEMM launches of the
+ * generic tcgen05 kernel instead of 2 * num_kernels -- the same algebra as the fused stage kernels,
+ *
+ *     sum_j out_j = [ sum_j conv2_j(A1_j) + conv_sum(A0) ] + sum_j (b1_j + b2_j) + nk * X0
+ *     A1_j = half(lrelu(conv1_j(A0) + b1_j + X0))                  (vec2wav/models.py:65-70,135-141)
+ *
+ * laid out for the wide stages (C = 256), where no window of the fused kernels fits TMEM:
+ *   launch 1 (V2W_OP_MRF_WIDE1): ONE GEMM with N = nk * C, column tile t = branch t with branch t's tap
+ *     list, input A0; the epilogue adds b1_t and the SAME residual X0 to every branch's columns and
+ *     writes only the 16-bit A1 = [A1_0 | ... | A1_{nk-1}] into a [rows, (nk + 1) * C] tensor whose
+ *     last C columns already hold A0 (written there by the stage's transposed conv).  No fp32
+ *     intermediate reaches memory.
+ *   launch 2 (V2W_OP_MRF_WIDE2): ONE GEMM with N = C and K = (nk + 1) * C in nk + 1 K-groups: group j < nk
+ *     = conv2_j over A1_j's channels with conv2_j's own weights and tap list, group nk = the `sum`
+ *     convolution over A0 (per-offset sums of the conv1 weights, `wsum_off`); the MRF sum happens in the
+ *     accumulator.  Epilogue: + bsum + nk * X0, * 1/nk, leaky-relu, 16-bit (and / or fp32) output.
+ * 21 tap matrices become 21 + 21 + 11 (the `sum` convolution is the price), fp32 round trips of six
+ * epilogues become one 16-bit tensor written once and read once. */
+typedef struct v2w_wide_desc {
+  int32_t ok;
+  int32_t channels, num_branches;
+  int32_t first_layer;         /* layer index of branch 0's first conv (2 layers per branch) */
+  int32_t sum_taps;            /* taps of the `sum` convolution: union of the conv1 offsets */
+  int32_t sum_off[V2W_MAX_TAPS];
+  int64_t wsum_off;            /* packed: 16-bit [sum_taps][channels][channels] (n, c) */
+  int64_t b1cat_off;           /* packed: fp32 [num_branches * channels]: b1 of branch 0, 1, ... */
+  int64_t bsum_off;            /* packed: fp32 [channels] = sum_j (b1_j + b2_j) */
+} v2w_wide_desc;
+
 /* Kinds of op in a plan's execution list. */
 #define V2W_OP_TRANSPOSE_IN 0  /* x[B,Cin,T] fp32 -> [B,T,Cin] (fp32 or bf16) */
 #define V2W_OP_COND_AFFINE 1   /* fcs + spectral-norm Linear + BN fold -> scale/shift per (b, stage, c) */
@@ -219,6 +248,8 @@ typedef struct v2w_fused_desc {
 #define V2W_OP_CONV_POST 3     /* lrelu(0.01) -> Conv1d(16->1,k7) -> tanh */
 #define V2W_OP_MRF_FUSED 4     /* one whole multi-receptive-field stage (ResBlock2, C <= 128) */
 #define V2W_OP_PAIR_FUSED 5    /* one ResBlock1 conv pair (C <= 64): conv, leaky-relu, conv, + residual (+ MRF sum) */
+#define V2W_OP_MRF_WIDE1 6     /* wide stage, launch 1: the first convs of all branches N-stacked (v2w_wide_desc) */
+#define V2W_OP_MRF_WIDE2 7     /* wide stage, launch 2: the second convs + the `sum` convolution K-grouped */
 
 #define V2W_ENGINE_SIMT 0      /* FFMA tap-GEMM */
 #define V2W_ENGINE_TC 1        /* tcgen05 / TMEM / TMA tap-GEMM */
@@ -246,6 +277,10 @@ typedef struct v2w_op_desc {
   int32_t stage;               /* upsample stage of an MRF_FUSED / PAIR_FUSED op, else -1 */
   int32_t pair;                /* PAIR_FUSED: index for v2w_model_get_pair, else -1 */
   int32_t post;                /* MRF_FUSED: 1 when conv_post + tanh run inside this op (no CONV_POST op follows) */
+  int32_t out_bf16_pitch;      /* row pitch of out_bf16 in elements; 0 = dense (n_total).  The transposed conv of a
+                                  wide stage writes its 16-bit output into the last C columns of the stage's
+                                  [rows, (nk + 1) * C] operand tensor */
+  int32_t in_pitch;            /* row pitch of in_act in elements; 0 = dense (cin) */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -261,6 +296,7 @@ int32_t v2w_model_num_layers(const struct v2w_model* m);
 int32_t v2w_model_get_layer(const struct v2w_model* m, int32_t index, v2w_layer_desc* out);
 int32_t v2w_model_get_cond(const struct v2w_model* m, int32_t stage, v2w_cond_desc* out);
 int32_t v2w_model_get_fused(const struct v2w_model* m, int32_t stage, v2w_fused_desc* out);
+int32_t v2w_model_get_wide(const struct v2w_model* m, int32_t stage, v2w_wide_desc* out);
 int32_t v2w_model_num_pairs(const struct v2w_model* m);   /* fusable ResBlock1 conv pairs (0 for ResBlock2) */
 int32_t v2w_model_get_pair(const struct v2w_model* m, int32_t index, v2w_fused_desc* out);
 int32_t v2w_model_num_convs(const struct v2w_model* m);   /* expected v2w_params.num_convs */

@@ -264,6 +264,59 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                 ws[op.out_bf16] = half(lrelu(v, op.out_slope))
             if collect is not None:
                 collect[idx] = v
+        elif op.kind in (native.OP_MRF_WIDE1, native.OP_MRF_WIDE2):
+            # wide stage as two stacked tap-GEMMs (v2w_wide_desc): same algebra as the fused stage
+            Wd = native.WideDesc()
+            native.check(plan.lib.v2w_model_get_wide(plan.model, op.stage, C.byref(Wd)))
+            assert Wd.ok and op.in_pitch == (Wd.num_branches + 1) * Wd.channels
+            Cn, nb = Wd.channels, Wd.num_branches
+            X0 = ws[op.residual].reshape(op.batch, op.rows, Cn)
+
+            def conv_layer(A, L):
+                Wl = half_to_f32(u16(L.w16_off, L.num_taps * Cn * Cn)).reshape(L.num_taps, Cn, Cn)
+                acc = np.zeros((op.batch, op.rows, Cn), np.float32)
+                for j in range(L.num_taps):
+                    off = L.tap_off[j]
+                    sh = np.zeros_like(A)
+                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                    if hi > lo:
+                        sh[:, lo:hi] = A[:, lo + off: hi + off]
+                    acc += sh @ Wl[j].T
+                return acc
+
+            if op.kind == native.OP_MRF_WIDE1:
+                A0 = ws[op.in_act].reshape(op.batch, op.rows, Cn)       # written by the stage's ups op
+                assert op.out_bf16_pitch == op.in_pitch and op.out_f32 < 0
+                b1cat = f32(Wd.b1cat_off, nb * Cn)
+                parts = []
+                for j in range(nb):
+                    L = plan.layers[Wd.first_layer + 2 * j]
+                    assert np.array_equal(b1cat[j * Cn:(j + 1) * Cn], f32(L.bias_off, Cn))
+                    parts.append(half(lrelu(conv_layer(A0, L) + b1cat[j * Cn:(j + 1) * Cn] + X0, op.out_slope)))
+                ws[op.out_bf16] = np.concatenate(parts, axis=2)        # [A1_0 | ... | A1_{nb-1}]
+                if collect is not None:
+                    collect[idx] = ws[op.out_bf16]
+            else:
+                A1 = ws[op.in_act].reshape(op.batch, op.rows, nb * Cn)
+                A0 = ws[op.in_act + nb * Cn * 2].reshape(op.batch, op.rows, Cn)   # last C columns of the operand
+                acc = np.zeros((op.batch, op.rows, Cn), np.float32)
+                for j in range(nb):
+                    acc += conv_layer(A1[:, :, j * Cn:(j + 1) * Cn], plan.layers[Wd.first_layer + 2 * j + 1])
+                Ws = half_to_f32(u16(Wd.wsum_off, Wd.sum_taps * Cn * Cn)).reshape(Wd.sum_taps, Cn, Cn)
+                for t in range(Wd.sum_taps):
+                    off = Wd.sum_off[t]
+                    sh = np.zeros_like(A0)
+                    lo, hi = max(0, -off), min(op.rows, op.rows - off)
+                    if hi > lo:
+                        sh[:, lo:hi] = A0[:, lo + off: hi + off]
+                    acc += sh @ Ws[t].T
+                v = ((acc + f32(Wd.bsum_off, Cn) + np.float32(nb) * X0) * np.float32(op.out_scale)).astype(np.float32)
+                if op.out_f32 >= 0:
+                    ws[op.out_f32] = v
+                if op.out_bf16 >= 0:
+                    ws[op.out_bf16] = half(lrelu(v, op.out_slope))
+                if collect is not None:
+                    collect[idx] = v
         elif op.kind == native.OP_CONV_POST:
             L = plan.layers[op.layer]
             A = lrelu(ws[op.in_act].reshape(op.batch, op.rows, L.cin), op.in_slope)

@@ -64,7 +64,7 @@ def _run(name, precision):
 def test_fp32_plan_at_config_size(name):
     r = _run(name, "fp32")
     assert r["max_abs"] <= FP32_MAX_ABS
-    assert r["sum_err"] <= 1e-5 and r["sumsq_rel"] <= 1e-4
+    assert r["sum_err"] <= 1e-4 and r["sumsq_rel"] <= 1e-4   # fp32 summation noise over 160000 samples: ~1e-5
 
 
 @pytest.mark.gpu

@@ -187,6 +187,35 @@ def test_fused_stage_kernel_matches_separate_tapgemms(monkeypatch, name):
     assert fixtures.snr_db(g.y, fused) >= BF16_MIN_SNR_DB
 
 
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb2_768_stress_tiny", "rb2_1024_stress"])
+@pytest.mark.parametrize("mask", ["1", "3", "7"])
+def test_wide_stage_matches_separate_tapgemms(monkeypatch, name, mask):
+    """A stage as two stacked tap-GEMM launches (v2w_wide_desc: N-stacked conv1, K-grouped conv2 + sum)
+    against the six separate launches, on the device.  mask 1 = stage 0 only (the default plan), 3 / 7 =
+    stages 1 (C = 128) and 2 (C = 64) too, instead of their fused kernels."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    monkeypatch.setenv("V2W_WIDE_MASK", "0")
+    plain = _native(gen, g, "bf16")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    assert sum(op.kind in (native.OP_MRF_WIDE1, native.OP_MRF_WIDE2) for op in ops) == 0
+    monkeypatch.setenv("V2W_WIDE_MASK", mask)
+    gen.invalidate()
+    wide = _native(gen, g, "bf16")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    nw = bin(int(mask)).count("1")
+    assert sum(op.kind == native.OP_MRF_WIDE1 for op in ops) == nw
+    assert sum(op.kind == native.OP_MRF_WIDE2 for op in ops) == nw
+    snr = fixtures.snr_db(plain, wide)
+    print(f"{name} mask {mask}: wide vs separate on device {snr:.1f} dB; vs reference "
+          f"{fixtures.snr_db(g.y, wide):.1f} / {fixtures.snr_db(g.y, plain):.1f} dB")
+    assert snr >= 55.0
+    assert fixtures.snr_db(g.y, wide) >= BF16_MIN_SNR_DB
+    # fp16 operands through the same launches
+    wide16 = _native(gen, g, "fp16")
+    assert fixtures.snr_db(g.y, wide16) >= 60.0
+
+
 def test_forward_host_equals_forward_and_is_deterministic():
     g = load_golden("rb2_768_stress")
     gen = dropin_in_state(g, cache=False).to("cuda:0")

@@ -263,10 +263,26 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     fused = [op for op in fplan.ops if op.kind == native.OP_MRF_FUSED]
     assert [op.stage for op in fused] == [1, 2, 3, 4]
     assert [op.n_tile for op in fused] == [128, 64, 32, 16]
-    assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 12
+    # stage 0 (C = 256, no fused kernel): two stacked tap-GEMM launches instead of six (v2w_wide_desc)
+    assert len([op for op in fplan.ops if op.kind == native.OP_TAPGEMM]) == 6
+    wide = [op for op in fplan.ops if op.kind in (native.OP_MRF_WIDE1, native.OP_MRF_WIDE2)]
+    assert [(op.kind, op.stage, op.n_tile, op.n_tiles, op.in_pitch) for op in wide] == \
+        [(native.OP_MRF_WIDE1, 0, 256, 3, 1024), (native.OP_MRF_WIDE2, 0, 256, 1, 1024)]
+    ups0 = fplan.ops[3]
+    assert ups0.kind == native.OP_TAPGEMM and ups0.out_bf16_pitch == 1024
+    assert ups0.out_bf16 == wide[0].in_act == wide[1].in_act + 3 * 256 * 2 and wide[0].out_bf16 == wide[1].in_act
+    Wd = native.WideDesc()
+    native.check(eng._lib.v2w_model_get_wide(eng._model, 0, C.byref(Wd)))
+    assert (Wd.ok, Wd.channels, Wd.num_branches, Wd.sum_taps) == (1, 256, 3, 11)
+    assert list(Wd.sum_off[:11]) == list(range(-5, 6))
     assert sum(op.flops for op in fplan.ops) == total
-    # conv_post + tanh run inside the last stage's final pass: 18 launches, no CONV_POST op
-    assert len(fplan.ops) == 18 and fplan.ops[-1].kind == native.OP_MRF_FUSED
+    # conv_post + tanh run inside the last stage's final pass: 14 launches, no CONV_POST op
+    assert len(fplan.ops) == 14 and fplan.ops[-1].kind == native.OP_MRF_FUSED
+    # $V2W_WIDE_MASK=0: the six separate tap-GEMMs of stage 0 again
+    monkeypatch.setenv("V2W_WIDE_MASK", "0")
+    oplan = plan_interp.HostPlan(eng, 16, 200, "bf16")
+    assert len(oplan.ops) == 18 and sum(op.flops for op in oplan.ops) == total
+    monkeypatch.delenv("V2W_WIDE_MASK")
     assert [op.post for op in fused] == [0, 0, 0, 1] and fused[-1].out_f32 < 0 and fused[-1].out_bf16 < 0
     F4 = native.FusedDesc()
     native.check(eng._lib.v2w_model_get_fused(eng._model, 4, C.byref(F4)))

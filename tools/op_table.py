@@ -74,6 +74,12 @@ def main():
             by = op.batch * op.rows * C * (2 + 4 + (4 if op.out_f32 >= 0 else 0) + (2 if op.out_bf16 >= 0 else 0))
             rows.append(dict(i=i, kind="fused", stage=op.stage, cin=C, rows=op.rows, ms=ms,
                              tflops=op.flops / ms / 1e9, gbs=by / ms / 1e6, mb=by / 1e6))
+        elif op.kind in (native.OP_MRF_WIDE1, native.OP_MRF_WIDE2):
+            C = op.n_tile
+            half = 1 if op.kind == native.OP_MRF_WIDE1 else 2
+            by = op.batch * op.rows * C * ((2 + 4 + 3 * 2) if half == 1 else (4 * 2 + 4 + 2))
+            rows.append(dict(i=i, kind="fused", stage=op.stage, cin=C, rows=op.rows, ms=ms, wide=half,
+                             tflops=op.flops / ms / 1e9, gbs=by / ms / 1e6, mb=by / 1e6))
         else:
             rows.append(dict(i=i, kind={0: "transpose", 1: "cond", 3: "post"}[op.kind], ms=ms))
     for r in rows:
@@ -83,7 +89,8 @@ def main():
                   f"taps={r['taps']} {r['ms'] * 1e3:8.1f} us {r['tflops']:7.1f} TF/s "
                   f"{r['gbs']:7.0f} GB/s ({r['mb']:.0f} MB)")
         elif r["kind"] == "fused":
-            print(f"{r['i']:3d} FUSED MRF stage {r['stage']} C={r['cin']:3d} rows={r['rows']:6d} "
+            tag = f"WIDE{r['wide']}" if r.get("wide") else "FUSED"
+            print(f"{r['i']:3d} {tag} MRF stage {r['stage']} C={r['cin']:3d} rows={r['rows']:6d} "
                   f"{r['ms'] * 1e3:8.1f} us {r['tflops']:7.1f} TF/s {r['gbs']:7.0f} GB/s ({r['mb']:.0f} MB)")
         else:
             print(f"{r['i']:3d} {r['kind']:9s} {r['ms'] * 1e3:8.1f} us")

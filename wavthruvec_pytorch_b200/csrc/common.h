@@ -102,6 +102,7 @@ struct v2w_model {
   std::vector<v2w_layer_desc> layers;
   std::vector<v2w::CondLayout> cond;
   std::vector<v2w_fused_desc> fused;   // per stage; ok == 0 when not fusable
+  std::vector<v2w_wide_desc> wide;     // per stage; ok == 0 when the stage cannot run as two stacked tap-GEMMs
   std::vector<v2w_fused_desc> pairs;   // ResBlock1: one per fusable (stage, branch, step) conv pair
   std::vector<int> pair_of_layer;      // layer index of a pair's first conv -> index into `pairs`, else -1
   std::vector<int> stage_channels;  // C_i

@@ -78,7 +78,21 @@ struct Params {
   int off_min[V2W_MAX_TILES];
   int halo[V2W_MAX_TILES];
   int tap_off[V2W_MAX_TILES][V2W_MAX_TAPS];
-  int tap_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  // First row of the (tap list, tap) weight block in the W tensor map (rows of `w_cols` 16-bit
+  // elements), column tile included: tap_row * n_total + nt * n_tile for a layer's own [taps][n][cin]
+  // array; arbitrary for stacked ops whose blocks live in several arrays (plan.cu TcExtra).
+  int w_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  // K-grouped operand (kgroups > 0, n_tiles == 1): the input's channels are `kgroups` groups of `cpg`
+  // K-chunks, each with its OWN tap list (list g instead of list nt) and its own weight array whose
+  // rows hold only the group's channels -- the branches of a multi-receptive-field stage side by
+  // side along K (conv2_j reads A1_j), accumulated in ONE accumulator.  off_min / halo of list 0 span
+  // every group.
+  int kgroups, cpg;
+  // Residual geometry: row pitch and column period of the residual tensor (0 = n_total: dense, no
+  // wrap) -- the N-stacked conv1 of a stage adds the SAME [rows, C] residual to every branch's columns.
+  int res_pitch, res_cols;
+  float res_scale;
+  int h_pitch;          // row pitch of the 16-bit output in elements (direct-store path; 0 = n_total)
   const float* bias;
   const float* scale;
   const float* shift;
@@ -446,7 +460,6 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
-      const int ntaps = p.num_taps[nt];
       const int q0t = st * tile_rows;                       // first row of the (pair's) tile
       if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0t)) continue;
       const int q0 = q0t + (int)rank * p.msub * kMTile;     // first row of this CTA's half
@@ -455,8 +468,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nsub = min(p.msub, (p.rows - q0t + kMTile - 1) / kMTile);
       const int nbox = (nsub * kMTile + p.halo[nt] + p.box_rows - 1) / p.box_rows;
       const int row0 = q0 + p.off_min[nt];
-      const int wcol = nt * p.n_tile + (int)rank * w_rows;
+      const int wrank = (int)rank * w_rows;
       for (int c = 0; c < p.num_chunks; ++c) {
+        const int li = p.kgroups ? c / p.cpg : nt;          // tap list of this K-chunk
+        const int wc = p.kgroups ? (c - li * p.cpg) * KC : c * KC;   // column in the weight array
+        const int ntaps = p.num_taps[li];
         mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1u);
         if (elect_one()) {
           const uint32_t bar = full_a + 8 * ra.s;
@@ -480,12 +496,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t bar = full_w + 8 * rw.s;
             if constexpr (kPair) {
               if (rank == 0) mbar_expect_tx(bar, 2 * w_bytes);
-              tma_load_2d_pair(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
-                               p.tap_row[nt][j] * p.n_total + wcol, bar);
+              tma_load_2d_pair(smem_w + rw.s * p.stage_w_bytes, &tmW, wc, p.w_row[li][j] + wrank, bar);
             } else {
               mbar_expect_tx(bar, w_bytes);
-              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, c * KC,
-                          p.tap_row[nt][j] * p.n_total + wcol, bar);
+              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, wc, p.w_row[li][j] + wrank, bar);
             }
           }
           __syncwarp();
@@ -505,7 +519,6 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int rem = tile - b * tiles_per_b;
       const int st = rem / p.n_tiles;
       const int nt = rem - st * p.n_tiles;
-      const int ntaps = p.num_taps[nt];
       const int off_min = p.off_min[nt];
       const int q0 = st * tile_rows;
       if (tile_skipped(p.row_limit, p.rows_per_frame, b, q0)) continue;
@@ -516,13 +529,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + as * stage_cols;
       for (int c = 0; c < p.num_chunks; ++c) {
+        const int li = p.kgroups ? c / p.cpg : nt;
+        const int ntaps = p.num_taps[li];
         mbar_wait(full_a + 8 * ra.s, ra.ph);
         const uint32_t a_stage = smem_a + ra.s * p.stage_a_bytes;
         for (int j = 0; j < ntaps; ++j) {
           mbar_wait(full_w + 8 * rw.s, rw.ph);
           tcgen05_fence_after();
           if (elect_one()) {
-            const uint32_t a_addr = a_stage + (p.tap_off[nt][j] - off_min) * kRowBytes;
+            const uint32_t a_addr = a_stage + (p.tap_off[li][j] - off_min) * kRowBytes;
             const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
             const uint32_t acc0 = (c | j) != 0;
             for (int m = 0; m < nsub; ++m) {
@@ -598,13 +613,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int row0w = q0 + m * kMTile + quarter * 32;   // first row of this warp's slab
         const int row = row0w + lane;
         const bool valid = row < p.rows;
-        const size_t row_base = (static_cast<size_t>(b) * p.rows + row) * p.n_total;
+        const size_t row_lin = static_cast<size_t>(b) * p.rows + row;
+        const size_t row_base = row_lin * p.n_total;
+        const size_t res_base = p.res_pitch ? row_lin * p.res_pitch : row_base;
         for (int cc = 0; cc < p.n_tile; cc += 16) {
           const int col = nt * p.n_tile + cc;
           // issue the global reads first so that they overlap the TMEM load
           float4 res[4], acc[4];
           if (valid && p.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + row_base + col);
+            const int rcol = p.res_cols ? col % p.res_cols : col;
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + res_base + rcol);
 #pragma unroll
             for (int e = 0; e < 4; ++e) res[e] = rp[e];
           }
@@ -639,10 +657,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (p.residual) {
+              const float rs = p.res_scale;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                v[4 * e] += res[e].x; v[4 * e + 1] += res[e].y;
-                v[4 * e + 2] += res[e].z; v[4 * e + 3] += res[e].w;
+                v[4 * e] = fmaf(rs, res[e].x, v[4 * e]); v[4 * e + 1] = fmaf(rs, res[e].y, v[4 * e + 1]);
+                v[4 * e + 2] = fmaf(rs, res[e].z, v[4 * e + 2]); v[4 * e + 3] = fmaf(rs, res[e].w, v[4 * e + 3]);
               }
             }
             if (p.accum_in) {
@@ -691,7 +710,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int e = 0; e < 8; ++e)
                   h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
                                     p.fp16);
-                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + col);
+                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + (p.h_pitch ? row_lin * p.h_pitch : row_base) + col);
                 op[0] = make_uint4(h[0], h[1], h[2], h[3]);
                 op[1] = make_uint4(h[4], h[5], h[6], h[7]);
               }

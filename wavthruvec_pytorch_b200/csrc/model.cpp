@@ -352,6 +352,33 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
 
 using namespace v2w;
 
+// Wide stage (v2w_wide_desc, include/v2w.h): ResBlock2 stages with C >= 64 can run as two stacked
+// tap-GEMM launches.  Called right after the stage's layers were pushed.
+static v2w_wide_desc plan_wide_stage(const v2w_model* m, int stage, int first_layer) {
+  v2w_wide_desc W;
+  std::memset(&W, 0, sizeof(W));
+  const v2w_config& c = m->cfg;
+  const int C = m->stage_channels[stage];
+  const int nb = c.num_kernels;
+  W.channels = C;
+  W.num_branches = nb;
+  W.first_layer = first_layer;
+  if (c.resblock_type != 2 || C < 64 || C % 64 || C > 256 || nb + 1 > V2W_MAX_TILES) return W;
+  // union of the conv1 offsets, ascending
+  std::vector<int> offs;
+  for (int j = 0; j < nb; ++j) {
+    const v2w_layer_desc& L = m->layers[first_layer + 2 * j];
+    for (int t = 0; t < L.num_taps; ++t)
+      if (std::find(offs.begin(), offs.end(), L.tap_off[t]) == offs.end()) offs.push_back(L.tap_off[t]);
+  }
+  std::sort(offs.begin(), offs.end());
+  if ((int)offs.size() > V2W_MAX_TAPS) return W;
+  W.sum_taps = (int)offs.size();
+  for (int t = 0; t < W.sum_taps; ++t) W.sum_off[t] = offs[t];
+  W.ok = 1;
+  return W;
+}
+
 extern "C" {
 
 int32_t v2w_abi_version(void) { return V2W_ABI_VERSION; }
@@ -465,6 +492,7 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
     m->stage_channels.push_back(ch);
     m->stage_up.push_back(up_total);
     m->fused.push_back(plan_fused_stage(m, i, (int)m->layers.size()));
+    const int stage_first_layer = (int)m->layers.size();
     for (int j = 0; j < c->num_kernels; ++j) {
       const int k = c->resblock_kernel_sizes[j];
       const int block = i * c->num_kernels + j;
@@ -490,6 +518,7 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
         }
       }
     }
+    m->wide.push_back(plan_wide_stage(m, i, stage_first_layer));
   }
   m->total_up = up_total;
   m->num_convs = rb_conv_base + U * c->num_kernels * convs_per_block + 1;
@@ -536,6 +565,15 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
       F.bsum_off = off;
       off = align_up(off + (int64_t)F.channels * 4, 1024);
     }
+  }
+  for (auto& W : m->wide) {
+    if (!W.ok) continue;
+    W.wsum_off = off;
+    off = align_up(off + (int64_t)W.sum_taps * W.channels * W.channels * 2, 1024);
+    W.b1cat_off = off;
+    off = align_up(off + (int64_t)W.num_branches * W.channels * 4, 1024);
+    W.bsum_off = off;
+    off = align_up(off + (int64_t)W.channels * 4, 1024);
   }
   m->pair_of_layer.resize(m->layers.size(), -1);
   m->packed_bytes = align_up(off, 1024);
@@ -613,6 +651,15 @@ int32_t v2w_model_get_fused(const v2w_model* m, int32_t i, v2w_fused_desc* out) 
     return V2W_ERR_INVALID;
   }
   *out = m->fused[i];
+  return V2W_OK;
+}
+
+int32_t v2w_model_get_wide(const v2w_model* m, int32_t i, v2w_wide_desc* out) {
+  if (!m || !out || i < 0 || i >= (int32_t)m->wide.size()) {
+    set_error("v2w_model_get_wide: bad stage %d", i);
+    return V2W_ERR_INVALID;
+  }
+  *out = m->wide[i];
   return V2W_OK;
 }
 
@@ -837,6 +884,41 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
           uint16_t* dst = wf + ((size_t)F.w_row[ent] + (size_t)q * C) * C;
           for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = half_bits(acc[e]);
         }
+      }
+    }
+  });
+  // wide stages: the `sum` convolution (per-offset sums of the conv1 tap matrices, branch order), the
+  // concatenated first-conv biases and the total bias
+  parallel_for((int)m->wide.size(), nthreads, [&](int wi) {
+    const v2w_wide_desc& W = m->wide[(size_t)wi];
+    if (!W.ok) return;
+    const int C = W.channels, nb = W.num_branches;
+    uint16_t* ws = reinterpret_cast<uint16_t*>(base + W.wsum_off);
+    std::vector<float> acc((size_t)C * C);
+    for (int t = 0; t < W.sum_taps; ++t) {
+      std::fill(acc.begin(), acc.end(), 0.f);
+      for (int j = 0; j < nb; ++j) {
+        const v2w_layer_desc& L = m->layers[W.first_layer + 2 * j];
+        int lt = -1;
+        for (int u = 0; u < L.num_taps; ++u)
+          if (L.tap_off[u] == W.sum_off[t]) lt = u;
+        if (lt < 0) continue;
+        const float* w32 = reinterpret_cast<const float*>(base + L.w32_off) + (size_t)lt * C * C;
+        for (int ci = 0; ci < C; ++ci)
+          for (int n = 0; n < C; ++n) acc[(size_t)n * C + ci] += w32[(size_t)ci * C + n];
+      }
+      uint16_t* dst = ws + (size_t)t * C * C;
+      for (size_t e = 0; e < (size_t)C * C; ++e) dst[e] = half_bits(acc[e]);
+    }
+    float* b1cat = reinterpret_cast<float*>(base + W.b1cat_off);
+    float* bsum = reinterpret_cast<float*>(base + W.bsum_off);
+    for (int ch = 0; ch < C; ++ch) bsum[ch] = 0.f;
+    for (int j = 0; j < 2 * nb; ++j) {
+      const float* bl = reinterpret_cast<const float*>(base + m->layers[W.first_layer + j].bias_off);
+      for (int ch = 0; ch < C; ++ch) bsum[ch] += bl[ch];
+      if (!(j & 1)) {
+        // (a bias of 0.f + b is b: the device packer's `a = 0.f; a += b` gives the same bits)
+        for (int ch = 0; ch < C; ++ch) b1cat[(size_t)(j / 2) * C + ch] = 0.f + bl[ch];
       }
     }
   });

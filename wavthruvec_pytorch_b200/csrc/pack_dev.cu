@@ -341,6 +341,43 @@ int32_t v2w_packer_create(const v2w_model* m, v2w_packer** out) {
       }
     }
   }
+  // wide stages: `sum` convolution blocks, concatenated first-conv biases, total bias
+  for (const v2w_wide_desc& W : m->wide) {
+    if (!W.ok) continue;
+    const int C = W.channels, nb = W.num_branches;
+    if (2 * nb > 8) {
+      set_error("v2w_packer_create: more than 8 bias vectors in a wide stage");
+      return V2W_ERR_INVALID;
+    }
+    for (int t = 0; t < W.sum_taps; ++t) {
+      FusedTask k;
+      std::memset(&k, 0, sizeof(k));
+      k.C = C;
+      k.dst_off = W.wsum_off + (int64_t)t * C * C * 2;
+      for (int j = 0; j < nb; ++j) {
+        const v2w_layer_desc& L = m->layers[W.first_layer + 2 * j];
+        int lt = -1;
+        for (int u = 0; u < L.num_taps; ++u)
+          if (L.tap_off[u] == W.sum_off[t]) lt = u;
+        if (lt < 0) continue;
+        k.src_off[k.nsrc++] = L.w32_off + (int64_t)lt * C * C * 4;
+      }
+      ft.push_back(k);
+    }
+    FusedTask b;
+    std::memset(&b, 0, sizeof(b));
+    b.C = C; b.is_bsum = 1; b.dst_off = W.bsum_off;
+    for (int j = 0; j < 2 * nb; ++j) b.src_off[b.nsrc++] = m->layers[W.first_layer + j].bias_off;
+    ft.push_back(b);
+    for (int j = 0; j < nb; ++j) {
+      FusedTask c1;
+      std::memset(&c1, 0, sizeof(c1));
+      c1.C = C; c1.is_bsum = 1; c1.nsrc = 1;
+      c1.dst_off = W.b1cat_off + (int64_t)j * C * 4;
+      c1.src_off[0] = m->layers[W.first_layer + 2 * j].bias_off;
+      ft.push_back(c1);
+    }
+  }
   v2w_packer* pk = new v2w_packer();
   pk->model = m;
   if (cudaGetDevice(&pk->device) != cudaSuccess) {

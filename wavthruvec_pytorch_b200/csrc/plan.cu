@@ -41,6 +41,7 @@ struct Act {        // one logical activation tensor [B, rows, C]
   int64_t f32 = -1;   // fp32 copy (pre-activation values)
   int64_t bf16 = -1;  // bf16 copy of leaky_relu(value, slope)
   float slope = 1.f;  // the activation the consumer must see
+  int pitch16 = 0;    // row pitch of the 16-bit copy in elements (0 = dense): a column range of a wider tensor
 };
 
 struct TcLaunch {
@@ -74,6 +75,12 @@ struct Op {
   v2w_tapgemm_args g_raw;
   TcLaunch tcl_raw;
   bool has_raw = false;
+};
+
+// workspace of a wide stage: the [rows, (nk + 1) * C] 16-bit operand tensor [A1_0 | ... | A1_{nk-1} | A0]
+struct WideBuf {
+  int64_t a1cat = -1;
+  int width = 0;
 };
 
 }  // namespace v2w
@@ -223,7 +230,22 @@ static int validate_gemm(const v2w_tapgemm_args& a) {
   return V2W_OK;
 }
 
-static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
+// Geometry beyond a single layer's own arrays (all fields optional, zero = the plain layout): operand /
+// output tensors that are column ranges of wider tensors, weights gathered from several packed arrays,
+// K-grouped tap lists, residual column wrap -- what the two launches of a wide stage need (v2w_wide_desc).
+struct TcExtra {
+  int a_pitch = 0;       // elements per row of the input tensor (0 = cin)
+  int h_pitch = 0;       // elements per row of the 16-bit output tensor (0 = n_total)
+  int res_pitch = 0, res_cols = 0;
+  float res_scale = 1.f;
+  int kgroups = 0, cpg = 0;
+  int w_cols = 0;        // 16-bit elements per row of the weight arrays (0 = cin)
+  bool abs_rows = false; // w_row[list][tap]: first row of the block relative to `w16`, in rows of w_cols elements
+  int w_row[V2W_MAX_TILES][V2W_MAX_TAPS];
+  int64_t w_total_rows = 0;
+};
+
+static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex = nullptr) {
   if (!a.in_is_bf16 || a.in_slope != 1.0f) {
     set_error("tapgemm(TC): input must be pre-activated bf16");
     return V2W_ERR_INVALID;
@@ -249,8 +271,20 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
   p.batch = a.batch; p.rows = a.rows; p.cin = a.cin; p.n_total = a.n_total; p.cmod = a.cmod;
   p.n_tile = a.n_tile; p.n_tiles = a.n_tiles;
   p.num_chunks = a.cin / kc;
+  p.res_scale = 1.f;
+  const int nlists = (ex && ex->kgroups) ? ex->kgroups : a.n_tiles;
+  if (ex) {
+    p.kgroups = ex->kgroups; p.cpg = ex->cpg;
+    p.res_pitch = ex->res_pitch; p.res_cols = ex->res_cols; p.res_scale = ex->res_scale;
+    p.h_pitch = ex->h_pitch;
+    if (ex->kgroups && (a.n_tiles != 1 || ex->kgroups > V2W_MAX_TILES || ex->kgroups * ex->cpg != p.num_chunks)) {
+      set_error("tapgemm(TC): bad K-group geometry (%d groups x %d chunks, %d chunks, %d column tiles)",
+                ex->kgroups, ex->cpg, p.num_chunks, a.n_tiles);
+      return V2W_ERR_INVALID;
+    }
+  }
   int halo_max = 0;
-  for (int t = 0; t < a.n_tiles; ++t) {
+  for (int t = 0; t < nlists; ++t) {
     p.num_taps[t] = a.num_taps[t];
     p.off_min[t] = a.tap_off[t][0];
     const int halo = a.tap_off[t][a.num_taps[t] - 1] - a.tap_off[t][0];
@@ -258,8 +292,18 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     halo_max = std::max(halo_max, halo);
     for (int j = 0; j < a.num_taps[t]; ++j) {
       p.tap_off[t][j] = a.tap_off[t][j];
-      p.tap_row[t][j] = a.tap_row[t][j];
+      p.w_row[t][j] = (ex && ex->abs_rows) ? ex->w_row[t][j] : a.tap_row[t][j] * a.n_total + t * a.n_tile;
     }
+  }
+  if (ex && ex->kgroups) {
+    // one input tile serves every group: its first row / extent span all the tap lists
+    int lo = p.off_min[0], hi = p.off_min[0] + p.halo[0];
+    for (int t = 1; t < nlists; ++t) {
+      lo = std::min(lo, p.off_min[t]);
+      hi = std::max(hi, p.off_min[t] + p.halo[t]);
+    }
+    for (int t = 0; t < V2W_MAX_TILES; ++t) { p.off_min[t] = lo; p.halo[t] = hi - lo; }
+    halo_max = hi - lo;
   }
   p.acc_cols = std::max(32, pow2_ceil(a.n_tile));
   p.fp16 = (a.tc_flags & 0x100) ? 1 : 0;   // V2W_TC_FLAG_FP16
@@ -318,8 +362,9 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
                                           : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                       : CU_TENSOR_MAP_SWIZZLE_32B);
   {
+    const cuuint64_t a_pitch = (ex && ex->a_pitch) ? ex->a_pitch : a.cin;
     cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
-    cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.rows * a.cin * 2};
+    cuuint64_t strides[2] = {a_pitch * 2, (cuuint64_t)a.rows * a_pitch * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&L->tm_a, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
@@ -335,8 +380,11 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
     int max_row = 0;
     for (int t = 0; t < a.n_tiles; ++t)
       for (int j = 0; j < a.num_taps[t]; ++j) max_row = std::max(max_row, a.tap_row[t][j]);
-    cuuint64_t dims[2] = {(cuuint64_t)a.cin, (cuuint64_t)(max_row + 1) * a.n_total};
-    cuuint64_t strides[1] = {(cuuint64_t)a.cin * 2};
+    const cuuint64_t w_cols = (ex && ex->w_cols) ? ex->w_cols : a.cin;
+    const cuuint64_t w_rows_total = (ex && ex->abs_rows) ? (cuuint64_t)ex->w_total_rows
+                                                        : (cuuint64_t)(max_row + 1) * a.n_total;
+    cuuint64_t dims[2] = {w_cols, w_rows_total};
+    cuuint64_t strides[1] = {w_cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)w_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&L->tm_w, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -366,7 +414,8 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L) {
       }
     }
     if (a.out_bf16) {
-      cuuint64_t strides[2] = {(cuuint64_t)a.n_total * 2, (cuuint64_t)a.rows * a.n_total * 2};
+      const cuuint64_t h_pitch = (ex && ex->h_pitch) ? ex->h_pitch : a.n_total;
+      cuuint64_t strides[2] = {h_pitch * 2, (cuuint64_t)a.rows * h_pitch * 2};
       CUresult r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                        3, a.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -956,6 +1005,18 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     }
   }
   const int64_t next_bf16 = bf ? ws.take(max_e * 2) : -1;
+  // Wide stages (two stacked tap-GEMM launches, v2w_wide_desc): by default the stages no fused kernel
+  // covers (C = 256); $V2W_WIDE_MASK = bitmask of stages overrides (0 = the six separate tap-GEMMs).
+  const int wide_mask = std::getenv("V2W_WIDE_MASK") ? std::atoi(std::getenv("V2W_WIDE_MASK")) : -1;
+  std::vector<WideBuf> widebuf((size_t)U);
+  for (int i = 0; i < U; ++i) {
+    const bool fusable = m->fused[i].ok && ((fuse_mask >> i) & 1);
+    const bool want = wide_mask >= 0 ? ((wide_mask >> i) & 1) : !fusable;
+    if (bf && !force_simt && !no_fuse && m->wide[i].ok && want) {
+      widebuf[i].width = (m->wide[i].num_branches + 1) * m->stage_channels[i];
+      widebuf[i].a1cat = ws.take((int64_t)B * T * m->stage_up[i] * widebuf[i].width * 2);
+    }
+  }
   P->tr_y = y1.f32;
   for (int i = 0; i < U; ++i) {
     P->tr_sums[i] = ws.take((int64_t)2 * m->stage_channels[i] * 8);
@@ -1010,6 +1071,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     if (bf) {
       o.d.in_act = in.bf16; o.d.in_is_bf16 = 1; o.d.in_slope = 1.f;
       o.d.out_f32 = out.f32; o.d.out_bf16 = out.bf16; o.d.out_slope = out.slope;
+      o.d.out_bf16_pitch = out.pitch16;
     } else {
       o.d.in_act = in.f32; o.d.in_is_bf16 = 0; o.d.in_slope = in.slope;
       o.d.out_f32 = out.f32; o.d.out_bf16 = -1; o.d.out_slope = 1.f;
@@ -1034,7 +1096,16 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   for (int i = 0; i < U; ++i) {
     const bool last_stage = i == U - 1;
     // x = cbns[i](ups[i](leaky_relu(x)), fcs[i](spk_noise))   (models.py:128-134)
-    emit(li++, rows, cur_in, i, -1, -1, 1.f, x0);
+    const bool wide = widebuf[i].a1cat >= 0;
+    if (wide) {
+      // the 16-bit copy of the stage input goes straight into the last C columns of the stage's operand tensor
+      Act x0w = x0;
+      x0w.bf16 = widebuf[i].a1cat + (int64_t)m->wide[i].num_branches * m->stage_channels[i] * 2;
+      x0w.pitch16 = widebuf[i].width;
+      emit(li++, rows, cur_in, i, -1, -1, 1.f, x0w);
+    } else {
+      emit(li++, rows, cur_in, i, -1, -1, 1.f, x0);
+    }
     rows *= c.upsample_rates[i];
     Act stage_out;   // x = xs / num_kernels (models.py:141), as the next consumer wants it
     stage_out.slope = last_stage ? kLreluSlopePost : kLreluSlope;
@@ -1042,6 +1113,40 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     stage_out.bf16 = (bf && !last_stage) ? next_bf16 : -1;
     Act partial;     // running MRF sum xs (models.py:136-140)
     partial.f32 = sum_f32;
+    if (wide) {
+      const v2w_wide_desc& W = m->wide[i];
+      const int C = W.channels, nb = W.num_branches;
+      for (int half = 0; half < 2; ++half) {
+        Op o = blank(half == 0 ? V2W_OP_MRF_WIDE1 : V2W_OP_MRF_WIDE2);
+        o.d.engine = V2W_ENGINE_TC;
+        o.d.layer = li;
+        o.d.stage = i;
+        o.d.batch = B;
+        o.d.rows = rows;
+        o.d.n_tile = C;
+        o.d.in_is_bf16 = 1;
+        o.d.in_pitch = widebuf[i].width;
+        o.d.residual = x0.f32;
+        if (half == 0) {
+          o.d.n_tiles = nb;
+          o.d.in_act = widebuf[i].a1cat + (int64_t)nb * C * 2;     // A0
+          o.d.out_bf16 = widebuf[i].a1cat;                        // A1_0 | ... | A1_{nb-1}
+          o.d.out_bf16_pitch = widebuf[i].width;
+          o.d.out_slope = kLreluSlope;
+        } else {
+          o.d.n_tiles = 1;
+          o.d.in_act = widebuf[i].a1cat;
+          o.d.out_scale = 1.0f / nk;
+          o.d.out_f32 = stage_out.f32; o.d.out_bf16 = stage_out.bf16; o.d.out_slope = stage_out.slope;
+        }
+        for (int q = 0; q < nb; ++q)
+          o.d.flops += 2 * m->layers[li + 2 * q + half].macs_per_row * (int64_t)rows * B;
+        P->ops.push_back(o);
+      }
+      li += 2 * nk;
+      cur_in = stage_out;
+      continue;
+    }
     if (bf && !force_simt && !no_fuse && m->fused[i].ok && ((fuse_mask >> i) & 1)) {
       // whole stage in one kernel (kernels_fused.cuh)
       Op o = blank(V2W_OP_MRF_FUSED);
@@ -1167,11 +1272,106 @@ int32_t v2w_plan_set_engine(v2w_plan* p, int32_t i, int32_t engine) {
     set_error("v2w_plan_set_engine: the tensor-core engine needs a BF16/FP16 plan");
     return V2W_ERR_INVALID;
   }
+  if (engine == V2W_ENGINE_SIMT && (o.d.out_bf16_pitch || o.d.in_pitch)) {
+    set_error("v2w_plan_set_engine: op %d writes into a wide stage's operand tensor (tensor-core engine only)", i);
+    return V2W_ERR_INVALID;
+  }
   if (engine == V2W_ENGINE_SIMT && p->precision == V2W_PREC_FP16) {
     set_error("v2w_plan_set_engine: the FFMA engine reads fp32 or bf16 activations, not fp16");
     return V2W_ERR_INVALID;
   }
   o.d.engine = engine;
+  return V2W_OK;
+}
+
+// The two launches of a wide stage (v2w_wide_desc) as tap-GEMMs over the packed arrays that already
+// exist: launch 1 reads the conv1 weights of every branch in place (column tile t = branch t), launch 2
+// the conv2 weights (K-group j = branch j) and the `sum` convolution (last K-group).  All of them are
+// [taps][C][C] arrays, so one weight tensor map with rows of C elements covers them; a block's row is its
+// byte distance from the lowest array divided by the row size (every section is 1024-byte aligned).
+static int prepare_wide(v2w_plan* p, Op& o, int tc_flags) {
+  const v2w_model* m = p->model;
+  const v2w_wide_desc& W = m->wide[o.d.stage];
+  const int C = W.channels, nb = W.num_branches;
+  const bool first = o.d.kind == V2W_OP_MRF_WIDE1;
+  v2w_tapgemm_args& g = o.g;
+  std::memset(&g, 0, sizeof(g));
+  TcExtra ex;
+  std::memset(ex.w_row, 0, sizeof(ex.w_row));
+  g.engine = V2W_ENGINE_TC;
+  g.batch = o.d.batch; g.rows = o.d.rows;
+  g.in_is_bf16 = 1; g.in_slope = 1.f;
+  g.tc_flags = tc_flags;
+  auto at = [&](int64_t off) -> uint8_t* { return off < 0 ? nullptr : p->ws + off; };
+  g.in_act = at(o.d.in_act);
+  g.residual = reinterpret_cast<const float*>(at(o.d.residual));
+  g.out_scale = o.d.out_scale;
+  g.out_f32 = reinterpret_cast<float*>(at(o.d.out_f32));
+  g.out_bf16 = at(o.d.out_bf16);
+  g.out_slope = o.d.out_slope;
+  ex.a_pitch = o.d.in_pitch;
+  ex.h_pitch = o.d.out_bf16_pitch;
+  ex.res_pitch = C; ex.res_cols = C;
+  ex.w_cols = C;
+  ex.abs_rows = true;
+  const int64_t row_bytes = (int64_t)C * 2;
+  // lowest / highest byte of the weight arrays this launch reads
+  int64_t lo = -1, hi = -1;
+  auto span = [&](int64_t off, int64_t bytes) {
+    lo = lo < 0 ? off : std::min(lo, off);
+    hi = std::max(hi, off + bytes);
+  };
+  for (int j = 0; j < nb; ++j) {
+    const v2w_layer_desc& L = m->layers[W.first_layer + 2 * j + (first ? 0 : 1)];
+    span(L.w16_off, (int64_t)L.num_taps * C * row_bytes);
+  }
+  if (!first) span(W.wsum_off, (int64_t)W.sum_taps * C * row_bytes);
+  if (lo % row_bytes) {
+    set_error("wide stage %d: weight arrays are not aligned to their row size", o.d.stage);
+    return V2W_ERR_STATE;
+  }
+  g.w16 = p->packed + lo;
+  ex.w_total_rows = (hi - lo) / row_bytes;
+  auto rows_of = [&](int64_t off) { return (int)((off - lo) / row_bytes); };
+  if (first) {
+    g.cin = C; g.n_total = nb * C; g.cmod = nb * C; g.n_tile = C; g.n_tiles = nb;
+    g.bias = reinterpret_cast<const float*>(p->packed + W.b1cat_off);
+    ex.res_scale = 1.f;
+    for (int t = 0; t < nb; ++t) {
+      const v2w_layer_desc& L = m->layers[W.first_layer + 2 * t];
+      g.num_taps[t] = L.num_taps;
+      for (int j = 0; j < L.num_taps; ++j) {
+        g.tap_off[t][j] = L.tap_off[j];
+        g.tap_row[t][j] = j;
+        ex.w_row[t][j] = rows_of(L.w16_off) + j * C;
+      }
+    }
+  } else {
+    g.cin = (nb + 1) * C; g.n_total = C; g.cmod = C; g.n_tile = C; g.n_tiles = 1;
+    g.bias = reinterpret_cast<const float*>(p->packed + W.bsum_off);
+    ex.res_scale = (float)nb;
+    ex.kgroups = nb + 1;
+    ex.cpg = C / 64;
+    for (int t = 0; t < nb; ++t) {
+      const v2w_layer_desc& L = m->layers[W.first_layer + 2 * t + 1];
+      g.num_taps[t] = L.num_taps;
+      for (int j = 0; j < L.num_taps; ++j) {
+        g.tap_off[t][j] = L.tap_off[j];
+        g.tap_row[t][j] = j;
+        ex.w_row[t][j] = rows_of(L.w16_off) + j * C;
+      }
+    }
+    g.num_taps[nb] = W.sum_taps;
+    for (int j = 0; j < W.sum_taps; ++j) {
+      g.tap_off[nb][j] = W.sum_off[j];
+      g.tap_row[nb][j] = j;
+      ex.w_row[nb][j] = rows_of(W.wsum_off) + j * C;
+    }
+  }
+  int rc = prepare_tc(g, &o.tcl, &ex);
+  if (rc) return rc;
+  o.tc_ready = true;
+  o.has_raw = false;
   return V2W_OK;
 }
 
@@ -1215,6 +1415,11 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       if (rc) return rc;
       continue;
     }
+    if (o.d.kind == V2W_OP_MRF_WIDE1 || o.d.kind == V2W_OP_MRF_WIDE2) {
+      rc = prepare_wide(p, o, tc_flags);
+      if (rc) return rc;
+      continue;
+    }
     if (o.d.kind != V2W_OP_TAPGEMM) continue;
     const v2w_layer_desc& L = m->layers[o.d.layer];
     v2w_tapgemm_args& g = o.g;
@@ -1251,9 +1456,14 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
     if (rc) return rc;
     o.tc_ready = false;
     if (g.engine == V2W_ENGINE_TC) {
-      rc = prepare_tc(g, &o.tcl);
+      TcExtra ex;
+      ex.h_pitch = o.d.out_bf16_pitch;
+      rc = prepare_tc(g, &o.tcl, o.d.out_bf16_pitch ? &ex : nullptr);
       if (rc) return rc;
       o.tc_ready = true;
+    } else if (o.d.out_bf16_pitch) {
+      set_error("v2w_plan_bind: op writes a pitched 16-bit output, which needs the tensor-core engine");
+      return V2W_ERR_STATE;
     }
     o.has_raw = false;
     if (o.d.cond_stage >= 0) {
@@ -1530,6 +1740,13 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
         ++launches;
         break;
       }
+      case V2W_OP_MRF_WIDE1:
+      case V2W_OP_MRF_WIDE2: {
+        int rc = launch_tc(o.tcl, st, lim, o.d.rows / p->frames);
+        if (rc) return rc;
+        ++launches;
+        break;
+      }
       case V2W_OP_PAIR_FUSED:
       case V2W_OP_MRF_FUSED: {
         PostFold pf;
@@ -1605,6 +1822,8 @@ int32_t v2w_forward_graph(v2w_plan* p, const float* x_dev, const float* spk_dev,
     return V2W_ERR_INVALID;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->profiling)   // per-op events are recorded by the plain path only
+    return v2w_forward(p, x_dev, spk_dev, noise_dev, out_dev, stream, gpu_launches);
   for (v2w_plan::GraphEntry& g : p->graphs) {
     if (g.x == x_dev && g.spk == spk_dev && g.noise == noise_dev && g.out == out_dev) {
       V2W_CUDA(cudaGraphLaunch(g.exec, st));

@@ -28,6 +28,9 @@ ENGINE_SIMT = 0
 ENGINE_TC = 1
 OUT_F32, OUT_PCM16 = 0, 1
 OP_TRANSPOSE_IN, OP_COND_AFFINE, OP_TAPGEMM, OP_CONV_POST, OP_MRF_FUSED, OP_PAIR_FUSED = 0, 1, 2, 3, 4, 5
+OP_MRF_WIDE1, OP_MRF_WIDE2 = 6, 7
+#: op kinds that run on the tcgen05 engines and carry algorithmic FLOPs
+GEMM_OPS = (OP_TAPGEMM, OP_MRF_FUSED, OP_PAIR_FUSED, OP_MRF_WIDE1, OP_MRF_WIDE2)
 FUSED_MAX_SEG, FUSED_MAX_TAPS = 16, 96
 SEG_CONV1, SEG_SUM, SEG_CONV2 = 0, 1, 2
 ROLE_CONV_PRE, ROLE_UPSAMPLE, ROLE_RESBLOCK, ROLE_CONV_POST = 0, 1, 2, 3
@@ -116,6 +119,16 @@ class OpDesc(C.Structure):
         ("stage", C.c_int32),
         ("pair", C.c_int32),
         ("post", C.c_int32),
+        ("out_bf16_pitch", C.c_int32),
+        ("in_pitch", C.c_int32),
+    ]
+
+
+class WideDesc(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int32), ("channels", C.c_int32), ("num_branches", C.c_int32), ("first_layer", C.c_int32),
+        ("sum_taps", C.c_int32), ("sum_off", C.c_int32 * MAX_TAPS),
+        ("wsum_off", C.c_int64), ("b1cat_off", C.c_int64), ("bsum_off", C.c_int64),
     ]
 
 
@@ -181,6 +194,7 @@ _SIGNATURES = [
     ("v2w_model_get_layer", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(LayerDesc)]),
     ("v2w_model_get_cond", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(CondDesc)]),
     ("v2w_model_get_fused", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FusedDesc)]),
+    ("v2w_model_get_wide", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(WideDesc)]),
     ("v2w_model_num_pairs", C.c_int32, [C.c_void_p]),
     ("v2w_model_get_pair", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(FusedDesc)]),
     ("v2w_model_num_convs", C.c_int32, [C.c_void_p]),
