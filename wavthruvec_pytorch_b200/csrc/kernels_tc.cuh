@@ -92,7 +92,11 @@ struct Params {
   // wrap) -- the N-stacked conv1 of a stage adds the SAME [rows, C] residual to every branch's columns.
   int res_pitch, res_cols;
   float res_scale;
-  int h_pitch;          // row pitch of the 16-bit output in elements (direct-store path; 0 = n_total)
+  int h_pitch;          // row pitch of the 16-bit output in elements (0 = n_total: dense)
+  // Pitched 16-bit output of a polyphase (transposed-conv) op: the GEMM row [up * cout] is `up` consecutive
+  // rows of the channels-last signal, each of which starts h_pitch elements after the previous one -- a 4-D
+  // tensor (cout, up, rows, batch).  h_cout = cout in that case (4-D tensor map), else 0.
+  int h_cout;
   const float* bias;
   const float* scale;
   const float* shift;
@@ -203,6 +207,13 @@ __device__ __forceinline__ void tma_store_3d(const void* tm, uint32_t src, int c
       "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
           reinterpret_cast<uint64_t>(tm)),
       "r"(src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tm)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
@@ -710,7 +721,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int e = 0; e < 8; ++e)
                   h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
                                     p.fp16);
-                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + (p.h_pitch ? row_lin * p.h_pitch : row_base) + col);
+                size_t ho = row_base + col;
+                if (p.h_cout) {
+                  const int ph = col / p.h_cout;
+                  ho = (row_lin * (p.n_total / p.h_cout) + ph) * p.h_pitch + (col - ph * p.h_cout);
+                } else if (p.h_pitch) {
+                  ho = row_lin * p.h_pitch + col;
+                }
+                uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + ho);
                 op[0] = make_uint4(h[0], h[1], h[2], h[3]);
                 op[1] = make_uint4(h[4], h[5], h[6], h[7]);
               }
@@ -726,7 +744,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0 && row0w < p.rows) {
               const int col = nt * p.n_tile + cc;
               if (p.out_f32) tma_store_3d(&tmY, ybuf + sbuf * kStageYBytes, col, row0w, b);
-              if (p.out_bf16) tma_store_3d(&tmH, hbuf + sbuf * kStageHBytes, col, row0w, b);
+              if (p.out_bf16) {
+                if (p.h_cout) {
+                  const int ph = col / p.h_cout;
+                  tma_store_4d(&tmH, hbuf + sbuf * kStageHBytes, col - ph * p.h_cout, ph, row0w, b);
+                } else {
+                  tma_store_3d(&tmH, hbuf + sbuf * kStageHBytes, col, row0w, b);
+                }
+              }
               tma_store_commit();
               tma_store_wait_read<1>();
             }

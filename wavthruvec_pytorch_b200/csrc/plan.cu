@@ -236,6 +236,7 @@ static int validate_gemm(const v2w_tapgemm_args& a) {
 struct TcExtra {
   int a_pitch = 0;       // elements per row of the input tensor (0 = cin)
   int h_pitch = 0;       // elements per row of the 16-bit output tensor (0 = n_total)
+  int h_cout = 0;        // polyphase op with a pitched output: channels of one output row (4-D output tensor)
   int res_pitch = 0, res_cols = 0;
   float res_scale = 1.f;
   int kgroups = 0, cpg = 0;
@@ -277,6 +278,11 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
     p.kgroups = ex->kgroups; p.cpg = ex->cpg;
     p.res_pitch = ex->res_pitch; p.res_cols = ex->res_cols; p.res_scale = ex->res_scale;
     p.h_pitch = ex->h_pitch;
+    p.h_cout = (ex->h_pitch && ex->h_cout && ex->h_cout != a.n_total) ? ex->h_cout : 0;
+    if (p.h_cout && (a.n_total % p.h_cout || p.h_cout % 16)) {
+      set_error("tapgemm(TC): bad pitched polyphase output (n_total %d, cout %d)", a.n_total, p.h_cout);
+      return V2W_ERR_INVALID;
+    }
     if (ex->kgroups && (a.n_tiles != 1 || ex->kgroups > V2W_MAX_TILES || ex->kgroups * ex->cpg != p.num_chunks)) {
       set_error("tapgemm(TC): bad K-group geometry (%d groups x %d chunks, %d chunks, %d column tiles)",
                 ex->kgroups, ex->cpg, p.num_chunks, a.n_tiles);
@@ -416,7 +422,19 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
     if (a.out_bf16) {
       const cuuint64_t h_pitch = (ex && ex->h_pitch) ? ex->h_pitch : a.n_total;
       cuuint64_t strides[2] = {h_pitch * 2, (cuuint64_t)a.rows * h_pitch * 2};
-      CUresult r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+      CUresult r;
+      if (p.h_cout) {
+        // (cout, up, rows, batch): one GEMM row is `up` output rows, h_pitch elements apart
+        const cuuint64_t up = (cuuint64_t)(a.n_total / p.h_cout);
+        cuuint64_t dims4[4] = {(cuuint64_t)p.h_cout, up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+        cuuint64_t strides4[3] = {h_pitch * 2, up * h_pitch * 2, (cuuint64_t)a.rows * up * h_pitch * 2};
+        cuuint32_t box4[4] = {16, 1, 32, 1};
+        cuuint32_t estr4[4] = {1, 1, 1, 1};
+        r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                4, a.out_bf16, dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else
+      r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                        3, a.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1458,6 +1476,7 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
     if (g.engine == V2W_ENGINE_TC) {
       TcExtra ex;
       ex.h_pitch = o.d.out_bf16_pitch;
+      ex.h_cout = L.cout;       // a transposed conv's GEMM row is `up` output rows of cout channels
       rc = prepare_tc(g, &o.tcl, o.d.out_bf16_pitch ? &ex : nullptr);
       if (rc) return rc;
       o.tc_ready = true;
