@@ -329,24 +329,40 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
   int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
   if (forced >= 1 && forced <= msub) msub = forced;
-  for (;; msub >>= 1) {
-    p.msub = msub;
-    p.box_rows = msub == 1 ? 32 : 64;
-    const int boxes = (msub * tc::kMTile + halo_max + p.box_rows - 1) / p.box_rows;
+  // Wave quantisation: among the heights that pass the test above, take the one whose last round wastes
+  // the least -- the launch lasts rounds(msub) x msub sub-tile times (cfg2, ups[3]: 500 super-tiles of 4 on
+  // 148 SMs = 4 rounds x 4, against 1000 of 2 = 7 rounds x 2).  Ties go to the taller tile (fewer W fetches);
+  // $V2W_TC_NO_QUANT=1 restores "tallest that leaves two items per SM".
+  static const bool no_quant = [] { const char* e = std::getenv("V2W_TC_NO_QUANT"); return e && std::atoi(e); }();
+  auto geometry = [&](int ms) {
+    p.msub = ms;
+    p.box_rows = ms == 1 ? 32 : 64;
+    const int boxes = (ms * tc::kMTile + halo_max + p.box_rows - 1) / p.box_rows;
     p.stage_a_bytes = boxes * p.box_rows * kc * 2;
-    const int tile_rows = (L->pair ? 2 : 1) * msub * tc::kMTile;
+    const int tile_rows = (L->pair ? 2 : 1) * ms * tc::kMTile;
     p.s_tiles = (a.rows + tile_rows - 1) / tile_rows;
-    const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
+    return (int64_t)a.batch * p.s_tiles * a.n_tiles;
+  };
+  const int slots = L->pair ? sms / 2 : sms;
+  int best = 0;
+  int64_t best_cost = 0;
+  for (int ms = msub; ms >= 1; ms >>= 1) {
+    const int64_t tiles = geometry(ms);
     const bool fits = 2 * p.stage_a_bytes + 3 * p.stage_w_bytes <= budget;
-    if (msub == 1 || (fits && (tiles >= (L->pair ? sms : 2 * sms) || forced))) {
-      if (!fits) {
-        set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)",
-                  p.stage_a_bytes, p.stage_w_bytes);
-        return V2W_ERR_INVALID;
-      }
-      break;
+    const bool ok = ms == 1 || (fits && (tiles >= (L->pair ? sms : 2 * sms) || forced));
+    if (!ok) continue;
+    if (ms == 1 && !fits) {
+      set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)", p.stage_a_bytes, p.stage_w_bytes);
+      return V2W_ERR_INVALID;
     }
+    const int64_t cost = ((tiles + slots - 1) / slots) * ms;
+    if (!best || cost < best_cost) {
+      best = ms;
+      best_cost = cost;
+    }
+    if (forced || no_quant) break;     // first admissible height, as before
   }
+  geometry(best);
   p.stages_a = 2;
   p.stages_w = std::min((budget - 2 * p.stage_a_bytes) / p.stage_w_bytes, tc::kMaxStagesW);
   p.stages_a = std::max(2, std::min((budget - p.stages_w * p.stage_w_bytes) / p.stage_a_bytes,
