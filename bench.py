@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-scale-ref", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the forward from a CUDA graph (latency path)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -308,6 +309,38 @@ def parity_check(args, dev, local_batch, frames, feat):
             "pass": bool(bar_ok and not worst["nan"])}
 
 
+def cfg5_on_one_gpu(args, dev, micro=64, warm=2, steps=5):
+    import torch
+    from wavthruvec_pytorch_b200 import Generator
+    g_batch, frames, feat = CONFIGS["cfg5"]
+    h = make_hparams(args, feat)
+    torch.manual_seed(1234)
+    gen = Generator(h).eval().to(dev)
+    gen.precision = args.precision
+    rng = torch.Generator().manual_seed(4321)
+    x = torch.randn(micro, feat, frames, generator=rng).to(dev)
+    s = torch.randn(micro, h.spk_dim, generator=rng).to(dev)
+    n = torch.randn(micro, h.noise_dim, generator=rng).to(dev)
+    n_micro = g_batch // micro
+    with torch.no_grad():
+        for _ in range(warm * n_micro):
+            gen(x, s, n)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps * n_micro):
+            gen(x, s, n)
+        b.record()
+        torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / steps
+    del gen
+    torch.cuda.empty_cache()
+    return {"value": g_batch * frames / FRAMES_PER_SECOND / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "micro_batches": n_micro, "micro_batch": micro,
+            "note": "cfg5 (512 x 10 s) on ONE GPU as 8 micro-batches of 64 through one plan, device-resident inputs, "
+                    "CUDA events around the whole job; the working set (>6 GB per micro-batch) is far larger than L2"}
+
+
 # --------------------------------------------------------------------------------------------
 # native arm
 # --------------------------------------------------------------------------------------------
@@ -531,6 +564,15 @@ def run_native_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": sample, "host_cpu_count": os.cpu_count(),
                                     "cpu_model": cpu_model()}
+        if world == 1 and args.config == "cfg2" and not args.no_scale_ref:
+            # Reference point for the strong-scaling runs (N > 1 shards cfg5 = 512 x 10 s): the SAME job on this
+            # one GPU, as 8 micro-batches of 64 utterances through one plan (the whole batch's workspace would be
+            # 49 GB).  The driver's N = 1 line stays cfg2 (BASELINE configs[1]); efficiency of the cfg5 job is
+            # value_N / (N * cfg5_single_gpu.value).
+            try:
+                line["cfg5_single_gpu"] = cfg5_on_one_gpu(args, dev)
+            except Exception as e:
+                line["cfg5_single_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and not args.no_eager:
             # Context only: the reference's own op sequence -- stock PyTorch/cuDNN ops,
             # weight-norm hooks re-run every call -- on this same GPU, same inputs.  It is the

@@ -627,21 +627,30 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const size_t row_lin = static_cast<size_t>(b) * p.rows + row;
         const size_t row_base = row_lin * p.n_total;
         const size_t res_base = p.res_pitch ? row_lin * p.res_pitch : row_base;
-        for (int cc = 0; cc < p.n_tile; cc += 16) {
-          const int col = nt * p.n_tile + cc;
-          // issue the global reads first so that they overlap the TMEM load
-          float4 res[4], acc[4];
+        // The residual / running-sum reads of a chunk are issued ONE CHUNK AHEAD: a cold global (L2) read
+        // on the critical path of every 16-column chunk made the k = 3 convolutions epilogue-bound.
+        // (The tensors may alias out_f32: chunks touch disjoint columns, so reading ahead is safe.)
+        float4 res[4], acc[4], res_n[4], acc_n[4];
+        auto load_ra = [&](int cc2, float4 (&r4)[4], float4 (&a4)[4]) {
+          const int col2 = nt * p.n_tile + cc2;
           if (valid && p.residual) {
-            const int rcol = p.res_cols ? col % p.res_cols : col;
+            const int rcol = p.res_cols ? col2 % p.res_cols : col2;
             const float4* rp = reinterpret_cast<const float4*>(p.residual + res_base + rcol);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) res[e] = rp[e];
+            for (int e = 0; e < 4; ++e) r4[e] = rp[e];
           }
           if (valid && p.accum_in) {
-            const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + col);
+            const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + col2);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] = ap[e];
+            for (int e = 0; e < 4; ++e) a4[e] = ap[e];
           }
+        };
+        load_ra(0, res_n, acc_n);
+        for (int cc = 0; cc < p.n_tile; cc += 16) {
+          const int col = nt * p.n_tile + cc;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { res[e] = res_n[e]; acc[e] = acc_n[e]; }
+          if (cc + 16 < p.n_tile) load_ra(cc + 16, res_n, acc_n);
           uint32_t r[16];
           tmem_ld16(t_lane + m * p.acc_cols + cc, r);
           tmem_ld_wait();
