@@ -19,7 +19,7 @@ sizes)
   done
   for c in cfg2 cfg5_per_gpu; do python tools/op_table.py --config $c --out gpurun_out/r2_ops_$c.json > gpurun_out/r2_ops_$c.txt 2>&1; done; tail -n 3 gpurun_out/r2_ops_cfg2.txt ;;
 ncu)
-  for c in cfg2 cfg3 cfg5_per_gpu; do
+  for c in ${NCU_CFGS:-cfg2 cfg3 cfg5_per_gpu}; do
     timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
        -o /tmp/prof/$c -f python tools/prof_forward.py $c > gpurun_out/r2_ncu_$c.log 2>&1; tail -n 1 gpurun_out/r2_ncu_$c.log | cut -c1-200
     python tools/ncu_summary.py /tmp/prof/$c.ncu-rep > gpurun_out/r2_ncu_full_$c.csv 2>> gpurun_out/r2_ncu_$c.log; wc -l gpurun_out/r2_ncu_full_$c.csv
