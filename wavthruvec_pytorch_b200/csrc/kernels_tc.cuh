@@ -39,6 +39,22 @@
 
 #include "v2w.h"
 
+// Developer timeline of the generic kernel (build with V2W_NVCC_EXTRA=-DV2W_TRACE_TC): CTA 0 prints SM-clock
+// stamps of its MMA warp and of epilogue warp 4 for tile V2W_TRTC_TILE (default 1: steady state).
+#ifdef V2W_TRACE_TC
+#ifndef V2W_TRTC_TILE
+#define V2W_TRTC_TILE 1
+#endif
+#define V2W_TRTC_DECL long long trc_t[120]; int trc_tag[120]; int trc_n = 0; const long long trc_base = clock64();
+#define V2W_TRTC(tile_it, tag) do { if (blockIdx.x == 0 && trc_n < 120 && (int)(tile_it) == V2W_TRTC_TILE) { trc_tag[trc_n] = (tag); trc_t[trc_n++] = clock64() - trc_base; } } while (0)
+#define V2W_TRTC_DUMP(name) do { if (blockIdx.x == 0 && lane == 0) for (int q = 0; q < trc_n; ++q) \
+    printf("TRTC %s %d %d %lld\n", name, q, trc_tag[q], trc_t[q]); } while (0)
+#else
+#define V2W_TRTC_DECL
+#define V2W_TRTC(tile_it, tag) do { } while (0)
+#define V2W_TRTC_DUMP(name) do { } while (0)
+#endif
+
 namespace v2w {
 namespace tc {
 
@@ -47,10 +63,10 @@ constexpr int kMTile = 128;
 constexpr int kMaxStagesA = 4;
 constexpr int kMaxStagesW = 8;
 constexpr int kMaxSub = 4;
-// Output staging per epilogue warp: 2 x (32 rows x 16 fp32 = 2 KB) + 2 x (32 rows x 16 half = 1 KB)
-constexpr int kStageYBytes = 2048, kStageHBytes = 1024;
-constexpr int kStageWarpBytes = 2 * kStageYBytes + 2 * kStageHBytes;
-constexpr int kStageBytes = 8 * kStageWarpBytes;   // 48 KB
+// Output staging per epilogue warp: two buffers per output tensor, each one TMA store box of 32 rows x
+// y_cols fp32 / h_cols 16-bit columns (Params::y_cols, h_cols: 16, 32 or 64; sized per op on the host).
+// 16-column boxes by default: wider boxes (fewer, larger TMA stores; 128-byte rows) were measured slower,
+// see plan.cu prepare_tc.
 // per epilogue warp: this tile's bias | scale | shift column vectors (n_tile <= 256 floats each),
 // staged once per tile so that the chunk loop reads them with LDS broadcasts instead of L1 round trips
 // (3 * n_tile * 4 bytes per warp: Params::cvec_warp_bytes)
@@ -72,6 +88,8 @@ struct Params {
   int acc_cols;         // TMEM columns per accumulator (per sub-tile)
   int fp16;             // 16-bit operand format: 0 = bf16, 1 = fp16
   int tma_out;          // outputs leave through shared-memory staging + TMA stores
+  int y_cols, h_cols;   // TMA store box widths (columns) of the fp32 / 16-bit output; multiples of 16 dividing n_tile
+  int stage_warp_bytes; // staging per epilogue warp: 2 * 32 * y_cols * 4 (if fp32 out) + 2 * 32 * h_cols * 2 (if 16-bit out)
   // 32-bit entries on purpose: see the note at fused::Segment (ptxas merges 16-bit loads of
   // dynamically indexed parameter arrays incorrectly at some alignments).
   int num_taps[V2W_MAX_TILES];
@@ -523,6 +541,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // (pair mode: the leader CTA issues M = 256 MMAs for both; commits are multicast)
     Ring ra, rw;
     uint32_t tile_iter = 0;
+    V2W_TRTC_DECL
     const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kMTile : kMTile, p.n_tile, p.fp16);
     const uint32_t dhi = smem_desc_hi<KC>();
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -536,17 +555,21 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nsub = min(p.msub, (p.rows - q0 + kMTile - 1) / kMTile);
       const uint32_t as = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
       ++tile_iter;   // counts processed tiles only
+      V2W_TRTC(tile_iter - 1, 1);
       mbar_wait(acc_empty + 8 * as, aph ^ 1u);
       tcgen05_fence_after();
+      V2W_TRTC(tile_iter - 1, 2);
       const uint32_t d_tmem = tmem_base + as * stage_cols;
       for (int c = 0; c < p.num_chunks; ++c) {
         const int li = p.kgroups ? c / p.cpg : nt;
         const int ntaps = p.num_taps[li];
         mbar_wait(full_a + 8 * ra.s, ra.ph);
+        V2W_TRTC(tile_iter - 1, 10 + c);
         const uint32_t a_stage = smem_a + ra.s * p.stage_a_bytes;
         for (int j = 0; j < ntaps; ++j) {
           mbar_wait(full_w + 8 * rw.s, rw.ph);
           tcgen05_fence_after();
+          V2W_TRTC(tile_iter - 1, 100 + c * 16 + j);
           if (elect_one()) {
             const uint32_t a_addr = a_stage + (p.tap_off[li][j] - off_min) * kRowBytes;
             const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
@@ -579,16 +602,26 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         ra.advance(p.stages_a);
       }
+      V2W_TRTC(tile_iter - 1, 3);
     }
+    V2W_TRTC_DUMP("mma");
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
     const int group = (warp - 4) >> 2;  // accumulator stage this warp drains
     const int quarter = warp & 3;       // TMEM lane quarter this warp may read
     const bool pow2 = (p.cmod & (p.cmod - 1)) == 0;
-    const uint32_t ybuf = stage_base + (warp - 4) * kStageWarpBytes;
-    const uint32_t cvec = stage_base + (p.tma_out ? kStageBytes : 0) + (warp - 4) * p.cvec_warp_bytes;
-    const uint32_t hbuf = ybuf + 2 * kStageYBytes;
-    uint32_t sbuf = 0;
+    const uint32_t ybuf = stage_base + (warp - 4) * p.stage_warp_bytes;
+    const uint32_t cvec = stage_base + (p.tma_out ? 8 * p.stage_warp_bytes : 0) + (warp - 4) * p.cvec_warp_bytes;
+    const uint32_t y_box = p.out_f32 ? 32u * p.y_cols * 4u : 0u;      // bytes of one staging box
+    const uint32_t h_box = 32u * p.h_cols * 2u;
+    const uint32_t hbuf = ybuf + 2 * y_box;
+    const uint32_t y_row = p.y_cols * 4u, h_row = p.h_cols * 2u;      // 64 / 128 and 32 / 64 / 128 bytes
+    // XOR of the 16-byte unit index inside a row, as the TMA swizzle of that row size applies it
+    const uint32_t y_sw = y_row == 128 ? (lane & 7) : ((lane >> 1) & 3);
+    const uint32_t h_sw = h_row == 128 ? (lane & 7) : (h_row == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+    const int y_sub = p.y_cols >> 4, h_sub = p.h_cols >> 4;           // 16-column chunks per box
+    uint32_t sy = 0, sh = 0;                                           // staging buffer in use
+    V2W_TRTC_DECL
     uint32_t tile_iter = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_b;
@@ -616,8 +649,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       __syncwarp();
+      V2W_TRTC(it, 1);
       mbar_wait(acc_full + 8 * group, aph);
       tcgen05_fence_after();
+      V2W_TRTC(it, 2);
       const uint32_t t_lane = tmem_base + group * stage_cols +
                               (static_cast<uint32_t>(quarter * 32) << 16);
       for (int m = 0; m < nsub; ++m) {
@@ -627,45 +662,54 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const size_t row_lin = static_cast<size_t>(b) * p.rows + row;
         const size_t row_base = row_lin * p.n_total;
         const size_t res_base = p.res_pitch ? row_lin * p.res_pitch : row_base;
-        // The residual / running-sum reads of a chunk are issued ONE CHUNK AHEAD: a cold global (L2) read
-        // on the critical path of every 16-column chunk made the k = 3 convolutions epilogue-bound.
-        // (The tensors may alias out_f32: chunks touch disjoint columns, so reading ahead is safe.)
-        float4 res[4], acc[4], res_n[4], acc_n[4];
-        auto load_ra = [&](int cc2, float4 (&r4)[4], float4 (&a4)[4]) {
-          const int col2 = nt * p.n_tile + cc2;
-          if (valid && p.residual) {
-            const int rcol = p.res_cols ? col2 % p.res_cols : col2;
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + res_base + rcol);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) r4[e] = rp[e];
-          }
-          if (valid && p.accum_in) {
-            const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + col2);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a4[e] = ap[e];
-          }
-        };
-        load_ra(0, res_n, acc_n);
+        // ---- chunk loop: 16 accumulator columns per step ----
+        // Instruction-latency-bound: two epilogue warps per scheduler, one dependent chain each.  The timeline
+        // of tools/trace_tc.py showed ~2000 clk per chunk in round 1's loop -- ~1000 clk of ALU work with a
+        // uniform branch per packed pair (the 16-bit format test), ~390 clk to issue ONE TMA store from under
+        // `if (lane == 0)` (ptxas wraps it in a BRA.U.ANY waterfall loop) and ~300 clk of loop overhead -- which
+        // made every k = 3 convolution and every transposed conv epilogue-bound.  So: loop invariants hoisted,
+        // the format branch taken once per chunk, no runtime division, stores issued by an ELECTED lane.
+        const bool has_res = valid && p.residual != nullptr;
+        const bool has_acc = valid && p.accum_in != nullptr;
+        const int col0 = nt * p.n_tile;
+        const size_t res_off = res_base + (p.res_cols ? col0 % p.res_cols : col0);   // once per sub-tile
+        const size_t acc_off = row_base + col0;
+        const uint32_t y_mask = y_sub - 1, h_mask = h_sub - 1;    // boxes are 1, 2 or 4 chunks wide
+        const float out_scale = p.out_scale, out_slope = p.out_slope, res_scale = p.res_scale;
+        const bool do_scale = out_scale != 1.0f, fp16 = p.fp16 != 0;
+        const bool has_bias = p.bias != nullptr, has_affine = p.scale != nullptr;
+        const bool st_y = p.out_f32 != nullptr, st_h = p.out_bf16 != nullptr, tma_out = p.tma_out != 0;
         for (int cc = 0; cc < p.n_tile; cc += 16) {
-          const int col = nt * p.n_tile + cc;
+          const int col = col0 + cc;
+          // issue the global reads first so that they overlap the TMEM load
+          float4 res[4], acc[4];
+          if (has_res) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + res_off + cc);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { res[e] = res_n[e]; acc[e] = acc_n[e]; }
-          if (cc + 16 < p.n_tile) load_ra(cc + 16, res_n, acc_n);
+            for (int e = 0; e < 4; ++e) res[e] = rp[e];
+          }
+          if (has_acc) {
+            const float4* ap = reinterpret_cast<const float4*>(p.accum_in + acc_off + cc);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = ap[e];
+          }
           uint32_t r[16];
+          V2W_TRTC(it, 1000 + cc);
           tmem_ld16(t_lane + m * p.acc_cols + cc, r);
           tmem_ld_wait();
+          V2W_TRTC(it, 2000 + cc);
           if (valid) {
             float v[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-            if (p.bias) {
+            if (has_bias) {
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
                 const float4 t = ld_shared_f4(cvec + (cc + e) * 4);
                 v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
               }
             }
-            if (p.scale) {
+            if (has_affine) {
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
                 const float4 s4 = ld_shared_f4(cvec + (p.n_tile + cc + e) * 4);
@@ -676,60 +720,59 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
               }
             }
-            if (p.residual) {
-              const float rs = p.res_scale;
+            if (has_res) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                v[4 * e] = fmaf(rs, res[e].x, v[4 * e]); v[4 * e + 1] = fmaf(rs, res[e].y, v[4 * e + 1]);
-                v[4 * e + 2] = fmaf(rs, res[e].z, v[4 * e + 2]); v[4 * e + 3] = fmaf(rs, res[e].w, v[4 * e + 3]);
+                v[4 * e] = fmaf(res_scale, res[e].x, v[4 * e]); v[4 * e + 1] = fmaf(res_scale, res[e].y, v[4 * e + 1]);
+                v[4 * e + 2] = fmaf(res_scale, res[e].z, v[4 * e + 2]); v[4 * e + 3] = fmaf(res_scale, res[e].w, v[4 * e + 3]);
               }
             }
-            if (p.accum_in) {
+            if (has_acc) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 v[4 * e] += acc[e].x; v[4 * e + 1] += acc[e].y;
                 v[4 * e + 2] += acc[e].z; v[4 * e + 3] += acc[e].w;
               }
             }
-            if (p.out_scale != 1.0f) {
+            if (do_scale) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] *= p.out_scale;
+              for (int e = 0; e < 16; ++e) v[e] *= out_scale;
             }
-            if (p.tma_out) {
-              // own row -> staging tile in the TMA swizzle layout (64B / 32B swizzle: conflict-free)
-              if (p.out_f32) {
-                const uint32_t yb = ybuf + sbuf * kStageYBytes + lane * 64;
-                const uint32_t sw = (lane >> 1) & 3;
+            uint32_t h[8];
+            if (st_h) {          // one format branch per chunk, not one per packed pair
+              if (fp16) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = pack_half2(lrelu(v[2 * e], out_slope), lrelu(v[2 * e + 1], out_slope), 1);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = pack_bf16x2(lrelu(v[2 * e], out_slope), lrelu(v[2 * e + 1], out_slope));
+              }
+            }
+            if (tma_out) {
+              // own row -> staging box in the TMA swizzle layout (conflict-free 16-byte stores)
+              if (st_y) {
+                const uint32_t yb = ybuf + sy * y_box + lane * y_row;
+                const uint32_t u0 = (static_cast<uint32_t>(cc >> 4) & y_mask) * 4u;   // first 16-byte unit of this chunk
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  st_shared_v4u(yb + ((e ^ sw) << 4), __float_as_uint(v[4 * e]),
+                  st_shared_v4u(yb + (((u0 + e) ^ y_sw) << 4), __float_as_uint(v[4 * e]),
                                 __float_as_uint(v[4 * e + 1]), __float_as_uint(v[4 * e + 2]),
                                 __float_as_uint(v[4 * e + 3]));
               }
-              if (p.out_bf16) {
-                uint32_t h[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
-                                    p.fp16);
-                const uint32_t hb = hbuf + sbuf * kStageHBytes + lane * 32;
-                const uint32_t sw = (lane >> 2) & 1;
-                st_shared_v4u(hb + ((0 ^ sw) << 4), h[0], h[1], h[2], h[3]);
-                st_shared_v4u(hb + ((1 ^ sw) << 4), h[4], h[5], h[6], h[7]);
+              if (st_h) {
+                const uint32_t hb = hbuf + sh * h_box + lane * h_row;
+                const uint32_t u0 = (static_cast<uint32_t>(cc >> 4) & h_mask) * 2u;
+                st_shared_v4u(hb + ((u0 ^ h_sw) << 4), h[0], h[1], h[2], h[3]);
+                st_shared_v4u(hb + (((u0 + 1) ^ h_sw) << 4), h[4], h[5], h[6], h[7]);
               }
             } else {
-              if (p.out_f32) {
+              if (st_y) {
                 float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + col);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                   op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
               }
-              if (p.out_bf16) {
-                uint32_t h[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
-                                    p.fp16);
+              if (st_h) {
                 size_t ho = row_base + col;
                 if (p.h_cout) {
                   const int ph = col / p.h_cout;
@@ -743,29 +786,41 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (p.tma_out) {
-            // every lane's rows are in shared memory -> one lane hands the 32-row slab to TMA.
-            // Rows past the utterance end are clipped by the 3-D tensor map.  Double buffered:
-            // before the warp moves on, the store issued one chunk earlier has finished READING
-            // its buffer (the one the next chunk writes).
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0 && row0w < p.rows) {
-              const int col = nt * p.n_tile + cc;
-              if (p.out_f32) tma_store_3d(&tmY, ybuf + sbuf * kStageYBytes, col, row0w, b);
-              if (p.out_bf16) {
-                if (p.h_cout) {
-                  const int ph = col / p.h_cout;
-                  tma_store_4d(&tmH, hbuf + sbuf * kStageHBytes, col - ph * p.h_cout, ph, row0w, b);
-                } else {
-                  tma_store_3d(&tmH, hbuf + sbuf * kStageHBytes, col, row0w, b);
+          if (tma_out) {
+            // A box is complete when its last 16-column chunk has been staged: the elected lane hands the
+            // 32-row box to TMA.  Rows past the utterance end are clipped by the tensor map.  Double buffered
+            // per output tensor: after every commit the lane waits until at most the NEWEST group still reads
+            // shared memory, so the box written two stores ago (the buffer about to be reused) has been read.
+            const uint32_t cidx = static_cast<uint32_t>(cc >> 4);
+            const bool y_done = st_y && (cidx & y_mask) == y_mask;
+            const bool h_done = st_h && (cidx & h_mask) == h_mask;
+            V2W_TRTC(it, 3000 + cc);
+            if (y_done || h_done) {
+              fence_proxy_async();
+              __syncwarp();
+              V2W_TRTC(it, 4000 + cc);
+              if (row0w < p.rows) {          // warp-uniform
+                if (elect_one()) {
+                  if (y_done) tma_store_3d(&tmY, ybuf + sy * y_box, col + 16 - p.y_cols, row0w, b);
+                  if (h_done) {
+                    const int hc0 = col + 16 - p.h_cols;
+                    if (p.h_cout) {
+                      const int ph = hc0 / p.h_cout;
+                      tma_store_4d(&tmH, hbuf + sh * h_box, hc0 - ph * p.h_cout, ph, row0w, b);
+                    } else {
+                      tma_store_3d(&tmH, hbuf + sh * h_box, hc0, row0w, b);
+                    }
+                  }
+                  tma_store_commit();
+                  V2W_TRTC(it, 5000 + cc);
+                  tma_store_wait_read<1>();
                 }
               }
-              tma_store_commit();
-              tma_store_wait_read<1>();
+              __syncwarp();
+              V2W_TRTC(it, 6000 + cc);
+              if (y_done) sy ^= 1u;
+              if (h_done) sh ^= 1u;
             }
-            __syncwarp();
-            sbuf ^= 1u;
           }
         }
       }
@@ -776,7 +831,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else mbar_arrive(acc_empty + 8 * group);
       }
     }
-    if (p.tma_out && lane == 0) tma_store_wait_all();
+    if (p.tma_out) {
+      if (elect_one()) tma_store_wait_all();      // the same lane that issued (and committed) every store
+    }
+    if (warp == 4 || warp == 8) V2W_TRTC_DUMP(warp == 4 ? "epi4" : "epi8");
   }
 
   tcgen05_fence_before();

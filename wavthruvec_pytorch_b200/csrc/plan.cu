@@ -323,8 +323,22 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
   p.cvec_warp_bytes = 3 * a.n_tile * 4;
+  // TMA store boxes.  Optional wide boxes: as wide as the column tile allows, up to 128-byte rows (fp32: 32
+  // columns; 16-bit: 64 columns when it is the only output, else 32 -- two outputs with 128-byte rows would
+  // take 128 KB of staging).
+  // MEASURED SLOWER than 16-column boxes (ups[2..4] 39-45 -> 52 us at cfg2, marginal k = 3 tile 8.9 -> 9.9 us:
+  // profiles/r02_notes.md), so 16 columns stay the default; $V2W_TC_WIDE_BOX=1 enables the wide boxes.
+  static const bool box16 = [] { const char* e = std::getenv("V2W_TC_WIDE_BOX"); return !(e && std::atoi(e)); }();
+  const int h_unit = (ex && ex->h_cout && ex->h_pitch) ? ex->h_cout : a.n_tile;   // a pitched polyphase box stays inside one phase
+  p.y_cols = (!box16 && a.n_tile % 32 == 0) ? 32 : 16;
+  p.h_cols = 16;
+  if (!box16) {
+    if (!a.out_f32 && a.n_tile % 64 == 0 && h_unit % 64 == 0) p.h_cols = 64;
+    else if (a.n_tile % 32 == 0 && h_unit % 32 == 0) p.h_cols = 32;
+  }
+  p.stage_warp_bytes = (a.out_f32 ? 2 * 32 * p.y_cols * 4 : 0) + (a.out_bf16 ? 2 * 32 * p.h_cols * 2 : 0);
   // barriers (+ output staging) + per-warp column vectors
-  const int tail_bytes = 1024 + (p.tma_out ? tc::kStageBytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
+  const int tail_bytes = 1024 + (p.tma_out ? 8 * p.stage_warp_bytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
   const int budget = 227 * 1024 - 1024 - tail_bytes;
   const int forced = std::getenv("V2W_TC_MSUB") ? std::atoi(std::getenv("V2W_TC_MSUB")) : 0;
   int msub = std::min(tc::kMaxSub, 256 / p.acc_cols);
@@ -423,12 +437,16 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   if (p.tma_out) {
     // output slabs: 32 rows x 16 columns per epilogue warp and chunk (kernels_tc.cuh)
     cuuint64_t dims[3] = {(cuuint64_t)a.n_total, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
-    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t box[3] = {(cuuint32_t)p.y_cols, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    auto swz_of = [](int row_bytes) {
+      return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    };
     if (a.out_f32) {
       cuuint64_t strides[2] = {(cuuint64_t)a.n_total * 4, (cuuint64_t)a.rows * a.n_total * 4};
       CUresult r = enc(&L->tm_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out_f32, dims, strides, box,
-                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(p.y_cols * 4),
                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(out f32) failed with CUresult %d", (int)r);
@@ -444,16 +462,17 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
         const cuuint64_t up = (cuuint64_t)(a.n_total / p.h_cout);
         cuuint64_t dims4[4] = {(cuuint64_t)p.h_cout, up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
         cuuint64_t strides4[3] = {h_pitch * 2, up * h_pitch * 2, (cuuint64_t)a.rows * up * h_pitch * 2};
-        cuuint32_t box4[4] = {16, 1, 32, 1};
+        cuuint32_t box4[4] = {(cuuint32_t)p.h_cols, 1, 32, 1};
         cuuint32_t estr4[4] = {1, 1, 1, 1};
         r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                 4, a.out_bf16, dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      } else
-      r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                       3, a.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                swz_of(p.h_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        cuuint32_t boxh[3] = {(cuuint32_t)p.h_cols, 32, 1};
+        r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                3, a.out_bf16, dims, strides, boxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swz_of(p.h_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
       if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(out 16-bit) failed with CUresult %d", (int)r);
         return V2W_ERR_CUDA;
