@@ -65,8 +65,8 @@ constexpr int kMaxStagesW = 8;
 constexpr int kMaxSub = 4;
 // Output staging per epilogue warp: two buffers per output tensor, each one TMA store box of 32 rows x
 // y_cols fp32 / h_cols 16-bit columns (Params::y_cols, h_cols: 16, 32 or 64; sized per op on the host).
-// 16-column boxes by default: wider boxes (fewer, larger TMA stores; 128-byte rows) were measured slower,
-// see plan.cu prepare_tc.
+// Boxes are as wide as the tile and shared memory allow (plan.cu prepare_tc): one fence, one store issue and
+// one wait per box instead of per 16-column chunk.
 // per epilogue warp: this tile's bias | scale | shift column vectors (n_tile <= 256 floats each),
 // staged once per tile so that the chunk loop reads them with LDS broadcasts instead of L1 round trips
 // (3 * n_tile * 4 bytes per warp: Params::cvec_warp_bytes)

@@ -323,12 +323,12 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
   p.cvec_warp_bytes = 3 * a.n_tile * 4;
-  // TMA store boxes.  Optional wide boxes: as wide as the column tile allows, up to 128-byte rows (fp32: 32
-  // columns; 16-bit: 64 columns when it is the only output, else 32 -- two outputs with 128-byte rows would
-  // take 128 KB of staging).
-  // MEASURED SLOWER than 16-column boxes (ups[2..4] 39-45 -> 52 us at cfg2, marginal k = 3 tile 8.9 -> 9.9 us:
-  // profiles/r02_notes.md), so 16 columns stay the default; $V2W_TC_WIDE_BOX=1 enables the wide boxes.
-  static const bool box16 = [] { const char* e = std::getenv("V2W_TC_WIDE_BOX"); return !(e && std::atoi(e)); }();
+  // TMA store boxes: as wide as the column tile allows, up to 128-byte rows (fp32: 32 columns; 16-bit: 64
+  // columns when it is the only output, else 32 -- two outputs with 128-byte rows would take 128 KB of
+  // staging): one fence / store issue / wait per box instead of per 16-column chunk.  Measured with the
+  // round-2 epilogue (profiles/r02_notes.md): marginal k = 3 tile 7.7 -> 6.8 us, ups[3] 37.0 -> 34.7 us.
+  // $V2W_TC_BOX16=1: 16-column boxes.
+  static const bool box16 = [] { const char* e = std::getenv("V2W_TC_BOX16"); return e && std::atoi(e); }();
   const int h_unit = (ex && ex->h_cout && ex->h_pitch) ? ex->h_cout : a.n_tile;   // a pitched polyphase box stays inside one phase
   p.y_cols = (!box16 && a.n_tile % 32 == 0) ? 32 : 16;
   p.h_cols = 16;
