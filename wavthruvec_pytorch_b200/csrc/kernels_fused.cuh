@@ -429,10 +429,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[4 * e + 2] = fmaf(ax, xr[e].z, __uint_as_float(r[4 * e + 2]) + bb.z);
                 v[4 * e + 3] = fmaf(ax, xr[e].w, __uint_as_float(r[4 * e + 3]) + bb.w);
               }
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                h[e] = pack_half2(lrelu(v[2 * e], p.mid_slope), lrelu(v[2 * e + 1], p.mid_slope),
-                                  p.fp16);
+              tc::lrelu_pack16(v, p.mid_slope, p.fp16 != 0, h);
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) h[e] = 0u;   // conv2's zero padding outside [0, L)
@@ -516,10 +513,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (p.out_bf16) {
               uint32_t h[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                h[e] = pack_half2(lrelu(v[2 * e], p.out_slope), lrelu(v[2 * e + 1], p.out_slope),
-                                  p.fp16);
+              tc::lrelu_pack16(v, p.out_slope, p.fp16 != 0, h);
               uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_base + cc);
               op[0] = make_uint4(h[0], h[1], h[2], h[3]);
               op[1] = make_uint4(h[4], h[5], h[6], h[7]);

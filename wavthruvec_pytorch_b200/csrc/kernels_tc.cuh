@@ -381,7 +381,9 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int fp16 = 0) 
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+// leaky-relu for slopes in [0, 1] (0.1, 0.01 and 1 = identity here): max(v, slope * v) -- two instructions
+// instead of compare + multiply + select, same value for every input (NaN and the infinities included)
+__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, v * slope); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -396,6 +398,18 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi, int fp16) {
     return *reinterpret_cast<uint32_t*>(&h);
   }
   return pack_bf16x2(lo, hi);
+}
+
+// sixteen values -> leaky-relu -> eight packed 16-bit pairs with ONE format branch (inlined per pair, the
+// `fp16` test becomes a uniform branch per pair: eight per 16-column chunk on the epilogue's critical path)
+__device__ __forceinline__ void lrelu_pack16(const float (&v)[16], float slope, bool fp16, uint32_t (&h)[8]) {
+  if (fp16) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = pack_half2(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope), 1);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = pack_bf16x2(lrelu(v[2 * e], slope), lrelu(v[2 * e + 1], slope));
+  }
 }
 
 struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
@@ -739,15 +753,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int e = 0; e < 16; ++e) v[e] *= out_scale;
             }
             uint32_t h[8];
-            if (st_h) {          // one format branch per chunk, not one per packed pair
-              if (fp16) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = pack_half2(lrelu(v[2 * e], out_slope), lrelu(v[2 * e + 1], out_slope), 1);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = pack_bf16x2(lrelu(v[2 * e], out_slope), lrelu(v[2 * e + 1], out_slope));
-              }
-            }
+            if (st_h) lrelu_pack16(v, out_slope, fp16, h);   // one format branch per chunk, not one per packed pair
             if (tma_out) {
               // own row -> staging box in the TMA swizzle layout (conflict-free 16-byte stores)
               if (st_y) {
