@@ -73,8 +73,12 @@ def _read_wav(path):
 
 @pytest.mark.gpu
 def test_files_to_wav_matches_generate_varlen(tmp_path):
+    _run_files_roundtrip(tmp_path, "cuda:0")
+
+
+def _run_files_roundtrip(tmp_path, device):
     g = load_golden("rb2_768_stress")
-    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    gen = dropin_in_state(g, cache=False).to(device)
     lengths = [37, 12, 50, 1, 29, 44, 8]
     speakers = ["A", "B", "A", "C", "B", "A", "C"]
     feat_dir, spk_dir, lst, items = _make_tree(tmp_path, gen.h.num_wv_feat, lengths, speakers)
@@ -82,16 +86,16 @@ def test_files_to_wav_matches_generate_varlen(tmp_path):
     stats = files.synthesize_files(gen, files.read_list(lst), feat_dir, spk_dir, str(out_dir), seed=77, readers=3)
     assert stats.utterances == 7 and stats.batches == 1 and abs(stats.audio_s - sum(lengths) / 50) < 1e-9
     # the same batch through generate_varlen with the same device noise
-    rng = torch.Generator(device="cuda:0")
+    rng = torch.Generator(device=device)
     rng.manual_seed(77)
-    noise = torch.randn(7, gen.h.noise_dim, device="cuda:0", generator=rng)
+    noise = torch.randn(7, gen.h.noise_dim, device=device, generator=rng)
     cache = files.SpeakerCache(spk_dir, gen.h.spk_dim)
-    feats = [files.load_features(f"{feat_dir}/{it.name}.npy", gen.h.num_wv_feat).cuda() for it in items]
-    spk = torch.stack([cache.get(it.speaker) for it in items]).cuda()
-    spk = torch.cat([spk, torch.zeros(1, gen.h.spk_dim, device="cuda:0")])     # 7 real + 1 dummy (count -> 8)
+    feats = [files.load_features(f"{feat_dir}/{it.name}.npy", gen.h.num_wv_feat).to(device) for it in items]
+    spk = torch.stack([cache.get(it.speaker) for it in items]).to(device)
+    spk = torch.cat([spk, torch.zeros(1, gen.h.spk_dim, device=device)])     # 7 real + 1 dummy (count -> 8)
     rng.manual_seed(77)
-    noise = torch.randn(8, gen.h.noise_dim, device="cuda:0", generator=rng)
-    feats.append(torch.zeros(1, gen.h.num_wv_feat, device="cuda:0"))
+    noise = torch.randn(8, gen.h.noise_dim, device=device, generator=rng)
+    feats.append(torch.zeros(1, gen.h.num_wv_feat, device=device))
     packed = gen.engine().forward_ragged(torch.cat(feats), lengths + [1], spk, noise, plan_frames=64, pcm16=True)
     want, off = [], 0
     for n in lengths:
@@ -183,3 +187,14 @@ def test_plan_batches_bounds_the_padded_plan_rectangle():
     # homogeneous corpora are unaffected
     rows = [200] * 64
     assert files.plan_batches(rows, 6400, 32, max_plan_frames=12800) == files.plan_batches(rows, 6400, 32)
+
+
+@pytest.mark.gpu
+def test_files_pipeline_on_a_non_current_device(tmp_path):
+    """the generator may live on a device that is not the caller's current device; the pipeline's
+    events must be recorded on that device's stream (wrong-device events let the prefetch thread overwrite a
+    pinned arena mid-copy)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    _run_files_roundtrip(tmp_path, "cuda:1")

@@ -608,3 +608,20 @@ def test_refold_in_place_keeps_plans(monkeypatch):
         y3 = gen(x, s, n)
         want = gen._forward_autograd(x, s, n)
     assert (y3 - want).abs().max().item() < 1e-4
+
+
+def test_parameters_frozen_skips_change_detection():
+    g = load_golden("rb2_768_stress_tiny")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    x, s, n = (t(a).cuda() for a in (g.x, g.spk, g.noise))
+    with torch.no_grad():
+        a = gen(x, s, n).clone()
+        gen.parameters_frozen = True
+        gen.conv_post.bias.add_(0.25)              # NOT seen: the caller promised not to do this
+        assert torch.equal(gen(x, s, n), a)
+        gen.invalidate()                           # ... unless it says so
+        b = gen(x, s, n)
+        assert not torch.equal(a, b)
+        gen.parameters_frozen = False
+        gen.conv_post.bias.sub_(0.25)
+        assert (gen(x, s, n) - a).abs().max().item() < 1e-5

@@ -168,12 +168,22 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (sticky CUDA error reported
-// through the C-ABI), never as a hung GPU.
+// through the C-ABI), never as a hung GPU.  The bound is a build-time option: 2^V2W_WAIT_TRAP_LOG2 polls
+// (default 2^28, several seconds -- a debugger stop or an MPS time slice must not kill a healthy kernel;
+// round 1 trapped after 2^24, ~0.3 s); -DV2W_WAIT_TRAP_LOG2=0 compiles the trap out.
+#ifndef V2W_WAIT_TRAP_LOG2
+#define V2W_WAIT_TRAP_LOG2 28
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if V2W_WAIT_TRAP_LOG2 > 0
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << V2W_WAIT_TRAP_LOG2)) __trap();
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 // Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
 __device__ __forceinline__ void pdl_launch_dependents() {

@@ -292,7 +292,10 @@ class NativeEngine:
             return self._plan_locked(batch, frames, precision, device, train)
 
     def _plan_locked(self, batch, frames, precision, device, train):
-        self._refresh(train)
+        # `module.parameters_frozen`: the caller guarantees that no parameter or buffer changes between
+        # calls (serving): skip the per-call walk over ~150 (data_ptr, _version) pairs
+        if not (getattr(self._module, "parameters_frozen", False) and self._packed_sig is not None and self._packed):
+            self._refresh(train)
         with torch.cuda.device(device):
             stream_id = torch.cuda.current_stream(device).cuda_stream
         key = (batch, frames, precision, device, stream_id)

@@ -134,6 +134,10 @@ class Generator(nn.Module):
         #: replay eval()-mode forwards from a CUDA graph (latency path for batch-1 / long-form requests;
         #: see v2w_forward_graph in include/v2w.h).  Also via $V2W_CUDA_GRAPH=1.
         self.use_cuda_graph = bool(int(os.environ.get("V2W_CUDA_GRAPH", "0") or 0))
+        #: serving: set True once the checkpoint is loaded and the module will not change any more -- the native
+        #: path then skips its per-call change detection (parameter versions / storage pointers).  Any later
+        #: parameter edit must be followed by `invalidate()` (or by setting this back to False).
+        self.parameters_frozen = False
 
     # ------------------------------------------------------------------------------------------
     # native engine plumbing
