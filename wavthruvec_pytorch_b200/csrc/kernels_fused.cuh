@@ -84,7 +84,12 @@ struct Params {
   __nv_bfloat16* out_bf16;
 };
 
-template <int C>
+// kSub: 128-row accumulators per window.  2 = the 256-row window described above.  1 (C = 128 only, "narrow"):
+// a 128-row window, so that T1 + T2 of TWO windows fit the 512 TMEM columns and every buffer is double
+// buffered like at C <= 64 -- the MMAs of one window overlap the epilogue passes of the other, at the price of
+// 98 instead of 226 central rows per window (15 % more MMA work per output row).  The eight epilogue warps
+// then split a pass by COLUMN halves instead of row halves.
+template <int C, int kSub = 2>
 struct Cfg {
   static constexpr int kKC = C < 64 ? C : 64;            // channels per K-chunk
   static constexpr int kChunks = C / kKC;
@@ -92,11 +97,12 @@ struct Cfg {
   static constexpr int kKSteps = kKC / 16;
   static constexpr int kAccCols = C < 32 ? 32 : C;       // TMEM columns per 128-row accumulator
   static constexpr bool kResident = C <= 32;             // weights stay in shared memory
-  static constexpr int kSlots = C <= 64 ? 2 : 1;         // buffering depth of A0 / T1 / A1 / T2
+  static constexpr int kSlots = (C <= 64 || kSub == 1) ? 2 : 1;   // buffering depth of A0 / T1 / A1 / T2
+  static constexpr int kWinRows = kSub * 128;            // window rows per tile
   static constexpr bool kCacheX0 = C <= 32;              // keep the thread's X0 row in registers
-  static constexpr uint32_t kT1Cols = 2 * kAccCols;      // two sub-tiles
+  static constexpr uint32_t kT1Cols = kSub * kAccCols;   // kSub sub-tiles
   static constexpr uint32_t kTmemCols = 2 * kSlots * kT1Cols;   // 512 / 512 / 256 / 256
-  static constexpr uint32_t kA1ChunkBytes = kWin * kRowBytes;
+  static constexpr uint32_t kA1ChunkBytes = kWinRows * kRowBytes;
   static constexpr uint32_t kA1Bytes = kChunks * kA1ChunkBytes;
   static constexpr uint32_t kBoxBytes = kBoxRows * kRowBytes;
   static constexpr uint32_t kWBytes = C * kRowBytes;     // one (tap, K-chunk) block
@@ -115,11 +121,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // (6 KB instead of 8 KB of operand reads per CTA and MMA at N = 128).  Barrier plumbing as in
 // tapgemm_tc_kernel: loads land on the leader's full barriers, commits are multicast, the epilogue
 // warps of both CTAs arrive on the leader's barriers.
-template <int C, bool kPair = false>
+template <int C, bool kPair = false, int kSub = 2>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ Params p) {
-  using K = Cfg<C>;
+  using K = Cfg<C, kSub>;
+  static_assert(kSub == 2 || (kSub == 1 && C == 128), "narrow windows are wired for C = 128");
   constexpr int kRowBytes = K::kRowBytes;
   constexpr int kSlots = K::kSlots;
 
@@ -141,7 +148,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.tiles_per_b;
-  static_assert(!kPair || !Cfg<C>::kResident, "CTA pairs are wired for the streamed-weight configuration");
+  static_assert(!kPair || !K::kResident, "CTA pairs are wired for the streamed-weight configuration");
   // Tile slots: without pairs a slot is a tile; with pairs slot ts holds tiles 2 ts (leader) and
   // 2 ts + 1 (peer; possibly past the end -- that CTA then runs on zero-filled loads and stores nothing)
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -318,7 +325,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t bd = smem_desc(dhi, w_addr);
               const uint32_t acc0 = (sg.type == kSegConv2 && !p.pair) || (t != 0) || (c != 0);
 #pragma unroll
-              for (int m = 0; m < 2; ++m) {
+              for (int m = 0; m < kSub; ++m) {
                 const uint64_t ad = (static_cast<uint64_t>(dhi) << 32) |
                                     (a_t + ((c * a_chunk_bytes + m * (kMTile * kRowBytes)) >> 4));
 #pragma unroll
@@ -359,12 +366,15 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
-    const int sub = (warp - 4) >> 2;              // which 128-row accumulator
+    const int half = (warp - 4) >> 2;             // kSub = 2: which 128-row accumulator; kSub = 1: which column half
+    const int sub = kSub == 2 ? half : 0;
     const int quarter = warp & 3;                 // TMEM lane quarter
     const int i = sub * kMTile + quarter * 32 + lane;   // window row of this thread
     const uint32_t t_lane = (static_cast<uint32_t>(quarter * 32) << 16) + sub * K::kAccCols;
     const uint32_t swz = K::kKC == 64 ? (i & 7) : (K::kKC == 32 ? ((i >> 1) & 3) : ((i >> 2) & 1));
-    constexpr int kNC = C / 16;                   // 16-column chunks per row
+    constexpr int kNCrow = C / 16;                // 16-column chunks per row
+    constexpr int kNC = kSub == 2 ? kNCrow : kNCrow / 2;   // ... per thread and pass
+    const int ci0 = kSub == 2 ? 0 : half * kNC;   // first chunk of this thread (even: the look-ahead window's parity holds)
     constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
     for (int ts = slot_first; ts < num_slots; ts += slot_step) {
@@ -380,7 +390,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c - p.hc + i;
         const bool valid = live && gr >= 0 && gr < p.rows;
         const float4* xrow = reinterpret_cast<const float4*>(
-            p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
+            p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C) + ci0 * 4;   // this thread's first chunk
         float4 xc[kXc];
         if constexpr (K::kCacheX0) if (valid) {
           // this row of X0 is the same for every branch: read it once per tile, before the first
@@ -401,7 +411,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b1 = smem_bias + j * (C * 4);
 #pragma unroll
           for (int ci = 0; ci < kNC; ++ci) {
-            const int cc = ci * 16;
+            const int cc = (ci0 + ci) * 16;
             float4 xr[4];
             if constexpr (K::kCacheX0) {
 #pragma unroll
@@ -460,7 +470,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c + i;
         const bool valid = live && i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        const float4* xrow = reinterpret_cast<const float4*>(p.x0 + row_base);
+        const float4* xrow = reinterpret_cast<const float4*>(p.x0 + row_base) + ci0 * 4;
         float4 xc[kXc];
         if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
@@ -470,7 +480,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tcgen05_fence_after();
 #pragma unroll
         for (int ci = 0; ci < kNC; ++ci) {
-          const int cc = ci * 16;
+          const int cc = (ci0 + ci) * 16;
           float4 xr[4];
           if constexpr (K::kCacheX0) {
 #pragma unroll

@@ -300,15 +300,20 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   if (!(no_stack && std::atoi(no_stack)) && plan_stacked(m, i, F)) return F;
   const int h1 = d0 * (kmax - 1) / 2;
   total += kmax;
-  const int rc = 256 - 2 * hc;
-  const int a0_rows = 256 + hc + 2 * h1;
+  // C = 128, "narrow" windows ($V2W_FUSED_NARROW=1): 128 rows per window instead of 256, two windows in flight
+  // (kernels_fused.cuh Cfg<128, 1>)
+  const char* narrow_env = std::getenv("V2W_FUSED_NARROW");
+  const bool narrow = C == 128 && narrow_env && std::atoi(narrow_env);
+  const int win = narrow ? 128 : 256;
+  const int rc = win - 2 * hc;
+  const int a0_rows = win + hc + 2 * h1;
   if (rc < 64 || a0_rows > 64 * 7 || total > V2W_FUSED_MAX_TAPS || 2 * nb + 1 > V2W_FUSED_MAX_SEG)
     return F;
   F.hc = hc; F.h1 = h1; F.rc = rc;
   F.a0_boxes = (a0_rows + 63) / 64;
   // issue order with double-buffered T1/A1 (C <= 64): c1_0, c1_1, SUM, then c2_j, c1_{j+2};
   // single-buffered (C = 128):                            c1_0, SUM, then c2_j, c1_{j+1}
-  const int slots = C <= 64 ? 2 : 1;
+  const int slots = (C <= 64 || narrow) ? 2 : 1;
   int nseg = 0, ntap = 0;
   auto push = [&](int type, int j) {
     const int k = type == V2W_FUSED_SEG_SUM ? kmax : c.resblock_kernel_sizes[j];

@@ -59,6 +59,7 @@ struct FusedLaunch {
   stacked::Params sprm;    // stacked program (kernels_stacked.cuh)
   bool stacked = false;
   bool pair = false;       // plain program as CTA pairs (cta_group::2), C = 128
+  bool narrow = false;     // C = 128 with 128-row windows, two in flight (fused::Cfg<128, 1>)
   int grid = 0;
   int smem = 0;
   int channels = 0;
@@ -743,10 +744,12 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   }
   for (int t = 0; t < F.num_taps; ++t) p.shift[t] = F.shift[t];
   const int kc = C < 64 ? C : 64;        // K-chunk (fused::Cfg<C>)
-  const int slots = C <= 64 ? 2 : 1;
+  const int win = F.rc + 2 * F.hc;       // window rows: 256, or 128 for the narrow C = 128 variant
+  L->narrow = C == 128 && win == 128 && !F.pair;
+  const int slots = (C <= 64 || L->narrow) ? 2 : 1;
   p.stage_w_bytes = (int)align_up((int64_t)C * kc * 2, 1024);   // one (tap, K-chunk) block
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * C * 2;
-  const int a1_bytes = fused::kWin * C * 2;
+  const int a1_bytes = win * C * 2;
   const int bias_bytes = F.num_branches * C * 4;
   const int budget = 227 * 1024 - 1024 - 512 - bias_bytes;
   const int left = budget - slots * (a0_bytes + a1_bytes);
@@ -862,6 +865,10 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, false, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<64>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<32>,
@@ -890,7 +897,11 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
     V2W_CUDA(cudaGetLastError());
     return V2W_OK;
   }
-  if (L.channels == 128 && L.pair)
+  if (L.channels == 128 && L.narrow && L.pair)
+    V2W_CUDA(launch_ex<2>(fused::mrf_stage_kernel<128, true, 1>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+  else if (L.channels == 128 && L.narrow)
+    V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128, false, 1>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+  else if (L.channels == 128 && L.pair)
     V2W_CUDA(launch_ex<2>(fused::mrf_stage_kernel<128, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
   else if (L.channels == 128)
     V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
