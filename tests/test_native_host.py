@@ -316,6 +316,15 @@ def test_plan_structure_bf16_rb2(monkeypatch):
     assert (F.hc, F.h1, F.rc, F.a0_boxes, F.num_taps, F.num_segments, F.w_rows) == (15, 5, 226, 5, 53, 7, 53 * 128)
     assert list(F.seg_type[:7]) == [0, 1, 2, 0, 2, 0, 2] and list(F.seg_branch[:7]) == [0, -1, 0, 1, 1, 2, 2]
     assert list(F.seg_flags[:7]) == [0, 0, 0, 0, 0, 1, 2]
+    # optional schedule: the `sum` convolution in three pieces, one behind every conv1 (a model-level switch)
+    monkeypatch.setenv("V2W_FUSED_SUM_PIECES", "3")
+    eng3 = Generator(hparams(resblock=1, num_wv_feat=768)).engine()
+    native.check(eng3._lib.v2w_model_get_fused(eng3._model, 1, C.byref(F)))
+    assert (F.num_taps, F.num_segments) == (53, 9)
+    assert list(F.seg_type[:9]) == [0, 1, 2, 0, 1, 2, 0, 1, 2] and list(F.seg_ntaps[:9]) == [3, 3, 3, 7, 4, 7, 11, 4, 11]
+    assert list(F.seg_acc[:9]) == [0, 0, 0, 0, 1, 0, 0, 1, 0]
+    assert list(F.seg_flags[:9]) == [0, 0, 0, 0, 0, 0, 0, 1, 2]       # the last `sum` piece releases the input tile
+    monkeypatch.delenv("V2W_FUSED_SUM_PIECES")
     # transposed convs: column tiles are whole phase groups; a tile issues 2 taps when its phases
     # share a tap set, 3 when the cost model prefers a wider tile with a zero block
     for op in gemms:

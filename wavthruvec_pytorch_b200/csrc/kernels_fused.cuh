@@ -49,6 +49,7 @@ constexpr int kMaxTaps = 80;
 constexpr int kSegConv1 = 0, kSegSum = 1, kSegConv2 = 2;
 constexpr int kSegFlagReleaseA0 = 1;   // last reader of the A0 tile
 constexpr int kSegFlagLast = 2;        // last segment of the tile
+constexpr int kSegFlagAcc = 4;         // accumulate from the first MMA (a later piece of the `sum` convolution)
 
 // 32-bit fields on purpose: with four packed int16 ptxas (12.9) merged the constant-bank loads
 // of a dynamically indexed p.seg[s] and then read `first` from an unrelated register whenever
@@ -323,7 +324,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 w_addr = smem_w + r.s * p.stage_w_bytes;
               }
               const uint64_t bd = smem_desc(dhi, w_addr);
-              const uint32_t acc0 = (sg.type == kSegConv2 && !p.pair) || (t != 0) || (c != 0);
+              const uint32_t acc0 = (sg.type == kSegConv2 && !p.pair) || (sg.flags & kSegFlagAcc) || (t != 0) || (c != 0);
 #pragma unroll
               for (int m = 0; m < kSub; ++m) {
                 const uint64_t ad = (static_cast<uint64_t>(dhi) << 32) |

@@ -315,15 +315,19 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
   // single-buffered (C = 128):                            c1_0, SUM, then c2_j, c1_{j+1}
   const int slots = (C <= 64 || narrow) ? 2 : 1;
   int nseg = 0, ntap = 0;
-  auto push = [&](int type, int j) {
+  // A segment = taps [t_lo, t_hi) of one convolution.  The `sum` convolution may be issued in PIECES
+  // (seg_acc = 1 on every piece but the first: it accumulates from its first MMA).
+  auto push = [&](int type, int j, int t_lo = 0, int t_hi = -1) {
     const int k = type == V2W_FUSED_SEG_SUM ? kmax : c.resblock_kernel_sizes[j];
     const int dil = type == V2W_FUSED_SEG_CONV2 ? c.resblock_dilation_sizes[j][1] : d0;
+    if (t_hi < 0) t_hi = k;
     F.seg_type[nseg] = type;
     F.seg_branch[nseg] = j;
-    F.seg_ntaps[nseg] = k;
+    F.seg_ntaps[nseg] = t_hi - t_lo;
     F.seg_first[nseg] = ntap;
     F.seg_n[nseg] = C;
-    for (int t = 0; t < k; ++t) {
+    F.seg_acc[nseg] = (type == V2W_FUSED_SEG_SUM && t_lo > 0) ? 1 : 0;
+    for (int t = t_lo; t < t_hi; ++t) {
       const int off = (t - (k - 1) / 2) * dil;
       F.offset[ntap] = off;
       F.shift[ntap] = type == V2W_FUSED_SEG_CONV1 ? h1 + off
@@ -334,12 +338,27 @@ static v2w_fused_desc plan_fused_stage(const v2w_model* m, int i, int first_laye
     }
     ++nseg;
   };
+  // Single-buffered (C = 128, 256-row windows), optional ($V2W_FUSED_SUM_PIECES=n): the `sum` convolution cut into
+  // n pieces, one behind every conv1 --  c1_0 SUM_a c2_0 c1_1 SUM_b c2_1 c1_2 SUM_c c2_2  -- so that independent
+  // MMAs are queued while the per-branch pass T1_j -> A1_j runs.  MEASURED NEUTRAL (cfg2 119.5 vs 119.5 us, cfg5/GPU
+  // 1059 vs 1047 us): the stage is not waiting for those passes (profiles/r02_notes.md), so the default stays
+  // round 1's  c1_0 SUM c2_0 c1_1 c2_1 c1_2 c2_2.
+  int pieces = 1;
+  if (const char* e = std::getenv("V2W_FUSED_SUM_PIECES")) pieces = std::max(1, std::min(nb, std::atoi(e)));
+  if (slots != 1) pieces = 1;
+  if (2 * nb + pieces > V2W_FUSED_MAX_SEG) pieces = 1;
+  auto sum_piece = [&](int q) {     // taps [q * kmax / pieces, (q + 1) * kmax / pieces)
+    push(V2W_FUSED_SEG_SUM, -1, q * kmax / pieces, (q + 1) * kmax / pieces);
+  };
   push(V2W_FUSED_SEG_CONV1, 0);
   if (slots == 2 && nb > 1) push(V2W_FUSED_SEG_CONV1, 1);
-  push(V2W_FUSED_SEG_SUM, -1);
+  sum_piece(0);
   for (int j = 0; j < nb; ++j) {
     push(V2W_FUSED_SEG_CONV2, j);
-    if (j + slots < nb) push(V2W_FUSED_SEG_CONV1, j + slots);
+    if (j + slots < nb) {
+      push(V2W_FUSED_SEG_CONV1, j + slots);
+      if (j + 1 < pieces) sum_piece(j + 1);
+    }
   }
   int last_a0 = 0;
   for (int s = 0; s < nseg; ++s)

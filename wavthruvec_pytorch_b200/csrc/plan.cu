@@ -740,7 +740,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   for (int s = 0; s < F.num_segments; ++s) {
     p.seg[s].type = F.seg_type[s]; p.seg[s].branch = F.seg_branch[s];
     p.seg[s].ntaps = F.seg_ntaps[s]; p.seg[s].first = F.seg_first[s];
-    p.seg[s].flags = F.seg_flags[s];
+    p.seg[s].flags = F.seg_flags[s] | (F.seg_acc[s] ? fused::kSegFlagAcc : 0);
   }
   for (int t = 0; t < F.num_taps; ++t) p.shift[t] = F.shift[t];
   const int kc = C < 64 ? C : 64;        // K-chunk (fused::Cfg<C>)
