@@ -281,6 +281,10 @@ typedef struct v2w_op_desc {
                                   wide stage writes its 16-bit output into the last C columns of the stage's
                                   [rows, (nk + 1) * C] operand tensor */
   int32_t in_pitch;            /* row pitch of in_act in elements; 0 = dense (cin) */
+  int32_t f32_blocked;         /* TAPGEMM: out_f32 is written in the row-blocked layout [batch][ceil(L/32)][cout/4][32][4]
+                                  (L = rows * up output rows of cout channels); MRF_FUSED: `residual` is read in it.  The
+                                  fused stage kernels read their fp32 residual stream row-per-thread: in this layout a
+                                  warp's float4 load of one column quad is 512 contiguous bytes. */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */

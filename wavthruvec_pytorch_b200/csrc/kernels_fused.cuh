@@ -71,7 +71,8 @@ struct Params {
   int fp16;                     // 16-bit operand format: 0 = bf16, 1 = fp16
   Segment seg[kMaxSeg];
   int shift[kMaxTaps];          // operand row (sub-tile 0) of each tap inside its A tile
-  const float* x0;              // fp32 [B, L, C]
+  const float* x0;              // fp32 [B, L, C], or row-blocked (x0_blocked): [B][ceil(L / 32)][C / 4][32 rows][4]
+  int x0_blocked;               // see stacked::Params
   const float* bias1[V2W_MAX_KERNELS];
   const float* bsum;            // sum_j (b1_j + b2_j)   (ResBlock1 pair: b2)
   const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
@@ -273,6 +274,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1 && rank == 0) {
     // ====================================== MMA issuer ======================================
     Ring rw;
+    V2W_TRTC_DECL
     uint32_t tile_iter = 0, n1 = 0, n2 = 0;   // conv1 / conv2 segments issued so far
     const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kMTile : kMTile, C, p.fp16);
     const uint32_t dhi = smem_desc_hi<K::kKC>();
@@ -281,7 +283,9 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (slot_skipped(ts)) continue;
       const uint32_t buf = tile_iter % kSlots, tph = (tile_iter / kSlots) & 1u;
       ++tile_iter;
+      V2W_TRTC(tile_iter - 1, 1);
       mbar_wait(a0_full + 8 * buf, tph);
+      V2W_TRTC(tile_iter - 1, 2);
       const uint32_t a0 = smem_a0 + buf * a0_bytes;
       for (int s = 0; s < p.nseg; ++s) {
         const Segment sg = p.seg[s];
@@ -306,6 +310,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           a_chunk_bytes = K::kA1ChunkBytes;
         }
         tcgen05_fence_after();
+        V2W_TRTC(tile_iter - 1, 10 + s * 10);
         // One elected lane issues the whole segment: per tap only two descriptor words change
         // (A: row shift inside the tile, W: next tap matrix), everything else is loop-invariant.
         if (elect_one()) {
@@ -358,6 +363,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
+        V2W_TRTC(tile_iter - 1, 11 + s * 10);
         if (!K::kResident) {
           for (int t = 0; t < sg.ntaps * K::kChunks; ++t) rw.advance(p.stages_w);
         }
@@ -365,8 +371,10 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (sg.type == kSegConv2) ++n2;
       }
     }
+    V2W_TRTC_DUMP("fmma");
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
+    V2W_TRTC_DECL
     const int half = (warp - 4) >> 2;             // kSub = 2: which 128-row accumulator; kSub = 1: which column half
     const int sub = kSub == 2 ? half : 0;
     const int quarter = warp & 3;                 // TMEM lane quarter
@@ -378,6 +386,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ci0 = kSub == 2 ? 0 : half * kNC;   // first chunk of this thread (even: the look-ahead window's parity holds)
     constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
+    const int xs = p.x0_blocked ? 32 : 1;          // float4 units between column quads of an X0 row
+    const int x_nblk = ((p.rows + 31) >> 5) + tc::kBlockedPad;
     for (int ts = slot_first; ts < num_slots; ts += slot_step) {
       if (slot_skipped(ts)) continue;
       const int tile = kPair ? 2 * ts + (int)rank : ts;
@@ -390,24 +400,28 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       {
         const int gr = q0c - p.hc + i;
         const bool valid = live && gr >= 0 && gr < p.rows;
-        const float4* xrow = reinterpret_cast<const float4*>(
-            p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C) + ci0 * 4;   // this thread's first chunk
+        const int xr_ = valid ? gr : 0;
+        const float4* xrow = (p.x0_blocked
+            ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
+            : reinterpret_cast<const float4*>(p.x0 + (static_cast<size_t>(b) * p.rows + xr_) * C)) + ci0 * 4 * xs;   // first chunk of this thread
         float4 xc[kXc];
         if constexpr (K::kCacheX0) if (valid) {
           // this row of X0 is the same for every branch: read it once per tile, before the first
           // accumulator is even ready, so that no global latency sits between the MMAs
 #pragma unroll
-          for (int e = 0; e < kXc; ++e) xc[e] = __ldg(xrow + e);
+          for (int e = 0; e < kXc; ++e) xc[e] = __ldg(xrow + e * xs);
         }
         for (int j = 0; j < p.nbranch; ++j, ++e1) {
           const uint32_t slot = e1 % kSlots, ph = (e1 / kSlots) & 1u;
           if constexpr (!K::kCacheX0) if (valid) {   // look-ahead: chunks 0 and 1, before the waits
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e);
+            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e * xs);
           }
+          V2W_TRTC(tile_it, 100 + j * 10);
           mbar_wait(t1_full + 8 * slot, ph);
           mbar_wait(a1_empty + 8 * slot, ph ^ 1u);
           tcgen05_fence_after();
+          V2W_TRTC(tile_it, 101 + j * 10);
           const uint32_t a1_row = smem_a1 + slot * K::kA1Bytes + i * kRowBytes;
           const uint32_t b1 = smem_bias + j * (C * 4);
 #pragma unroll
@@ -422,7 +436,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
               if (valid && ci + 2 < kNC) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (ci + 2) * 4 + e);
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + ((ci + 2) * 4 + e) * xs);
               }
             }
             uint32_t r[16];
@@ -463,6 +477,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_arrive(t1_empty + 8 * slot);
             }
           }
+          V2W_TRTC(tile_it, 102 + j * 10);
         }
       }
       // ---- final: out = (T2 + bsum + nk * X0) / nk ----
@@ -471,14 +486,19 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c + i;
         const bool valid = live && i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
-        const float4* xrow = reinterpret_cast<const float4*>(p.x0 + row_base) + ci0 * 4;
+        const int xr_ = valid ? gr : 0;
+        const float4* xrow = (p.x0_blocked
+            ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
+            : reinterpret_cast<const float4*>(p.x0 + row_base)) + ci0 * 4 * xs;
         float4 xc[kXc];
         if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
-          for (int e = 0; e < (K::kCacheX0 ? kXc : 8); ++e) xc[e] = __ldg(xrow + e);
+          for (int e = 0; e < (K::kCacheX0 ? kXc : 8); ++e) xc[e] = __ldg(xrow + e * xs);
         }
+        V2W_TRTC(tile_it, 200);
         mbar_wait(t2_full + 8 * t2s, t2ph);
         tcgen05_fence_after();
+        V2W_TRTC(tile_it, 201);
 #pragma unroll
         for (int ci = 0; ci < kNC; ++ci) {
           const int cc = (ci0 + ci) * 16;
@@ -491,7 +511,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
             if (valid && ci + 2 < kNC) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (ci + 2) * 4 + e);
+              for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + ((ci + 2) * 4 + e) * xs);
             }
           }
           uint32_t r[16];
@@ -537,8 +557,10 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if constexpr (kPair) mbar_arrive_leader(t2_empty + 8 * t2s);
           else mbar_arrive(t2_empty + 8 * t2s);
         }
+        V2W_TRTC(tile_it, 202);
       }
     }
+    if (warp == 4) V2W_TRTC_DUMP("fepi");
   }
 
   tcgen05_fence_before();

@@ -91,7 +91,11 @@ struct Params {
   int a_off16[kMaxEnt];         // operand row shift of the entry in 16-byte units (negative for conv2 taps < 0)
   int w_off16[kMaxEnt];         // resident weights: offset of the entry's block in 16-byte units
   int w_row[kMaxEnt];           // first row of the entry's weight block (TMA coordinate)
-  const float* x0;              // fp32 [B, L, C]
+  const float* x0;              // fp32 [B, L, C], or row-blocked (x0_blocked): [B][ceil(L / 32)][C / 4][32 rows][4]
+  // Row-blocked X0: a warp's row-per-thread float4 read of one column quad is 512 contiguous bytes (4 L1
+  // wavefronts) instead of 32 rows 4 C bytes apart (32 wavefronts) -- the epilogue passes of the fused stages
+  // were bound by exactly those wavefronts (profiles/r02_notes.md, timeline of the C = 128 stage).
+  int x0_blocked;
   const float* bias1[V2W_MAX_KERNELS];   // by slot
   const float* bsum;
   const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
@@ -391,41 +395,52 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int kPair = kNC >= 2 ? 2 : 1;
     const bool central = i >= p.hc && i < p.hc + p.rc;
     // fp32 X0 row of tile `k` for this thread (clamped to a valid row; `valid` says whether it counts)
-    auto row_of = [&](int kt, bool& valid) -> const float4* {
+    // X0 row of this thread for tile `kt`: pointer to its first column quad; quad q is at ptr + q * xs.
+    // `lin` = b * rows + row (linear row index: addresses of every row-major tensor of the stage).
+    const int xs = p.x0_blocked ? 32 : 1;
+    const int x_nblk = ((p.rows + 31) >> 5) + tc::kBlockedPad;
+    auto row_of = [&](int kt, bool& valid, size_t& lin) -> const float4* {
       const int tile = tile_of(kt);
       const bool live_tile = tile < total_tiles;       // a peer tile past the end stores nothing
       const int b = live_tile ? tile / p.tiles_per_b : 0;
       const int ti = live_tile ? tile - b * p.tiles_per_b : 0;
       const int gr = ti * p.rc - p.hc + i;
       valid = live_tile && gr >= 0 && gr < p.rows;
-      return reinterpret_cast<const float4*>(
-          p.x0 + (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C);
+      const int r = valid ? gr : 0;
+      lin = static_cast<size_t>(b) * p.rows + r;
+      if (p.x0_blocked)
+        return reinterpret_cast<const float4*>(p.x0) +
+               (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
+      return reinterpret_cast<const float4*>(p.x0 + lin * C);
     };
     float4 xn[kCacheX0 ? kXc : 1];     // C <= 32: the next tile's row, fetched one tile ahead
     if constexpr (kCacheX0) {
       bool v;
-      const float4* x = row_of(min(live(0), n_my - 1), v);
+      size_t l0;
+      const float4* x = row_of(min(live(0), n_my - 1), v, l0);
 #pragma unroll
-      for (int e = 0; e < kXc; ++e) xn[e] = __ldg(x + e);
+      for (int e = 0; e < kXc; ++e) xn[e] = __ldg(x + e * xs);
     }
     V2W_TR_DECL
     float4 xc[kXc];
     if constexpr (!kCacheX0) {         // C = 64: chunks 0 and 1 of the first pass
       bool v;
-      const float4* x = row_of(min(live(0), n_my - 1), v);
+      size_t l0;
+      const float4* x = row_of(min(live(0), n_my - 1), v, l0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) xc[e] = __ldg(x + e);
+      for (int e = 0; e < 8; ++e) xc[e] = __ldg(x + e * xs);
     }
     // P(kt): T1_j := X0 + b1_j for every slot of the tile at local index kt (its accumulator set)
     auto preload_t1 = [&](int kt, uint32_t tb_p) {
       bool v;
-      const float4* x = row_of(kt, v);
+      size_t l0;
+      const float4* x = row_of(kt, v, l0);
       const uint32_t t1s = t_row + tb_p * p.tile_cols;
 #pragma unroll
       for (int ci = 0; ci < kNC; ++ci) {
         float4 xr[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) xr[e] = __ldg(x + ci * 4 + e);
+        for (int e = 0; e < 4; ++e) xr[e] = __ldg(x + (ci * 4 + e) * xs);
         for (int j = 0; j < p.nbranch; ++j) {
           uint32_t r[16];
 #pragma unroll
@@ -450,16 +465,17 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (p.preload && live(0) < n_my) preload_t1(live(0), 0);
     for (int kt = live(0), k = 0; kt < n_my; ++k) {
       bool valid, next_valid = false;
-      const float4* xrow = row_of(kt, valid);
+      size_t lin, lin_next;
+      const float4* xrow = row_of(kt, valid, lin);
       const int kt_next = live(kt + 1);
-      const float4* xnext = kt_next < n_my ? row_of(kt_next, next_valid) : xrow;
+      const float4* xnext = kt_next < n_my ? row_of(kt_next, next_valid, lin_next) : xrow;
       const uint32_t tb = k % p.t_bufs, tph = (k / p.t_bufs) & 1u;
       if constexpr (kCacheX0) {
 #pragma unroll
         for (int e = 0; e < kXc; ++e) xc[e] = xn[e];
         if (kt_next < n_my) {
 #pragma unroll
-          for (int e = 0; e < kXc; ++e) xn[e] = __ldg(xnext + e);
+          for (int e = 0; e < kXc; ++e) xn[e] = __ldg(xnext + e * xs);
         }
       }
       // ---- per slot: T1 -> A1 = half(lrelu(conv1 + b1 + X0)) in shared memory ----
@@ -498,7 +514,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const int nc = ci + 2 < kNC ? ci + 2 : ci + 2 - kNC;
               if (!p.preload) {   // (pre-loaded accumulators: this pass does not read X0 at all)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + nc * 4 + e);
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (nc * 4 + e) * xs);
               }
             }
             uint32_t h[8];
@@ -600,7 +616,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               sum += v;
             }
             const float y = tanhf(sum);
-            const size_t row_idx = (reinterpret_cast<const float*>(xrow) - p.x0) / C;   // b * rows + t
+            const size_t row_idx = lin;   // b * rows + t
             const int b = static_cast<int>(row_idx / p.rows);
             const int t = static_cast<int>(row_idx - static_cast<size_t>(b) * p.rows);
             if (!p.post_out.ragged) {
@@ -624,11 +640,11 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ---- final: out = (T2 + bsum + nk * X0) / nk on the central rows of the window ----
       {
         const bool out_valid = valid && central;
-        const size_t row_base = reinterpret_cast<const float*>(xrow) - p.x0;
+        const size_t row_base = lin * C;
         if constexpr (!kCacheX0) {
           if (p.preload) {   // the X0 window was not kept running by the per-slot passes: prime it here
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e);
+            for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e * xs);
           }
         }
         V2W_TR(k * 100 + 50);
@@ -655,10 +671,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
               // past the end of the tile's last pass the window moves on to the next tile's row
-              const float4* src = ci + 2 < kNC ? xrow + (ci + 2) * 4 : xnext + (ci + 2 - kNC) * 4;
+              const float4* src = ci + 2 < kNC ? xrow + (ci + 2) * 4 * xs : xnext + (ci + 2 - kNC) * 4 * xs;
               if (!p.preload || ci + 2 < kNC) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e);
+                for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e * xs);
               }
             }
             if (out_valid) {

@@ -58,6 +58,7 @@
 namespace v2w {
 namespace tc {
 
+constexpr int kBlockedPad = 4;     // spare 32-row blocks per utterance of a row-blocked tensor (>= the largest upsampling rate)
 constexpr int kThreads = 384;
 constexpr int kMTile = 128;
 constexpr int kMaxStagesA = 4;
@@ -115,6 +116,14 @@ struct Params {
   // rows of the channels-last signal, each of which starts h_pitch elements after the previous one -- a 4-D
   // tensor (cout, up, rows, batch).  h_cout = cout in that case (4-D tensor map), else 0.
   int h_cout;
+  // Row-blocked fp32 output (y_blocked): [batch][nblk][cout / 4][32 rows][4], nblk = ceil(L / 32) + kBlockedPad, with
+  // L = rows * up output rows of cout = 1 << y_cout_log2 channels, up = 1 << y_up_log2 -- the layout in which the
+  // fused stage kernels read their residual stream with coalesced row-per-thread float4 loads
+  // (stacked::Params::x0_blocked).  Written through the same staging + TMA store as a row-major output, with a 5-D
+  // tensor map (4 floats, phase, row / up inside a block, column quad, block): every (block, quad) run of the box
+  // is 512 contiguous bytes.  (Direct 16-byte stores were measured 1.2-2.2x slower for the whole launch:
+  // half-filled lines.)  Output rows of a box past the utterance's end land in the kBlockedPad spare blocks.
+  int y_blocked, y_cout_log2, y_up_log2;
   const float* bias;
   const float* scale;
   const float* shift;
@@ -242,6 +251,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tm, uint32_t src, int c
       "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
           reinterpret_cast<uint64_t>(tm)),
       "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(tm)),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
@@ -766,7 +782,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (st_h) lrelu_pack16(v, out_slope, fp16, h);   // one format branch per chunk, not one per packed pair
             if (tma_out) {
               // own row -> staging box in the TMA swizzle layout (conflict-free 16-byte stores)
-              if (st_y) {
+              if (st_y && p.y_blocked) {
+                // staging box in the blocked order [block][quad][row / up inside the block][4 floats]
+                const uint32_t rl = 5u - p.y_up_log2;                                  // log2(32 / up)
+                const uint32_t q0 = (static_cast<uint32_t>(cc >> 4) & y_mask) * 4u;     // first quad of this chunk in the box
+                const uint32_t nq = static_cast<uint32_t>(p.y_cols) >> 2;
+                const uint32_t base = ybuf + sy * y_box + (((lane >> rl) * nq) << (rl + 4)) + ((lane & ((1u << rl) - 1u)) << 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  st_shared_v4u(base + ((q0 + e) << (rl + 4)), __float_as_uint(v[4 * e]),
+                                __float_as_uint(v[4 * e + 1]), __float_as_uint(v[4 * e + 2]),
+                                __float_as_uint(v[4 * e + 3]));
+              }
+              if (st_y && !p.y_blocked) {
                 const uint32_t yb = ybuf + sy * y_box + lane * y_row;
                 const uint32_t u0 = (static_cast<uint32_t>(cc >> 4) & y_mask) * 4u;   // first 16-byte unit of this chunk
 #pragma unroll
@@ -782,7 +810,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 st_shared_v4u(hb + (((u0 + 1) ^ h_sw) << 4), h[4], h[5], h[6], h[7]);
               }
             } else {
-              if (st_y) {
+              if (st_y && !p.y_blocked) {
                 float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + col);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
@@ -817,7 +845,14 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               V2W_TRTC(it, 4000 + cc);
               if (row0w < p.rows) {          // warp-uniform
                 if (elect_one()) {
-                  if (y_done) tma_store_3d(&tmY, ybuf + sy * y_box, col + 16 - p.y_cols, row0w, b);
+                  if (y_done && p.y_blocked) {
+                    const int yc0 = col + 16 - p.y_cols;                      // first column of the box
+                    const int ph = yc0 >> p.y_cout_log2, c = yc0 - (ph << p.y_cout_log2);
+                    const int nblk = (((p.rows << p.y_up_log2) + 31) >> 5) + kBlockedPad;
+                    tma_store_5d(&tmY, ybuf + sy * y_box, 0, ph, 0, c >> 2, b * nblk + (row0w >> (5 - p.y_up_log2)));
+                  } else if (y_done) {
+                    tma_store_3d(&tmY, ybuf + sy * y_box, col + 16 - p.y_cols, row0w, b);
+                  }
                   if (h_done) {
                     const int hc0 = col + 16 - p.h_cols;
                     if (p.h_cout) {

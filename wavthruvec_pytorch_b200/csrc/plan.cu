@@ -42,6 +42,7 @@ struct Act {        // one logical activation tensor [B, rows, C]
   int64_t bf16 = -1;  // bf16 copy of leaky_relu(value, slope)
   float slope = 1.f;  // the activation the consumer must see
   int pitch16 = 0;    // row pitch of the 16-bit copy in elements (0 = dense): a column range of a wider tensor
+  bool f32_blocked = false;   // fp32 copy in the row-blocked layout (v2w_op_desc::f32_blocked)
 };
 
 struct TcLaunch {
@@ -238,6 +239,7 @@ struct TcExtra {
   int a_pitch = 0;       // elements per row of the input tensor (0 = cin)
   int h_pitch = 0;       // elements per row of the 16-bit output tensor (0 = n_total)
   int h_cout = 0;        // polyphase op with a pitched output: channels of one output row (4-D output tensor)
+  int y_blocked_cout = 0; // > 0: fp32 output in the row-blocked layout, rows of this many channels (tc::Params::y_blocked)
   int res_pitch = 0, res_cols = 0;
   float res_scale = 1.f;
   int kgroups = 0, cpg = 0;
@@ -278,6 +280,24 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   if (ex) {
     p.kgroups = ex->kgroups; p.cpg = ex->cpg;
     p.res_pitch = ex->res_pitch; p.res_cols = ex->res_cols; p.res_scale = ex->res_scale;
+    if (ex->y_blocked_cout) {
+      int lg = 0;
+      while ((1 << lg) < ex->y_blocked_cout) ++lg;
+      if ((1 << lg) != ex->y_blocked_cout || ex->y_blocked_cout < 16 || a.n_total % ex->y_blocked_cout) {
+        set_error("tapgemm(TC): row-blocked fp32 output needs a power-of-two channel count >= 16 (got %d)", ex->y_blocked_cout);
+        return V2W_ERR_INVALID;
+      }
+      const int up = a.n_total / ex->y_blocked_cout;
+      int ul = 0;
+      while ((1 << ul) < up) ++ul;
+      if ((1 << ul) != up || up > 32 || up > tc::kBlockedPad) {
+        set_error("tapgemm(TC): row-blocked fp32 output needs a power-of-two upsampling rate <= %d (got %d)", tc::kBlockedPad, up);
+        return V2W_ERR_INVALID;
+      }
+      p.y_blocked = 1;
+      p.y_cout_log2 = lg;
+      p.y_up_log2 = ul;
+    }
     p.h_pitch = ex->h_pitch;
     p.h_cout = (ex->h_pitch && ex->h_cout && ex->h_cout != a.n_total) ? ex->h_cout : 0;
     if (p.h_cout && (a.n_total % p.h_cout || p.h_cout % 16)) {
@@ -337,6 +357,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
     if (!a.out_f32 && a.n_tile % 64 == 0 && h_unit % 64 == 0) p.h_cols = 64;
     else if (a.n_tile % 32 == 0 && h_unit % 32 == 0) p.h_cols = 32;
   }
+  if (ex && ex->y_blocked_cout && p.y_cols > ex->y_blocked_cout) p.y_cols = 16;   // a blocked box stays inside one phase
   p.stage_warp_bytes = (a.out_f32 ? 2 * 32 * p.y_cols * 4 : 0) + (a.out_bf16 ? 2 * 32 * p.h_cols * 2 : 0);
   // barriers (+ output staging) + per-warp column vectors
   const int tail_bytes = 1024 + (p.tma_out ? 8 * p.stage_warp_bytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
@@ -444,7 +465,22 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     };
-    if (a.out_f32) {
+    if (a.out_f32 && p.y_blocked) {
+      // (4 floats, phase, GEMM row inside a block, column quad, block): see tc::Params::y_blocked
+      const cuuint64_t cout = 1ull << p.y_cout_log2, up = 1ull << p.y_up_log2;
+      const cuuint64_t nblk = (((cuuint64_t)a.rows * up + 31) >> 5) + tc::kBlockedPad;
+      cuuint64_t dims5[5] = {4, up, 32 / up, cout / 4, nblk * (cuuint64_t)a.batch};
+      cuuint64_t strides5[4] = {16, up * 16, 512, (cout / 4) * 512};
+      cuuint32_t box5[5] = {4, 1, (cuuint32_t)(32 / up), (cuuint32_t)(p.y_cols / 4), (cuuint32_t)up};
+      cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&L->tm_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, a.out_f32, dims5, strides5, box5, estr5,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out f32, row-blocked) failed with CUresult %d", (int)r);
+        return V2W_ERR_CUDA;
+      }
+    } else if (a.out_f32) {
       cuuint64_t strides[2] = {(cuuint64_t)a.n_total * 4, (cuuint64_t)a.rows * a.n_total * 4};
       CUresult r = enc(&L->tm_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out_f32, dims, strides, box,
                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(p.y_cols * 4),
@@ -696,6 +732,7 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
     p.w_region_bytes = p.stages_w * p.stage_w_bytes;
   }
   p.x0 = reinterpret_cast<const float*>(ws + d.residual);
+  p.x0_blocked = d.f32_blocked;
   for (int j = 0; j < nb; ++j)
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * F.order[j]].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
@@ -771,6 +808,7 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
     w_bytes_total = p.stages_w * p.stage_w_bytes;
   }
   p.x0 = reinterpret_cast<const float*>(ws + d.residual);
+  p.x0_blocked = d.f32_blocked;
   for (int j = 0; j < F.num_branches; ++j)
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * j].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
@@ -1051,7 +1089,10 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   else pre.f32 = ws.take((int64_t)B * T * c.upsample_initial_channel * 4);
   Act x0, y1, t1;
   x0.slope = y1.slope = t1.slope = kLreluSlope;
-  x0.f32 = ws.take(max_e * 4);
+  // (+ 32 rows per utterance: the row-blocked layout of the fused stages' residual stream pads L to 32)
+  int64_t cmax_stage = 0;
+  for (int i = 0; i < U; ++i) cmax_stage = std::max<int64_t>(cmax_stage, m->stage_channels[i]);
+  x0.f32 = ws.take(max_e * 4 + (int64_t)B * 32 * (1 + tc::kBlockedPad) * cmax_stage * 4);
   y1.f32 = ws.take(max_e * 4);
   const int64_t sum_f32 = ws.take(max_e * 4);
   if (bf) {
@@ -1136,6 +1177,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
       o.d.in_act = in.bf16; o.d.in_is_bf16 = 1; o.d.in_slope = 1.f;
       o.d.out_f32 = out.f32; o.d.out_bf16 = out.bf16; o.d.out_slope = out.slope;
       o.d.out_bf16_pitch = out.pitch16;
+      o.d.f32_blocked = (out.f32 >= 0 && out.f32_blocked) ? 1 : 0;
     } else {
       o.d.in_act = in.f32; o.d.in_is_bf16 = 0; o.d.in_slope = in.slope;
       o.d.out_f32 = out.f32; o.d.out_bf16 = -1; o.d.out_slope = 1.f;
@@ -1161,7 +1203,20 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     const bool last_stage = i == U - 1;
     // x = cbns[i](ups[i](leaky_relu(x)), fcs[i](spk_noise))   (models.py:128-134)
     const bool wide = widebuf[i].a1cat >= 0;
-    if (wide) {
+    // A fused stage reads its residual stream row-per-thread; in the row-blocked layout (v2w_op_desc::f32_blocked)
+    // those reads are coalesced, which takes 12-15 % off the C = 128 and 9 % off the C = 32 stage kernel -- but the
+    // transposed conv that PRODUCES the tensor then stores 16-byte fragments (its phases interleave row by row) and
+    // loses more than the stage gains except at C = 128 (profiles/r02_notes.md).  $V2W_BLOCKED_X0_MASK = bitmask of
+    // stages; default: stage 1 only.
+    static const int blocked_mask = [] { const char* e = std::getenv("V2W_BLOCKED_X0_MASK"); return e ? std::atoi(e) : 2; }();
+    const bool stage_fused = bf && !force_simt && !no_fuse && !wide && m->fused[i].ok && ((fuse_mask >> i) & 1);
+    const bool x0_blocked = stage_fused && ((blocked_mask >> i) & 1) && m->stage_channels[i] >= 16 &&
+                            c.upsample_rates[i] <= tc::kBlockedPad && (c.upsample_rates[i] & (c.upsample_rates[i] - 1)) == 0;
+    if (x0_blocked) {
+      Act x0b = x0;
+      x0b.f32_blocked = true;
+      emit(li++, rows, cur_in, i, -1, -1, 1.f, x0b);
+    } else if (wide) {
       // the 16-bit copy of the stage input goes straight into the last C columns of the stage's operand tensor
       Act x0w = x0;
       x0w.bf16 = widebuf[i].a1cat + (int64_t)m->wide[i].num_branches * m->stage_channels[i] * 2;
@@ -1223,6 +1278,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
       o.d.n_tiles = 1;
       o.d.in_act = x0.bf16; o.d.in_is_bf16 = 1;
       o.d.residual = x0.f32;
+      o.d.f32_blocked = x0_blocked ? 1 : 0;
       o.d.out_scale = 1.0f / nk;
       o.d.out_f32 = stage_out.f32; o.d.out_bf16 = stage_out.bf16; o.d.out_slope = stage_out.slope;
       for (int q = 0; q < 2 * nk; ++q)
@@ -1336,7 +1392,7 @@ int32_t v2w_plan_set_engine(v2w_plan* p, int32_t i, int32_t engine) {
     set_error("v2w_plan_set_engine: the tensor-core engine needs a BF16/FP16 plan");
     return V2W_ERR_INVALID;
   }
-  if (engine == V2W_ENGINE_SIMT && (o.d.out_bf16_pitch || o.d.in_pitch)) {
+  if (engine == V2W_ENGINE_SIMT && (o.d.out_bf16_pitch || o.d.in_pitch || o.d.f32_blocked)) {
     set_error("v2w_plan_set_engine: op %d writes into a wide stage's operand tensor (tensor-core engine only)", i);
     return V2W_ERR_INVALID;
   }
@@ -1523,11 +1579,12 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       TcExtra ex;
       ex.h_pitch = o.d.out_bf16_pitch;
       ex.h_cout = L.cout;       // a transposed conv's GEMM row is `up` output rows of cout channels
-      rc = prepare_tc(g, &o.tcl, o.d.out_bf16_pitch ? &ex : nullptr);
+      ex.y_blocked_cout = o.d.f32_blocked ? L.cout : 0;
+      rc = prepare_tc(g, &o.tcl, (o.d.out_bf16_pitch || o.d.f32_blocked) ? &ex : nullptr);
       if (rc) return rc;
       o.tc_ready = true;
-    } else if (o.d.out_bf16_pitch) {
-      set_error("v2w_plan_bind: op writes a pitched 16-bit output, which needs the tensor-core engine");
+    } else if (o.d.out_bf16_pitch || o.d.f32_blocked) {
+      set_error("v2w_plan_bind: op writes a pitched / row-blocked output, which needs the tensor-core engine");
       return V2W_ERR_STATE;
     }
     o.has_raw = false;

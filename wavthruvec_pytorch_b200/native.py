@@ -121,6 +121,7 @@ class OpDesc(C.Structure):
         ("post", C.c_int32),
         ("out_bf16_pitch", C.c_int32),
         ("in_pitch", C.c_int32),
+        ("f32_blocked", C.c_int32),
     ]
 
 
