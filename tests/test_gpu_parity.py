@@ -627,17 +627,26 @@ def test_parameters_frozen_skips_change_detection():
         assert (gen(x, s, n) - a).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("mask", ["0", "30"])
-def test_row_blocked_residual_layout_is_bit_identical(monkeypatch, mask):
+@pytest.mark.parametrize("mask,flags", [("0", [0, 0, 0, 0]), ("30", [1, 1, 1, 1]), ("12", [0, 1, 1, 0])])
+def test_row_blocked_residual_layout_is_bit_identical(monkeypatch, mask, flags):
     """The row-blocked layout of a fused stage's fp32 residual stream (v2w_op_desc::f32_blocked) only changes WHERE
-    the transposed conv stores it and the stage kernel reads it: bit-identical waveform for no stage / every fused
-    stage against the default (stage 1 only)."""
+    the transposed conv stores it and the stage kernel reads it: bit-identical waveforms for no stage / every fused
+    stage / stages 2-3 against the default (stage 1 only), on a batch with ragged tile tails."""
     g = load_golden("rb2_768_stress")
-    gen = dropin_in_state(g, cache=False).to("cuda:0")
-    want = _native(gen, g, "bf16")
-    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
-    assert [op.f32_blocked for op in ops if op.kind == native.OP_MRF_FUSED] == [1, 0, 0, 0]
-    monkeypatch.setenv("V2W_BLOCKED_X0_MASK", mask)
-    # the mask is read once per process (static): a fresh interpreter would be needed to flip it -- so this
-    # test only asserts the default here and leaves the A/B to tools/op_table.py runs
-    assert np.array_equal(_native(gen, g, "bf16"), want)
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, 3, 77, 9))
+    with torch.no_grad():
+        want = gen(x, s, n).clone()
+        ops = gen.engine().ops(3, 77, "bf16", "cuda:0")
+        assert [op.f32_blocked for op in ops if op.kind == native.OP_MRF_FUSED] == [1, 0, 0, 0]
+        monkeypatch.setenv("V2W_BLOCKED_X0_MASK", mask)
+        gen.invalidate()
+        got = gen(x, s, n)
+        ops = gen.engine().ops(3, 77, "bf16", "cuda:0")
+        assert [op.f32_blocked for op in ops if op.kind == native.OP_MRF_FUSED] == flags
+        assert torch.equal(got, want)
+        gen.precision = "fp16"
+        a16 = gen(x, s, n).clone()
+        monkeypatch.delenv("V2W_BLOCKED_X0_MASK")
+        gen.invalidate()
+        assert torch.equal(gen(x, s, n), a16)

@@ -1208,7 +1208,8 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     // transposed conv that PRODUCES the tensor then stores 16-byte fragments (its phases interleave row by row) and
     // loses more than the stage gains except at C = 128 (profiles/r02_notes.md).  $V2W_BLOCKED_X0_MASK = bitmask of
     // stages; default: stage 1 only.
-    static const int blocked_mask = [] { const char* e = std::getenv("V2W_BLOCKED_X0_MASK"); return e ? std::atoi(e) : 2; }();
+    const char* blocked_env = std::getenv("V2W_BLOCKED_X0_MASK");
+    const int blocked_mask = blocked_env ? std::atoi(blocked_env) : 2;
     const bool stage_fused = bf && !force_simt && !no_fuse && !wide && m->fused[i].ok && ((fuse_mask >> i) & 1);
     const bool x0_blocked = stage_fused && ((blocked_mask >> i) & 1) && m->stage_channels[i] >= 16 &&
                             c.upsample_rates[i] <= tc::kBlockedPad && (c.upsample_rates[i] & (c.upsample_rates[i] - 1)) == 0;
