@@ -650,3 +650,19 @@ def test_row_blocked_residual_layout_is_bit_identical(monkeypatch, mask, flags):
         monkeypatch.delenv("V2W_BLOCKED_X0_MASK")
         gen.invalidate()
         assert torch.equal(gen(x, s, n), a16)
+
+
+def test_micro_batched_forward_is_bit_identical():
+    """Batches above Generator.max_batch_frames run as consecutive micro-batches through one plan: the same
+    numbers as one launch (utterances are independent), including a ragged last micro-batch."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, 7, 40, 3))
+    with torch.no_grad():
+        gen.max_batch_frames = None
+        want = gen(x, s, n)
+        one = gen.engine().last_launches
+        gen.max_batch_frames = 120                 # 3 utterances per launch: 3 + 3 + 1
+        got = gen(x, s, n)
+        assert gen.engine().last_launches == 3 * one
+    assert torch.equal(got, want)

@@ -354,8 +354,28 @@ class NativeEngine:
         spk = spk.detach().to(torch.float32).contiguous()
         noise = noise.detach().to(torch.float32).contiguous()
         B, _, T = x.shape
-        handle, _ws = self.plan(B, T, self._module.precision, dev)
         out = torch.empty((B, 1, T * self.total_upsample()), dtype=torch.float32, device=dev)
+        # Micro-batches: utterances are independent, so a large batch is run as consecutive launches of at most
+        # `max_batch_frames` frames through ONE plan (workspace ~96 KB per frame: 256 x 500 frames would take
+        # 12 GB and, measured at the cfg5 shard sizes, run 5 % slower per utterance than 4 x 64 x 500 --
+        # the working set of a stage falls out of L2).  Each launch writes its slice of `out` in place.
+        limit = getattr(self._module, "max_batch_frames", None)
+        if limit and B > 1 and B * T > limit:
+            chunks = -(-(B * T) // int(limit))          # as few launches as the limit allows, ...
+            mb = max(1, -(-B // chunks))                # ... of equal size (one plan shape, except a ragged tail)
+            total = 0
+            for lo in range(0, B, mb):
+                hi = min(B, lo + mb)
+                total += self._launch(x[lo:hi], spk[lo:hi], noise[lo:hi], out[lo:hi], dev)
+            self.last_launches = total
+            return out
+        self.last_launches = self._launch(x, spk, noise, out, dev)
+        return out
+
+    def _launch(self, x, spk, noise, out, dev) -> int:
+        """One v2w_forward (or graph replay) of contiguous fp32 device tensors into `out`."""
+        B, _, T = x.shape
+        handle, _ws = self.plan(B, T, self._module.precision, dev)
         n = C.c_int32(0)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -371,8 +391,7 @@ class NativeEngine:
                 native.check(self._lib.v2w_forward(handle, x.data_ptr(), spk.data_ptr(),
                                                    noise.data_ptr(), out.data_ptr(),
                                                    C.c_void_p(stream), C.byref(n)))
-        self.last_launches = n.value
-        return out
+        return n.value
 
     def forward_into(self, x: torch.Tensor, spk: torch.Tensor, noise: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """forward() into a caller-owned output tensor: with `use_cuda_graph` and preallocated
@@ -531,7 +550,9 @@ class NativeEngine:
             for _ in range(reps):
                 if before_each is not None:
                     before_each()
-                self.forward(x, spk, noise)
+                out = torch.empty((B, 1, T * self.total_upsample()), dtype=torch.float32, device=dev)
+                self._launch(x.detach().to(torch.float32).contiguous(), spk.detach().to(torch.float32).contiguous(),
+                             noise.detach().to(torch.float32).contiguous(), out, dev)   # ONE launch of this plan (no micro-batches)
                 torch.cuda.synchronize(dev)
                 for i in range(len(ops)):
                     ms = float(self._lib.v2w_plan_op_time_ms(handle, i))

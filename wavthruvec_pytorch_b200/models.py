@@ -138,6 +138,9 @@ class Generator(nn.Module):
         #: path then skips its per-call change detection (parameter versions / storage pointers).  Any later
         #: parameter edit must be followed by `invalidate()` (or by setting this back to False).
         self.parameters_frozen = False
+        #: eval()-mode batches larger than this many frames (batch x frames) run as consecutive micro-batches
+        #: through one plan (utterances are independent; see NativeEngine.forward).  None = never split.
+        self.max_batch_frames = int(os.environ.get("V2W_MAX_BATCH_FRAMES", "32768") or 0) or None
 
     # ------------------------------------------------------------------------------------------
     # native engine plumbing
