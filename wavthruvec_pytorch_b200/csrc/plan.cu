@@ -723,7 +723,10 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
       return V2W_ERR_INVALID;
     }
   } else {
-    p.stage_w_bytes = (int)align_up((int64_t)max_n * row_bytes, 1024);
+    // (CTA pairs: each CTA holds HALF of every stacked weight block, so a ring stage is half as big and the
+    // ring twice as deep -- 5 instead of 2 stages at C = 64; the timeline showed ~10k of 31k clk per tile in
+    // gaps between segments waiting for streamed weights)
+    p.stage_w_bytes = (int)align_up((int64_t)(L->pair ? max_n / 2 : max_n) * row_bytes, 1024);
     p.stages_w = std::min(left / p.stage_w_bytes, tc::kMaxStagesW);
     if (p.stages_w < 2) {
       set_error("fused stage: does not fit shared memory");
@@ -784,7 +787,10 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   const int win = F.rc + 2 * F.hc;       // window rows: 256, or 128 for the narrow C = 128 variant
   L->narrow = C == 128 && win == 128 && !F.pair;
   const int slots = (C <= 64 || L->narrow) ? 2 : 1;
-  p.stage_w_bytes = (int)align_up((int64_t)C * kc * 2, 1024);   // one (tap, K-chunk) block
+  static const bool no_pair_f = [] { const char* e = std::getenv("V2W_FUSED_NO_PAIR"); return e && std::atoi(e); }();
+  const bool will_pair = C == 128 && !no_pair_f && sms >= 2;
+  // one (tap, K-chunk) block; a CTA of a pair holds half of it (twice the ring depth in the same space)
+  p.stage_w_bytes = (int)align_up((int64_t)(will_pair ? C / 2 : C) * kc * 2, 1024);
   const int a0_bytes = F.a0_boxes * fused::kBoxRows * C * 2;
   const int a1_bytes = win * C * 2;
   const int bias_bytes = F.num_branches * C * 4;
