@@ -101,7 +101,7 @@ struct Params {
   // elements), column tile included: tap_row * n_total + nt * n_tile for a layer's own [taps][n][cin]
   // array; arbitrary for stacked ops whose blocks live in several arrays (plan.cu TcExtra).
   int w_row[V2W_MAX_TILES][V2W_MAX_TAPS];
-  // K-grouped operand (kgroups > 0, n_tiles == 1): the input's channels are `kgroups` groups of `cpg`
+  // K-grouped operand (kgroups > 0): the input's channels are `kgroups` groups of `cpg`
   // K-chunks, each with its OWN tap list (list g instead of list nt) and its own weight array whose
   // rows hold only the group's channels -- the branches of a multi-receptive-field stage side by
   // side along K (conv2_j reads A1_j), accumulated in ONE accumulator.  off_min / halo of list 0 span
@@ -537,7 +537,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nsub = min(p.msub, (p.rows - q0t + kMTile - 1) / kMTile);
       const int nbox = (nsub * kMTile + p.halo[nt] + p.box_rows - 1) / p.box_rows;
       const int row0 = q0 + p.off_min[nt];
-      const int wrank = (int)rank * w_rows;
+      // (K-grouped ops list their blocks per group: the column tile's rows are added here)
+      const int wrank = (int)rank * w_rows + (p.kgroups ? nt * p.n_tile : 0);
       for (int c = 0; c < p.num_chunks; ++c) {
         const int li = p.kgroups ? c / p.cpg : nt;          // tap list of this K-chunk
         const int wc = p.kgroups ? (c - li * p.cpg) * KC : c * KC;   // column in the weight array

@@ -304,7 +304,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       set_error("tapgemm(TC): bad pitched polyphase output (n_total %d, cout %d)", a.n_total, p.h_cout);
       return V2W_ERR_INVALID;
     }
-    if (ex->kgroups && (a.n_tiles != 1 || ex->kgroups > V2W_MAX_TILES || ex->kgroups * ex->cpg != p.num_chunks)) {
+    if (ex->kgroups && (ex->kgroups > V2W_MAX_TILES || ex->kgroups * ex->cpg != p.num_chunks)) {
       set_error("tapgemm(TC): bad K-group geometry (%d groups x %d chunks, %d chunks, %d column tiles)",
                 ex->kgroups, ex->cpg, p.num_chunks, a.n_tiles);
       return V2W_ERR_INVALID;
@@ -1260,7 +1260,11 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
           o.d.out_bf16_pitch = widebuf[i].width;
           o.d.out_slope = kLreluSlope;
         } else {
-          o.d.n_tiles = 1;
+          // one column tile, unless that leaves most SM pairs idle (cfg1: 2 pair tiles, cfg4: 30 of 74): then two
+          // column tiles of C / 2 -- every tile walks the whole K = (nk + 1) C, so halving N halves its time
+          const int64_t pair_tiles = (int64_t)B * ((rows + 255) / 256);
+          o.d.n_tiles = (C >= 256 && pair_tiles <= 148 / 4) ? 2 : 1;
+          o.d.n_tile = C / o.d.n_tiles;
           o.d.in_act = widebuf[i].a1cat;
           o.d.out_scale = 1.0f / nk;
           o.d.out_f32 = stage_out.f32; o.d.out_bf16 = stage_out.bf16; o.d.out_slope = stage_out.slope;
@@ -1474,7 +1478,7 @@ static int prepare_wide(v2w_plan* p, Op& o, int tc_flags) {
       }
     }
   } else {
-    g.cin = (nb + 1) * C; g.n_total = C; g.cmod = C; g.n_tile = C; g.n_tiles = 1;
+    g.cin = (nb + 1) * C; g.n_total = C; g.cmod = C; g.n_tile = o.d.n_tile; g.n_tiles = o.d.n_tiles;
     g.bias = reinterpret_cast<const float*>(p->packed + W.bsum_off);
     ex.res_scale = (float)nb;
     ex.kgroups = nb + 1;
