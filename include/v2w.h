@@ -57,10 +57,17 @@ extern "C" {
 #define V2W_PREC_BF16 1  /* tcgen05 bf16 x bf16 -> fp32 (TMEM), fp32 residual stream: SNR >= 45 dB */
 #define V2W_PREC_FP16 2  /* same kernels with fp16 operands (3 more mantissa bits, same tensor rate;
                             activations are clamped to +-65504).  Needed by ResBlock1 to reach 45 dB. */
+#define V2W_PREC_FP32_TC 3 /* fp32 values on the tensor cores: every operand is the pair hi = fp16(v), lo = fp16(v - hi)
+                            (22 significant bits) and every product the three-term sum A_hi W_hi + A_lo W_hi + A_hi W_lo
+                            in the fp32 accumulator -- one tap-GEMM per convolution over K' = 3 cin, no fused stages.
+                            Meets the fp32 bar (max-abs <= 1e-4) at about 1/3 of the 16-bit tensor rate instead of the
+                            FFMA rate.  Needs a V2W_HALF_FP16_SPLIT weight buffer. */
 
 /* 16-bit operand format of a packed weight buffer */
 #define V2W_HALF_BF16 0
 #define V2W_HALF_FP16 1
+#define V2W_HALF_FP16_SPLIT 2   /* fp16 hi values in every layer's array, the lo values (fp16(w - hi)) in the second
+                                   half of the same section (v2w_layer_desc::w16_off) */
 #define V2W_PACKED_HEADER_BYTES 1024   /* {uint32 magic 'V2WP', abi, half_format} then zeros */
 
 /* Hyper-parameters.  Replaces the attribute bag `h` of Generator.__init__
@@ -138,7 +145,8 @@ typedef struct v2w_layer_desc {
   int32_t tap_off[V2W_MAX_TAPS];
   /* tap_mask[j] bit p set  <=>  (tap j, phase p) carries a kernel element */
   uint32_t tap_mask[V2W_MAX_TAPS];
-  int64_t w16_off;             /* byte offset in the packed buffer: bf16 [num_taps][n_total][cin]  */
+  int64_t w16_off;             /* byte offset in the packed buffer: 16-bit [2][num_taps][n_total][cin]; [0] = the
+                                  operands, [1] = their lo halves (V2W_HALF_FP16_SPLIT buffers, else zeros) */
   int64_t w32_off;             /* byte offset: fp32 [num_taps][cin][n_total] */
   int64_t bias_off;            /* byte offset: fp32 [cout] */
   int64_t macs_per_row;        /* real multiply-accumulates per input row (zero blocks excluded) */
@@ -285,6 +293,8 @@ typedef struct v2w_op_desc {
                                   (L = rows * up output rows of cout channels); MRF_FUSED: `residual` is read in it.  The
                                   fused stage kernels read their fp32 residual stream row-per-thread: in this layout a
                                   warp's float4 load of one column quad is 512 contiguous bytes. */
+  int32_t split;               /* TAPGEMM of a V2W_PREC_FP32_TC plan: in_act / out_bf16 are [rows, hi | lo] fp16 tensors
+                                  (pitches 2 cin / 2 cout), three-term product */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */

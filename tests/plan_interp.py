@@ -85,14 +85,20 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
     """Returns the waveform [B,1,L] (fp32).  `collect`, if a dict, receives every op's fp32
     output keyed by op index."""
     f32, u16, conds = _packed_views(plan, packed)
-    bf = plan.precision in ("bf16", "fp16")
+    bf = plan.precision in ("bf16", "fp16", "fp32tc")
+    split = plan.precision == "fp32tc"
     half = fp16_round if plan.precision == "fp16" else bf16_round
+    if split:
+        # split-fp16 operands (V2W_PREC_FP32_TC): a 16-bit tensor is the pair (hi, lo) = (fp16(v), fp16(v - hi))
+        def half(v):
+            hi = fp16_round(v)
+            return hi, fp16_round(v - hi)
     hdr = packed[:12].view(np.uint32)
-    assert hdr[0] == 0x50573256 and (not bf or hdr[2] == (1 if plan.precision == "fp16" else 0)), \
+    assert hdr[0] == 0x50573256 and (not bf or hdr[2] == native.HALF_OF_PRECISION[plan.precision]), \
         "packed buffer format does not match the plan precision"
 
     def half_to_f32(bits):      # packed 16-bit weights -> fp32
-        if plan.precision == "fp16":
+        if plan.precision in ("fp16", "fp32tc"):
             return bits.view(np.float16).astype(np.float32)
         return (bits.astype(np.uint32) << 16).view(np.float32)
     ws = {}       # workspace offset -> ndarray [B, rows, C] (values as the device buffer holds them)
@@ -118,12 +124,21 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
         elif op.kind == native.OP_TAPGEMM:
             L = plan.layers[op.layer]
             # an upsample op's output row [u*Cout] is u consecutive channels-last rows [Cout]
-            A = ws[op.in_act].reshape(op.batch, op.rows, L.cin)
+            assert bool(op.split) == split
+            A_lo = None
+            if split:
+                assert op.in_pitch == 2 * L.cin and (op.out_bf16 < 0 or op.out_bf16_pitch == 2 * L.cout)
+                A, A_lo = (a.reshape(op.batch, op.rows, L.cin) for a in ws[op.in_act])
+            else:
+                A = ws[op.in_act].reshape(op.batch, op.rows, L.cin)
             if op.in_slope != 1.0:
                 A = lrelu(A, op.in_slope)
             if bf:     # TC engine semantics: bf16 weights [taps][n_total][cin]
                 W = half_to_f32(u16(L.w16_off, L.num_taps * L.n_total * L.cin)).reshape(
                     L.num_taps, L.n_total, L.cin)
+                if split:   # the lo halves follow the operands in the same section
+                    W_lo = half_to_f32(u16(L.w16_off + 2 * L.num_taps * L.n_total * L.cin,
+                                           L.num_taps * L.n_total * L.cin)).reshape(L.num_taps, L.n_total, L.cin)
             else:      # FFMA engine: fp32 [taps][cin][n_total]
                 W = f32(L.w32_off, L.num_taps * L.cin * L.n_total).reshape(
                     L.num_taps, L.cin, L.n_total).transpose(0, 2, 1)
@@ -138,6 +153,12 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                     if hi > lo:
                         sh[:, lo:hi] = A[:, lo + off: hi + off]
                     acc[:, :, cols] += sh @ W[j][cols].T
+                    if split:   # + A_lo W_hi + A_hi W_lo
+                        sl = np.zeros_like(A_lo)
+                        if hi > lo:
+                            sl[:, lo:hi] = A_lo[:, lo + off: hi + off]
+                        acc[:, :, cols] += sl @ W[j][cols].T
+                        acc[:, :, cols] += sh @ W_lo[j][cols].T
             bias = f32(L.bias_off, L.cout)
             n_idx = np.arange(L.n_total) % L.cout
             v = acc + bias[n_idx]

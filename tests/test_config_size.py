@@ -69,6 +69,15 @@ def test_fp32_plan_at_config_size(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", PINS)
+def test_fp32tc_plan_at_config_size(name):
+    """fp32 values on the tensor cores (split-fp16 operands): the fp32 bar at the benchmarked sizes."""
+    r = _run(name, "fp32tc")
+    assert r["max_abs"] <= FP32_MAX_ABS
+    assert r["sum_err"] <= 1e-4 and r["sumsq_rel"] <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PINS)
 def test_16bit_plan_at_config_size(name):
     r = _run(name, "fp16" if "rb1" in name else "bf16")
     assert r["snr_db"] >= MIN_SNR_DB

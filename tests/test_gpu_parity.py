@@ -102,6 +102,34 @@ def test_fp32_plan_max_abs(name):
     assert err <= FP32_MAX_ABS
 
 
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_warm",
+                                  "rb1_1024_stress", "rb2_768_stress_tiny", "rb2_1024_stress"])
+def test_fp32tc_plan_max_abs(name):
+    """fp32 values on the tensor cores (split-fp16 operands, three MMAs per product): the fp32 bar."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "fp32tc")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "fp32tc", "cuda:0")
+    gemms = [o for o in ops if o.kind == native.OP_TAPGEMM]
+    assert gemms and all(o.engine == native.ENGINE_TC and o.split for o in gemms)
+    assert not any(o.kind in (native.OP_MRF_FUSED, native.OP_PAIR_FUSED, native.OP_MRF_WIDE1) for o in ops)
+    err = np.abs(y - g.y).max()
+    print(f"{name}: fp32tc max-abs {err:.2e}  SNR {fixtures.snr_db(g.y, y):.1f} dB")
+    assert err <= FP32_MAX_ABS / 10
+
+
+def test_fp32tc_plan_matches_cpu_emulation():
+    """Same rounding points as tests/plan_interp.py (hi / lo split of every operand, three-term products):
+    what is left is fp32 summation order."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "fp32tc")
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "fp32tc")
+    want = plan_interp.run(plan, eng.pack_host(native.HALF_FP16_SPLIT).numpy(), g.x, g.spk, g.noise)
+    assert np.abs(y - want).max() < 2e-5
+
+
 def test_fp32_plan_fresh_state():
     g = load_golden("rb2_768_fresh")
     gen = dropin_in_state(g, cache=False).to("cuda:0")
@@ -334,8 +362,9 @@ TRAIN_BF16_MIN_SNR_DB = 40.0   # bf16 operands under batch-statistic BN: 42.0 dB
 
 
 @pytest.mark.parametrize("name,precision", [("rb2_768_stress", "fp32"), ("rb2_768_stress", "auto"),
-                                            ("rb2_768_stress", "bf16"),
-                                            ("rb1_1024_stress", "fp32"), ("rb1_1024_stress", "auto")])
+                                            ("rb2_768_stress", "bf16"), ("rb2_768_stress", "fp32tc"),
+                                            ("rb1_1024_stress", "fp32"), ("rb1_1024_stress", "auto"),
+                                            ("rb1_1024_stress", "fp32tc")])
 def test_train_mode_forward_matches_reference(name, precision):
     """Outputs and mutated buffers of consecutive train()-mode forwards against the unmodified
     reference (tests/golden/*_train.npz)."""
@@ -350,9 +379,9 @@ def test_train_mode_forward_matches_reference(name, precision):
         torch.cuda.synchronize()
         assert gen.engine().last_launches > 18       # the native path ran (stats + power iteration kernels too)
         y = y.cpu().numpy()
-        if precision == "fp32":
+        if precision in ("fp32", "fp32tc"):
             err = np.abs(y - tg.y[k]).max()
-            print(f"{name} train step {k}: fp32 max-abs {err:.2e}")
+            print(f"{name} train step {k}: {precision} max-abs {err:.2e}")
             assert err <= FP32_MAX_ABS
             _check_buffers(gen.state_dict(), tg.after[k], 1e-4, 1e-5)
         else:
@@ -551,12 +580,12 @@ def test_plan_cache_is_bounded_and_stream_keyed():
 # device-side weight fold (v2w_packer_*): bit-identical to the host packer, plans survive a re-fold
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_stress"])
-@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+@pytest.mark.parametrize("fmt", ["bf16", "fp16", "fp16split"])
 def test_device_fold_matches_host_packer(name, fmt):
     g = load_golden(name)
     gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
     eng = gen.engine()
-    half = native.HALF_FP16 if fmt == "fp16" else native.HALF_BF16
+    half = {"bf16": native.HALF_BF16, "fp16": native.HALF_FP16, "fp16split": native.HALF_FP16_SPLIT}[fmt]
     eng._tensors = eng._state_tensors()
     assert eng._device_foldable(torch.device("cuda:0"))
     dev_buf = eng.pack_device(torch.device("cuda:0"), half)

@@ -199,6 +199,41 @@ def test_bf16_plan_predicted_snr(name, min_snr):
     assert snr >= min_snr
 
 
+@pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_stress"])
+def test_fp32tc_plan_predicted_error(name):
+    """fp32 values on the tensor cores (V2W_PREC_FP32_TC): every operand split into fp16 hi + lo, three-term
+    products, one tap-GEMM per convolution -- emulated on the host with the device's rounding points, the plan
+    meets the fp32 bar (max-abs <= 1e-4) with two orders of magnitude to spare."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "fp32tc")
+    kinds = {op.kind for op in plan.ops}
+    assert kinds == {native.OP_TRANSPOSE_IN, native.OP_COND_AFFINE, native.OP_TAPGEMM, native.OP_CONV_POST}
+    for op in plan.ops:
+        if op.kind == native.OP_TAPGEMM:
+            L = plan.layers[op.layer]
+            assert op.split == 1 and op.engine == native.ENGINE_TC and op.in_pitch == 2 * L.cin
+    packed = eng.pack_host(native.HALF_FP16_SPLIT).numpy()
+    y = plan_interp.run(plan, packed, g.x, g.spk, g.noise)
+    err = np.abs(y - g.y).max()
+    print(f"{name}: predicted fp32tc max-abs {err:.2e}")
+    assert err < 2e-6
+    # the lo halves: fp16(w - fp16(w)) right after each layer's operands; hi + lo holds w to 2^-22
+    L = plan.layers[1]
+    n = L.num_taps * L.n_total * L.cin
+    hi = packed[L.w16_off: L.w16_off + 2 * n].view(np.float16).astype(np.float32)
+    lo = packed[L.w16_off + 2 * n: L.w16_off + 4 * n].view(np.float16).astype(np.float32)
+    w32 = packed[L.w32_off: L.w32_off + 4 * n].view(np.float32).reshape(L.num_taps, L.cin, L.n_total)
+    w = np.ascontiguousarray(w32.transpose(0, 2, 1)).ravel()
+    assert np.array_equal(hi, w.astype(np.float16).astype(np.float32))
+    assert np.array_equal(lo, (w - hi).astype(np.float16).astype(np.float32))
+    assert np.abs(hi + lo - w).max() <= 2.0 ** -21 * np.abs(w).max()
+    # a plain fp16 buffer leaves the second half zero
+    plain = eng.pack_host(native.HALF_FP16).numpy()
+    assert not plain[L.w16_off + 2 * n: L.w16_off + 4 * n].any()
+
+
 @pytest.mark.parametrize("name,min_snr", [("rb1_768_stress", 55.0), ("rb1_1024_stress", 55.0),
                                           ("rb2_768_stress", 60.0)])
 def test_fp16_plan_predicted_snr(name, min_snr):

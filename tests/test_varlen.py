@@ -139,7 +139,7 @@ def _varlen_case(g, gen, seed=11):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,precision", [("rb2_768_stress", "bf16"), ("rb1_768_stress", "fp16"),
-                                            ("rb2_768_stress", "fp32")])
+                                            ("rb2_768_stress", "fp32"), ("rb2_768_stress", "fp32tc")])
 def test_ragged_equals_padded_forward(name, precision):
     """generate_varlen == padded forward truncated, sample for sample, on the same engine."""
     g = load_golden(name)

@@ -29,6 +29,12 @@ ncu)
   cp /tmp/prof/cfg2.ncu-rep gpurun_out/r2_cfg2.ncu-rep 2>/dev/null; ls -la gpurun_out/*.ncu-rep ;;
 one)
   timeout 900 python -m pytest tests -m gpu -x -q -s -k "$ONE" 2>&1 | tail -n 40 > gpurun_out/r2_pytest_one.log; tail -n 30 gpurun_out/r2_pytest_one.log ;;
+fp32tc)
+  timeout 1200 python -m pytest tests -m gpu -q -s -k "fp32tc or device_fold or test_fp32_plan_max_abs" 2>&1 | grep -v "^$" | tail -n 70 > gpurun_out/r2_pytest_fp32tc.log; tail -n 45 gpurun_out/r2_pytest_fp32tc.log
+  for pr in fp32tc fp32; do
+    timeout 600 python bench.py --precision $pr --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_cfg2_$pr.json 2> gpurun_out/r2_bench_cfg2_$pr.err; echo "$pr rc=$?"; cut -c1-250 gpurun_out/r2_bench_cfg2_$pr.json
+  done
+  python tools/op_table.py --config cfg2 --precision fp32tc --out gpurun_out/r2_ops_cfg2_fp32tc.json > gpurun_out/r2_ops_cfg2_fp32tc.txt 2>&1; tail -n 45 gpurun_out/r2_ops_cfg2_fp32tc.txt ;;
 multi)
   N=${GPUS:-2}
   timeout 900 python -m pytest tests/test_sharding.py -m gpu -x -q 2>&1 | tail -n 8 > gpurun_out/r2_pytest_multi.log; tail -n 3 gpurun_out/r2_pytest_multi.log

@@ -52,6 +52,29 @@ static inline uint16_t fp16_bits(float f) {
   return (uint16_t)(sign | h);
 }
 
+// IEEE fp16 bit pattern -> fp32 (exact)
+static inline float fp16_value(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+  uint32_t u;
+  if (exp == 0) {
+    if (man == 0) {
+      u = sign;
+    } else {                                                       // subnormal: man * 2^-24
+      float f = (float)man * 5.9604644775390625e-8f;
+      __builtin_memcpy(&u, &f, 4);
+      u |= sign;
+    }
+  } else if (exp == 31) {
+    u = sign | 0x7f800000u | (man << 13);
+  } else {
+    u = sign | ((exp + 112u) << 23) | (man << 13);
+  }
+  float f;
+  __builtin_memcpy(&f, &u, 4);
+  return f;
+}
+
 // fn(i) for i in [0, n) on up to `threads` host threads (dynamic scheduling; the caller's thread works
 // too).  For independent, infallible tasks -- the per-layer weight folds of v2w_model_pack.
 template <typename Fn>

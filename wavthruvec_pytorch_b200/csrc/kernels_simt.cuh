@@ -198,7 +198,7 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x,
                                                           const RaggedOffsets ro,
                                                           TOut* __restrict__ y, int C, int T,
-                                                          int* __restrict__ row_limit, int halo) {
+                                                          int* __restrict__ row_limit, int halo, int lo_off = 0) {
   const int b = blockIdx.y;
   const int first = ro.off[b];
   const int len = ro.off[b + 1] - first;
@@ -212,21 +212,29 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     if (t >= T) break;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < len) v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<size_t>(first) + t) * C) + c4);
-    TOut* dst = y + (static_cast<size_t>(b) * T + t) * C + 4 * c4;
-    dst[0] = cvt_out<TOut>(v.x); dst[1] = cvt_out<TOut>(v.y);
-    dst[2] = cvt_out<TOut>(v.z); dst[3] = cvt_out<TOut>(v.w);
+    // lo_off > 0 (split-fp16 operands): rows of [hi(C) | lo(C)], lo = the part of the value hi does not hold
+    TOut* dst = y + (static_cast<size_t>(b) * T + t) * (lo_off ? 2 * C : C) + 4 * c4;
+    const TOut h0 = cvt_out<TOut>(v.x), h1 = cvt_out<TOut>(v.y), h2 = cvt_out<TOut>(v.z), h3 = cvt_out<TOut>(v.w);
+    dst[0] = h0; dst[1] = h1; dst[2] = h2; dst[3] = h3;
+    if (lo_off) {
+      dst[lo_off] = cvt_out<TOut>(v.x - static_cast<float>(h0));
+      dst[lo_off + 1] = cvt_out<TOut>(v.y - static_cast<float>(h1));
+      dst[lo_off + 2] = cvt_out<TOut>(v.z - static_cast<float>(h2));
+      dst[lo_off + 3] = cvt_out<TOut>(v.w - static_cast<float>(h3));
+    }
   }
 }
 
 template <typename TOut>
 __global__ void __launch_bounds__(256) transpose_in_kernel(const float* __restrict__ x,
-                                                           TOut* __restrict__ y, int C, int T) {
+                                                           TOut* __restrict__ y, int C, int T, int lo_off = 0) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float* xb = x + static_cast<size_t>(b) * C * T;
-  TOut* yb = y + static_cast<size_t>(b) * C * T;
+  const int pitch = lo_off ? 2 * C : C;     // lo_off > 0 (split-fp16 operands): rows of [hi(C) | lo(C)]
+  TOut* yb = y + static_cast<size_t>(b) * pitch * T;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int c = c0 + ty + i, t = t0 + tx;
@@ -236,7 +244,12 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int t = t0 + ty + i, c = c0 + tx;
-    if (t < T && c < C) yb[static_cast<size_t>(t) * C + c] = cvt_out<TOut>(tile[tx][ty + i]);
+    if (t < T && c < C) {
+      const float v = tile[tx][ty + i];
+      const TOut hi = cvt_out<TOut>(v);
+      yb[static_cast<size_t>(t) * pitch + c] = hi;
+      if (lo_off) yb[static_cast<size_t>(t) * pitch + lo_off + c] = cvt_out<TOut>(v - static_cast<float>(hi));
+    }
   }
 }
 

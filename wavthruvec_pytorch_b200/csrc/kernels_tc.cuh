@@ -86,6 +86,11 @@ struct Params {
   int box_rows;         // rows per TMA box of A
   int stages_a, stages_w;
   int stage_a_bytes, stage_w_bytes;
+  // Taps per W stage: one barrier round trip (a ~90 clk try_wait on each side, a commit, the producer's wait for
+  // the slot) serves `tap_group` consecutive taps of the list -- each still its own TMA load, into consecutive
+  // blocks of the stage.  The narrow layers (C <= 64), whose MMAs are short, were bound by these round trips:
+  // ~500 clk per (K-chunk, tap) step whatever the MMA does (tools/trace_small.py).
+  int tap_group;
   int acc_cols;         // TMEM columns per accumulator (per sub-tile)
   int fp16;             // 16-bit operand format: 0 = bf16, 1 = fp16
   int tma_out;          // outputs leave through shared-memory staging + TMA stores
@@ -124,6 +129,14 @@ struct Params {
   // is 512 contiguous bytes.  (Direct 16-byte stores were measured 1.2-2.2x slower for the whole launch:
   // half-filled lines.)  Output rows of a box past the utterance's end land in the kBlockedPad spare blocks.
   int y_blocked, y_cout_log2, y_up_log2;
+  // Split-fp16 operands (fp32 values on the tensor cores, V2W_PREC_FP32_TC): every operand is the pair
+  // hi = fp16(v), lo = fp16(v - hi) -- 22 significant bits -- and the product is the three-term sum
+  //     A_hi W_hi + A_lo W_hi + A_hi W_lo        (A_lo W_lo ~ 2^-22 of the result, dropped)
+  // accumulated in the one fp32 accumulator, i.e. a GEMM over K' = 3 cin walked as three sections of
+  // `sec_chunks` K-chunks.  The operand tensor is [rows, hi(cin) | lo(cin)] (lo at column a_lo_col), the weight
+  // array [taps][n][cin] of hi values followed w_lo_row rows later by the same array of lo values.  The 16-bit
+  // output is written in the same form: hi at its column, lo h_lo_col columns further (a second staging box).
+  int split, sec_chunks, a_lo_col, w_lo_row, h_lo_col;
   const float* bias;
   const float* scale;
   const float* shift;
@@ -438,6 +451,20 @@ __device__ __forceinline__ void lrelu_pack16(const float (&v)[16], float slope, 
   }
 }
 
+// sixteen values -> leaky-relu -> the split-fp16 pair: hi = fp16(v) (clamped to the finite range), lo = fp16(v - hi)
+__device__ __forceinline__ void lrelu_split16(const float (&v)[16], float slope, uint32_t (&h)[8], uint32_t (&l)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = fminf(fmaxf(lrelu(v[2 * e], slope), -65504.f), 65504.f);
+    const float b = fminf(fmaxf(lrelu(v[2 * e + 1], slope), -65504.f), 65504.f);
+    const __half2 hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(a - back.x, b - back.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hi);
+    l[e] = *reinterpret_cast<const uint32_t*>(&lo);
+  }
+}
+
 struct Ring {   // stage index + phase bit of a circular mbarrier pipeline
   uint32_t s = 0, ph = 0;
   __device__ __forceinline__ void advance(uint32_t n) {
@@ -455,7 +482,7 @@ __device__ __forceinline__ bool tile_skipped(const int* row_limit, int rows_per_
   return row_limit != nullptr && row0 >= __ldg(row_limit + b) * rows_per_frame;
 }
 
-template <int KC, bool kPair = false>
+template <int KC, bool kPair = false, bool kSplit = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmH,
@@ -541,7 +568,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int wrank = (int)rank * w_rows + (p.kgroups ? nt * p.n_tile : 0);
       for (int c = 0; c < p.num_chunks; ++c) {
         const int li = p.kgroups ? c / p.cpg : nt;          // tap list of this K-chunk
-        const int wc = p.kgroups ? (c - li * p.cpg) * KC : c * KC;   // column in the weight array
+        int wc = p.kgroups ? (c - li * p.cpg) * KC : c * KC;   // column in the weight array
+        int ac = c * KC, wlo = 0;                           // column in the operand tensor, extra weight rows
+        if constexpr (kSplit) {
+          // section 0: A_hi W_hi, 1: A_lo W_hi, 2: A_hi W_lo
+          const int sec = c / p.sec_chunks;
+          wc = ac = (c - sec * p.sec_chunks) * KC;
+          if (sec == 1) ac += p.a_lo_col;
+          if (sec == 2) wlo = p.w_lo_row;
+        }
         const int ntaps = p.num_taps[li];
         mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1u);
         if (elect_one()) {
@@ -551,25 +586,29 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // both CTAs' bytes land on the LEADER's barrier; only the leader arms it
             if (rank == 0) mbar_expect_tx(bar, 2 * nbox * box_bytes);
             for (int bx = 0; bx < nbox; ++bx)
-              tma_load_3d_pair(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+              tma_load_3d_pair(dst + bx * box_bytes, &tmA, ac, row0 + bx * p.box_rows, b, bar);
           } else {
             mbar_expect_tx(bar, nbox * box_bytes);
             for (int bx = 0; bx < nbox; ++bx)
-              tma_load_3d(dst + bx * box_bytes, &tmA, c * KC, row0 + bx * p.box_rows, b, bar);
+              tma_load_3d(dst + bx * box_bytes, &tmA, ac, row0 + bx * p.box_rows, b, bar);
           }
         }
         __syncwarp();
         ra.advance(p.stages_a);
-        for (int j = 0; j < ntaps; ++j) {
+        for (int j0 = 0; j0 < ntaps; j0 += p.tap_group) {
+          const int gn = min(p.tap_group, ntaps - j0);
           mbar_wait(empty_w + 8 * rw.s, rw.ph ^ 1u);
           if (elect_one()) {
             const uint32_t bar = full_w + 8 * rw.s;
+            const uint32_t dst = smem_w + rw.s * p.stage_w_bytes;
             if constexpr (kPair) {
-              if (rank == 0) mbar_expect_tx(bar, 2 * w_bytes);
-              tma_load_2d_pair(smem_w + rw.s * p.stage_w_bytes, &tmW, wc, p.w_row[li][j] + wrank, bar);
+              if (rank == 0) mbar_expect_tx(bar, 2 * gn * w_bytes);
+              for (int t = 0; t < gn; ++t)
+                tma_load_2d_pair(dst + t * w_bytes, &tmW, wc, p.w_row[li][j0 + t] + wrank + wlo, bar);
             } else {
-              mbar_expect_tx(bar, w_bytes);
-              tma_load_2d(smem_w + rw.s * p.stage_w_bytes, &tmW, wc, p.w_row[li][j] + wrank, bar);
+              mbar_expect_tx(bar, gn * w_bytes);
+              for (int t = 0; t < gn; ++t)
+                tma_load_2d(dst + t * w_bytes, &tmW, wc, p.w_row[li][j0 + t] + wrank + wlo, bar);
             }
           }
           __syncwarp();
@@ -585,6 +624,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     V2W_TRTC_DECL
     const uint32_t idesc = make_idesc_bf16(kPair ? 2 * kMTile : kMTile, p.n_tile, p.fp16);
     const uint32_t dhi = smem_desc_hi<KC>();
+    const uint32_t w_bytes = (kPair ? p.n_tile / 2 : p.n_tile) * kRowBytes;   // one tap's block in a W stage
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_b;
       const int rem = tile - b * tiles_per_b;
@@ -607,35 +647,40 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(full_a + 8 * ra.s, ra.ph);
         V2W_TRTC(tile_iter - 1, 10 + c);
         const uint32_t a_stage = smem_a + ra.s * p.stage_a_bytes;
-        for (int j = 0; j < ntaps; ++j) {
+        for (int j0 = 0; j0 < ntaps; j0 += p.tap_group) {
+          const int gn = min(p.tap_group, ntaps - j0);
           mbar_wait(full_w + 8 * rw.s, rw.ph);
           tcgen05_fence_after();
-          V2W_TRTC(tile_iter - 1, 100 + c * 16 + j);
+          V2W_TRTC(tile_iter - 1, 100 + c * 16 + j0);
           if (elect_one()) {
-            const uint32_t a_addr = a_stage + (p.tap_off[li][j] - off_min) * kRowBytes;
-            const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes;
-            const uint32_t acc0 = (c | j) != 0;
-            for (int m = 0; m < nsub; ++m) {
-              const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
-              const uint64_t bd = smem_desc(dhi, w_addr);
+            for (int t = 0; t < gn; ++t) {
+              const int j = j0 + t;
+              const uint32_t a_addr = a_stage + (p.tap_off[li][j] - off_min) * kRowBytes;
+              const uint32_t w_addr = smem_w + rw.s * p.stage_w_bytes + t * w_bytes;
+              const uint32_t acc0 = (c | j) != 0;
+              for (int m = 0; m < nsub; ++m) {
+                const uint64_t ad = smem_desc(dhi, a_addr + m * (kMTile * kRowBytes));
+                const uint64_t bd = smem_desc(dhi, w_addr);
 #pragma unroll
-              for (int kk = 0; kk < kKSteps; ++kk) {
-                if constexpr (kPair)
-                  umma_bf16_pair(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
-                                 acc0 | (kk != 0));
-                else
-                  umma_bf16(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
-                            acc0 | (kk != 0));
+                for (int kk = 0; kk < kKSteps; ++kk) {
+                  if constexpr (kPair)
+                    umma_bf16_pair(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
+                                   acc0 | (kk != 0));
+                  else
+                    umma_bf16(d_tmem + m * p.acc_cols, ad + 2 * kk, bd + 2 * kk, idesc,
+                              acc0 | (kk != 0));
+                }
               }
             }
+            const bool last = j0 + gn == ntaps;
             if constexpr (kPair) {
               umma_commit_pair(empty_w + 8 * rw.s);
-              if (j == ntaps - 1) umma_commit_pair(empty_a + 8 * ra.s);
-              if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit_pair(acc_full + 8 * as);
+              if (last) umma_commit_pair(empty_a + 8 * ra.s);
+              if (last && c == p.num_chunks - 1) umma_commit_pair(acc_full + 8 * as);
             } else {
               umma_commit(empty_w + 8 * rw.s);
-              if (j == ntaps - 1) umma_commit(empty_a + 8 * ra.s);
-              if (j == ntaps - 1 && c == p.num_chunks - 1) umma_commit(acc_full + 8 * as);
+              if (last) umma_commit(empty_a + 8 * ra.s);
+              if (last && c == p.num_chunks - 1) umma_commit(acc_full + 8 * as);
             }
           }
           __syncwarp();
@@ -656,6 +701,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t y_box = p.out_f32 ? 32u * p.y_cols * 4u : 0u;      // bytes of one staging box
     const uint32_t h_box = 32u * p.h_cols * 2u;
     const uint32_t hbuf = ybuf + 2 * y_box;
+    const uint32_t lbuf = hbuf + 2 * h_box;                            // split operands: the lo halves' boxes
     const uint32_t y_row = p.y_cols * 4u, h_row = p.h_cols * 2u;      // 64 / 128 and 32 / 64 / 128 bytes
     // XOR of the 16-byte unit index inside a row, as the TMA swizzle of that row size applies it
     const uint32_t y_sw = y_row == 128 ? (lane & 7) : ((lane >> 1) & 3);
@@ -720,6 +766,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool do_scale = out_scale != 1.0f, fp16 = p.fp16 != 0;
         const bool has_bias = p.bias != nullptr, has_affine = p.scale != nullptr;
         const bool st_y = p.out_f32 != nullptr, st_h = p.out_bf16 != nullptr, tma_out = p.tma_out != 0;
+        constexpr bool split = kSplit;       // (a template parameter: the plain kernels' chunk loop carries none of it)
         for (int cc = 0; cc < p.n_tile; cc += 16) {
           const int col = col0 + cc;
           // issue the global reads first so that they overlap the TMEM load
@@ -779,8 +826,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] *= out_scale;
             }
-            uint32_t h[8];
-            if (st_h) lrelu_pack16(v, out_slope, fp16, h);   // one format branch per chunk, not one per packed pair
+            uint32_t h[8], hl[8];
+            if (st_h) {
+              if (split) lrelu_split16(v, out_slope, h, hl);
+              else lrelu_pack16(v, out_slope, fp16, h);       // one format branch per chunk, not one per packed pair
+            }
             if (tma_out) {
               // own row -> staging box in the TMA swizzle layout (conflict-free 16-byte stores)
               if (st_y && p.y_blocked) {
@@ -809,6 +859,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t u0 = (static_cast<uint32_t>(cc >> 4) & h_mask) * 2u;
                 st_shared_v4u(hb + ((u0 ^ h_sw) << 4), h[0], h[1], h[2], h[3]);
                 st_shared_v4u(hb + (((u0 + 1) ^ h_sw) << 4), h[4], h[5], h[6], h[7]);
+                if (split) {
+                  const uint32_t lb = lbuf + sh * h_box + lane * h_row;
+                  st_shared_v4u(lb + ((u0 ^ h_sw) << 4), hl[0], hl[1], hl[2], hl[3]);
+                  st_shared_v4u(lb + (((u0 + 1) ^ h_sw) << 4), hl[4], hl[5], hl[6], hl[7]);
+                }
               }
             } else {
               if (st_y && !p.y_blocked) {
@@ -828,6 +883,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + ho);
                 op[0] = make_uint4(h[0], h[1], h[2], h[3]);
                 op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                if (split) {
+                  uint4* lp = reinterpret_cast<uint4*>(p.out_bf16 + ho + p.h_lo_col);
+                  lp[0] = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+                  lp[1] = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+                }
               }
             }
           }
@@ -859,8 +919,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (p.h_cout) {
                       const int ph = hc0 / p.h_cout;
                       tma_store_4d(&tmH, hbuf + sh * h_box, hc0 - ph * p.h_cout, ph, row0w, b);
+                      if (split) tma_store_4d(&tmH, lbuf + sh * h_box, hc0 - ph * p.h_cout + p.h_lo_col, ph, row0w, b);
                     } else {
                       tma_store_3d(&tmH, hbuf + sh * h_box, hc0, row0w, b);
+                      if (split) tma_store_3d(&tmH, lbuf + sh * h_box, hc0 + p.h_lo_col, row0w, b);
                     }
                   }
                   tma_store_commit();

@@ -554,7 +554,7 @@ int32_t v2w_model_create(const v2w_config* c, v2w_model** out) {
   for (auto& L : m->layers) {
     if (L.role != V2W_ROLE_CONV_POST) {
       L.w16_off = off;
-      off = align_up(off + (int64_t)L.num_taps * L.n_total * L.cin * 2, 1024);
+      off = align_up(off + (int64_t)2 * L.num_taps * L.n_total * L.cin * 2, 1024);   // operands | lo halves
     } else {
       L.w16_off = -1;
     }
@@ -770,11 +770,12 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
     set_error("v2w_model_pack: null argument");
     return V2W_ERR_INVALID;
   }
-  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16) {
+  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16 && half_format != V2W_HALF_FP16_SPLIT) {
     set_error("v2w_model_pack: unknown 16-bit format %d", half_format);
     return V2W_ERR_INVALID;
   }
-  const bool f16 = half_format == V2W_HALF_FP16;
+  const bool f16 = half_format != V2W_HALF_BF16;
+  const bool split = half_format == V2W_HALF_FP16_SPLIT;
   auto half_bits = [f16](float w) { return f16 ? fp16_bits(w) : bf16_bits(w); };
   if (P->num_convs != m->num_convs || P->num_stages != (int)m->cond.size()) {
     set_error("v2w_model_pack: expected %d convs / %d stages, got %d / %d", m->num_convs,
@@ -834,6 +835,7 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
     const int K = L.kernel_size;
     const bool transposed = L.role == V2W_ROLE_UPSAMPLE;
     uint16_t* w16 = L.w16_off >= 0 ? reinterpret_cast<uint16_t*>(base + L.w16_off) : nullptr;
+    uint16_t* w16lo = (w16 && split) ? w16 + (size_t)L.num_taps * L.n_total * L.cin : nullptr;
     float* w32 = reinterpret_cast<float*>(base + L.w32_off);
     for (int p = 0; p < L.up; ++p) {
       if (!(L.tap_mask[j] >> p & 1u)) continue;
@@ -846,6 +848,7 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
           if (transposed) w = cp.v[((size_t)ci * L.cout + co) * K + kk] * scale[ci];
           else w = cp.v[((size_t)co * L.cin + ci) * K + kk] * scale[co];
           if (w16) w16[((size_t)j * L.n_total + n) * L.cin + ci] = half_bits(w);
+          if (w16lo) w16lo[((size_t)j * L.n_total + n) * L.cin + ci] = fp16_bits(w - fp16_value(fp16_bits(w)));
           w32[((size_t)j * L.cin + ci) * L.n_total + n] = w;
         }
       }

@@ -138,7 +138,14 @@ fold_weight_kernel(const DevLayer* __restrict__ layers, const WeightTask* __rest
       } else {
         w = v[((size_t)co * cin + ci) * K + j] * sc[co];
       }
-      if (w16) w16[((size_t)j * L.n_total + n) * cin + ci] = half_bits_dev(w, f16);
+      if (w16) {
+        const unsigned short hb = half_bits_dev(w, f16);
+        w16[((size_t)j * L.n_total + n) * cin + ci] = hb;
+        // V2W_HALF_FP16_SPLIT: the part of the weight its fp16 value does not hold, in the section's second half
+        if (f16 == V2W_HALF_FP16_SPLIT)
+          w16[((size_t)(L.num_taps + j) * L.n_total + n) * cin + ci] =
+              half_bits_dev(w - __half2float(__ushort_as_half(hb)), 1);
+      }
     }
     tile[e] = w;
   }
@@ -450,7 +457,7 @@ int32_t v2w_packer_run(v2w_packer* pk, const v2w_params* P, void* packed_dev, in
     return V2W_ERR_INVALID;
   }
   const v2w_model* m = pk->model;
-  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16) {
+  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16 && half_format != V2W_HALF_FP16_SPLIT) {
     set_error("v2w_packer_run: unknown 16-bit format %d", half_format);
     return V2W_ERR_INVALID;
   }
@@ -473,7 +480,7 @@ int32_t v2w_packer_run(v2w_packer* pk, const v2w_params* P, void* packed_dev, in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* base = static_cast<unsigned char*>(packed_dev);
-  const int f16 = half_format == V2W_HALF_FP16;
+  const int f16 = half_format;   // 0 = bf16, 1 = fp16, 2 = fp16 + lo halves
   // zero fill (dead polyphase blocks, padding) + header, like the host packer
   V2W_CUDA_P(cudaMemsetAsync(base, 0, (size_t)m->packed_bytes, st));
   const uint32_t hdr[3] = {kPackedMagic, V2W_ABI_VERSION, (uint32_t)half_format};

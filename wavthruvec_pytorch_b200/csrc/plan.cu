@@ -247,6 +247,10 @@ struct TcExtra {
   bool abs_rows = false; // w_row[list][tap]: first row of the block relative to `w16`, in rows of w_cols elements
   int w_row[V2W_MAX_TILES][V2W_MAX_TAPS];
   int64_t w_total_rows = 0;
+  // split-fp16 operands (tc::Params::split): input [rows, hi | lo] (a_pitch = 2 cin), 16-bit output likewise
+  // (h_pitch = 2 cout), the lo weights w_lo_row rows after the hi ones
+  bool split = false;
+  int w_lo_row = 0;
 };
 
 static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex = nullptr) {
@@ -276,6 +280,20 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   p.n_tile = a.n_tile; p.n_tiles = a.n_tiles;
   p.num_chunks = a.cin / kc;
   p.res_scale = 1.f;
+  const bool split = ex && ex->split;
+  if (split) {
+    if (ex->kgroups || ex->abs_rows || ex->a_pitch != 2 * a.cin || !(a.tc_flags & 0x100) ||
+        (a.out_bf16 && ex->h_pitch != 2 * (ex->h_cout ? ex->h_cout : a.n_total))) {
+      set_error("tapgemm(TC): split-fp16 operands need fp16 format, [hi | lo] pitches and a plain weight array");
+      return V2W_ERR_INVALID;
+    }
+    p.split = 1;
+    p.sec_chunks = p.num_chunks;
+    p.num_chunks *= 3;
+    p.a_lo_col = a.cin;
+    p.w_lo_row = ex->w_lo_row;
+    p.h_lo_col = ex->h_pitch / 2;
+  }
   const int nlists = (ex && ex->kgroups) ? ex->kgroups : a.n_tiles;
   if (ex) {
     p.kgroups = ex->kgroups; p.cpg = ex->cpg;
@@ -339,7 +357,14 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   static const bool no_pair = [] { const char* e = std::getenv("V2W_TC_NO_PAIR"); return e && std::atoi(e); }();
   L->pair = !no_pair && a.n_tile >= 128 && sms >= 2;
   const int w_rows = L->pair ? a.n_tile / 2 : a.n_tile;
-  p.stage_w_bytes = (int)align_up((int64_t)w_rows * kc * 2, 1024);
+  // Taps per W stage (tc::Params::tap_group): as many as 16 KB hold, at most the longest tap list.
+  // $V2W_TC_TAP_GROUP overrides (1 = one tap per barrier round trip, the round-1 behaviour).
+  int max_taps = 1;
+  for (int t = 0; t < nlists; ++t) max_taps = std::max(max_taps, (int)a.num_taps[t]);
+  static const int group_env = [] { const char* e = std::getenv("V2W_TC_TAP_GROUP"); return e ? std::atoi(e) : 0; }();
+  p.tap_group = std::max(1, std::min(max_taps, 16384 / (w_rows * kc * 2)));
+  if (group_env >= 1) p.tap_group = std::min(group_env, max_taps);
+  p.stage_w_bytes = (int)align_up((int64_t)p.tap_group * w_rows * kc * 2, 1024);
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
@@ -358,7 +383,16 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
     else if (a.n_tile % 32 == 0 && h_unit % 32 == 0) p.h_cols = 32;
   }
   if (ex && ex->y_blocked_cout && p.y_cols > ex->y_blocked_cout) p.y_cols = 16;   // a blocked box stays inside one phase
-  p.stage_warp_bytes = (a.out_f32 ? 2 * 32 * p.y_cols * 4 : 0) + (a.out_bf16 ? 2 * 32 * p.h_cols * 2 : 0);
+  auto staging = [&] {
+    return (a.out_f32 ? 2 * 32 * p.y_cols * 4 : 0) + (a.out_bf16 ? (split ? 4 : 2) * 32 * p.h_cols * 2 : 0);
+  };
+  // (split operands stage two 16-bit boxes per buffer: keep the epilogue's share of shared memory at the 12 KB per
+  // warp the widest plain op takes)
+  while (staging() > 12 * 1024 && (p.h_cols > 16 || p.y_cols > 16)) {
+    if (a.out_bf16 && p.h_cols > 16) p.h_cols >>= 1;
+    else p.y_cols >>= 1;
+  }
+  p.stage_warp_bytes = staging();
   // barriers (+ output staging) + per-warp column vectors
   const int tail_bytes = 1024 + (p.tma_out ? 8 * p.stage_warp_bytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
   const int budget = 227 * 1024 - 1024 - tail_bytes;
@@ -369,6 +403,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   // the least -- the launch lasts rounds(msub) x msub sub-tile times (cfg2, ups[3]: 500 super-tiles of 4 on
   // 148 SMs = 4 rounds x 4, against 1000 of 2 = 7 rounds x 2).  Ties go to the taller tile (fewer W fetches);
   // $V2W_TC_NO_QUANT=1 restores "tallest that leaves two items per SM".
+  static const bool no_step_cost = [] { const char* e = std::getenv("V2W_TC_NO_STEP_COST"); return e && std::atoi(e); }();
   static const bool no_quant = [] { const char* e = std::getenv("V2W_TC_NO_QUANT"); return e && std::atoi(e); }();
   auto geometry = [&](int ms) {
     p.msub = ms;
@@ -391,7 +426,15 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)", p.stage_a_bytes, p.stage_w_bytes);
       return V2W_ERR_INVALID;
     }
-    const int64_t cost = ((tiles + slots - 1) / slots) * ms;
+    // Duration of a tile, in clocks (fitted to the timelines of tools/trace_tc.py / trace_small.py): the MMA side
+    // pays ~450 clk of barrier round trip per W stage plus, per tap and sub-tile, kc / 16 instructions of
+    // ~(64 + N / 2) clk (N / 4 for a pair); the epilogue side ~1400 clk per 16-column chunk and sub-tile, two warp
+    // groups alternating tiles.  Without the fixed part the narrow layers chose msub = 1 and ran at the barrier rate.
+    const int64_t mma_clk = (int64_t)(kc / 16) * (64 + (L->pair ? a.n_tile / 4 : a.n_tile / 2));
+    const int64_t w_stages = (int64_t)p.num_chunks * ((max_taps + p.tap_group - 1) / p.tap_group);
+    const int64_t mma_tile = w_stages * 450 + (int64_t)p.num_chunks * max_taps * ms * mma_clk;
+    const int64_t epi_tile = (int64_t)ms * ((a.n_tile / 16) * 1400 + 400) / 2;
+    const int64_t cost = ((tiles + slots - 1) / slots) * (no_step_cost ? ms : std::max(mma_tile, epi_tile));
     if (!best || cost < best_cost) {
       best = ms;
       best_cost = cost;
@@ -421,7 +464,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
                                                       : CU_TENSOR_MAP_SWIZZLE_32B);
   {
     const cuuint64_t a_pitch = (ex && ex->a_pitch) ? ex->a_pitch : a.cin;
-    cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+    cuuint64_t dims[3] = {(cuuint64_t)(split ? 2 * a.cin : a.cin), (cuuint64_t)a.rows, (cuuint64_t)a.batch};
     cuuint64_t strides[2] = {a_pitch * 2, (cuuint64_t)a.rows * a_pitch * 2};
     cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)p.box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -440,7 +483,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       for (int j = 0; j < a.num_taps[t]; ++j) max_row = std::max(max_row, a.tap_row[t][j]);
     const cuuint64_t w_cols = (ex && ex->w_cols) ? ex->w_cols : a.cin;
     const cuuint64_t w_rows_total = (ex && ex->abs_rows) ? (cuuint64_t)ex->w_total_rows
-                                                        : (cuuint64_t)(max_row + 1) * a.n_total;
+                                                        : (cuuint64_t)(max_row + 1) * a.n_total + (split ? ex->w_lo_row : 0);
     cuuint64_t dims[2] = {w_cols, w_rows_total};
     cuuint64_t strides[1] = {w_cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)w_rows};
@@ -459,6 +502,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   if (p.tma_out) {
     // output slabs: 32 rows x 16 columns per epilogue warp and chunk (kernels_tc.cuh)
     cuuint64_t dims[3] = {(cuuint64_t)a.n_total, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+    cuuint64_t dims_h[3] = {(cuuint64_t)(split ? 2 * a.n_total : a.n_total), (cuuint64_t)a.rows, (cuuint64_t)a.batch};
     cuuint32_t box[3] = {(cuuint32_t)p.y_cols, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     auto swz_of = [](int row_bytes) {
@@ -497,7 +541,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       if (p.h_cout) {
         // (cout, up, rows, batch): one GEMM row is `up` output rows, h_pitch elements apart
         const cuuint64_t up = (cuuint64_t)(a.n_total / p.h_cout);
-        cuuint64_t dims4[4] = {(cuuint64_t)p.h_cout, up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+        cuuint64_t dims4[4] = {(cuuint64_t)(split ? 2 * p.h_cout : p.h_cout), up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
         cuuint64_t strides4[3] = {h_pitch * 2, up * h_pitch * 2, (cuuint64_t)a.rows * up * h_pitch * 2};
         cuuint32_t box4[4] = {(cuuint32_t)p.h_cols, 1, 32, 1};
         cuuint32_t estr4[4] = {1, 1, 1, 1};
@@ -507,7 +551,7 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       } else {
         cuuint32_t boxh[3] = {(cuuint32_t)p.h_cols, 32, 1};
         r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                3, a.out_bf16, dims, strides, boxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                3, a.out_bf16, dims_h, strides, boxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 swz_of(p.h_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       }
       if (r != CUDA_SUCCESS) {
@@ -565,46 +609,34 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int
   return launch_ex<1>(kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
+template <int KC, bool kPair, bool kSplit>
+static int launch_tc_as(const TcLaunch& L, cudaStream_t st) {
+  auto kernel = tc::tapgemm_tc_kernel<KC, kPair, kSplit>;
+  static std::atomic<uint64_t> attr_devs{0};     // (one per instantiation)
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_devs.load() & dev_bit) || !dev_bit) {
+    V2W_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_devs.fetch_or(dev_bit);
+  }
+  V2W_CUDA(launch_ex<kPair ? 2 : 1>(kernel, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
+  V2W_CUDA(cudaGetLastError());
+  return V2W_OK;
+}
+
+template <bool kPair, bool kSplit>
+static int launch_tc_kc(const TcLaunch& L, cudaStream_t st) {
+  if (L.kc == 64) return launch_tc_as<64, kPair, kSplit>(L, st);
+  if (L.kc == 32) return launch_tc_as<32, kPair, kSplit>(L, st);
+  return launch_tc_as<16, kPair, kSplit>(L, st);
+}
+
 static int launch_tc(const TcLaunch& L0, cudaStream_t st, const int* row_limit = nullptr,
                      int rows_per_frame = 0) {
   TcLaunch L = L0;
   L.prm.row_limit = row_limit;
   L.prm.rows_per_frame = rows_per_frame;
-  static std::atomic<uint64_t> attr_devs{0};
-  const uint64_t dev_bit = device_bit();
-  if (!(attr_devs.load() & dev_bit) || !dev_bit) {
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<32>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<64, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<32, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    V2W_CUDA(cudaFuncSetAttribute(tc::tapgemm_tc_kernel<16, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_devs.fetch_or(dev_bit);
-  }
-  if (L.pair) {
-    if (L.kc == 64)
-      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<64, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-    else if (L.kc == 32)
-      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<32, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-    else
-      V2W_CUDA(launch_ex<2>(tc::tapgemm_tc_kernel<16, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-    V2W_CUDA(cudaGetLastError());
-    return V2W_OK;
-  }
-  if (L.kc == 64)
-    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<64>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-  else if (L.kc == 32)
-    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-  else
-    V2W_CUDA(launch_pdl(tc::tapgemm_tc_kernel<16>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.tm_y, L.tm_h, L.prm));
-  V2W_CUDA(cudaGetLastError());
-  return V2W_OK;
+  if (L.prm.split) return L.pair ? launch_tc_kc<true, true>(L, st) : launch_tc_kc<false, true>(L, st);
+  return L.pair ? launch_tc_kc<true, false>(L, st) : launch_tc_kc<false, false>(L, st);
 }
 
 template <typename TIn>
@@ -1048,7 +1080,8 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     set_error("v2w_plan_create: batch=%d frames=%d out of range", batch, frames);
     return V2W_ERR_INVALID;
   }
-  if (precision != V2W_PREC_FP32 && precision != V2W_PREC_BF16 && precision != V2W_PREC_FP16) {
+  if (precision != V2W_PREC_FP32 && precision != V2W_PREC_BF16 && precision != V2W_PREC_FP16 &&
+      precision != V2W_PREC_FP32_TC) {
     set_error("v2w_plan_create: unknown precision %d", precision);
     return V2W_ERR_INVALID;
   }
@@ -1066,11 +1099,15 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   P->frames = frames;
   P->precision = precision;
   const bool bf = precision != V2W_PREC_FP32;   // 16-bit tensor-core operands (bf16 or fp16)
+  // fp32 values on the tensor cores: every operand tensor is [rows, hi | lo] fp16 (tc::Params::split), one
+  // tap-GEMM per convolution (the fused stage kernels keep their operands in shared memory as single 16-bit values)
+  const bool split = precision == V2W_PREC_FP32_TC;
+  const int hsz = split ? 4 : 2;                // bytes per element of a 16-bit operand tensor
   const v2w_config& c = m->cfg;
   const int U = c.num_upsamples;
   const int B = batch, T = frames;
   const bool force_simt = std::getenv("V2W_FORCE_SIMT") != nullptr;
-  const bool no_fuse = std::getenv("V2W_NO_FUSE") != nullptr;
+  const bool no_fuse = split || std::getenv("V2W_NO_FUSE") != nullptr;
   bool post_folded = false;   // conv_post runs inside the last fused stage
   const int fuse_mask = std::getenv("V2W_FUSE_MASK") ? std::atoi(std::getenv("V2W_FUSE_MASK")) : -1;
 
@@ -1086,12 +1123,12 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   int64_t max_e = 0;
   for (int i = 0; i < U; ++i)
     max_e = std::max(max_e, (int64_t)B * T * m->stage_up[i] * m->stage_channels[i]);
-  const int64_t esz = bf ? 2 : 4;
+  const int64_t esz = bf ? hsz : 4;
   P->row_limit = ws.take((int64_t)B * 4);
   P->xt = ws.take((int64_t)B * T * c.num_wv_feat * esz);
   Act pre;   // conv_pre output, leaky-relu'd for ups[0] (models.py:128)
   pre.slope = kLreluSlope;
-  if (bf) pre.bf16 = ws.take((int64_t)B * T * c.upsample_initial_channel * 2);
+  if (bf) pre.bf16 = ws.take((int64_t)B * T * c.upsample_initial_channel * hsz);
   else pre.f32 = ws.take((int64_t)B * T * c.upsample_initial_channel * 4);
   Act x0, y1, t1;
   x0.slope = y1.slope = t1.slope = kLreluSlope;
@@ -1102,20 +1139,20 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   y1.f32 = ws.take(max_e * 4);
   const int64_t sum_f32 = ws.take(max_e * 4);
   if (bf) {
-    x0.bf16 = ws.take(max_e * 2);
-    y1.bf16 = ws.take(max_e * 2);
+    x0.bf16 = ws.take(max_e * hsz);
+    y1.bf16 = ws.take(max_e * hsz);
   }
   Act y2;    // ResBlock1, fused conv pairs: a pair reads its input WITH halo rows, so it cannot run in place
   y2.slope = kLreluSlope;
   if (c.resblock_type == 1) {
-    if (bf) t1.bf16 = ws.take(max_e * 2);
+    if (bf) t1.bf16 = ws.take(max_e * hsz);
     else t1.f32 = ws.take(max_e * 4);
     if (bf) {
       y2.f32 = ws.take(max_e * 4);
-      y2.bf16 = ws.take(max_e * 2);
+      y2.bf16 = ws.take(max_e * hsz);
     }
   }
-  const int64_t next_bf16 = bf ? ws.take(max_e * 2) : -1;
+  const int64_t next_bf16 = bf ? ws.take(max_e * hsz) : -1;
   // Wide stages (two stacked tap-GEMM launches, v2w_wide_desc): by default the stages no fused kernel
   // covers (C = 256); $V2W_WIDE_MASK = bitmask of stages overrides (0 = the six separate tap-GEMMs).
   const int wide_mask = std::getenv("V2W_WIDE_MASK") ? std::atoi(std::getenv("V2W_WIDE_MASK")) : -1;
@@ -1174,7 +1211,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
                   int64_t accum, float out_scale, const Act& out) {
     const v2w_layer_desc& L = m->layers[layer];
     Op o = blank(V2W_OP_TAPGEMM);
-    o.d.engine = (bf && (!force_simt || precision == V2W_PREC_FP16)) ? V2W_ENGINE_TC : V2W_ENGINE_SIMT;
+    o.d.engine = (bf && (!force_simt || precision == V2W_PREC_FP16 || split)) ? V2W_ENGINE_TC : V2W_ENGINE_SIMT;
     o.d.layer = layer;
     o.d.batch = B;
     o.d.rows = rows;
@@ -1184,6 +1221,11 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
       o.d.out_f32 = out.f32; o.d.out_bf16 = out.bf16; o.d.out_slope = out.slope;
       o.d.out_bf16_pitch = out.pitch16;
       o.d.f32_blocked = (out.f32 >= 0 && out.f32_blocked) ? 1 : 0;
+      if (split) {
+        o.d.split = 1;
+        o.d.in_pitch = 2 * L.cin;
+        o.d.out_bf16_pitch = out.bf16 >= 0 ? 2 * L.cout : 0;
+      }
     } else {
       o.d.in_act = in.f32; o.d.in_is_bf16 = 0; o.d.in_slope = in.slope;
       o.d.out_f32 = out.f32; o.d.out_bf16 = -1; o.d.out_slope = 1.f;
@@ -1407,7 +1449,7 @@ int32_t v2w_plan_set_engine(v2w_plan* p, int32_t i, int32_t engine) {
     set_error("v2w_plan_set_engine: op %d writes into a wide stage's operand tensor (tensor-core engine only)", i);
     return V2W_ERR_INVALID;
   }
-  if (engine == V2W_ENGINE_SIMT && p->precision == V2W_PREC_FP16) {
+  if (engine == V2W_ENGINE_SIMT && (p->precision == V2W_PREC_FP16 || p->precision == V2W_PREC_FP32_TC)) {
     set_error("v2w_plan_set_engine: the FFMA engine reads fp32 or bf16 activations, not fp16");
     return V2W_ERR_INVALID;
   }
@@ -1531,14 +1573,17 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       set_error("v2w_plan_bind: packed_dev is not a v2w_model_pack buffer of this ABI");
       return V2W_ERR_INVALID;
     }
-    const int want = p->precision == V2W_PREC_FP16 ? V2W_HALF_FP16 : V2W_HALF_BF16;
+    static const char* const kFormatName[3] = {"bf16", "fp16", "split-fp16"};
+    const int want = p->precision == V2W_PREC_FP16 ? V2W_HALF_FP16
+                   : (p->precision == V2W_PREC_FP32_TC ? V2W_HALF_FP16_SPLIT : V2W_HALF_BF16);
     if (p->precision != V2W_PREC_FP32 && (int)hdr[2] != want) {
       set_error("v2w_plan_bind: packed weights hold %s operands but the plan computes in %s",
-                hdr[2] == V2W_HALF_FP16 ? "fp16" : "bf16", want == V2W_HALF_FP16 ? "fp16" : "bf16");
+                hdr[2] < 3 ? kFormatName[hdr[2]] : "unknown", kFormatName[want]);
       return V2W_ERR_INVALID;
     }
   }
-  const int tc_flags = p->precision == V2W_PREC_FP16 ? 0x100 : 0;
+  const bool split = p->precision == V2W_PREC_FP32_TC;
+  const int tc_flags = (p->precision == V2W_PREC_FP16 || split) ? 0x100 : 0;
   for (Op& o : p->ops) {
     if (o.d.kind == V2W_OP_MRF_FUSED || o.d.kind == V2W_OP_PAIR_FUSED) {
       const v2w_fused_desc& F = o.d.kind == V2W_OP_MRF_FUSED ? m->fused[o.d.stage] : m->pairs[o.d.pair];
@@ -1591,7 +1636,13 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       ex.h_pitch = o.d.out_bf16_pitch;
       ex.h_cout = L.cout;       // a transposed conv's GEMM row is `up` output rows of cout channels
       ex.y_blocked_cout = o.d.f32_blocked ? L.cout : 0;
-      rc = prepare_tc(g, &o.tcl, (o.d.out_bf16_pitch || o.d.f32_blocked) ? &ex : nullptr);
+      if (split) {
+        ex.split = true;
+        ex.a_pitch = 2 * L.cin;
+        ex.h_pitch = 2 * L.cout;
+        ex.w_lo_row = L.num_taps * L.n_total;
+      }
+      rc = prepare_tc(g, &o.tcl, (o.d.out_bf16_pitch || o.d.f32_blocked || split) ? &ex : nullptr);
       if (rc) return rc;
       o.tc_ready = true;
     } else if (o.d.out_bf16_pitch || o.d.f32_blocked) {
@@ -1608,7 +1659,12 @@ int32_t v2w_plan_bind(v2w_plan* p, const void* packed_dev, void* workspace_dev) 
       rc = validate_gemm(o.g_raw);
       if (rc) return rc;
       if (g.engine == V2W_ENGINE_TC) {
-        rc = prepare_tc(o.g_raw, &o.tcl_raw);
+        TcExtra exr;
+        exr.split = split;
+        exr.a_pitch = split ? 2 * L.cin : 0;
+        exr.h_cout = L.cout;
+        exr.w_lo_row = L.num_taps * L.n_total;
+        rc = prepare_tc(o.g_raw, &o.tcl_raw, split ? &exr : nullptr);
         if (rc) return rc;
       }
       o.has_raw = true;
@@ -1778,7 +1834,11 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
       case V2W_OP_TRANSPOSE_IN: {
         if (ragged) {
           dim3 grid((p->frames + 7) / 8, p->batch);
-          if (p->precision == V2W_PREC_FP16)
+          if (p->precision == V2W_PREC_FP32_TC)
+            simt::gather_rows_kernel<__half><<<grid, 256, 0, st>>>(
+                x_dev, *ro, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames,
+                reinterpret_cast<int*>(p->ws + p->row_limit), v2w_model_halo_frames(m), c.num_wv_feat);
+          else if (p->precision == V2W_PREC_FP16)
             simt::gather_rows_kernel<__half><<<grid, 256, 0, st>>>(
                 x_dev, *ro, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames,
                 reinterpret_cast<int*>(p->ws + p->row_limit), v2w_model_halo_frames(m));
@@ -1795,7 +1855,10 @@ static int32_t run_ops(v2w_plan* p, const float* x_dev, const float* spk_dev, co
           break;
         }
         dim3 grid((p->frames + 31) / 32, (c.num_wv_feat + 31) / 32, p->batch);
-        if (p->precision == V2W_PREC_FP16)
+        if (p->precision == V2W_PREC_FP32_TC)
+          simt::transpose_in_kernel<__half><<<grid, 256, 0, st>>>(
+              x_dev, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames, c.num_wv_feat);
+        else if (p->precision == V2W_PREC_FP16)
           simt::transpose_in_kernel<__half><<<grid, 256, 0, st>>>(
               x_dev, reinterpret_cast<__half*>(p->ws + p->xt), c.num_wv_feat, p->frames);
         else if (bf)

@@ -243,7 +243,7 @@ class NativeEngine:
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 for key, (plan, _ws) in self._plans.items():
-                    if key[3] == dev and (native.HALF_FP16 if key[2] == "fp16" else native.HALF_BF16) == fmt:
+                    if key[3] == dev and native.HALF_OF_PRECISION[key[2]] == fmt:
                         native.check(self._lib.v2w_plan_refresh_weights(plan, C.c_void_p(stream)))
         return True
 
@@ -304,7 +304,7 @@ class NativeEngine:
             self._plans.move_to_end(key)
             return hit
         prec = native.PRECISIONS[precision]
-        packed = self._packed_on(device, native.HALF_FP16 if precision == "fp16" else native.HALF_BF16)
+        packed = self._packed_on(device, native.HALF_OF_PRECISION[precision])
         handle = C.c_void_p()
         native.check(self._lib.v2w_plan_create(self._model, batch, frames, prec, C.byref(handle)))
         try:

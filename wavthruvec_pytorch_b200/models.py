@@ -148,7 +148,8 @@ class Generator(nn.Module):
     @property
     def precision(self) -> str:
         """Arithmetic of the native path: 'bf16' / 'fp16' (tcgen05 with 16-bit operands, fp32
-        accumulation and fp32 residual stream) or 'fp32' (FFMA).  Default 'auto' (also via
+        accumulation and fp32 residual stream), 'fp32tc' (fp32 values on the tensor cores: split-fp16
+        operands, three MMAs per product, meets the fp32 bar) or 'fp32' (FFMA).  Default 'auto' (also via
         $V2W_PRECISION): bf16 for ResBlock2; fp16 for ResBlock1, whose 97-conv chain does not reach
         the 45 dB waveform-SNR bar with bf16 operands."""
         import os
@@ -168,8 +169,8 @@ class Generator(nn.Module):
 
     @precision.setter
     def precision(self, value: str) -> None:
-        if value not in ("auto", "bf16", "fp16", "fp32"):
-            raise ValueError("precision must be 'auto', 'bf16', 'fp16' or 'fp32'")
+        if value not in ("auto", "bf16", "fp16", "fp32", "fp32tc"):
+            raise ValueError("precision must be 'auto', 'bf16', 'fp16', 'fp32tc' or 'fp32'")
         self._precision = value
 
     def engine(self):

@@ -20,10 +20,14 @@ MAX_TILES = 16
 PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_FP16 = 2
-HALF_BF16, HALF_FP16 = 0, 1
+PREC_FP32_TC = 3
+HALF_BF16, HALF_FP16, HALF_FP16_SPLIT = 0, 1, 2
 PACKED_HEADER_BYTES = 1024
 TC_FLAG_FP16 = 0x100
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp32tc": PREC_FP32_TC}
+# 16-bit operand format of the packed weight buffer a plan of each precision binds (the FFMA plan reads the
+# fp32 arrays, which every buffer holds)
+HALF_OF_PRECISION = {"fp32": HALF_BF16, "bf16": HALF_BF16, "fp16": HALF_FP16, "fp32tc": HALF_FP16_SPLIT}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
 OUT_F32, OUT_PCM16 = 0, 1
@@ -122,6 +126,7 @@ class OpDesc(C.Structure):
         ("out_bf16_pitch", C.c_int32),
         ("in_pitch", C.c_int32),
         ("f32_blocked", C.c_int32),
+        ("split", C.c_int32),
     ]
 
 
