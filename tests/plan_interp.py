@@ -49,6 +49,7 @@ class HostPlan:
             native.check(self.lib.v2w_plan_get_op(h, i, C.byref(d)))
             self.ops.append(d)
         self.layers = engine.layers()
+        self.packed_format = int(self.lib.v2w_plan_packed_format(h))   # the V2W_HALF_* buffer this plan binds
         self.workspace_bytes = int(self.lib.v2w_plan_workspace_bytes(h))
 
     def close(self):
@@ -94,7 +95,8 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             hi = fp16_round(v)
             return hi, fp16_round(v - hi)
     hdr = packed[:12].view(np.uint32)
-    assert hdr[0] == 0x50573256 and (not bf or hdr[2] == native.HALF_OF_PRECISION[plan.precision]), \
+    want_fmt = int(plan.lib.v2w_plan_packed_format(plan.handle))
+    assert hdr[0] == 0x50573256 and (not bf or hdr[2] == want_fmt), \
         "packed buffer format does not match the plan precision"
 
     def half_to_f32(bits):      # packed 16-bit weights -> fp32
@@ -124,7 +126,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
         elif op.kind == native.OP_TAPGEMM:
             L = plan.layers[op.layer]
             # an upsample op's output row [u*Cout] is u consecutive channels-last rows [Cout]
-            assert bool(op.split) == split
+            assert (op.split == 1) == split
             A_lo = None
             if split:
                 assert op.in_pitch == 2 * L.cin and (op.out_bf16 < 0 or op.out_bf16_pitch == 2 * L.cout)
@@ -136,7 +138,7 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
             if bf:     # TC engine semantics: bf16 weights [taps][n_total][cin]
                 W = half_to_f32(u16(L.w16_off, L.num_taps * L.n_total * L.cin)).reshape(
                     L.num_taps, L.n_total, L.cin)
-                if split:   # the lo halves follow the operands in the same section
+                if op.split:   # the lo halves follow the operands in the same section
                     W_lo = half_to_f32(u16(L.w16_off + 2 * L.num_taps * L.n_total * L.cin,
                                            L.num_taps * L.n_total * L.cin)).reshape(L.num_taps, L.n_total, L.cin)
             else:      # FFMA engine: fp32 [taps][cin][n_total]
@@ -153,11 +155,12 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
                     if hi > lo:
                         sh[:, lo:hi] = A[:, lo + off: hi + off]
                     acc[:, :, cols] += sh @ W[j][cols].T
-                    if split:   # + A_lo W_hi + A_hi W_lo
+                    if split:   # + A_lo W_hi
                         sl = np.zeros_like(A_lo)
                         if hi > lo:
                             sl[:, lo:hi] = A_lo[:, lo + off: hi + off]
                         acc[:, :, cols] += sl @ W[j][cols].T
+                    if op.split:   # + A_hi W_lo (op.split == 2: the weights are the only split operand)
                         acc[:, :, cols] += sh @ W_lo[j][cols].T
             bias = f32(L.bias_off, L.cout)
             n_idx = np.arange(L.n_total) % L.cout

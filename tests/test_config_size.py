@@ -82,3 +82,11 @@ def test_16bit_plan_at_config_size(name):
     r = _run(name, "fp16" if "rb1" in name else "bf16")
     assert r["snr_db"] >= MIN_SNR_DB
     assert r["sumsq_rel"] <= 2e-2      # every utterance's energy, not only the sampled ones
+
+
+@pytest.mark.gpu
+def test_resblock1_bf16_plan_at_config_size():
+    """ResBlock1 with bf16 operands and hi + lo weights (v2w_op_desc::split == 2): the bf16 bar north_star names."""
+    r = _run("cfg2_rb1_stress", "bf16")
+    assert r["snr_db"] >= MIN_SNR_DB
+    assert r["sumsq_rel"] <= 5e-2      # (46 dB: the energy of an utterance moves by up to 2.5 %)

@@ -147,6 +147,34 @@ def test_bf16_plan_snr(name):
     assert snr >= BF16_MIN_SNR_DB
 
 
+@pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress"])
+def test_resblock1_bf16_plan_snr(name):
+    """ResBlock1 with bf16 operands: the weights enter as hi + lo (two MMAs per product, one tap-GEMM per
+    convolution) -- rounding them once costs the 97-conv chain the bar (40.8 dB on rb1_768_stress)."""
+    g = load_golden(name)
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "bf16")
+    eng = gen.engine()
+    ops = eng.ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    gemms = [o for o in ops if o.kind == native.OP_TAPGEMM]
+    assert len(gemms) == 96 and all(o.split == 2 and o.engine == native.ENGINE_TC for o in gemms)
+    assert (torch.device("cuda:0"), native.HALF_BF16_SPLIT) in eng._packed
+    snr = fixtures.snr_db(g.y, y)
+    print(f"{name}: ResBlock1 bf16 (hi + lo weights) SNR {snr:.1f} dB")
+    assert snr >= BF16_MIN_SNR_DB
+
+
+def test_resblock1_bf16_fused_pairs_remain_available(monkeypatch):
+    """$V2W_RB1_BF16_FUSED=1: single-rounded bf16 weights in the fused conv pairs (round 1's plan: faster, ~41 dB)."""
+    monkeypatch.setenv("V2W_RB1_BF16_FUSED", "1")
+    g = load_golden("rb1_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0")
+    y = _native(gen, g, "bf16")
+    ops = gen.engine().ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
+    assert sum(o.kind == native.OP_PAIR_FUSED for o in ops) == 36 and not any(o.split for o in ops)
+    assert 38.0 <= fixtures.snr_db(g.y, y) < BF16_MIN_SNR_DB
+
+
 @pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress", "rb2_768_stress"])
 def test_fp16_plan_snr(name):
     """fp16 operands: the 16-bit tensor-core path that ResBlock1 needs (and the 'auto' default
@@ -186,7 +214,7 @@ def test_bf16_plan_matches_cpu_emulation(name, min_snr):
     gen = dropin_in_state(g, cache=False)
     eng = gen.engine()
     plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "bf16")
-    emu = plan_interp.run(plan, eng.pack_host().numpy(), g.x, g.spk, g.noise)
+    emu = plan_interp.run(plan, eng.pack_host(plan.packed_format).numpy(), g.x, g.spk, g.noise)
     gen = gen.to("cuda:0")
     y = _native(gen, g, "bf16")
     snr = fixtures.snr_db(emu, y)
@@ -580,12 +608,13 @@ def test_plan_cache_is_bounded_and_stream_keyed():
 # device-side weight fold (v2w_packer_*): bit-identical to the host packer, plans survive a re-fold
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["rb2_768_stress", "rb1_768_stress", "rb2_1024_stress"])
-@pytest.mark.parametrize("fmt", ["bf16", "fp16", "fp16split"])
+@pytest.mark.parametrize("fmt", ["bf16", "fp16", "fp16split", "bf16split"])
 def test_device_fold_matches_host_packer(name, fmt):
     g = load_golden(name)
     gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
     eng = gen.engine()
-    half = {"bf16": native.HALF_BF16, "fp16": native.HALF_FP16, "fp16split": native.HALF_FP16_SPLIT}[fmt]
+    half = {"bf16": native.HALF_BF16, "fp16": native.HALF_FP16, "fp16split": native.HALF_FP16_SPLIT,
+            "bf16split": native.HALF_BF16_SPLIT}[fmt]
     eng._tensors = eng._state_tensors()
     assert eng._device_foldable(torch.device("cuda:0"))
     dev_buf = eng.pack_device(torch.device("cuda:0"), half)

@@ -234,6 +234,32 @@ def test_fp32tc_plan_predicted_error(name):
     assert not plain[L.w16_off + 2 * n: L.w16_off + 4 * n].any()
 
 
+@pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress"])
+def test_resblock1_bf16_plan_predicted_snr(name, monkeypatch):
+    """ResBlock1 with bf16 operands: rounding the WEIGHTS once costs its 97-conv chain the 45 dB bar; as hi + lo
+    (two MMAs per product, activations still single bf16 values) the plan clears it."""
+    g = load_golden(name)
+    gen = dropin_in_state(g)
+    eng = gen.engine()
+    plan = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "bf16")
+    assert plan.packed_format == native.HALF_BF16_SPLIT
+    gemms = [op for op in plan.ops if op.kind == native.OP_TAPGEMM]
+    assert len(gemms) == 96 and all(op.split == 2 for op in gemms)
+    assert not any(op.kind == native.OP_PAIR_FUSED for op in plan.ops)
+    y = plan_interp.run(plan, eng.pack_host(native.HALF_BF16_SPLIT).numpy(), g.x, g.spk, g.noise)
+    snr = fixtures.snr_db(g.y, y)
+    monkeypatch.setenv("V2W_RB1_BF16_FUSED", "1")
+    old = plan_interp.HostPlan(eng, g.x.shape[0], g.x.shape[2], "bf16")
+    assert old.packed_format == native.HALF_BF16 and sum(op.kind == native.OP_PAIR_FUSED for op in old.ops) == 36
+    snr_old = fixtures.snr_db(g.y, plan_interp.run(old, eng.pack_host().numpy(), g.x, g.spk, g.noise))
+    print(f"{name}: predicted bf16 SNR {snr:.1f} dB with hi + lo weights, {snr_old:.1f} dB single-rounded")
+    assert snr >= 45.0 and snr > snr_old
+    # ResBlock2 plans are untouched
+    g2 = load_golden("rb2_768_stress_tiny")
+    p2 = plan_interp.HostPlan(dropin_in_state(g2).engine(), 1, 8, "bf16")
+    assert p2.packed_format == native.HALF_BF16 and not any(op.split for op in p2.ops)
+
+
 @pytest.mark.parametrize("name,min_snr", [("rb1_768_stress", 55.0), ("rb1_1024_stress", 55.0),
                                           ("rb2_768_stress", 60.0)])
 def test_fp16_plan_predicted_snr(name, min_snr):

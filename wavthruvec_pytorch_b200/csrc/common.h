@@ -52,6 +52,13 @@ static inline uint16_t fp16_bits(float f) {
   return (uint16_t)(sign | h);
 }
 
+static inline float bf16_value(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  __builtin_memcpy(&f, &u, 4);
+  return f;
+}
+
 // IEEE fp16 bit pattern -> fp32 (exact)
 static inline float fp16_value(uint16_t h) {
   const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;

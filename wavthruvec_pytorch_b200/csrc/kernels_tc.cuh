@@ -136,6 +136,7 @@ struct Params {
   // `sec_chunks` K-chunks.  The operand tensor is [rows, hi(cin) | lo(cin)] (lo at column a_lo_col), the weight
   // array [taps][n][cin] of hi values followed w_lo_row rows later by the same array of lo values.  The 16-bit
   // output is written in the same form: hi at its column, lo h_lo_col columns further (a second staging box).
+  // split == 2: the weights only -- A (W_hi + W_lo), two sections, plain 16-bit activations in and out.
   int split, sec_chunks, a_lo_col, w_lo_row, h_lo_col;
   const float* bias;
   const float* scale;
@@ -570,12 +571,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int li = p.kgroups ? c / p.cpg : nt;          // tap list of this K-chunk
         int wc = p.kgroups ? (c - li * p.cpg) * KC : c * KC;   // column in the weight array
         int ac = c * KC, wlo = 0;                           // column in the operand tensor, extra weight rows
-        if constexpr (kSplit) {
-          // section 0: A_hi W_hi, 1: A_lo W_hi, 2: A_hi W_lo
+        if (p.split) {
+          // split == 1, sections 0: A_hi W_hi, 1: A_lo W_hi, 2: A_hi W_lo; split == 2 (weights only), 0: A W_hi, 1: A W_lo
           const int sec = c / p.sec_chunks;
           wc = ac = (c - sec * p.sec_chunks) * KC;
-          if (sec == 1) ac += p.a_lo_col;
-          if (sec == 2) wlo = p.w_lo_row;
+          if (p.split == 1) {
+            if (sec == 1) ac += p.a_lo_col;
+            if (sec == 2) wlo = p.w_lo_row;
+          } else if (sec == 1) {
+            wlo = p.w_lo_row;
+          }
         }
         const int ntaps = p.num_taps[li];
         mbar_wait(empty_a + 8 * ra.s, ra.ph ^ 1u);

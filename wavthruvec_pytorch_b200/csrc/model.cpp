@@ -770,12 +770,15 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
     set_error("v2w_model_pack: null argument");
     return V2W_ERR_INVALID;
   }
-  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16 && half_format != V2W_HALF_FP16_SPLIT) {
+  if (half_format < V2W_HALF_BF16 || half_format > V2W_HALF_BF16_SPLIT) {
     set_error("v2w_model_pack: unknown 16-bit format %d", half_format);
     return V2W_ERR_INVALID;
   }
-  const bool f16 = half_format != V2W_HALF_BF16;
-  const bool split = half_format == V2W_HALF_FP16_SPLIT;
+  const bool f16 = half_format == V2W_HALF_FP16 || half_format == V2W_HALF_FP16_SPLIT;
+  const bool split = half_format == V2W_HALF_FP16_SPLIT || half_format == V2W_HALF_BF16_SPLIT;
+  auto half_lo_bits = [f16](float w) {     // the part of w its 16-bit value does not hold, in the same format
+    return f16 ? fp16_bits(w - fp16_value(fp16_bits(w))) : bf16_bits(w - bf16_value(bf16_bits(w)));
+  };
   auto half_bits = [f16](float w) { return f16 ? fp16_bits(w) : bf16_bits(w); };
   if (P->num_convs != m->num_convs || P->num_stages != (int)m->cond.size()) {
     set_error("v2w_model_pack: expected %d convs / %d stages, got %d / %d", m->num_convs,
@@ -848,7 +851,7 @@ int32_t v2w_model_pack_half(const v2w_model* m, const v2w_params* P, void* packe
           if (transposed) w = cp.v[((size_t)ci * L.cout + co) * K + kk] * scale[ci];
           else w = cp.v[((size_t)co * L.cin + ci) * K + kk] * scale[co];
           if (w16) w16[((size_t)j * L.n_total + n) * L.cin + ci] = half_bits(w);
-          if (w16lo) w16lo[((size_t)j * L.n_total + n) * L.cin + ci] = fp16_bits(w - fp16_value(fp16_bits(w)));
+          if (w16lo) w16lo[((size_t)j * L.n_total + n) * L.cin + ci] = half_lo_bits(w);
           w32[((size_t)j * L.cin + ci) * L.n_total + n] = w;
         }
       }

@@ -108,7 +108,7 @@ fold_scale_kernel(const DevLayer* __restrict__ layers, const ScaleTask* __restri
 __global__ void __launch_bounds__(256)
 fold_weight_kernel(const DevLayer* __restrict__ layers, const WeightTask* __restrict__ tasks,
                    const __grid_constant__ ConvPtrs P, const float* __restrict__ scale,
-                   unsigned char* __restrict__ base, int f16) {
+                   unsigned char* __restrict__ base, int f16, int split) {
   __shared__ float tile[kChunk];
   const WeightTask t = tasks[blockIdx.x];
   const DevLayer& L = layers[t.layer];
@@ -142,9 +142,10 @@ fold_weight_kernel(const DevLayer* __restrict__ layers, const WeightTask* __rest
         const unsigned short hb = half_bits_dev(w, f16);
         w16[((size_t)j * L.n_total + n) * cin + ci] = hb;
         // V2W_HALF_FP16_SPLIT: the part of the weight its fp16 value does not hold, in the section's second half
-        if (f16 == V2W_HALF_FP16_SPLIT)
-          w16[((size_t)(L.num_taps + j) * L.n_total + n) * cin + ci] =
-              half_bits_dev(w - __half2float(__ushort_as_half(hb)), 1);
+        if (split) {
+          const float held = f16 ? __half2float(__ushort_as_half(hb)) : __bfloat162float(__ushort_as_bfloat16(hb));
+          w16[((size_t)(L.num_taps + j) * L.n_total + n) * cin + ci] = half_bits_dev(w - held, f16);
+        }
       }
     }
     tile[e] = w;
@@ -457,7 +458,7 @@ int32_t v2w_packer_run(v2w_packer* pk, const v2w_params* P, void* packed_dev, in
     return V2W_ERR_INVALID;
   }
   const v2w_model* m = pk->model;
-  if (half_format != V2W_HALF_BF16 && half_format != V2W_HALF_FP16 && half_format != V2W_HALF_FP16_SPLIT) {
+  if (half_format < V2W_HALF_BF16 || half_format > V2W_HALF_BF16_SPLIT) {
     set_error("v2w_packer_run: unknown 16-bit format %d", half_format);
     return V2W_ERR_INVALID;
   }
@@ -480,14 +481,15 @@ int32_t v2w_packer_run(v2w_packer* pk, const v2w_params* P, void* packed_dev, in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* base = static_cast<unsigned char*>(packed_dev);
-  const int f16 = half_format;   // 0 = bf16, 1 = fp16, 2 = fp16 + lo halves
+  const int f16 = half_format == V2W_HALF_FP16 || half_format == V2W_HALF_FP16_SPLIT;
+  const int split = half_format == V2W_HALF_FP16_SPLIT || half_format == V2W_HALF_BF16_SPLIT;   // + the lo halves
   // zero fill (dead polyphase blocks, padding) + header, like the host packer
   V2W_CUDA_P(cudaMemsetAsync(base, 0, (size_t)m->packed_bytes, st));
   const uint32_t hdr[3] = {kPackedMagic, V2W_ABI_VERSION, (uint32_t)half_format};
   V2W_CUDA_P(cudaMemcpyAsync(base, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
   fold_scale_kernel<<<pk->n_scale_tasks, 256, 0, st>>>(pk->d_layers, pk->d_scale_tasks, cv, pk->d_scale);
   V2W_CUDA_P(cudaGetLastError());
-  fold_weight_kernel<<<pk->n_weight_tasks, 256, 0, st>>>(pk->d_layers, pk->d_weight_tasks, cv, pk->d_scale, base, f16);
+  fold_weight_kernel<<<pk->n_weight_tasks, 256, 0, st>>>(pk->d_layers, pk->d_weight_tasks, cv, pk->d_scale, base, f16, split);
   V2W_CUDA_P(cudaGetLastError());
   fold_cond_kernel<<<P->num_stages, 256, 0, st>>>(cp, base, kBnEps);
   V2W_CUDA_P(cudaGetLastError());

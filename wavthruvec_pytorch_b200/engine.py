@@ -243,7 +243,7 @@ class NativeEngine:
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
                 for key, (plan, _ws) in self._plans.items():
-                    if key[3] == dev and native.HALF_OF_PRECISION[key[2]] == fmt:
+                    if key[3] == dev and int(self._lib.v2w_plan_packed_format(plan)) == fmt:
                         native.check(self._lib.v2w_plan_refresh_weights(plan, C.c_void_p(stream)))
         return True
 
@@ -304,10 +304,10 @@ class NativeEngine:
             self._plans.move_to_end(key)
             return hit
         prec = native.PRECISIONS[precision]
-        packed = self._packed_on(device, native.HALF_OF_PRECISION[precision])
         handle = C.c_void_p()
         native.check(self._lib.v2w_plan_create(self._model, batch, frames, prec, C.byref(handle)))
         try:
+            packed = self._packed_on(device, int(self._lib.v2w_plan_packed_format(handle)))
             ws_bytes = int(self._lib.v2w_plan_workspace_bytes(handle))
             self._evict(ws_bytes)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)

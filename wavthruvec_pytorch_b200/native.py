@@ -21,12 +21,13 @@ PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_FP16 = 2
 PREC_FP32_TC = 3
-HALF_BF16, HALF_FP16, HALF_FP16_SPLIT = 0, 1, 2
+HALF_BF16, HALF_FP16, HALF_FP16_SPLIT, HALF_BF16_SPLIT = 0, 1, 2, 3
 PACKED_HEADER_BYTES = 1024
 TC_FLAG_FP16 = 0x100
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp32tc": PREC_FP32_TC}
 # 16-bit operand format of the packed weight buffer a plan of each precision binds (the FFMA plan reads the
-# fp32 arrays, which every buffer holds)
+# fp32 arrays, which every buffer holds).  A BF16 plan of a ResBlock1 generator binds HALF_BF16_SPLIT: ask the
+# plan (v2w_plan_packed_format) rather than this table.
 HALF_OF_PRECISION = {"fp32": HALF_BF16, "bf16": HALF_BF16, "fp16": HALF_FP16, "fp32tc": HALF_FP16_SPLIT}
 ENGINE_SIMT = 0
 ENGINE_TC = 1
@@ -214,6 +215,7 @@ _SIGNATURES = [
      [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     ("v2w_plan_destroy", None, [C.c_void_p]),
     ("v2w_plan_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("v2w_plan_packed_format", C.c_int32, [C.c_void_p]),
     ("v2w_plan_num_ops", C.c_int32, [C.c_void_p]),
     ("v2w_plan_get_op", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(OpDesc)]),
     ("v2w_plan_set_engine", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
