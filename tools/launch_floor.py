@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 from wavthruvec_pytorch_b200 import native  # noqa: E402
 
 
-def case(B, rows, cin, n_total, n_tile, k, d, resid=False, f32=True, b16=True, reps=12):
+def case(B, rows, cin, n_total, n_tile, k, d, resid=False, f32=True, b16=True, reps=12, affine=False):
     lib = native.load()
     dev = torch.device("cuda:0")
     A = torch.randn(B, rows, cin, device=dev).to(torch.bfloat16)
@@ -36,6 +36,10 @@ def case(B, rows, cin, n_total, n_tile, k, d, resid=False, f32=True, b16=True, r
     a.in_act, a.in_is_bf16, a.in_slope = A.data_ptr(), 1, 1.0
     a.w16 = W.data_ptr()
     a.bias = bias.data_ptr()
+    if affine:   # per-(utterance, channel) scale / shift: the conditional batch norm of a transposed conv's epilogue
+        scale = torch.randn(B, n_total, device=dev)
+        shift = torch.randn(B, n_total, device=dev)
+        a.scale, a.shift = scale.data_ptr(), shift.data_ptr()
     a.residual = res.data_ptr() if resid else None
     a.out_scale, a.out_slope = 1.0, 0.1
     a.out_f32 = o32.data_ptr() if f32 else None

@@ -19,4 +19,8 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 11
 rows = int(sys.argv[3]) if len(sys.argv) > 3 else 64000
 batch = int(sys.argv[4]) if len(sys.argv) > 4 else 16
-print(launch_floor.case(batch, rows, C, C, C, k, 1, resid=True, f32=True, b16=True, reps=3))
+if len(sys.argv) > 5 and sys.argv[5] == "ups":
+    # the epilogue of a transposed conv: affine, fp32 + 16-bit output, no residual; two column tiles (phases)
+    print(launch_floor.case(batch, rows, C, 2 * C, C, k, 1, resid=False, f32=True, b16=True, reps=3, affine=True))
+else:
+    print(launch_floor.case(batch, rows, C, C, C, k, 1, resid=True, f32=True, b16=True, reps=3))

@@ -37,6 +37,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "v2w.h"
 
 // Developer timeline of the generic kernel (build with V2W_NVCC_EXTRA=-DV2W_TRACE_TC): CTA 0 prints SM-clock
@@ -138,6 +140,7 @@ struct Params {
   // output is written in the same form: hi at its column, lo h_lo_col columns further (a second staging box).
   // split == 2: the weights only -- A (W_hi + W_lo), two sections, plain 16-bit activations in and out.
   int split, sec_chunks, a_lo_col, w_lo_row, h_lo_col;
+  int epi_mode;         // compiled copy of the epilogue's chunk loop (0 = all tests at run time), see the kernel
   const float* bias;
   const float* scale;
   const float* shift;
@@ -761,17 +764,29 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // `if (lane == 0)` (ptxas wraps it in a BRA.U.ANY waterfall loop) and ~300 clk of loop overhead -- which
         // made every k = 3 convolution and every transposed conv epilogue-bound.  So: loop invariants hoisted,
         // the format branch taken once per chunk, no runtime division, stores issued by an ELECTED lane.
-        const bool has_res = valid && p.residual != nullptr;
-        const bool has_acc = valid && p.accum_in != nullptr;
         const int col0 = nt * p.n_tile;
         const size_t res_off = res_base + (p.res_cols ? col0 % p.res_cols : col0);   // once per sub-tile
         const size_t acc_off = row_base + col0;
         const uint32_t y_mask = y_sub - 1, h_mask = h_sub - 1;    // boxes are 1, 2 or 4 chunks wide
         const float out_scale = p.out_scale, out_slope = p.out_slope, res_scale = p.res_scale;
-        const bool do_scale = out_scale != 1.0f, fp16 = p.fp16 != 0;
-        const bool has_bias = p.bias != nullptr, has_affine = p.scale != nullptr;
-        const bool st_y = p.out_f32 != nullptr, st_h = p.out_bf16 != nullptr, tma_out = p.tma_out != 0;
+        const bool fp16 = p.fp16 != 0;
         constexpr bool split = kSplit;       // (a template parameter: the plain kernels' chunk loop carries none of it)
+        // The loop body tests eight op properties (bias, affine, residual, running sum, scale, which outputs, how
+        // they leave).  As run-time flags each test is a constant-bank load -> uniform compare -> uniform branch
+        // chain per CHUNK (the SASS of round 2's loop: 26 LDCU, 19 UISETP, 20 BRA for ~100 ALU instructions), and
+        // these chains, not the arithmetic, were most of the ~870-1700 clk per chunk.  The combinations the plans
+        // actually emit are compiled as their own copies of the loop (Params::epi_mode, chosen on the host);
+        // mode 0 keeps every test at run time.
+        auto chunk_loop = [&](auto mode_c) {
+        constexpr int M = decltype(mode_c)::value;
+        const bool has_res = valid && (M == 0 ? p.residual != nullptr : M >= 3);
+        const bool has_acc = valid && (M == 0 ? p.accum_in != nullptr : false);
+        const bool do_scale = M == 0 ? out_scale != 1.0f : M == 4;
+        const bool has_bias = M == 0 ? p.bias != nullptr : true;
+        const bool has_affine = M == 0 ? p.scale != nullptr : M == 2;
+        const bool st_y = M == 0 ? p.out_f32 != nullptr : (M == 2 || M == 5);
+        const bool st_h = M == 0 ? p.out_bf16 != nullptr : true;
+        const bool tma_out = M == 0 ? p.tma_out != 0 : true;
         for (int cc = 0; cc < p.n_tile; cc += 16) {
           const int col = col0 + cc;
           // issue the global reads first so that they overlap the TMEM load
@@ -802,6 +817,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
               }
             }
+            V2W_TRTC(it, 2100 + cc);
             if (has_affine) {
 #pragma unroll
               for (int e = 0; e < 16; e += 4) {
@@ -813,6 +829,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
               }
             }
+            V2W_TRTC(it, 2200 + cc);
             if (has_res) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -831,11 +848,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] *= out_scale;
             }
+            V2W_TRTC(it, 2300 + cc);
             uint32_t h[8], hl[8];
             if (st_h) {
               if (split) lrelu_split16(v, out_slope, h, hl);
               else lrelu_pack16(v, out_slope, fp16, h);       // one format branch per chunk, not one per packed pair
             }
+            V2W_TRTC(it, 2400 + cc);
             if (tma_out) {
               // own row -> staging box in the TMA swizzle layout (conflict-free 16-byte stores)
               if (st_y && p.y_blocked) {
@@ -941,6 +960,15 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (h_done) sh ^= 1u;
             }
           }
+        }
+        };
+        switch (p.epi_mode) {
+          case 1: chunk_loop(std::integral_constant<int, 1>{}); break;    // bias; 16-bit out
+          case 2: chunk_loop(std::integral_constant<int, 2>{}); break;    // bias, affine; fp32 + 16-bit out (transposed convs)
+          case 3: chunk_loop(std::integral_constant<int, 3>{}); break;    // bias, residual; 16-bit out
+          case 4: chunk_loop(std::integral_constant<int, 4>{}); break;    // bias, residual, scale; 16-bit out
+          case 5: chunk_loop(std::integral_constant<int, 5>{}); break;    // bias, residual; fp32 + 16-bit out
+          default: chunk_loop(std::integral_constant<int, 0>{}); break;
         }
       }
       tcgen05_fence_before();

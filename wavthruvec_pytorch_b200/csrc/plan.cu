@@ -436,14 +436,16 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       set_error("tapgemm(TC): tile does not fit shared memory (A %d B, W %d B)", p.stage_a_bytes, p.stage_w_bytes);
       return V2W_ERR_INVALID;
     }
-    // Duration of a tile, in clocks (fitted to the timelines of tools/trace_tc.py / trace_small.py): the MMA side
-    // pays ~450 clk of barrier round trip per W stage plus, per tap and sub-tile, kc / 16 instructions of
-    // ~(64 + N / 2) clk (N / 4 for a pair); the epilogue side ~1400 clk per 16-column chunk and sub-tile, two warp
-    // groups alternating tiles.  Without the fixed part the narrow layers chose msub = 1 and ran at the barrier rate.
+    // Duration of a tile, in clocks, fitted to timelines and to launches of one shape at every height
+    // (tools/trace_tc.py, trace_small.py; profiles/r02_notes.md section 8).  MMA side: ~1000 clk per tile (accumulator
+    // and operand waits, commits) + ~450 clk of barrier round trip per W stage + per tap and sub-tile kc / 16
+    // instructions of ~(64 + N / 2) clk (N / 4 for a pair).  Epilogue side: ~2000 clk per tile (column vectors from
+    // global memory, accumulator wait, hand-back) + ~1400 clk per 16-column chunk and sub-tile; two warp groups
+    // alternate tiles.  Without the fixed parts the narrow layers chose msub = 1 and ran at the barrier rate.
     const int64_t mma_clk = (int64_t)(kc / 16) * (64 + (L->pair ? a.n_tile / 4 : a.n_tile / 2));
     const int64_t w_stages = (int64_t)p.num_chunks * ((max_taps + p.tap_group - 1) / p.tap_group);
-    const int64_t mma_tile = w_stages * 450 + (int64_t)p.num_chunks * max_taps * ms * mma_clk;
-    const int64_t epi_tile = (int64_t)ms * ((a.n_tile / 16) * 1400 + 400) / 2;
+    const int64_t mma_tile = 1000 + w_stages * 450 + (int64_t)p.num_chunks * max_taps * ms * mma_clk;
+    const int64_t epi_tile = (2000 + (int64_t)ms * ((a.n_tile / 16) * 1400 + 100)) / 2;
     const int64_t cost = ((tiles + slots - 1) / slots) * (no_step_cost ? ms : std::max(mma_tile, epi_tile));
     if (!best || cost < best_cost) {
       best = ms;
@@ -461,6 +463,17 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   p.out_scale = a.out_scale; p.out_f32 = a.out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_slope = a.out_slope;
+  // compiled copies of the epilogue's chunk loop (tc::Params::epi_mode); $V2W_TC_EPI_GENERIC=1: run-time tests only
+  static const bool epi_generic = [] { const char* e = std::getenv("V2W_TC_EPI_GENERIC"); return e && std::atoi(e); }();
+  p.epi_mode = 0;
+  if (!epi_generic && p.tma_out && a.bias && !a.accum_in && a.out_bf16) {
+    const bool scaled = a.out_scale != 1.0f;
+    if (!a.scale && !a.residual && !scaled && !a.out_f32) p.epi_mode = 1;
+    else if (a.scale && !a.residual && !scaled && a.out_f32) p.epi_mode = 2;
+    else if (!a.scale && a.residual && !scaled && !a.out_f32) p.epi_mode = 3;
+    else if (!a.scale && a.residual && scaled && !a.out_f32) p.epi_mode = 4;
+    else if (!a.scale && a.residual && !scaled && a.out_f32) p.epi_mode = 5;
+  }
   L->kc = kc;
   L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + tail_bytes + 1024;
   const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
