@@ -141,6 +141,7 @@ struct Params {
   // split == 2: the weights only -- A (W_hi + W_lo), two sections, plain 16-bit activations in and out.
   int split, sec_chunks, a_lo_col, w_lo_row, h_lo_col;
   int epi_mode;         // compiled copy of the epilogue's chunk loop (0 = all tests at run time), see the kernel
+  int epi_wide;         // epi_mode != 0 and y_cols == h_cols == 32: the 32-columns-per-step copy of that loop
   const float* bias;
   const float* scale;
   const float* shift;
@@ -962,6 +963,126 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         };
+        // The same loop, 32 columns per step, for the compiled flavours when both staging boxes are 32 columns wide
+        // (Params::epi_wide): two independent 16-column computations per step for the scheduler to interleave (a lone
+        // warp issues ~0.25 instructions per clock in the 16-column loop: dependent fixed-latency chains), and the box
+        // bookkeeping, fence, store issue and wait once per 32 columns without any "is the box complete" test.
+        auto chunk_loop_wide = [&](auto mode_c) {
+        constexpr int M = decltype(mode_c)::value;
+        static_assert(M >= 1 && M <= 5, "compiled flavours only");
+        constexpr bool kRes = M >= 3;
+        const bool has_res = valid && kRes;
+        constexpr bool do_scale = M == 4, has_affine = M == 2, st_y = (M == 2 || M == 5);
+        for (int cc = 0; cc < p.n_tile; cc += 32) {
+          const int col = col0 + cc;
+          float4 res[8];
+          if (has_res) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + res_off + cc);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) res[e] = rp[e];
+          }
+          uint32_t r0[16], r1[16];
+          tmem_ld16(t_lane + m * p.acc_cols + cc, r0);
+          tmem_ld16(t_lane + m * p.acc_cols + cc + 16, r1);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(u == 0 ? r0[e] : r1[e]);
+              const int cu = cc + 16 * u;
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 t = ld_shared_f4(cvec + (cu + e) * 4);
+                v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+              }
+              if constexpr (has_affine) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                  const float4 s4 = ld_shared_f4(cvec + (p.n_tile + cu + e) * 4);
+                  const float4 h4 = ld_shared_f4(cvec + (2 * p.n_tile + cu + e) * 4);
+                  v[e] = fmaf(v[e], s4.x, h4.x);
+                  v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                  v[e + 2] = fmaf(v[e + 2], s4.z, h4.z);
+                  v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+                }
+              }
+              if constexpr (kRes) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 q = res[4 * u + e];
+                  v[4 * e] = fmaf(res_scale, q.x, v[4 * e]); v[4 * e + 1] = fmaf(res_scale, q.y, v[4 * e + 1]);
+                  v[4 * e + 2] = fmaf(res_scale, q.z, v[4 * e + 2]); v[4 * e + 3] = fmaf(res_scale, q.w, v[4 * e + 3]);
+                }
+              }
+              if constexpr (do_scale) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] *= out_scale;
+              }
+              uint32_t h[8];
+              lrelu_pack16(v, out_slope, fp16, h);
+              if constexpr (st_y) {
+                if (p.y_blocked) {
+                  const uint32_t rl = 5u - p.y_up_log2;
+                  const uint32_t base = ybuf + sy * y_box + (((lane >> rl) * 8u) << (rl + 4)) + ((lane & ((1u << rl) - 1u)) << 4);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    st_shared_v4u(base + ((4u * u + e) << (rl + 4)), __float_as_uint(v[4 * e]),
+                                  __float_as_uint(v[4 * e + 1]), __float_as_uint(v[4 * e + 2]),
+                                  __float_as_uint(v[4 * e + 3]));
+                } else {
+                  const uint32_t yb = ybuf + sy * y_box + lane * 128u;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    st_shared_v4u(yb + (((4u * u + e) ^ (lane & 7u)) << 4), __float_as_uint(v[4 * e]),
+                                  __float_as_uint(v[4 * e + 1]), __float_as_uint(v[4 * e + 2]),
+                                  __float_as_uint(v[4 * e + 3]));
+                }
+              }
+              const uint32_t hb = hbuf + sh * h_box + lane * 64u;
+              const uint32_t hs = (lane >> 1) & 3u;
+              st_shared_v4u(hb + (((2u * u) ^ hs) << 4), h[0], h[1], h[2], h[3]);
+              st_shared_v4u(hb + (((2u * u + 1u) ^ hs) << 4), h[4], h[5], h[6], h[7]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (row0w < p.rows) {          // warp-uniform
+            if (elect_one()) {
+              if constexpr (st_y) {
+                if (p.y_blocked) {
+                  const int ph = col >> p.y_cout_log2, c = col - (ph << p.y_cout_log2);
+                  const int nblk = (((p.rows << p.y_up_log2) + 31) >> 5) + kBlockedPad;
+                  tma_store_5d(&tmY, ybuf + sy * y_box, 0, ph, 0, c >> 2, b * nblk + (row0w >> (5 - p.y_up_log2)));
+                } else {
+                  tma_store_3d(&tmY, ybuf + sy * y_box, col, row0w, b);
+                }
+              }
+              if (p.h_cout) {
+                const int ph = col / p.h_cout;
+                tma_store_4d(&tmH, hbuf + sh * h_box, col - ph * p.h_cout, ph, row0w, b);
+              } else {
+                tma_store_3d(&tmH, hbuf + sh * h_box, col, row0w, b);
+              }
+              tma_store_commit();
+              tma_store_wait_read<1>();
+            }
+          }
+          __syncwarp();
+          if constexpr (st_y) sy ^= 1u;
+          sh ^= 1u;
+        }
+        };
+        if constexpr (!kSplit) {
+          if (p.epi_wide) {
+            // (flavours with a residual stay on the 16-column loop: 32 residual registers on top of two chunks
+            // in flight spill at this kernel's 168-register cap)
+            if (p.epi_mode == 1) chunk_loop_wide(std::integral_constant<int, 1>{});
+            else chunk_loop_wide(std::integral_constant<int, 2>{});
+            continue;
+          }
+        }
         switch (p.epi_mode) {
           case 1: chunk_loop(std::integral_constant<int, 1>{}); break;    // bias; 16-bit out
           case 2: chunk_loop(std::integral_constant<int, 2>{}); break;    // bias, affine; fp32 + 16-bit out (transposed convs)

@@ -379,6 +379,17 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   // columns) and shared memory allow, while keeping >= 2 work items per SM.
   p.tma_out = std::getenv("V2W_TC_NO_TMA_OUT") ? 0 : 1;
   p.cvec_warp_bytes = 3 * a.n_tile * 4;
+  // compiled copies of the epilogue's chunk loop (tc::Params::epi_mode); $V2W_TC_EPI_GENERIC=1: run-time tests only
+  static const bool epi_generic = [] { const char* e = std::getenv("V2W_TC_EPI_GENERIC"); return e && std::atoi(e); }();
+  p.epi_mode = 0;
+  if (!epi_generic && p.tma_out && a.bias && !a.accum_in && a.out_bf16) {
+    const bool scaled = a.out_scale != 1.0f;
+    if (!a.scale && !a.residual && !scaled && !a.out_f32) p.epi_mode = 1;
+    else if (a.scale && !a.residual && !scaled && a.out_f32) p.epi_mode = 2;
+    else if (!a.scale && a.residual && !scaled && !a.out_f32) p.epi_mode = 3;
+    else if (!a.scale && a.residual && scaled && !a.out_f32) p.epi_mode = 4;
+    else if (!a.scale && a.residual && !scaled && a.out_f32) p.epi_mode = 5;
+  }
   // TMA store boxes: as wide as the column tile allows, up to 128-byte rows (fp32: 32 columns; 16-bit: 64
   // columns when it is the only output, else 32 -- two outputs with 128-byte rows would take 128 KB of
   // staging): one fence / store issue / wait per box instead of per 16-column chunk.  Measured with the
@@ -401,6 +412,14 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   while (staging() > 12 * 1024 && (p.h_cols > 16 || p.y_cols > 16)) {
     if (a.out_bf16 && p.h_cols > 16) p.h_cols >>= 1;
     else p.y_cols >>= 1;
+  }
+  // 32 columns per epilogue step (tc::Params::epi_wide): both boxes exactly 32 columns.  $V2W_TC_EPI_NARROW=1: off.
+  static const bool epi_narrow = [] { const char* e = std::getenv("V2W_TC_EPI_NARROW"); return e && std::atoi(e); }();
+  p.epi_wide = 0;
+  if (!epi_narrow && (p.epi_mode == 1 || p.epi_mode == 2) && !split && a.n_tile % 32 == 0 && h_unit % 32 == 0 && !box16 &&
+      (!a.out_f32 || p.y_cols == 32)) {
+    p.h_cols = 32;
+    if (staging() <= 12 * 1024) p.epi_wide = 1;
   }
   p.stage_warp_bytes = staging();
   // barriers (+ output staging) + per-warp column vectors
@@ -463,17 +482,6 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   p.out_scale = a.out_scale; p.out_f32 = a.out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   p.out_slope = a.out_slope;
-  // compiled copies of the epilogue's chunk loop (tc::Params::epi_mode); $V2W_TC_EPI_GENERIC=1: run-time tests only
-  static const bool epi_generic = [] { const char* e = std::getenv("V2W_TC_EPI_GENERIC"); return e && std::atoi(e); }();
-  p.epi_mode = 0;
-  if (!epi_generic && p.tma_out && a.bias && !a.accum_in && a.out_bf16) {
-    const bool scaled = a.out_scale != 1.0f;
-    if (!a.scale && !a.residual && !scaled && !a.out_f32) p.epi_mode = 1;
-    else if (a.scale && !a.residual && !scaled && a.out_f32) p.epi_mode = 2;
-    else if (!a.scale && a.residual && !scaled && !a.out_f32) p.epi_mode = 3;
-    else if (!a.scale && a.residual && scaled && !a.out_f32) p.epi_mode = 4;
-    else if (!a.scale && a.residual && !scaled && a.out_f32) p.epi_mode = 5;
-  }
   L->kc = kc;
   L->smem = p.stages_a * p.stage_a_bytes + p.stages_w * p.stage_w_bytes + tail_bytes + 1024;
   const int64_t tiles = (int64_t)a.batch * p.s_tiles * a.n_tiles;
