@@ -685,18 +685,20 @@ def test_parameters_frozen_skips_change_detection():
         assert (gen(x, s, n) - a).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("mask,flags", [("0", [0, 0, 0, 0]), ("30", [1, 1, 1, 1]), ("12", [0, 1, 1, 0])])
+@pytest.mark.parametrize("mask,flags", [("0", [0, 0, 0, 0]), ("30", [1, 1, 1, 1]), ("12", [0, 1, 1, 0]), ("2", [1, 0, 0, 0])])
 def test_row_blocked_residual_layout_is_bit_identical(monkeypatch, mask, flags):
     """The row-blocked layout of a fused stage's fp32 residual stream (v2w_op_desc::f32_blocked) only changes WHERE
     the transposed conv stores it and the stage kernel reads it: bit-identical waveforms for no stage / every fused
-    stage / stages 2-3 against the default (stage 1 only), on a batch with ragged tile tails."""
+    stage / stages 2-3 / stage 1 against the default (stages 1 and 3), on a batch with ragged tile tails.  Stages 3-4
+    (and stage 2, whose transposed conv becomes one column tile) take the phase-interleaved store path of the generic
+    kernel (tc::Params::epi_phased), stage 1 the 5-D tensor map."""
     g = load_golden("rb2_768_stress")
     gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
     x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, 3, 77, 9))
     with torch.no_grad():
         want = gen(x, s, n).clone()
         ops = gen.engine().ops(3, 77, "bf16", "cuda:0")
-        assert [op.f32_blocked for op in ops if op.kind == native.OP_MRF_FUSED] == [1, 0, 0, 0]
+        assert [op.f32_blocked for op in ops if op.kind == native.OP_MRF_FUSED] == [1, 0, 1, 0]
         monkeypatch.setenv("V2W_BLOCKED_X0_MASK", mask)
         gen.invalidate()
         got = gen(x, s, n)

@@ -142,6 +142,7 @@ struct Params {
   int split, sec_chunks, a_lo_col, w_lo_row, h_lo_col;
   int epi_mode;         // compiled copy of the epilogue's chunk loop (0 = all tests at run time), see the kernel
   int epi_wide;         // epi_mode != 0 and y_cols == h_cols == 32: the 32-columns-per-step copy of that loop
+  int epi_phased;       // transposed conv, row-blocked fp32 output, one column tile: all phases of 16 channels per step
   const float* bias;
   const float* scale;
   const float* shift;
@@ -1074,6 +1075,69 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           sh ^= 1u;
         }
         };
+        // Transposed conv with a row-blocked fp32 output (Params::epi_phased): one step = ALL phases of 16 output
+        // channels, so that every (32-row block, column quad) run of the blocked tensor leaves complete -- 512
+        // contiguous bytes per run, `up` blocks x 4 quads per TMA store -- instead of the 16-byte fragments a
+        // phase-by-phase walk produces (measured 1.2-2.2x slower for the whole launch).  The 16-bit operand leaves
+        // as one (16 channels, up phases, 32 rows) box.  Needs the column tile to hold every phase (n_tile == n_total).
+        auto chunk_loop_phased = [&]() {
+          const uint32_t upl = p.y_up_log2, up = 1u << upl, rl = 5u - upl;
+          const int cout = 1 << p.y_cout_log2;
+          const uint32_t yb_bytes = up * 2048u, hb_bytes = up * 1024u, nbuf = up == 2u ? 2u : 1u;
+          const uint32_t ybase = ybuf, hbase = ybuf + nbuf * yb_bytes;
+          const uint32_t blk = lane >> rl, pos0 = (lane & ((1u << rl) - 1u)) << upl;
+          const int nblk = (((p.rows << upl) + 31) >> 5) + kBlockedPad;
+          for (int c0 = 0; c0 < cout; c0 += 16) {
+            for (uint32_t ph = 0; ph < up; ++ph) {
+              const int cc = static_cast<int>(ph) * cout + c0;     // accumulator column of this (phase, channel chunk)
+              uint32_t r[16];
+              tmem_ld16(t_lane + m * p.acc_cols + cc, r);
+              tmem_ld_wait();
+              if (valid) {
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                  const float4 t = ld_shared_f4(cvec + (cc + e) * 4);
+                  const float4 s4 = ld_shared_f4(cvec + (p.n_tile + cc + e) * 4);
+                  const float4 h4 = ld_shared_f4(cvec + (2 * p.n_tile + cc + e) * 4);
+                  v[e] = fmaf(__uint_as_float(r[e]) + t.x, s4.x, h4.x);
+                  v[e + 1] = fmaf(__uint_as_float(r[e + 1]) + t.y, s4.y, h4.y);
+                  v[e + 2] = fmaf(__uint_as_float(r[e + 2]) + t.z, s4.z, h4.z);
+                  v[e + 3] = fmaf(__uint_as_float(r[e + 3]) + t.w, s4.w, h4.w);
+                }
+                uint32_t h[8];
+                lrelu_pack16(v, out_slope, fp16, h);
+                const uint32_t ya = ybase + sy * yb_bytes + ((blk * 4u) << 9) + ((pos0 + ph) << 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  st_shared_v4u(ya + (static_cast<uint32_t>(e) << 9), __float_as_uint(v[4 * e]), __float_as_uint(v[4 * e + 1]),
+                                __float_as_uint(v[4 * e + 2]), __float_as_uint(v[4 * e + 3]));
+                const uint32_t ha = hbase + sh * hb_bytes + lane * (up * 32u) + ph * 32u;
+                st_shared_v4u(ha, h[0], h[1], h[2], h[3]);
+                st_shared_v4u(ha + 16u, h[4], h[5], h[6], h[7]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (row0w < p.rows) {          // warp-uniform
+              if (elect_one()) {
+                tma_store_3d(&tmY, ybase + sy * yb_bytes, 0, c0 >> 2, b * nblk + (row0w >> rl));
+                tma_store_4d(&tmH, hbase + sh * hb_bytes, c0, 0, row0w, b);
+                tma_store_commit();
+                if (nbuf == 2u) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
+              }
+            }
+            __syncwarp();
+            if (nbuf == 2u) { sy ^= 1u; sh ^= 1u; }
+          }
+        };
+        if constexpr (!kSplit) {
+          if (p.epi_phased) {
+            chunk_loop_phased();
+            continue;
+          }
+        }
         if constexpr (!kSplit) {
           if (p.epi_wide) {
             // (flavours with a residual stay on the 16-column loop: 32 residual registers on top of two chunks

@@ -422,6 +422,16 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
     if (staging() <= 12 * 1024) p.epi_wide = 1;
   }
   p.stage_warp_bytes = staging();
+  // Row-blocked fp32 output of a transposed conv whose one column tile holds every phase: the phase-interleaved
+  // walk (tc::Params::epi_phased).  Staging per warp: nbuf x up x (2 KB fp32 + 1 KB 16-bit).  $V2W_TC_NO_PHASED=1: off.
+  static const bool no_phased = [] { const char* e = std::getenv("V2W_TC_NO_PHASED"); return e && std::atoi(e); }();
+  p.epi_phased = 0;
+  if (!no_phased && p.y_blocked && p.epi_mode == 2 && a.n_tiles == 1 && !split && (ex->h_pitch == 0) &&
+      (p.y_up_log2 == 1 || p.y_up_log2 == 2) && ex->y_blocked_cout % 16 == 0) {
+    p.epi_phased = 1;
+    p.epi_wide = 0;
+    p.stage_warp_bytes = (p.y_up_log2 == 1 ? 2 : 1) * (1 << p.y_up_log2) * 3072;
+  }
   // barriers (+ output staging) + per-warp column vectors
   const int tail_bytes = 1024 + (p.tma_out ? 8 * p.stage_warp_bytes : 0) + (int)align_up(8 * p.cvec_warp_bytes, 1024);
   const int budget = 227 * 1024 - 1024 - tail_bytes;
@@ -540,7 +550,22 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     };
-    if (a.out_f32 && p.y_blocked) {
+    if (a.out_f32 && p.epi_phased) {
+      // (one 512-byte run = 32 rows x 4 floats, column quad, block): boxes of `up` blocks x 4 quads
+      const cuuint64_t cout = 1ull << p.y_cout_log2, up = 1ull << p.y_up_log2;
+      const cuuint64_t nblk = (((cuuint64_t)a.rows * up + 31) >> 5) + tc::kBlockedPad;
+      cuuint64_t dims3[3] = {128, cout / 4, nblk * (cuuint64_t)a.batch};
+      cuuint64_t strides3[2] = {512, (cout / 4) * 512};
+      cuuint32_t box3[3] = {128, 4, (cuuint32_t)up};
+      cuuint32_t estr3[3] = {1, 1, 1};
+      CUresult r = enc(&L->tm_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out_f32, dims3, strides3, box3, estr3,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(out f32, row-blocked runs) failed with CUresult %d", (int)r);
+        return V2W_ERR_CUDA;
+      }
+    } else if (a.out_f32 && p.y_blocked) {
       // (4 floats, phase, GEMM row inside a block, column quad, block): see tc::Params::y_blocked
       const cuuint64_t cout = 1ull << p.y_cout_log2, up = 1ull << p.y_up_log2;
       const cuuint64_t nblk = (((cuuint64_t)a.rows * up + 31) >> 5) + tc::kBlockedPad;
@@ -569,7 +594,17 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
       const cuuint64_t h_pitch = (ex && ex->h_pitch) ? ex->h_pitch : a.n_total;
       cuuint64_t strides[2] = {h_pitch * 2, (cuuint64_t)a.rows * h_pitch * 2};
       CUresult r;
-      if (p.h_cout) {
+      if (p.epi_phased) {
+        // (cout, up, rows, batch) over the dense [rows][up * cout] operand: boxes of 16 channels x every phase x 32 rows
+        const cuuint64_t cout = 1ull << p.y_cout_log2, up = 1ull << p.y_up_log2;
+        cuuint64_t dims4[4] = {cout, up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
+        cuuint64_t strides4[3] = {cout * 2, up * cout * 2, (cuuint64_t)a.rows * up * cout * 2};
+        cuuint32_t box4[4] = {16, (cuuint32_t)up, 32, 1};
+        cuuint32_t estr4[4] = {1, 1, 1, 1};
+        r = enc(&L->tm_h, p.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                4, a.out_bf16, dims4, strides4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else if (p.h_cout) {
         // (cout, up, rows, batch): one GEMM row is `up` output rows, h_pitch elements apart
         const cuuint64_t up = (cuuint64_t)(a.n_total / p.h_cout);
         cuuint64_t dims4[4] = {(cuuint64_t)(split ? 2 * p.h_cout : p.h_cout), up, (cuuint64_t)a.rows, (cuuint64_t)a.batch};
@@ -1255,6 +1290,14 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     o.d.batch = B;
     o.d.rows = rows;
     choose_tiles(L, B, rows, &o.d);
+    if (bf && out.f32 >= 0 && out.f32_blocked && o.d.n_tiles > 1 && L.n_total <= 256) {
+      // a row-blocked output leaves complete 512-byte runs only when one column tile holds every phase
+      // (tc::Params::epi_phased): one tile with the union of the taps (dead (tap, phase) blocks are zero weights)
+      o.d.n_tile = L.n_total;
+      o.d.n_tiles = 1;
+      o.d.num_taps[0] = L.num_taps;
+      for (int j = 0; j < L.num_taps; ++j) o.d.tap_index[0][j] = j;
+    }
     if (bf) {
       o.d.in_act = in.bf16; o.d.in_is_bf16 = 1; o.d.in_slope = 1.f;
       o.d.out_f32 = out.f32; o.d.out_bf16 = out.bf16; o.d.out_slope = out.slope;
@@ -1293,12 +1336,15 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     // x = cbns[i](ups[i](leaky_relu(x)), fcs[i](spk_noise))   (models.py:128-134)
     const bool wide = widebuf[i].a1cat >= 0;
     // A fused stage reads its residual stream row-per-thread; in the row-blocked layout (v2w_op_desc::f32_blocked)
-    // those reads are coalesced, which takes 12-15 % off the C = 128 and 9 % off the C = 32 stage kernel -- but the
-    // transposed conv that PRODUCES the tensor then stores 16-byte fragments (its phases interleave row by row) and
-    // loses more than the stage gains except at C = 128 (profiles/r02_notes.md).  $V2W_BLOCKED_X0_MASK = bitmask of
-    // stages; default: stage 1 only.
+    // those reads are coalesced, which takes 12-15 % off the C = 128 and 9 % off the C = 32 stage kernel.  The
+    // transposed conv that PRODUCES the tensor must then emit complete 512-byte runs: with one column tile that
+    // holds every phase it walks its accumulator phase-interleaved (tc::Params::epi_phased; rate-2 stages: same
+    // speed as the row-major output), otherwise it stores 16-byte fragments and loses more than the stage gains
+    // except at C = 128.  Measured per stage (profiles/r02_notes.md section 9): stage 1 -10 us at cfg2, stage 3
+    // -9 us (-100 us at cfg5 per GPU), stage 2 (rate 4: single-buffered staging) and stage 4 a wash.
+    // $V2W_BLOCKED_X0_MASK = bitmask of stages; default: stages 1 and 3.
     const char* blocked_env = std::getenv("V2W_BLOCKED_X0_MASK");
-    const int blocked_mask = blocked_env ? std::atoi(blocked_env) : 2;
+    const int blocked_mask = blocked_env ? std::atoi(blocked_env) : 10;
     const bool stage_fused = bf && !force_simt && !no_fuse && !wide && m->fused[i].ok && ((fuse_mask >> i) & 1);
     const bool x0_blocked = stage_fused && ((blocked_mask >> i) & 1) && m->stage_channels[i] >= 16 &&
                             c.upsample_rates[i] <= tc::kBlockedPad && (c.upsample_rates[i] & (c.upsample_rates[i] - 1)) == 0;
