@@ -25,7 +25,12 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = next(it)
-            cur = cur.replace("(int)", "").replace("(bool)1", "pair").replace("(bool)0", "single")
+            cur = cur.replace("(int)", "")
+            # tapgemm_tc_kernel<KC, kPair, kSplit>: the second bool is the split-operand flavour
+            m3 = re.match(r"(.*tapgemm_tc_kernel<\d+, \(bool\)[01], )\(bool\)([01])>", cur)
+            if m3:
+                cur = m3.group(1) + ("split" if m3.group(2) == "1" else "plain") + ">"
+            cur = cur.replace("(bool)1", "pair").replace("(bool)0", "single")
             cur = re.sub(r"\(.*", "", cur).replace("void ", "").replace("v2w::", "")
             per[cur] = Counter()
             continue
