@@ -254,6 +254,16 @@ def test_resblock1_bf16_plan_predicted_snr(name, monkeypatch):
     snr_old = fixtures.snr_db(g.y, plan_interp.run(old, eng.pack_host().numpy(), g.x, g.spk, g.noise))
     print(f"{name}: predicted bf16 SNR {snr:.1f} dB with hi + lo weights, {snr_old:.1f} dB single-rounded")
     assert snr >= 45.0 and snr > snr_old
+    # the packed lo halves: bf16(w - bf16(w)) right after each layer's operands
+    packed = eng.pack_host(native.HALF_BF16_SPLIT).numpy()
+    L = plan.layers[3]
+    cnt = L.num_taps * L.n_total * L.cin
+    as_f32 = lambda off: (packed[off: off + 2 * cnt].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+    hi, lo = as_f32(L.w16_off), as_f32(L.w16_off + 2 * cnt)
+    w = np.ascontiguousarray(packed[L.w32_off: L.w32_off + 4 * cnt].view(np.float32).reshape(
+        L.num_taps, L.cin, L.n_total).transpose(0, 2, 1)).ravel()
+    assert np.array_equal(hi, plan_interp.bf16_round(w)) and np.array_equal(lo, plan_interp.bf16_round(w - hi))
+    assert np.abs(hi + lo - w).max() <= 2.0 ** -15 * np.abs(w).max()
     # ResBlock2 plans are untouched
     g2 = load_golden("rb2_768_stress_tiny")
     p2 = plan_interp.HostPlan(dropin_in_state(g2).engine(), 1, 8, "bf16")
