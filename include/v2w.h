@@ -370,6 +370,22 @@ int32_t v2w_plan_packed_format(const struct v2w_plan* p);
 int64_t v2w_plan_workspace_bytes(const struct v2w_plan* p);
 int32_t v2w_plan_num_ops(const struct v2w_plan* p);
 int32_t v2w_plan_get_op(const struct v2w_plan* p, int32_t index, v2w_op_desc* out);
+/* Launch geometry of op `index` of a BOUND plan (introspection: tests assert that the intended code paths are
+ * the ones that run; tools print it).  For ops of the generic tensor-core tap-GEMM (TAPGEMM with V2W_ENGINE_TC,
+ * MRF_WIDE1/2) every field is set; for other ops only grid / smem_bytes / cta_pair, the rest 0. */
+typedef struct v2w_launch_desc {
+  int32_t grid, smem_bytes;
+  int32_t cta_pair;      /* 1: clusters of two CTAs (cta_group::2) */
+  int32_t k_chunk;       /* K elements per shared-memory chunk (16 / 32 / 64) */
+  int32_t msub;          /* 128-row sub-tiles per tile */
+  int32_t stages_a, stages_w, tap_group;   /* operand / weight ring depths; taps per weight stage */
+  int32_t y_cols, h_cols;                  /* TMA store box widths of the fp32 / 16-bit output */
+  int32_t epi_mode;      /* compiled flavour of the epilogue's chunk loop, 0 = run-time tests */
+  int32_t epi_wide;      /* 32 columns per epilogue step */
+  int32_t epi_phased;    /* phase-interleaved walk of a transposed conv with a row-blocked fp32 output */
+  int32_t split;         /* 0 / 1 (operands and weights as hi + lo) / 2 (weights only) */
+} v2w_launch_desc;
+int32_t v2w_plan_get_launch(const struct v2w_plan* p, int32_t index, v2w_launch_desc* out);
 /* Debug: force op `index` onto an engine (V2W_ENGINE_*). Only meaningful for TAPGEMM ops of
  * a BF16 plan; must be called before v2w_plan_bind. */
 int32_t v2w_plan_set_engine(struct v2w_plan* p, int32_t index, int32_t engine);

@@ -726,3 +726,39 @@ def test_micro_batched_forward_is_bit_identical():
         got = gen(x, s, n)
         assert gen.engine().last_launches == 3 * one
     assert torch.equal(got, want)
+
+
+# ----------------------------------------------------------------------------------------------
+# the intended code paths are the ones that run (v2w_plan_get_launch)
+# ----------------------------------------------------------------------------------------------
+def test_launch_geometry_of_the_benchmarked_plan():
+    """cfg2's bf16 plan: every generic tap-GEMM launch runs a compiled flavour of the epilogue loop, the
+    residual-free ones 32 columns per step, the transposed conv in front of stage 3 the phase-interleaved walk;
+    fp32tc and ResBlock1-bf16 plans run the split kernels."""
+    g = load_golden("rb2_768_stress")
+    gen = dropin_in_state(g, cache=False).to("cuda:0").eval()
+    eng = gen.engine()
+    ops = eng.ops(16, 200, "bf16", "cuda:0")
+    geo = eng.launches(16, 200, "bf16", "cuda:0")
+    assert len(ops) == len(geo) == 14
+    kinds = [o.kind for o in ops]
+    assert kinds[2:] == [native.OP_TAPGEMM, native.OP_TAPGEMM, native.OP_MRF_WIDE1, native.OP_MRF_WIDE2,
+                         native.OP_TAPGEMM, native.OP_MRF_FUSED, native.OP_TAPGEMM, native.OP_MRF_FUSED,
+                         native.OP_TAPGEMM, native.OP_MRF_FUSED, native.OP_TAPGEMM, native.OP_MRF_FUSED]
+    pre, ups0, w1, w2, ups1, _s1, ups2, _s2, ups3, _s3, ups4, _s4 = geo[2:]
+    assert (pre.epi_mode, pre.epi_wide, pre.cta_pair, pre.tap_group) == (1, 1, 1, 2)
+    assert (w1.epi_mode, w2.epi_mode, w1.cta_pair, w2.cta_pair) == (3, 4, 1, 1)
+    for u in (ups0, ups2, ups4):
+        assert (u.epi_mode, u.epi_wide, u.epi_phased) == (2, 1, 0)
+    assert (ups1.epi_mode, ups1.epi_phased) == (2, 0) and ops[6].f32_blocked == 1     # 5-D map: two column tiles
+    assert (ups3.epi_mode, ups3.epi_phased, ups3.epi_wide) == (2, 1, 0) and ops[10].f32_blocked == 1
+    assert all(d.grid > 0 and d.smem_bytes > 0 for d in geo[2:]) and all(d.split == 0 for d in geo)
+    assert all(d.msub >= 2 for d in (ups3, ups4))            # not one barrier round trip per 128 rows
+    split = [d for o, d in zip(eng.ops(2, 24, "fp32tc", "cuda:0"), eng.launches(2, 24, "fp32tc", "cuda:0"))
+             if o.kind == native.OP_TAPGEMM]
+    assert split and all(d.split == 1 and d.epi_wide == 0 for d in split)
+    g1 = load_golden("rb1_768_stress")
+    e1 = dropin_in_state(g1, cache=False).to("cuda:0").eval().engine()
+    w = [d for o, d in zip(e1.ops(2, 24, "bf16", "cuda:0"), e1.launches(2, 24, "bf16", "cuda:0"))
+         if o.kind == native.OP_TAPGEMM]
+    assert w and all(d.split == 2 for d in w)

@@ -372,7 +372,10 @@ static int prepare_tc(const v2w_tapgemm_args& a, TcLaunch* L, const TcExtra* ex 
   int max_taps = 1;
   for (int t = 0; t < nlists; ++t) max_taps = std::max(max_taps, (int)a.num_taps[t]);
   static const int group_env = [] { const char* e = std::getenv("V2W_TC_TAP_GROUP"); return e ? std::atoi(e) : 0; }();
-  p.tap_group = std::max(1, std::min(max_taps, 16384 / (w_rows * kc * 2)));
+  // (a row-blocked output stages 12 KB per epilogue warp -- see epi_phased below: 8 KB of taps per stage there, so
+  // that two-sub-tile operand stages still fit)
+  const int w_stage_cap = (ex && ex->y_blocked_cout) ? 8192 : 16384;
+  p.tap_group = std::max(1, std::min(max_taps, w_stage_cap / (w_rows * kc * 2)));
   if (group_env >= 1) p.tap_group = std::min(group_env, max_taps);
   p.stage_w_bytes = (int)align_up((int64_t)p.tap_group * w_rows * kc * 2, 1024);
   // Super-tile height: as many 128-row sub-tiles as TMEM (2 stages x msub x acc_cols <= 512
@@ -1511,6 +1514,31 @@ int32_t v2w_plan_get_op(const v2w_plan* p, int32_t i, v2w_op_desc* out) {
     return V2W_ERR_INVALID;
   }
   *out = p->ops[i].d;
+  return V2W_OK;
+}
+
+int32_t v2w_plan_get_launch(const v2w_plan* p, int32_t i, v2w_launch_desc* out) {
+  if (!p || !out || i < 0 || i >= (int32_t)p->ops.size()) {
+    set_error("v2w_plan_get_launch: bad index %d", i);
+    return V2W_ERR_INVALID;
+  }
+  if (!p->bound) {
+    set_error("v2w_plan_get_launch: plan is not bound (launch geometry is decided in v2w_plan_bind)");
+    return V2W_ERR_STATE;
+  }
+  std::memset(out, 0, sizeof(*out));
+  const Op& o = p->ops[(size_t)i];
+  if (o.d.kind == V2W_OP_MRF_FUSED || o.d.kind == V2W_OP_PAIR_FUSED) {
+    out->grid = o.fl.grid; out->smem_bytes = o.fl.smem; out->cta_pair = o.fl.pair ? 1 : 0;
+    return V2W_OK;
+  }
+  if (!o.tc_ready) return V2W_OK;     // not a launch of the generic tensor-core kernel
+  const TcLaunch& L = o.tcl;
+  out->grid = L.grid; out->smem_bytes = L.smem; out->cta_pair = L.pair ? 1 : 0; out->k_chunk = L.kc;
+  out->msub = L.prm.msub; out->stages_a = L.prm.stages_a; out->stages_w = L.prm.stages_w;
+  out->tap_group = L.prm.tap_group; out->y_cols = L.prm.y_cols; out->h_cols = L.prm.h_cols;
+  out->epi_mode = L.prm.epi_mode; out->epi_wide = L.prm.epi_wide; out->epi_phased = L.prm.epi_phased;
+  out->split = L.prm.split;
   return V2W_OK;
 }
 

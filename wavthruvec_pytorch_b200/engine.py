@@ -328,6 +328,16 @@ class NativeEngine:
             out.append(d)
         return out
 
+    def launches(self, batch: int, frames: int, precision: str, device) -> List[native.LaunchDesc]:
+        """Launch geometry of every op of the (bound) plan: v2w_plan_get_launch."""
+        handle, _ = self.plan(batch, frames, precision, torch.device(device))
+        out = []
+        for i in range(self._lib.v2w_plan_num_ops(handle)):
+            d = native.LaunchDesc()
+            native.check(self._lib.v2w_plan_get_launch(handle, i, C.byref(d)))
+            out.append(d)
+        return out
+
     # ------------------------------------------------------------------------------------------
     def _check_inputs(self, x, spk, noise):
         h = self._module.h

@@ -109,6 +109,12 @@ class CondDesc(C.Structure):
         (n, C.c_int64) for n in ("fcw_off", "fcb_off", "snw_off", "snb_off", "rstd_off", "mean_off")]
 
 
+class LaunchDesc(C.Structure):   # v2w_launch_desc
+    _fields_ = [(n, C.c_int32) for n in (
+        "grid", "smem_bytes", "cta_pair", "k_chunk", "msub", "stages_a", "stages_w", "tap_group", "y_cols", "h_cols",
+        "epi_mode", "epi_wide", "epi_phased", "split")]
+
+
 class OpDesc(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("engine", C.c_int32), ("layer", C.c_int32),
@@ -218,6 +224,7 @@ _SIGNATURES = [
     ("v2w_plan_packed_format", C.c_int32, [C.c_void_p]),
     ("v2w_plan_num_ops", C.c_int32, [C.c_void_p]),
     ("v2w_plan_get_op", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(OpDesc)]),
+    ("v2w_plan_get_launch", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(LaunchDesc)]),
     ("v2w_plan_set_engine", C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     ("v2w_plan_bind", C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("v2w_plan_refresh_weights", C.c_int32, [C.c_void_p, C.c_void_p]),
