@@ -334,11 +334,16 @@ def test_full_size_against_autograd_delegate(rb):
             y16 = gen(x, s, n).cpu().numpy()
             gen.precision = "fp16"
             yh = gen(x, s, n).cpu().numpy()
+            gen.precision = "fp32tc"
+            ytc = gen(x, s, n).cpu().numpy()
         err = np.abs(y32 - ref).max()
+        err_tc = np.abs(ytc - ref).max()
         snr = fixtures.snr_db(ref, y16)
         snr_h = fixtures.snr_db(ref, yh)
-        print(f"rb={rb!r} B={B} T={T}: fp32 max-abs {err:.2e}, bf16 SNR {snr:.1f} dB, fp16 SNR {snr_h:.1f} dB")
+        print(f"rb={rb!r} B={B} T={T}: fp32 max-abs {err:.2e}, fp32tc max-abs {err_tc:.2e}, bf16 SNR {snr:.1f} dB, "
+              f"fp16 SNR {snr_h:.1f} dB")
         assert err <= FP32_MAX_ABS
+        assert err_tc <= FP32_MAX_ABS
         assert snr_h >= BF16_MIN_SNR_DB
         if rb == 1:
             assert snr >= BF16_MIN_SNR_DB
@@ -485,7 +490,7 @@ def test_shortest_inputs_against_delegate(B, T):
     x, s, n = (a.cuda() for a in fixtures.make_inputs(gen.h, B, T, 40 + T))
     with torch.no_grad():
         ref = gen._forward_autograd(x, s, n).cpu().numpy()
-        for precision, check in (("fp32", None), ("bf16", BF16_MIN_SNR_DB), ("fp16", BF16_MIN_SNR_DB)):
+        for precision, check in (("fp32", None), ("fp32tc", None), ("bf16", BF16_MIN_SNR_DB), ("fp16", BF16_MIN_SNR_DB)):
             gen.precision = precision
             y = gen(x, s, n).cpu().numpy()
             assert y.shape == (B, 1, 320 * T)
