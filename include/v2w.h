@@ -68,8 +68,9 @@ extern "C" {
 #define V2W_HALF_FP16 1
 #define V2W_HALF_FP16_SPLIT 2   /* fp16 hi values in every layer's array, the lo values (fp16(w - hi)) in the second
                                    half of the same section (v2w_layer_desc::w16_off) */
-#define V2W_HALF_BF16_SPLIT 3   /* the same with bf16 values: what a BF16 plan of a ResBlock1 generator binds (its weights
-                                   enter as hi + lo, two MMAs per product: v2w_op_desc::split == 2) */
+#define V2W_HALF_BF16_SPLIT 3   /* the same with bf16 values: what a BF16 plan of a ResBlock1 generator binds (operands and
+                                   weights as bf16 pairs, v2w_op_desc::split == 1; or, $V2W_RB1_BF16=weights, the weights
+                                   only as hi + lo, split == 2) */
 #define V2W_PACKED_HEADER_BYTES 1024   /* {uint32 magic 'V2WP', abi, half_format} then zeros */
 
 /* Hyper-parameters.  Replaces the attribute bag `h` of Generator.__init__
@@ -295,10 +296,11 @@ typedef struct v2w_op_desc {
                                   (L = rows * up output rows of cout channels); MRF_FUSED: `residual` is read in it.  The
                                   fused stage kernels read their fp32 residual stream row-per-thread: in this layout a
                                   warp's float4 load of one column quad is 512 contiguous bytes. */
-  int32_t split;               /* 1: TAPGEMM of a V2W_PREC_FP32_TC plan: in_act / out_bf16 are [rows, hi | lo] fp16 tensors
-                                  (pitches 2 cin / 2 cout), three-term product.  2: weights only -- A (W_hi + W_lo), two
-                                  MMAs per product, plain 16-bit activations (BF16 plans of ResBlock1 generators: bf16
-                                  weight rounding alone costs that 97-conv chain the 45 dB bar) */
+  int32_t split;               /* 1: in_act / out_bf16 are [rows, hi | lo] tensors of 16-bit pairs (pitches 2 cin / 2 cout),
+                                  three-term product: V2W_PREC_FP32_TC plans (fp16 pairs) and BF16 plans of ResBlock1
+                                  generators (bf16 pairs: single bf16 values cost that 97-conv chain the 45 dB bar,
+                                  DESIGN.md section 5).  2: weights only -- A (W_hi + W_lo), two MMAs per product, plain
+                                  16-bit activations ($V2W_RB1_BF16=weights) */
 } v2w_op_desc;
 
 /* ---- library ------------------------------------------------------------------------ */

@@ -87,13 +87,16 @@ def run(plan: HostPlan, packed: np.ndarray, x, spk, noise, collect=None):
     output keyed by op index."""
     f32, u16, conds = _packed_views(plan, packed)
     bf = plan.precision in ("bf16", "fp16", "fp32tc")
-    split = plan.precision == "fp32tc"
+    # split operands (v2w_op_desc::split == 1: the fp32tc plan with fp16 pairs, the ResBlock1 bf16 plan with bf16 pairs):
+    # a 16-bit tensor is the pair (hi, lo) = (round(v), round(v - hi))
+    split = any(op.kind == native.OP_TAPGEMM and op.split == 1 for op in plan.ops)
     half = fp16_round if plan.precision == "fp16" else bf16_round
     if split:
-        # split-fp16 operands (V2W_PREC_FP32_TC): a 16-bit tensor is the pair (hi, lo) = (fp16(v), fp16(v - hi))
+        one = fp16_round if plan.precision == "fp32tc" else bf16_round
+
         def half(v):
-            hi = fp16_round(v)
-            return hi, fp16_round(v - hi)
+            hi = one(v)
+            return hi, one(v - hi)
     hdr = packed[:12].view(np.uint32)
     want_fmt = int(plan.lib.v2w_plan_packed_format(plan.handle))
     assert hdr[0] == 0x50573256 and (not bf or hdr[2] == want_fmt), \

@@ -148,20 +148,25 @@ def test_bf16_plan_snr(name):
 
 
 @pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress"])
-def test_resblock1_bf16_plan_snr(name):
-    """ResBlock1 with bf16 operands: the weights enter as hi + lo (two MMAs per product, one tap-GEMM per
-    convolution) -- rounding them once costs the 97-conv chain the bar (40.8 dB on rb1_768_stress)."""
+@pytest.mark.parametrize("mode", ["pairs", "weights"])
+def test_resblock1_bf16_plan_snr(monkeypatch, name, mode):
+    """ResBlock1 with bf16 operands (single bf16 values: 40.8 dB on rb1_768_stress, below the bar).  Default: operands
+    and weights as bf16 PAIRS, three MMAs per product, one tap-GEMM per convolution; $V2W_RB1_BF16=weights: only the
+    weights as hi + lo (two MMAs) -- over the bar on this fixture, not on every state."""
+    if mode == "weights":
+        monkeypatch.setenv("V2W_RB1_BF16", "weights")
     g = load_golden(name)
     gen = dropin_in_state(g, cache=False).to("cuda:0")
     y = _native(gen, g, "bf16")
     eng = gen.engine()
     ops = eng.ops(g.x.shape[0], g.x.shape[2], "bf16", "cuda:0")
     gemms = [o for o in ops if o.kind == native.OP_TAPGEMM]
-    assert len(gemms) == 96 and all(o.split == 2 and o.engine == native.ENGINE_TC for o in gemms)
+    want_split = 1 if mode == "pairs" else 2
+    assert len(gemms) == 96 and all(o.split == want_split and o.engine == native.ENGINE_TC for o in gemms)
     assert (torch.device("cuda:0"), native.HALF_BF16_SPLIT) in eng._packed
     snr = fixtures.snr_db(g.y, y)
-    print(f"{name}: ResBlock1 bf16 (hi + lo weights) SNR {snr:.1f} dB")
-    assert snr >= BF16_MIN_SNR_DB
+    print(f"{name}: ResBlock1 bf16 ({mode}) SNR {snr:.1f} dB")
+    assert snr >= (70.0 if mode == "pairs" else BF16_MIN_SNR_DB)
 
 
 def test_resblock1_bf16_fused_pairs_remain_available(monkeypatch):
@@ -345,8 +350,7 @@ def test_full_size_against_autograd_delegate(rb):
         assert err <= FP32_MAX_ABS
         assert err_tc <= FP32_MAX_ABS
         assert snr_h >= BF16_MIN_SNR_DB
-        if rb == 1:
-            assert snr >= BF16_MIN_SNR_DB
+        assert snr >= BF16_MIN_SNR_DB      # (ResBlock1: bf16 pairs; single bf16 values give 32-38 dB on this state)
 
 
 def test_linearity_property_of_resblock_free_path():
@@ -766,4 +770,4 @@ def test_launch_geometry_of_the_benchmarked_plan():
     e1 = dropin_in_state(g1, cache=False).to("cuda:0").eval().engine()
     w = [d for o, d in zip(e1.ops(2, 24, "bf16", "cuda:0"), e1.launches(2, 24, "bf16", "cuda:0"))
          if o.kind == native.OP_TAPGEMM]
-    assert w and all(d.split == 2 for d in w)
+    assert w and all(d.split == 1 for d in w)         # bf16 pairs

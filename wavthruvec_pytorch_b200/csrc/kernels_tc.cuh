@@ -458,7 +458,20 @@ __device__ __forceinline__ void lrelu_pack16(const float (&v)[16], float slope, 
 }
 
 // sixteen values -> leaky-relu -> the split-fp16 pair: hi = fp16(v) (clamped to the finite range), lo = fp16(v - hi)
-__device__ __forceinline__ void lrelu_split16(const float (&v)[16], float slope, uint32_t (&h)[8], uint32_t (&l)[8]) {
+__device__ __forceinline__ void lrelu_split16(const float (&v)[16], float slope, bool fp16, uint32_t (&h)[8],
+                                              uint32_t (&l)[8]) {
+  if (!fp16) {      // bf16 pairs: 16 significant bits, no range clamp
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = lrelu(v[2 * e], slope), b = lrelu(v[2 * e + 1], slope);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+      const float2 back = __bfloat1622float2(hi);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(a - back.x, b - back.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hi);
+      l[e] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float a = fminf(fmaxf(lrelu(v[2 * e], slope), -65504.f), 65504.f);
@@ -853,7 +866,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             V2W_TRTC(it, 2300 + cc);
             uint32_t h[8], hl[8];
             if (st_h) {
-              if (split) lrelu_split16(v, out_slope, h, hl);
+              if (split) lrelu_split16(v, out_slope, fp16, h, hl);
               else lrelu_pack16(v, out_slope, fp16, h);       // one format branch per chunk, not one per packed pair
             }
             V2W_TRTC(it, 2400 + cc);
