@@ -2,8 +2,6 @@
 import sys
 from pathlib import Path
 
-import torch
-
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from bench import CONFIGS  # noqa: E402
 from wavthruvec_pytorch_b200 import Generator, HParams  # noqa: E402

@@ -1,7 +1,7 @@
 """What bounds a transposed-conv launch of the generic kernel: one cfg5-per-GPU-sized shape at every super-tile
 height and with either output switched off (CUDA events around single v2w_tapgemm launches).
 usage (GPU box): python tools/ups_probe.py"""
-import json, os, sys
+import os, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
