@@ -296,6 +296,9 @@ typedef struct v2w_op_desc {
                                   (L = rows * up output rows of cout channels); MRF_FUSED: `residual` is read in it.  The
                                   fused stage kernels read their fp32 residual stream row-per-thread: in this layout a
                                   warp's float4 load of one column quad is 512 contiguous bytes. */
+  int32_t out_blocked;         /* PAIR_FUSED: out_f32 is written in the row-blocked layout (f32_blocked of a PAIR_FUSED op says
+                                  the same of its `residual` input) */
+  int32_t acc_blocked;         /* PAIR_FUSED: accum_in is read in the row-blocked layout */
   int32_t split;               /* 1: in_act / out_bf16 are [rows, hi | lo] tensors of 16-bit pairs (pitches 2 cin / 2 cout),
                                   three-term product: V2W_PREC_FP32_TC plans (fp16 pairs) and BF16 plans of ResBlock1
                                   generators (bf16 pairs: single bf16 values cost that 97-conv chain the 45 dB bar,

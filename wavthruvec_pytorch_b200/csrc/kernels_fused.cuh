@@ -73,6 +73,7 @@ struct Params {
   int shift[kMaxTaps];          // operand row (sub-tile 0) of each tap inside its A tile
   const float* x0;              // fp32 [B, L, C], or row-blocked (x0_blocked): [B][ceil(L / 32)][C / 4][32 rows][4]
   int x0_blocked;               // see stacked::Params
+  int out_blocked, acc_blocked; // fp32 output / running sum in the same row-blocked layout (stacked::Params)
   const float* bias1[V2W_MAX_KERNELS];
   const float* bsum;            // sum_j (b1_j + b2_j)   (ResBlock1 pair: b2)
   const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
@@ -490,6 +491,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float4* xrow = (p.x0_blocked
             ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
             : reinterpret_cast<const float4*>(p.x0 + row_base)) + ci0 * 4 * xs;
+        // the row's first column quad in a row-blocked [B, L, C] tensor, float4 units (quad q: + 32 q)
+        const size_t boff = (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31);
         float4 xc[kXc];
         if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
@@ -521,9 +524,11 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[16];
             float4 acc4[4];
             if (p.accum_in) {
-              const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+              const float4* ap = p.acc_blocked ? reinterpret_cast<const float4*>(p.accum_in) + boff + (cc >> 2) * 32
+                                               : reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+              const int as = p.acc_blocked ? 32 : 1;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e);
+              for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e * as);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) acc4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -537,10 +542,12 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
             }
             if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+              float4* op = p.out_blocked ? reinterpret_cast<float4*>(p.out_f32) + boff + (cc >> 2) * 32
+                                         : reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+              const int os = p.out_blocked ? 32 : 1;
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                op[e * os] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
             }
             if (p.out_bf16) {
               uint32_t h[8];

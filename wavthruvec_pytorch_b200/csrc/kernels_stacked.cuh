@@ -96,6 +96,10 @@ struct Params {
   // wavefronts) instead of 32 rows 4 C bytes apart (32 wavefronts) -- the epilogue passes of the fused stages
   // were bound by exactly those wavefronts (profiles/r02_notes.md, timeline of the C = 128 stage).
   int x0_blocked;
+  // The same layout for the fp32 OUTPUT and for the running MRF sum (ResBlock1 conv pairs: the fp32 stream between
+  // the pairs of a block, and the sum between blocks, never leave it): the final pass's row-per-thread float4
+  // stores / loads become 512-byte runs instead of one 16-byte piece of 32 different lines each.
+  int out_blocked, acc_blocked;
   const float* bias1[V2W_MAX_KERNELS];   // by slot
   const float* bsum;
   const float* accum_in;        // fp32 [B, L, C] added in the final pass (running MRF sum), or nullptr
@@ -399,6 +403,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // `lin` = b * rows + row (linear row index: addresses of every row-major tensor of the stage).
     const int xs = p.x0_blocked ? 32 : 1;
     const int x_nblk = ((p.rows + 31) >> 5) + tc::kBlockedPad;
+    size_t boff = 0;     // the row's first column quad in a row-blocked [B, L, C] tensor, in float4 units (quad q: + 32 q)
     auto row_of = [&](int kt, bool& valid, size_t& lin) -> const float4* {
       const int tile = tile_of(kt);
       const bool live_tile = tile < total_tiles;       // a peer tile past the end stores nothing
@@ -408,9 +413,8 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       valid = live_tile && gr >= 0 && gr < p.rows;
       const int r = valid ? gr : 0;
       lin = static_cast<size_t>(b) * p.rows + r;
-      if (p.x0_blocked)
-        return reinterpret_cast<const float4*>(p.x0) +
-               (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
+      boff = (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
+      if (p.x0_blocked) return reinterpret_cast<const float4*>(p.x0) + boff;
       return reinterpret_cast<const float4*>(p.x0 + lin * C);
     };
     float4 xn[kCacheX0 ? kXc : 1];     // C <= 32: the next tile's row, fetched one tile ahead
@@ -467,6 +471,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       bool valid, next_valid = false;
       size_t lin, lin_next;
       const float4* xrow = row_of(kt, valid, lin);
+      const size_t cur_boff = boff;       // (the look-ahead call below overwrites it)
       const int kt_next = live(kt + 1);
       const float4* xnext = kt_next < n_my ? row_of(kt_next, next_valid, lin_next) : xrow;
       const uint32_t tb = k % p.t_bufs, tph = (k / p.t_bufs) & 1u;
@@ -641,6 +646,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       {
         const bool out_valid = valid && central;
         const size_t row_base = lin * C;
+        const size_t out_boff = cur_boff;
         if constexpr (!kCacheX0) {
           if (p.preload) {   // the X0 window was not kept running by the per-slot passes: prime it here
 #pragma unroll
@@ -681,9 +687,11 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float v[16];
               float4 acc4[4];
               if (p.accum_in) {
-                const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+                const float4* ap = p.acc_blocked ? reinterpret_cast<const float4*>(p.accum_in) + out_boff + ci * 4 * 32
+                                                 : reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+                const int as = p.acc_blocked ? 32 : 1;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e);
+                for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e * as);
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -697,10 +705,12 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
               }
               if (p.out_f32) {
-                float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+                float4* op = p.out_blocked ? reinterpret_cast<float4*>(p.out_f32) + out_boff + ci * 4 * 32
+                                           : reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+                const int os = p.out_blocked ? 32 : 1;
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                  op[e * os] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
               }
               if (p.out_bf16) {
                 uint32_t h[8];

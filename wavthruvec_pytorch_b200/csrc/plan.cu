@@ -838,6 +838,8 @@ static int prepare_stacked(const v2w_model* m, const v2w_fused_desc& F, const v2
   }
   p.x0 = reinterpret_cast<const float*>(ws + d.residual);
   p.x0_blocked = d.f32_blocked;
+  p.out_blocked = d.out_blocked;
+  p.acc_blocked = d.acc_blocked;
   for (int j = 0; j < nb; ++j)
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * F.order[j]].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
@@ -917,6 +919,8 @@ static int prepare_fused(const v2w_model* m, const v2w_fused_desc& F, const v2w_
   }
   p.x0 = reinterpret_cast<const float*>(ws + d.residual);
   p.x0_blocked = d.f32_blocked;
+  p.out_blocked = d.out_blocked;
+  p.acc_blocked = d.acc_blocked;
   for (int j = 0; j < F.num_branches; ++j)
     p.bias1[j] = reinterpret_cast<const float*>(packed + m->layers[F.first_layer + 2 * j].bias_off);
   p.bsum = reinterpret_cast<const float*>(packed + F.bsum_off);
@@ -1220,9 +1224,10 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
   // (+ 32 rows per utterance: the row-blocked layout of the fused stages' residual stream pads L to 32)
   int64_t cmax_stage = 0;
   for (int i = 0; i < U; ++i) cmax_stage = std::max<int64_t>(cmax_stage, m->stage_channels[i]);
-  x0.f32 = ws.take(max_e * 4 + (int64_t)B * 32 * (1 + tc::kBlockedPad) * cmax_stage * 4);
-  y1.f32 = ws.take(max_e * 4);
-  const int64_t sum_f32 = ws.take(max_e * 4);
+  const int64_t blocked_pad = (int64_t)B * 32 * (1 + tc::kBlockedPad) * cmax_stage * 4;
+  x0.f32 = ws.take(max_e * 4 + blocked_pad);
+  y1.f32 = ws.take(max_e * 4 + blocked_pad);
+  const int64_t sum_f32 = ws.take(max_e * 4 + blocked_pad);
   if (bf) {
     x0.bf16 = ws.take(max_e * hsz);
     y1.bf16 = ws.take(max_e * hsz);
@@ -1233,7 +1238,7 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     if (bf) t1.bf16 = ws.take(max_e * hsz);
     else t1.f32 = ws.take(max_e * 4);
     if (bf) {
-      y2.f32 = ws.take(max_e * 4);
+      y2.f32 = ws.take(max_e * 4 + blocked_pad);
       y2.bf16 = ws.take(max_e * hsz);
     }
   }
@@ -1355,9 +1360,13 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
     // -9 us (-100 us at cfg5 per GPU), stage 2 (rate 4: single-buffered staging) and stage 4 a wash.
     // $V2W_BLOCKED_X0_MASK = bitmask of stages; default: stages 1 and 3.
     const char* blocked_env = std::getenv("V2W_BLOCKED_X0_MASK");
-    const int blocked_mask = blocked_env ? std::atoi(blocked_env) : 10;
+    // (ResBlock1: the conv-pair kernels of the C <= 128 stages read it the same way, three times per stage -- the
+    // first pair of every block -- so that every fused stage wins: default there stages 1-4)
+    const bool rb1_pairs = c.resblock_type == 1 && bf && !force_simt && !no_fuse && ((fuse_mask >> i) & 1) &&
+                           m->stage_channels[i] <= 128 && m->stage_channels[i] >= 16;
+    const int blocked_mask = blocked_env ? std::atoi(blocked_env) : (c.resblock_type == 1 ? 30 : 10);
     const bool stage_fused = bf && !force_simt && !no_fuse && !wide && m->fused[i].ok && ((fuse_mask >> i) & 1);
-    const bool x0_blocked = stage_fused && ((blocked_mask >> i) & 1) && m->stage_channels[i] >= 16 &&
+    const bool x0_blocked = (stage_fused || rb1_pairs) && ((blocked_mask >> i) & 1) && m->stage_channels[i] >= 16 &&
                             c.upsample_rates[i] <= tc::kBlockedPad && (c.upsample_rates[i] & (c.upsample_rates[i] - 1)) == 0;
     if (x0_blocked) {
       Act x0b = x0;
@@ -1458,6 +1467,14 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
       } else {
         // ResBlock1 (models.py:37-44): x = c2(lrelu(c1(lrelu(x)))) + x, three times
         Act cur = x0;
+        // The fp32 stream between the conv pairs of a block and the running MRF sum between blocks stay in the
+        // row-blocked layout (conv-pair kernels, C <= 128): their final passes store / load row-per-thread, which
+        // in the row-major layout is one 16-byte piece of 32 different lines per instruction.  Not the last stage's
+        // sum, which is conv_post's row-major input.  $V2W_RB1_NO_BLOCKED=1: row-major everywhere.
+        // cfg2, fp16 operands: 3.85 -> 3.28 ms per forward (profiles/r02_notes.md section 10).
+        static const bool rb1_no_blocked = [] { const char* e = std::getenv("V2W_RB1_NO_BLOCKED"); return e && std::atoi(e); }();
+        const bool rb1_blk = !rb1_no_blocked && m->stage_channels[i] <= 128;
+        bool cur_blocked = x0_blocked;
         for (int s = 0; s < 3; ++s) {
           const int pi = (bf && !force_simt && !no_fuse && ((fuse_mask >> i) & 1)) ? m->pair_of_layer[li] : -1;
           if (pi >= 0) {
@@ -1479,6 +1496,10 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
             o.d.accum_in = tail ? accum : -1;
             o.d.out_scale = tail ? scale : 1.f;
             o.d.out_f32 = dst.f32; o.d.out_bf16 = dst.bf16; o.d.out_slope = dst.slope;
+            o.d.f32_blocked = cur_blocked ? 1 : 0;
+            o.d.out_blocked = (rb1_blk && dst.f32 >= 0 && !(tail && last_stage)) ? 1 : 0;
+            o.d.acc_blocked = (rb1_blk && o.d.accum_in >= 0 && !last_stage) ? 1 : 0;
+            cur_blocked = o.d.out_blocked != 0;
             o.d.flops = 2 * (m->layers[li].macs_per_row + m->layers[li + 1].macs_per_row) * (int64_t)rows * B;
             P->ops.push_back(o);
             li += 2;

@@ -133,6 +133,8 @@ class OpDesc(C.Structure):
         ("out_bf16_pitch", C.c_int32),
         ("in_pitch", C.c_int32),
         ("f32_blocked", C.c_int32),
+        ("out_blocked", C.c_int32),
+        ("acc_blocked", C.c_int32),
         ("split", C.c_int32),
     ]
 
