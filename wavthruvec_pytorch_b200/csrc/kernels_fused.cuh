@@ -124,7 +124,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // (6 KB instead of 8 KB of operand reads per CTA and MMA at N = 128).  Barrier plumbing as in
 // tapgemm_tc_kernel: loads land on the leader's full barriers, commits are multicast, the epilogue
 // warps of both CTAs arrive on the leader's barriers.
-template <int C, bool kPair = false, int kSub = 2>
+// kBlk: see stacked::mrf_stacked_kernel (row-blocked fp32 output / running sum of the ResBlock1 conv pairs)
+template <int C, bool kPair = false, int kSub = 2, bool kBlk = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ Params p) {
@@ -492,7 +493,8 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
             : reinterpret_cast<const float4*>(p.x0 + row_base)) + ci0 * 4 * xs;
         // the row's first column quad in a row-blocked [B, L, C] tensor, float4 units (quad q: + 32 q)
-        const size_t boff = (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31);
+        size_t boff = 0;
+        if constexpr (kBlk) boff = (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31);
         float4 xc[kXc];
         if (valid) {   // issued before the wait: overlaps the last conv2 MMAs
 #pragma unroll
@@ -524,9 +526,14 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[16];
             float4 acc4[4];
             if (p.accum_in) {
-              const float4* ap = p.acc_blocked ? reinterpret_cast<const float4*>(p.accum_in) + boff + (cc >> 2) * 32
-                                               : reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
-              const int as = p.acc_blocked ? 32 : 1;
+              const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+              int as = 1;
+              if constexpr (kBlk) {
+                if (p.acc_blocked) {
+                  ap = reinterpret_cast<const float4*>(p.accum_in) + boff + (cc >> 2) * 32;
+                  as = 32;
+                }
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e * as);
             } else {
@@ -542,9 +549,14 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
             }
             if (p.out_f32) {
-              float4* op = p.out_blocked ? reinterpret_cast<float4*>(p.out_f32) + boff + (cc >> 2) * 32
-                                         : reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
-              const int os = p.out_blocked ? 32 : 1;
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+              int os = 1;
+              if constexpr (kBlk) {
+                if (p.out_blocked) {
+                  op = reinterpret_cast<float4*>(p.out_f32) + boff + (cc >> 2) * 32;
+                  os = 32;
+                }
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 op[e * os] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);

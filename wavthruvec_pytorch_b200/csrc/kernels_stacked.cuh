@@ -125,7 +125,10 @@ struct Params {
 // of shared memory and 256 TMEM columns: two CTAs share an SM and hide each other's waits.
 // kPair (C = 64): CTA pairs in lockstep, each with its own window and buffers, sharing the weight
 // operand through cta_group::2 MMAs -- the same construction as mrf_stage_kernel<128, true>.
-template <int C, bool kPair = false>
+// kBlk: the instantiation whose final pass can write its fp32 output / read the running sum row-blocked
+// (Params::out_blocked, acc_blocked: ResBlock1 conv pairs).  A template parameter because the extra address
+// arithmetic, compiled into the ResBlock2 stage kernels as run-time selects, cost them 1-7 % (stage 3: 108 -> 115 us).
+template <int C, bool kPair = false, bool kBlk = false>
 __global__ void __launch_bounds__(kThreads, (C == 16 && !kPair) ? 2 : 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ Params p) {
@@ -413,8 +416,10 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       valid = live_tile && gr >= 0 && gr < p.rows;
       const int r = valid ? gr : 0;
       lin = static_cast<size_t>(b) * p.rows + r;
-      boff = (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
-      if (p.x0_blocked) return reinterpret_cast<const float4*>(p.x0) + boff;
+      if constexpr (kBlk) boff = (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
+      if (p.x0_blocked)
+        return reinterpret_cast<const float4*>(p.x0) +
+               (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
       return reinterpret_cast<const float4*>(p.x0 + lin * C);
     };
     float4 xn[kCacheX0 ? kXc : 1];     // C <= 32: the next tile's row, fetched one tile ahead
@@ -687,9 +692,14 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float v[16];
               float4 acc4[4];
               if (p.accum_in) {
-                const float4* ap = p.acc_blocked ? reinterpret_cast<const float4*>(p.accum_in) + out_boff + ci * 4 * 32
-                                                 : reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
-                const int as = p.acc_blocked ? 32 : 1;
+                const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
+                int as = 1;
+                if constexpr (kBlk) {
+                  if (p.acc_blocked) {
+                    ap = reinterpret_cast<const float4*>(p.accum_in) + out_boff + ci * 4 * 32;
+                    as = 32;
+                  }
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc4[e] = __ldg(ap + e * as);
               } else {
@@ -705,9 +715,14 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
               }
               if (p.out_f32) {
-                float4* op = p.out_blocked ? reinterpret_cast<float4*>(p.out_f32) + out_boff + ci * 4 * 32
-                                           : reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
-                const int os = p.out_blocked ? 32 : 1;
+                float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
+                int os = 1;
+                if constexpr (kBlk) {
+                  if (p.out_blocked) {
+                    op = reinterpret_cast<float4*>(p.out_f32) + out_boff + ci * 4 * 32;
+                    os = 32;
+                  }
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                   op[e * os] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);

@@ -1033,7 +1033,41 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // the instantiations with a row-blocked fp32 output / running sum (ResBlock1 conv pairs)
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, false, 2, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true, 2, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64, true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<32, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_devs.fetch_or(dev_bit);
+  }
+  const bool blk = L.stacked ? (L.sprm.out_blocked || L.sprm.acc_blocked) : (L.prm.out_blocked || L.prm.acc_blocked);
+  if (blk) {
+    if (L.stacked && L.channels == 64 && L.pair)
+      V2W_CUDA(launch_ex<2>(stacked::mrf_stacked_kernel<64, true, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.stacked && L.channels == 64)
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<64, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.stacked && L.channels == 32)
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<32, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.stacked && L.channels == 16)
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<16, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (!L.stacked && L.channels == 128 && !L.narrow && L.pair)
+      V2W_CUDA(launch_ex<2>(fused::mrf_stage_kernel<128, true, 2, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+    else if (!L.stacked && L.channels == 128 && !L.narrow)
+      V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128, false, 2, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+    else {
+      set_error("fused stage: no kernel with a row-blocked output for C = %d%s", L.channels, L.narrow ? " (narrow windows)" : "");
+      return V2W_ERR_STATE;
+    }
+    V2W_CUDA(cudaGetLastError());
+    return V2W_OK;
   }
   if (L.stacked) {
     if (L.channels == 64 && L.pair)
