@@ -305,7 +305,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           a_chunk_bytes = a0_chunk_bytes;
         } else {
           slot = n2 % kSlots;
-          if (p.pair) mbar_wait(t2_empty + 8 * buf, tph ^ 1u);   // no `sum` segment: conv2 is T2's first writer
+          if (kBlk && p.pair) mbar_wait(t2_empty + 8 * buf, tph ^ 1u);   // no `sum` segment: conv2 is T2's first writer
           mbar_wait(a1_full + 8 * slot, (n2 / kSlots) & 1u);
           d_tmem = tmem_t2 + buf * K::kT1Cols;
           a_tile = smem_a1 + slot * K::kA1Bytes;
@@ -331,7 +331,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 w_addr = smem_w + r.s * p.stage_w_bytes;
               }
               const uint64_t bd = smem_desc(dhi, w_addr);
-              const uint32_t acc0 = (sg.type == kSegConv2 && !p.pair) || (sg.flags & kSegFlagAcc) || (t != 0) || (c != 0);
+              const uint32_t acc0 = (sg.type == kSegConv2 && !(kBlk && p.pair)) || (sg.flags & kSegFlagAcc) || (t != 0) || (c != 0);
 #pragma unroll
               for (int m = 0; m < kSub; ++m) {
                 const uint64_t ad = (static_cast<uint64_t>(dhi) << 32) |
@@ -450,7 +450,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
-                const float ax = p.pair ? 0.f : 1.f;
+                const float ax = (kBlk && p.pair) ? 0.f : 1.f;
                 v[4 * e] = fmaf(ax, xr[e].x, __uint_as_float(r[4 * e]) + bb.x);
                 v[4 * e + 1] = fmaf(ax, xr[e].y, __uint_as_float(r[4 * e + 1]) + bb.y);
                 v[4 * e + 2] = fmaf(ax, xr[e].z, __uint_as_float(r[4 * e + 2]) + bb.z);
@@ -525,7 +525,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (valid) {
             float v[16];
             float4 acc4[4];
-            if (p.accum_in) {
+            if (kBlk && p.accum_in) {      // (only the conv-pair programs carry a running sum)
               const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
               int as = 1;
               if constexpr (kBlk) {

@@ -132,6 +132,13 @@ template <int C, bool kPair = false, bool kBlk = false>
 __global__ void __launch_bounds__(kThreads, (C == 16 && !kPair) ? 2 : 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ Params p) {
+  // kBlk = false is THE ResBlock2 stage program of this width: pre-loaded accumulators iff C = 64, a folded conv_post
+  // only at C <= 32, no running sum, residual in the middle activation -- compile-time facts there.  (As run-time
+  // tests in these loops `preload` alone cost the C = 32 / 16 stages 7 / 15 %: it guards global loads.)  kBlk = true
+  // keeps every test at run time: conv-pair programs, and a C = 64 stage program without pre-load ($V2W_FUSED_NO_PRELOAD).
+  const bool preload = kBlk ? p.preload != 0 : (C == 64);
+  const bool post = (!kBlk && C <= 32) ? p.post != 0 : false;
+
   constexpr int kRowBytes = C * 2;              // one K-chunk: the whole channel dimension
   constexpr int kKSteps = C / 16;
   constexpr bool kResident = C <= 32;
@@ -325,7 +332,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const Segment sg = p.seg[s];
         for (uint32_t w = sg.wait; w; w &= w - 1) {
           const int bit = __ffs(w) - 1;
-          if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), p.preload ? tph : (tph ^ 1u));
+          if (bit < 4) mbar_wait(t1_empty + 8 * (tb * 4 + bit), preload ? tph : (tph ^ 1u));
           else if (bit == 4) mbar_wait(t2_empty + 8 * tb, tph ^ 1u);
           else if (bit == 5) mbar_wait(a0_full + 8 * ab, aph);
           else mbar_wait(a1_full + 8 * (tb * 4 + bit - 8), tph);
@@ -471,7 +478,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         else mbar_arrive(t1_empty + 8 * (tb_p * 4));
       }
     };
-    if (p.preload && live(0) < n_my) preload_t1(live(0), 0);
+    if (preload && live(0) < n_my) preload_t1(live(0), 0);
     for (int kt = live(0), k = 0; kt < n_my; ++k) {
       bool valid, next_valid = false;
       size_t lin, lin_next;
@@ -522,7 +529,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               // C = 64: a two-chunk window that runs ahead of the consumer -- past the end of
               // this pass it wraps to chunks 0, 1 of the next pass (same row, L1/L2 hits)
               const int nc = ci + 2 < kNC ? ci + 2 : ci + 2 - kNC;
-              if (!p.preload) {   // (pre-loaded accumulators: this pass does not read X0 at all)
+              if (!preload) {   // (pre-loaded accumulators: this pass does not read X0 at all)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(xrow + (nc * 4 + e) * xs);
               }
@@ -534,7 +541,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int e = 0; e < 4; ++e) {
                 const float4 bb = ld_shared_f4(b1 + (cc + 4 * e) * 4);
                 // selects, not multiplies by 0: in pre-load mode this pass does not load xr
-                const bool ax = p.e1_add_x0 && !p.preload, ab = !p.preload;
+                const bool ax = (kBlk ? p.e1_add_x0 != 0 : true) && !preload, ab = !preload;
                 v[4 * e] = __uint_as_float(r[4 * e]) + (ab ? bb.x : 0.f) + (ax ? xr[e].x : 0.f);
                 v[4 * e + 1] = __uint_as_float(r[4 * e + 1]) + (ab ? bb.y : 0.f) + (ax ? xr[e].y : 0.f);
                 v[4 * e + 2] = __uint_as_float(r[4 * e + 2]) + (ab ? bb.z : 0.f) + (ax ? xr[e].z : 0.f);
@@ -556,20 +563,20 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {              // one arrival per warp: 256 arrivals serialise on the barrier
           if constexpr (kPair) {
             mbar_arrive_leader(a1_full + 8 * (tb * 4 + j));
-            if (!p.preload) mbar_arrive_leader(t1_empty + 8 * (tb * 4 + j));
+            if (!preload) mbar_arrive_leader(t1_empty + 8 * (tb * 4 + j));
           } else {
             mbar_arrive(a1_full + 8 * (tb * 4 + j));
-            if (!p.preload) mbar_arrive(t1_empty + 8 * (tb * 4 + j));
+            if (!preload) mbar_arrive(t1_empty + 8 * (tb * 4 + j));
           }
         }
         V2W_TR(k * 100 + j * 10 + 3);
       }
       // every T1 of this tile has been consumed: pre-load the next tile's (single accumulator set),
       // in the time the tensor pipe spends on this tile's conv2 segments
-      if (p.preload && kt_next < n_my) preload_t1(kt_next, 0);
+      if (preload && kt_next < n_my) preload_t1(kt_next, 0);
       // ---- final pass with conv_post folded in (last stage, C <= 32) ----
       if constexpr (C <= 32) {
-        if (p.post) {
+        if (post) {
           // rows conv_post needs from this window: the central rows and 3 on either side (all of them
           // have complete conv2 sums: the true halo is hc - 3)
           const bool need = valid && i >= p.hc - 3 && i < p.hc + p.rc + 3;
@@ -653,7 +660,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const size_t row_base = lin * C;
         const size_t out_boff = cur_boff;
         if constexpr (!kCacheX0) {
-          if (p.preload) {   // the X0 window was not kept running by the per-slot passes: prime it here
+          if (preload) {   // the X0 window was not kept running by the per-slot passes: prime it here
 #pragma unroll
             for (int e = 0; e < 8; ++e) xc[e] = __ldg(xrow + e * xs);
           }
@@ -683,7 +690,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int e = 0; e < 4; ++e) xr[e] = xc[(ci & 1) * 4 + e];
               // past the end of the tile's last pass the window moves on to the next tile's row
               const float4* src = ci + 2 < kNC ? xrow + (ci + 2) * 4 * xs : xnext + (ci + 2 - kNC) * 4 * xs;
-              if (!p.preload || ci + 2 < kNC) {
+              if (!preload || ci + 2 < kNC) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) xc[(ci & 1) * 4 + e] = __ldg(src + e * xs);
               }
@@ -691,7 +698,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (out_valid) {
               float v[16];
               float4 acc4[4];
-              if (p.accum_in) {
+              if (kBlk && p.accum_in) {      // (only the conv-pair programs carry a running sum)
                 const float4* ap = reinterpret_cast<const float4*>(p.accum_in + row_base + cc);
                 int as = 1;
                 if constexpr (kBlk) {
