@@ -125,7 +125,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // tapgemm_tc_kernel: loads land on the leader's full barriers, commits are multicast, the epilogue
 // warps of both CTAs arrive on the leader's barriers.
 // kBlk: see stacked::mrf_stacked_kernel (row-blocked fp32 output / running sum of the ResBlock1 conv pairs)
-template <int C, bool kPair = false, int kSub = 2, bool kBlk = false>
+// kX0B: stage program whose residual stream is row-blocked (compile-time there, run-time in the kBlk instantiations)
+template <int C, bool kPair = false, int kSub = 2, bool kBlk = false, bool kX0B = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ Params p) {
@@ -388,7 +389,9 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ci0 = kSub == 2 ? 0 : half * kNC;   // first chunk of this thread (even: the look-ahead window's parity holds)
     constexpr int kXc = K::kCacheX0 ? C / 4 : 8;  // cached row, or a 2-chunk look-ahead window
     uint32_t tile_iter = 0, e1 = 0;
-    const int xs = p.x0_blocked ? 32 : 1;          // float4 units between column quads of an X0 row
+    // (compile-time only in the C = 128, 256-row-window stage program -- the one that runs by default)
+    const bool x0_blocked = (kBlk || C != 128 || kSub != 2) ? p.x0_blocked != 0 : kX0B;
+    const int xs = x0_blocked ? 32 : 1;            // float4 units between column quads of an X0 row
     const int x_nblk = ((p.rows + 31) >> 5) + tc::kBlockedPad;
     for (int ts = slot_first; ts < num_slots; ts += slot_step) {
       if (slot_skipped(ts)) continue;
@@ -403,7 +406,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int gr = q0c - p.hc + i;
         const bool valid = live && gr >= 0 && gr < p.rows;
         const int xr_ = valid ? gr : 0;
-        const float4* xrow = (p.x0_blocked
+        const float4* xrow = (x0_blocked
             ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
             : reinterpret_cast<const float4*>(p.x0 + (static_cast<size_t>(b) * p.rows + xr_) * C)) + ci0 * 4 * xs;   // first chunk of this thread
         float4 xc[kXc];
@@ -489,7 +492,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool valid = live && i < p.rc && gr < p.rows;
         const size_t row_base = (static_cast<size_t>(b) * p.rows + (valid ? gr : 0)) * C;
         const int xr_ = valid ? gr : 0;
-        const float4* xrow = (p.x0_blocked
+        const float4* xrow = (x0_blocked
             ? reinterpret_cast<const float4*>(p.x0) + (static_cast<size_t>(b) * x_nblk + (xr_ >> 5)) * (C / 4) * 32 + (xr_ & 31)
             : reinterpret_cast<const float4*>(p.x0 + row_base)) + ci0 * 4 * xs;
         // the row's first column quad in a row-blocked [B, L, C] tensor, float4 units (quad q: + 32 q)

@@ -128,7 +128,8 @@ struct Params {
 // kBlk: the instantiation whose final pass can write its fp32 output / read the running sum row-blocked
 // (Params::out_blocked, acc_blocked: ResBlock1 conv pairs).  A template parameter because the extra address
 // arithmetic, compiled into the ResBlock2 stage kernels as run-time selects, cost them 1-7 % (stage 3: 108 -> 115 us).
-template <int C, bool kPair = false, bool kBlk = false>
+// kX0B: stage program whose residual stream is row-blocked (compile-time there, run-time in the kBlk instantiations)
+template <int C, bool kPair = false, bool kBlk = false, bool kX0B = false>
 __global__ void __launch_bounds__(kThreads, (C == 16 && !kPair) ? 2 : 1)
 mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ Params p) {
@@ -411,7 +412,8 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // fp32 X0 row of tile `k` for this thread (clamped to a valid row; `valid` says whether it counts)
     // X0 row of this thread for tile `kt`: pointer to its first column quad; quad q is at ptr + q * xs.
     // `lin` = b * rows + row (linear row index: addresses of every row-major tensor of the stage).
-    const int xs = p.x0_blocked ? 32 : 1;
+    const bool x0_blocked = kBlk ? p.x0_blocked != 0 : kX0B;
+    const int xs = x0_blocked ? 32 : 1;
     const int x_nblk = ((p.rows + 31) >> 5) + tc::kBlockedPad;
     size_t boff = 0;     // the row's first column quad in a row-blocked [B, L, C] tensor, in float4 units (quad q: + 32 q)
     auto row_of = [&](int kt, bool& valid, size_t& lin) -> const float4* {
@@ -424,7 +426,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int r = valid ? gr : 0;
       lin = static_cast<size_t>(b) * p.rows + r;
       if constexpr (kBlk) boff = (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
-      if (p.x0_blocked)
+      if (x0_blocked)
         return reinterpret_cast<const float4*>(p.x0) +
                (static_cast<size_t>(b) * x_nblk + (r >> 5)) * (C / 4) * 32 + (r & 31);
       return reinterpret_cast<const float4*>(p.x0 + lin * C);

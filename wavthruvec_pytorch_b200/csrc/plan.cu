@@ -1046,6 +1046,18 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16, false, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, true, 2, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(fused::mrf_stage_kernel<128, false, 2, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64, true, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<64, false, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<32, false, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    V2W_CUDA(cudaFuncSetAttribute(stacked::mrf_stacked_kernel<16, false, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_devs.fetch_or(dev_bit);
   }
   // (every conv-pair program runs the kBlk instantiation; the other one is the ResBlock2 stage program with the pair /
@@ -1073,6 +1085,18 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
     V2W_CUDA(cudaGetLastError());
     return V2W_OK;
   }
+  if (L.stacked && L.sprm.x0_blocked) {      // stage programs with a row-blocked residual stream
+    if (L.channels == 64 && L.pair)
+      V2W_CUDA(launch_ex<2>(stacked::mrf_stacked_kernel<64, true, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.channels == 64)
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<64, false, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else if (L.channels == 32)
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<32, false, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    else
+      V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<16, false, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    V2W_CUDA(cudaGetLastError());
+    return V2W_OK;
+  }
   if (L.stacked) {
     if (L.channels == 64 && L.pair)
       V2W_CUDA(launch_ex<2>(stacked::mrf_stacked_kernel<64, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
@@ -1082,6 +1106,14 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
       V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<32>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
     else
       V2W_CUDA(launch_pdl(stacked::mrf_stacked_kernel<16>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
+    V2W_CUDA(cudaGetLastError());
+    return V2W_OK;
+  }
+  if (L.channels == 128 && !L.narrow && L.prm.x0_blocked) {      // stage program with a row-blocked residual stream
+    if (L.pair)
+      V2W_CUDA(launch_ex<2>(fused::mrf_stage_kernel<128, true, 2, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
+    else
+      V2W_CUDA(launch_pdl(fused::mrf_stage_kernel<128, false, 2, false, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.prm));
     V2W_CUDA(cudaGetLastError());
     return V2W_OK;
   }
