@@ -551,7 +551,7 @@ mrf_stage_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z + acc4[e].z) * p.out_scale;
               v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
             }
-            if (p.out_f32) {
+            if ((kBlk || C != 128 || kSub != 2) && p.out_f32) {   // (the default stage program has no fp32 output)
               float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
               int os = 1;
               if constexpr (kBlk) {

@@ -723,7 +723,7 @@ mrf_stacked_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 v[4 * e + 2] = (__uint_as_float(r[4 * e + 2]) + bb.z + p.res_scale * xr[e].z + acc4[e].z) * p.out_scale;
                 v[4 * e + 3] = (__uint_as_float(r[4 * e + 3]) + bb.w + p.res_scale * xr[e].w + acc4[e].w) * p.out_scale;
               }
-              if (p.out_f32) {
+              if (kBlk && p.out_f32) {      // (a stage program with an fp32 output runs the kBlk instantiation)
                 float4* op = reinterpret_cast<float4*>(p.out_f32 + row_base + cc);
                 int os = 1;
                 if constexpr (kBlk) {

@@ -1063,8 +1063,9 @@ static int launch_fused(const FusedLaunch& L0, cudaStream_t st, const int* row_l
   // (every conv-pair program runs the kBlk instantiation; the other one is the ResBlock2 stage program with the pair /
   // running-sum tests compiled out)
   const bool blk = L.stacked ? (L.sprm.out_blocked || L.sprm.acc_blocked || !L.sprm.e1_add_x0 ||
-                                (L.channels == 64) != (L.sprm.preload != 0))
-                             : (L.prm.out_blocked || L.prm.acc_blocked || L.prm.pair);
+                                (L.channels == 64) != (L.sprm.preload != 0) || L.sprm.out_f32 != nullptr)
+                             : (L.prm.out_blocked || L.prm.acc_blocked || L.prm.pair ||
+                                (L.channels == 128 && !L.narrow && L.prm.out_f32 != nullptr));
   if (blk) {
     if (L.stacked && L.channels == 64 && L.pair)
       V2W_CUDA(launch_ex<2>(stacked::mrf_stacked_kernel<64, true, true>, L.grid, tc::kThreads, L.smem, st, L.tm_a, L.tm_w, L.sprm));
