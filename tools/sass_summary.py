@@ -30,6 +30,11 @@ def main():
             m3 = re.match(r"(.*tapgemm_tc_kernel<\d+, \(bool\)[01], )\(bool\)([01])>", cur)
             if m3:
                 cur = m3.group(1) + ("split" if m3.group(2) == "1" else "plain") + ">"
+            # mrf_stacked_kernel<C, kPair, kBlk, kX0B>, mrf_stage_kernel<C, kPair, kSub, kBlk, kX0B>: name the last two
+            m4 = re.match(r"(.*(?:mrf_stacked_kernel<\d+, \(bool\)[01]|mrf_stage_kernel<\d+, \(bool\)[01], \d+), )\(bool\)([01]), \(bool\)([01])>", cur)
+            if m4:
+                cur = (m4.group(1) + ("any-program" if m4.group(2) == "1" else "stage-program") + ", " +
+                       ("x0-blocked" if m4.group(3) == "1" else "x0-rows") + ">")
             cur = cur.replace("(bool)1", "pair").replace("(bool)0", "single")
             cur = re.sub(r"\(.*", "", cur).replace("void ", "").replace("v2w::", "")
             per[cur] = Counter()
