@@ -48,12 +48,12 @@ def main():
             per[cur]["_total"] += 1
     arch = re.search(r"arch = (\S+)", sass)
     print(f"# cuobjdump -sass {LIB.name}  ({arch.group(1) if arch else '?'}); instructions per kernel")
-    print(f"{'kernel':58s} {'total':>7s} " + " ".join(f"{w:>8s}" for w in WANT))
+    print(f"{'kernel':72s} {'total':>7s} " + " ".join(f"{w:>8s}" for w in WANT))
     tot = Counter()
     for k, c in per.items():
-        print(f"{k[:58]:58s} {c['_total']:7d} " + " ".join(f"{c[w]:8d}" for w in WANT))
+        print(f"{k[:72]:72s} {c['_total']:7d} " + " ".join(f"{c[w]:8d}" for w in WANT))
         tot.update(c)
-    print(f"{'TOTAL':58s} {tot['_total']:7d} " + " ".join(f"{tot[w]:8d}" for w in WANT))
+    print(f"{'TOTAL':72s} {tot['_total']:7d} " + " ".join(f"{tot[w]:8d}" for w in WANT))
 
 
 if __name__ == "__main__":
