@@ -23,6 +23,14 @@
 // Stage indices and phase bits are running counters (no div/mod in the loops); K-chunk width is
 // a template parameter.
 //
+// Round 2 (DESIGN.md sections 3.1, 3.13, 3.16-3.18), all in Params:
+//   * several taps per W stage (tap_group): one barrier round trip serves up to 16 KB of taps;
+//   * K-grouped / N-stacked operands for the two launches of a wide stage (kgroups, w_row, res_cols, h_pitch);
+//   * split operands (split, template kSplit): fp32-grade products as A_hi W_hi + A_lo W_hi + A_hi W_lo over pairs of
+//     16-bit values (fp32tc plans: fp16 pairs; ResBlock1 bf16 plans: bf16 pairs), or the weights only (split == 2);
+//   * the epilogue's chunk loop compiled per op flavour (epi_mode), 32 columns per step for the residual-free ones
+//     (epi_wide), and the phase-interleaved walk of a transposed conv whose fp32 output is row-blocked (epi_phased).
+//
 // Halo reuse: the A tile for one K-chunk holds rows [q0 + off_min, q0 + 128*msub + off_max) and is
 // loaded ONCE; every tap (and every dilation) is a row-shifted view of it -- the UMMA shared-memory
 // descriptor's start address is advanced by shift * row_bytes.  Measured on B200 (tools/tc_probe.py):
