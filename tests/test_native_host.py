@@ -234,6 +234,39 @@ def test_fp32tc_plan_predicted_error(name):
     assert not plain[L.w16_off + 2 * n: L.w16_off + 4 * n].any()
 
 
+def test_resblock1_row_blocked_stream_wiring(monkeypatch):
+    """ResBlock1, fp16 plan: the fp32 stream between the conv pairs is row-blocked -- every pair of the C <= 128 stages
+    writes x' blocked and reads a blocked residual from the second pair of a block on; the running sum is blocked
+    except in the last stage, whose sum is conv_post's row-major input; the transposed convs in front of stages 1-4
+    write X0 blocked, so the first pair of every block reads it blocked as well."""
+    g = load_golden("rb1_768_stress")
+    eng = dropin_in_state(g).engine()
+    plan = plan_interp.HostPlan(eng, 2, 24, "fp16")
+    pairs = [op for op in plan.ops if op.kind == native.OP_PAIR_FUSED]
+    assert len(pairs) == 36
+    for st in (1, 2, 3, 4):
+        ops = [op for op in pairs if op.stage == st]
+        assert len(ops) == 9
+        last = st == 4
+        for n, op in enumerate(ops):
+            s_in_block, block = n % 3, n // 3
+            tail = s_in_block == 2
+            assert op.f32_blocked == 1                        # X0 (first pair) or the previous pair's output
+            want_out = 0 if (tail and (last or block == 2)) else 1       # last block's tail: 16-bit output only
+            assert op.out_blocked == want_out, (st, n)
+            assert op.acc_blocked == (1 if (tail and block > 0 and not last) else 0), (st, n)
+    ups = [op for op in plan.ops if op.kind == native.OP_TAPGEMM and plan.layers[op.layer].role == 1]
+    assert [op.f32_blocked for op in ups] == [0, 1, 1, 1, 1]
+    assert [(op.n_tile, op.n_tiles) for op in ups][2] == (256, 1)      # ups[2]: ONE column tile holding its 4 phases
+    monkeypatch.setenv("V2W_RB1_NO_BLOCKED", "1")
+    monkeypatch.setenv("V2W_BLOCKED_X0_MASK", "0")
+    plain = plan_interp.HostPlan(eng, 2, 24, "fp16")
+    assert not any(op.f32_blocked or op.out_blocked or op.acc_blocked for op in plain.ops)
+    # same arithmetic either way: the layout is invisible to the numpy interpreter
+    packed = eng.pack_host(native.HALF_FP16).numpy()
+    assert np.array_equal(plan_interp.run(plan, packed, g.x, g.spk, g.noise), plan_interp.run(plain, packed, g.x, g.spk, g.noise))
+
+
 @pytest.mark.parametrize("name", ["rb1_768_stress", "rb1_1024_stress"])
 def test_resblock1_bf16_plan_predicted_snr(name, monkeypatch):
     """ResBlock1 with bf16 operands: rounding the WEIGHTS once costs its 97-conv chain the 45 dB bar.  Default plan:

@@ -1543,7 +1543,8 @@ int32_t v2w_plan_create(const v2w_model* m, int32_t batch, int32_t frames, int32
         // in the row-major layout is one 16-byte piece of 32 different lines per instruction.  Not the last stage's
         // sum, which is conv_post's row-major input.  $V2W_RB1_NO_BLOCKED=1: row-major everywhere.
         // cfg2, fp16 operands: 3.85 -> 3.28 ms per forward (profiles/r02_notes.md section 10).
-        static const bool rb1_no_blocked = [] { const char* e = std::getenv("V2W_RB1_NO_BLOCKED"); return e && std::atoi(e); }();
+        const char* nb_env = std::getenv("V2W_RB1_NO_BLOCKED");      // (read per plan, like $V2W_BLOCKED_X0_MASK)
+        const bool rb1_no_blocked = nb_env && std::atoi(nb_env);
         const bool rb1_blk = !rb1_no_blocked && m->stage_channels[i] <= 128;
         bool cur_blocked = x0_blocked;
         for (int s = 0; s < 3; ++s) {
